@@ -1,0 +1,369 @@
+// rt_api.cu -- host side of the C ABI declared in include/rt_b200.h.
+//
+// Owns the context (device, stream, device-resident scene), converts the reference's
+// AoS/FP64 data model (include/sphere.h:8-20, include/scene.h:10-38) into the device layout
+// described in rt_device.h, and sequences the kernels.  No rendering arithmetic happens on
+// the host; there is no CPU fallback.
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "rt_device.h"
+#include "rt_internal.h"
+#include "rt_kernels.h"
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+// ------------------------------------------------------------------------------------------
+// errors
+static thread_local std::string g_last_error;
+int rt_fail(int code, const std::string &msg) { g_last_error = msg; return code; }
+extern "C" const char *rt_last_error(void) { return g_last_error.c_str(); }
+extern "C" int rt_abi_version(void) { return RT_ABI_VERSION; }
+
+#define RT_CUDA(call)                                                                              \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return rt_fail(RT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));             \
+  } while (0)
+
+extern "C" int rt_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------
+// context
+struct rt_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int mode = 0;          // 0 fast, 1 exact
+  int counters_on = 1;
+  // scene
+  bool have_scene = false;
+  int N = 0, L = 0;
+  double fov = 60.0;
+  RtFrameConst frame;
+  unsigned long long scene_version = 0;
+  double4 *d_sph64 = nullptr;
+  float4 *d_mat = nullptr;
+  float2 *d_matx = nullptr;
+  RtFastScene fast;      // FP32 filter tables (rt_kernels.h)
+  // per-resolution tables
+  int tabW = 0, tabH = 0;
+  double tab_fov = 0;
+  double *d_su = nullptr, *d_sv = nullptr;
+  // buffers
+  uint8_t *d_rgb = nullptr; size_t rgb_cap = 0;
+  int32_t *d_hit = nullptr; size_t hit_cap = 0;
+  uint32_t *d_mask = nullptr; size_t mask_cap = 0;
+  unsigned long long *d_counters = nullptr;
+  RtFastWork work;       // queues / accumulators of the fast path
+};
+
+// which (ctx, scene_version) last wrote each device's __constant__ bank
+static std::mutex g_const_mutex;
+static const rt_ctx *g_const_owner[64] = {nullptr};
+static unsigned long long g_const_version[64] = {0};
+
+extern "C" int rt_create(int device, rt_ctx **out) {
+  if (!out) return rt_fail(RT_ERR_ARG, "rt_create: NULL out");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return rt_fail(RT_ERR_CUDA, "rt_create: no CUDA device (this library has no CPU fallback)");
+  }
+  if (device < 0 || device >= n || device >= 64) return rt_fail(RT_ERR_ARG, "rt_create: bad device index");
+  cudaDeviceProp prop;
+  RT_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return rt_fail(RT_ERR_CUDA, std::string("rt_create: device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                                    ", this library is built for sm_100a only");
+  RT_CUDA(cudaSetDevice(device));
+  rt_ctx *c = new (std::nothrow) rt_ctx();
+  if (!c) return rt_fail(RT_ERR_NOMEM, "rt_create: out of memory");
+  c->device = device;
+  memset(&c->frame, 0, sizeof(c->frame));
+  memset(&c->fast, 0, sizeof(c->fast));
+  memset(&c->work, 0, sizeof(c->work));
+  c->work.num_sms = prop.multiProcessorCount;
+  RT_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  RT_CUDA(cudaEventCreate(&c->ev0));
+  RT_CUDA(cudaEventCreate(&c->ev1));
+  RT_CUDA(cudaMalloc(&c->d_counters, RT_CNT_TOTAL * sizeof(unsigned long long)));
+  int r = rtk_fast_init(c->device);
+  if (r != 0) return rt_fail(RT_ERR_CUDA, std::string("rt_create: kernel attribute setup failed: ") + cudaGetErrorString((cudaError_t)-r));
+  *out = c;
+  return RT_OK;
+}
+
+static void free_scene(rt_ctx *c) {
+  cudaFree(c->d_sph64); c->d_sph64 = nullptr;
+  cudaFree(c->d_mat); c->d_mat = nullptr;
+  cudaFree(c->d_matx); c->d_matx = nullptr;
+  rtk_fast_free_scene(&c->fast);
+  c->have_scene = false;
+}
+
+extern "C" void rt_destroy(rt_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  {
+    std::lock_guard<std::mutex> lk(g_const_mutex);
+    if (g_const_owner[c->device] == c) g_const_owner[c->device] = nullptr;
+  }
+  free_scene(c);
+  rtk_fast_free_work(&c->work);
+  cudaFree(c->d_su); cudaFree(c->d_sv);
+  cudaFree(c->d_rgb); cudaFree(c->d_hit); cudaFree(c->d_mask); cudaFree(c->d_counters);
+  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" int rt_set_option(rt_ctx *c, const char *key, long long value) {
+  if (!c || !key) return rt_fail(RT_ERR_ARG, "rt_set_option: NULL argument");
+  if (!strcmp(key, "mode")) {
+    if (value != 0 && value != 1) return rt_fail(RT_ERR_ARG, "rt_set_option: mode must be 0 or 1");
+    c->mode = (int)value;
+    return RT_OK;
+  }
+  if (!strcmp(key, "counters")) { c->counters_on = value != 0; return RT_OK; }
+  return rt_fail(RT_ERR_ARG, std::string("rt_set_option: unknown key ") + key);
+}
+
+// ------------------------------------------------------------------------------------------
+// scene upload
+namespace {
+struct V3 { double x, y, z; };
+inline V3 vsub(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline double vlen(V3 a) { return std::sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
+inline V3 vnorm(V3 a) { double l = vlen(a); return {a.x / l, a.y / l, a.z / l}; }
+inline V3 vcross(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+}  // namespace
+
+extern "C" int rt_upload_scene(rt_ctx *c, const double *spheres, int N, const double *lights, int L,
+                               const double ambient[3], const double cam_pos[3], const double cam_look[3],
+                               double fov_deg) {
+  if (!c || N < 0 || L < 0 || (N > 0 && !spheres) || (L > 0 && !lights) || !ambient || !cam_pos || !cam_look)
+    return rt_fail(RT_ERR_ARG, "rt_upload_scene: bad argument");
+  if (L > RT_MAX_LIGHTS)
+    return rt_fail(RT_ERR_UNSUPPORTED, "rt_upload_scene: more than " + std::to_string(RT_MAX_LIGHTS) + " lights");
+  RT_CUDA(cudaSetDevice(c->device));
+  RT_CUDA(cudaStreamSynchronize(c->stream));
+  free_scene(c);
+  c->N = N; c->L = L; c->fov = fov_deg;
+
+  // include/camera.h:10-15, in double on the host
+  RtFrameConst &f = c->frame;
+  memset(&f, 0, sizeof(f));
+  V3 pos{cam_pos[0], cam_pos[1], cam_pos[2]}, look{cam_look[0], cam_look[1], cam_look[2]};
+  V3 fwd = vnorm(vsub(look, pos));
+  V3 right = vnorm(vcross(fwd, V3{0, 1, 0}));
+  V3 up = vnorm(vcross(right, fwd));
+  f.cam_pos[0] = pos.x; f.cam_pos[1] = pos.y; f.cam_pos[2] = pos.z;
+  f.fwd[0] = fwd.x; f.fwd[1] = fwd.y; f.fwd[2] = fwd.z;
+  f.right[0] = right.x; f.right[1] = right.y; f.right[2] = right.z;
+  f.up[0] = up.x; f.up[1] = up.y; f.up[2] = up.z;
+  for (int l = 0; l < L; l++) {
+    const double *r = lights + (size_t)l * RT_LIGHT_STRIDE;
+    for (int k = 0; k < 3; k++) { f.light_pos[l][k] = r[k]; f.light_col[l][k] = (float)r[3 + k]; }
+  }
+  for (int k = 0; k < 3; k++) f.ambient[k] = (float)ambient[k];
+  f.nlights = L; f.nspheres = N;
+
+  std::vector<double4> s64((size_t)(N > 0 ? N : 1));
+  std::vector<float4> mat((size_t)(N > 0 ? N : 1));
+  std::vector<float2> matx((size_t)(N > 0 ? N : 1));
+  for (int i = 0; i < N; i++) {
+    const double *r = spheres + (size_t)i * RT_SPHERE_STRIDE;
+    s64[i] = make_double4(r[0], r[1], r[2], r[3] * r[3]);
+    mat[i] = make_float4((float)r[4], (float)r[5], (float)r[6], (float)r[7]);
+    matx[i] = make_float2((float)r[9], r[7] > 0 ? 1.0f : 0.0f);   // recurse flag decided in double
+  }
+  size_t n1 = (size_t)(N > 0 ? N : 1);
+  RT_CUDA(cudaMalloc(&c->d_sph64, n1 * sizeof(double4)));
+  RT_CUDA(cudaMalloc(&c->d_mat, n1 * sizeof(float4)));
+  RT_CUDA(cudaMalloc(&c->d_matx, n1 * sizeof(float2)));
+  RT_CUDA(cudaMemcpyAsync(c->d_sph64, s64.data(), n1 * sizeof(double4), cudaMemcpyHostToDevice, c->stream));
+  RT_CUDA(cudaMemcpyAsync(c->d_mat, mat.data(), n1 * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+  RT_CUDA(cudaMemcpyAsync(c->d_matx, matx.data(), n1 * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+  int r = rtk_fast_build_scene(&c->fast, spheres, N, &f, c->stream);
+  if (r != 0) return rt_fail(RT_ERR_CUDA, std::string("rt_upload_scene: filter table build failed: ") + cudaGetErrorString((cudaError_t)-r));
+  RT_CUDA(cudaStreamSynchronize(c->stream));
+  c->scene_version++;
+  c->have_scene = true;
+  return RT_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// render
+static int ensure_tables(rt_ctx *c, int W, int H) {
+  if (c->d_su && c->tabW == W && c->tabH == H && c->tab_fov == c->fov) return RT_OK;
+  cudaFree(c->d_su); cudaFree(c->d_sv); c->d_su = c->d_sv = nullptr;
+  // include/camera.h:18-22 and src/main.cpp:151-152, same operations in the same order
+  const double aspect = 1.0;
+  const double scale = std::tan(c->fov * 0.5 * M_PI / 180.0);
+  std::vector<double> su((size_t)W), sv((size_t)H);
+  for (int i = 0; i < W; i++) { double u = double(i) / (W - 1); su[i] = (u - 0.5) * scale * aspect; }
+  for (int j = 0; j < H; j++) { double v = double(j) / (H - 1); sv[j] = (v - 0.5) * scale; }
+  RT_CUDA(cudaMalloc(&c->d_su, (size_t)W * sizeof(double)));
+  RT_CUDA(cudaMalloc(&c->d_sv, (size_t)H * sizeof(double)));
+  RT_CUDA(cudaMemcpy(c->d_su, su.data(), (size_t)W * sizeof(double), cudaMemcpyHostToDevice));
+  RT_CUDA(cudaMemcpy(c->d_sv, sv.data(), (size_t)H * sizeof(double), cudaMemcpyHostToDevice));
+  c->tabW = W; c->tabH = H; c->tab_fov = c->fov;
+  return RT_OK;
+}
+
+template <typename T>
+static int ensure_cap(T *&ptr, size_t &cap, size_t need) {
+  if (cap >= need && ptr) return RT_OK;
+  cudaFree(ptr); ptr = nullptr; cap = 0;
+  RT_CUDA(cudaMalloc(&ptr, need * sizeof(T)));
+  cap = need;
+  return RT_OK;
+}
+
+extern "C" int rt_band_rows(int H, int band_h, int rank, int nranks) {
+  if (H < 0 || band_h < 1 || nranks < 1 || rank < 0 || rank >= nranks) return rt_fail(RT_ERR_ARG, "rt_band_rows: bad argument");
+  int rows = 0;
+  for (int b = rank; b * band_h < H; b += nranks) {
+    int j0 = b * band_h, j1 = j0 + band_h < H ? j0 + band_h : H;
+    rows += j1 - j0;
+  }
+  return rows;
+}
+
+extern "C" int rt_band_row_list(int H, int band_h, int rank, int nranks, int32_t *rows) {
+  int n = rt_band_rows(H, band_h, rank, nranks);
+  if (n < 0) return n;
+  if (!rows) return rt_fail(RT_ERR_ARG, "rt_band_row_list: NULL rows");
+  int k = 0;
+  for (int b = rank; b * band_h < H; b += nranks)
+    for (int j = b * band_h; j < (b + 1) * band_h && j < H; j++) rows[k++] = j;
+  return n;
+}
+
+static void fill_stats(rt_stats *st, const unsigned long long *cnt) {
+  st->closest_queries = cnt[RT_CNT_CLOSEST];
+  st->hits = cnt[RT_CNT_HITS];
+  st->shadow_queries = cnt[RT_CNT_SHADOW];
+  st->occluded = cnt[RT_CNT_OCCLUDED];
+  st->fp64_intersections = cnt[RT_CNT_FP64];
+  st->sphere_tests = cnt[RT_CNT_TESTS];
+  for (int k = 0; k < RT_MAX_LEVELS; k++) st->alive[k] = cnt[RT_CNT_ALIVE0 + k];
+}
+
+// Launches the kernels of one (possibly banded) render on `stream`.  When `stats` is given the
+// call synchronises the stream and fills it.
+static int render_common(rt_ctx *c, int W, int H, int depth, int band_h, int rank, int nranks, uint8_t *dev_rgb,
+                         int32_t *dev_hit, uint32_t *dev_mask, cudaStream_t stream, rt_stats *stats) {
+  if (!c->have_scene) return rt_fail(RT_ERR_STATE, "render: no scene uploaded (call rt_upload_scene first)");
+  if (W < 1 || H < 1 || depth < 0) return rt_fail(RT_ERR_ARG, "render: bad image size or depth");
+  if (depth > RT_MAX_LEVELS) return rt_fail(RT_ERR_UNSUPPORTED, "render: max_depth above RT_MAX_LEVELS");
+  int rows = rt_band_rows(H, band_h, rank, nranks);
+  if (rows < 0) return rows;
+  RT_CUDA(cudaSetDevice(c->device));
+  int rc = ensure_tables(c, W, H);
+  if (rc) return rc;
+  {
+    std::lock_guard<std::mutex> lk(g_const_mutex);
+    if (g_const_owner[c->device] != c || g_const_version[c->device] != c->scene_version) {
+      RT_CUDA(rtk_set_frame_const(&c->frame, stream));
+      g_const_owner[c->device] = c;
+      g_const_version[c->device] = c->scene_version;
+    }
+  }
+  const bool want_counters = c->counters_on && stats != nullptr;
+  RtRenderArgs a;
+  memset(&a, 0, sizeof(a));
+  a.W = W; a.H = H; a.max_depth = depth;
+  a.bands.band_h = band_h; a.bands.rank = rank; a.bands.nranks = nranks; a.bands.local_rows = rows;
+  a.su = c->d_su; a.sv = c->d_sv;
+  a.sph64 = c->d_sph64; a.mat = c->d_mat; a.matx = c->d_matx;
+  a.rgb = dev_rgb; a.hit_idx = dev_hit; a.shadow_mask = dev_mask;
+  a.counters = want_counters ? c->d_counters : nullptr;
+  if (want_counters) RT_CUDA(cudaMemsetAsync(c->d_counters, 0, RT_CNT_TOTAL * sizeof(unsigned long long), stream));
+  if (stats) RT_CUDA(cudaEventRecord(c->ev0, stream));
+  int launches = 0;
+  if (rows > 0) {
+    if (c->mode == 1) launches = rtk_launch_exact(a, stream);
+    else launches = rtk_launch_fast(a, &c->fast, &c->work, stream);
+    if (launches < 0) return rt_fail(RT_ERR_CUDA, std::string("render: launch failed: ") + cudaGetErrorString((cudaError_t)-launches));
+  }
+  if (stats) {
+    RT_CUDA(cudaEventRecord(c->ev1, stream));
+    RT_CUDA(cudaStreamSynchronize(stream));
+    float ms = 0;
+    RT_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    memset(stats, 0, sizeof(*stats));
+    stats->ms_device = ms;
+    stats->kernel_launches = launches;
+    stats->rows_rendered = rows;
+    if (want_counters) {
+      unsigned long long cnt[RT_CNT_TOTAL];
+      RT_CUDA(cudaMemcpy(cnt, c->d_counters, sizeof(cnt), cudaMemcpyDeviceToHost));
+      fill_stats(stats, cnt);
+    }
+  }
+  return RT_OK;
+}
+
+extern "C" int rt_render_bands(rt_ctx *c, int W, int H, int depth, int band_h, int rank, int nranks, void *dev_rgb,
+                               void *stream, rt_stats *stats) {
+  if (!c || !dev_rgb) return rt_fail(RT_ERR_ARG, "rt_render_bands: NULL argument");
+  cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+  auto t0 = std::chrono::steady_clock::now();
+  int rc = render_common(c, W, H, depth, band_h, rank, nranks, (uint8_t *)dev_rgb, nullptr, nullptr, s, stats);
+  if (rc == RT_OK && stats)
+    stats->ms_host = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return rc;
+}
+
+extern "C" int rt_render_debug(rt_ctx *c, int W, int H, int depth, uint8_t *host_rgb, int32_t *hit_idx,
+                               uint32_t *shadow_mask, rt_stats *stats) {
+  if (!c || !host_rgb) return rt_fail(RT_ERR_ARG, "rt_render: NULL argument");
+  if (W < 1 || H < 1 || depth < 0) return rt_fail(RT_ERR_ARG, "rt_render: bad image size or depth");
+  auto t0 = std::chrono::steady_clock::now();
+  RT_CUDA(cudaSetDevice(c->device));
+  const size_t npx = (size_t)W * H;
+  int rc = ensure_cap(c->d_rgb, c->rgb_cap, npx * 3 + 16);
+  if (rc) return rc;
+  const size_t nlev = npx * (size_t)(depth > 0 ? depth : 1);
+  if (hit_idx && (rc = ensure_cap(c->d_hit, c->hit_cap, nlev))) return rc;
+  if (shadow_mask && (rc = ensure_cap(c->d_mask, c->mask_cap, nlev))) return rc;
+  rt_stats local;
+  rc = render_common(c, W, H, depth, H, 0, 1, c->d_rgb, hit_idx ? c->d_hit : nullptr,
+                     shadow_mask ? c->d_mask : nullptr, c->stream, stats ? stats : &local);
+  if (rc) return rc;
+  RT_CUDA(cudaMemcpyAsync(host_rgb, c->d_rgb, npx * 3, cudaMemcpyDeviceToHost, c->stream));
+  if (hit_idx && depth > 0) RT_CUDA(cudaMemcpyAsync(hit_idx, c->d_hit, nlev * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (shadow_mask && depth > 0) RT_CUDA(cudaMemcpyAsync(shadow_mask, c->d_mask, nlev * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  RT_CUDA(cudaStreamSynchronize(c->stream));
+  if (stats) stats->ms_host = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return RT_OK;
+}
+
+extern "C" int rt_render(rt_ctx *c, int W, int H, int depth, uint8_t *host_rgb, rt_stats *stats) {
+  return rt_render_debug(c, W, H, depth, host_rgb, nullptr, nullptr, stats);
+}
+
+// Pinned host memory for callers that want the frame copy to run at full PCIe rate.
+extern "C" int rt_host_alloc(size_t bytes, void **out) {
+  if (!out || bytes == 0) return rt_fail(RT_ERR_ARG, "rt_host_alloc: bad argument");
+  RT_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+  return RT_OK;
+}
+extern "C" void rt_host_free(void *p) { if (p) cudaFreeHost(p); }

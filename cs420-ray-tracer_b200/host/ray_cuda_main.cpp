@@ -1,0 +1,74 @@
+// ray_cuda -- drop-in for the reference's ray_serial / ray_openmp / ray_cuda binaries.
+//
+// Process-level contract kept: positional scene path (default scenes/simple.txt,
+// src/main.cpp:101-110), "Loaded scene: N spheres, M lights", a "... time: X seconds" line that
+// makefile:61-62 / scripts/test.sh:62 / scripts/benchmark.sh:33 grep, output_gpu.ppm in the
+// reference's P3 format (scripts/test.sh:213), defaults 1280x720 depth 10 (src/main.cpp:95-97),
+// exit code 0.  All rendering goes through the C ABI of librt_b200.so; there is no CPU path.
+//
+// Extra flags (none collide with the reference's): --width N --height N --depth N
+//   --output FILE --device N --exact (FP64 diagnostic kernels) --frames N (repeat, report best)
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rt_b200.h"
+
+static int die(const char *what) {
+  std::fprintf(stderr, "ray_cuda: %s: %s\n", what, rt_last_error());
+  return 1;
+}
+
+int main(int argc, char **argv) {
+  int W = 1280, H = 720, depth = 10, device = 0, frames = 1;
+  bool exact = false;
+  std::string scene_file = "scenes/simple.txt", output = "output_gpu.ppm";
+  for (int i = 1; i < argc; i++) {
+    std::string a = argv[i];
+    auto next = [&](int &dst) { if (i + 1 < argc) dst = std::atoi(argv[++i]); };
+    if (a == "--width") next(W);
+    else if (a == "--height") next(H);
+    else if (a == "--depth") next(depth);
+    else if (a == "--device") next(device);
+    else if (a == "--frames") next(frames);
+    else if (a == "--output" && i + 1 < argc) output = argv[++i];
+    else if (a == "--exact") exact = true;
+    else if (a == "--openmp" || a == "-a") { /* accepted for command-line compatibility */ }
+    else scene_file = a;
+  }
+  std::printf("Testing scene loader with: %s\n\n", scene_file.c_str());
+  rt_scene *sc = nullptr;
+  if (rt_scene_load(scene_file.c_str(), 1, &sc) != RT_OK) {
+    // the reference throws std::runtime_error here and aborts (include/scene_loader.h:32-34)
+    std::fprintf(stderr, "terminate called after throwing an instance of 'std::runtime_error'\n  what():  %s\n", rt_last_error());
+    return 134;
+  }
+  int N = 0, L = 0, has_cam = 0;
+  const double *sph, *lig, *amb, *cam;
+  rt_scene_counts(sc, &N, &L, &has_cam);
+  rt_scene_data(sc, &sph, &lig, &amb, &cam);
+
+  rt_ctx *ctx = nullptr;
+  if (rt_create(device, &ctx) != RT_OK) return die("rt_create");
+  if (exact && rt_set_option(ctx, "mode", 1) != RT_OK) return die("rt_set_option");
+  if (rt_upload_scene(ctx, sph, N, lig, L, amb, cam, cam + 3, cam[6]) != RT_OK) return die("rt_upload_scene");
+  std::vector<uint8_t> rgb((size_t)W * H * 3);
+  std::printf("Rendering (GPU, B200 sm_100a)...\n");
+  rt_stats st;
+  double best = 1e30;
+  for (int f = 0; f < (frames > 0 ? frames : 1); f++) {
+    if (rt_render(ctx, W, H, depth, rgb.data(), &st) != RT_OK) return die("rt_render");
+    if (st.ms_device < best) best = st.ms_device;
+  }
+  std::printf("GPU rendering time: %g seconds\n", best * 1e-3);
+  unsigned long long rays = st.closest_queries + st.shadow_queries;
+  std::printf("rays: %llu closest + %llu shadow = %llu (%.1f Mrays/s), %d kernel launches\n",
+              (unsigned long long)st.closest_queries, (unsigned long long)st.shadow_queries, rays,
+              rays / (best * 1e-3) * 1e-6, st.kernel_launches);
+  if (rt_write_ppm(output.c_str(), rgb.data(), W, H) != RT_OK) return die("rt_write_ppm");
+  rt_destroy(ctx);
+  rt_scene_free(sc);
+  return 0;
+}

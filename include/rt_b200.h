@@ -1,0 +1,147 @@
+/*
+ * rt_b200.h -- C ABI of the B200-native sphere ray tracer (librt_b200.so).
+ *
+ * This is the drop-in boundary for the reference's one data-parallel hot path
+ * (camera rays -> brute-force ray/sphere closest hit -> Phong + shadow rays -> reflection
+ * bounces -> 8-bit RGB).  Plain pointers and sizes only: no C++ types, no torch types, no
+ * exceptions and no exit() cross this line.  Every function returns 0 on success or a
+ * negative rt_status; rt_last_error() returns the text of the calling thread's last failure.
+ *
+ * What each entry point replaces in the reference (paths relative to the reference root):
+ *
+ *   rt_scene_load / rt_scene_*     include/scene_loader.h:27-135   load_scene(filename)
+ *   rt_upload_scene                src/main_hybrid.cpp:196-279     GPUResources::upload_scene
+ *                                  src/kernel.cu:202-207           upload_lights_and_ambience
+ *                                  include/camera.h:10-15          Camera::Camera (basis vectors)
+ *   rt_render / rt_render_bands    src/main.cpp:146-157,185-199    the pixel loop + trace_ray
+ *                                  src/kernel.cu:185-200           launch_gpu_kernel (tile launch)
+ *                                  src/main.cpp:84-86              the 8-bit quantiser of write_ppm
+ *   rt_write_ppm                   src/main.cpp:69-91              write_ppm (P3 text)
+ *
+ * Semantics are those of the reference's SERIAL renderer (FP64; src/main.cpp + include/ *.h),
+ * not of its CUDA kernels: hit / sphere-index selection is bit-exact with ties to the lowest
+ * sphere index, 8-bit RGB within 1 LSB.
+ *
+ * Threading: one host thread per rt_ctx at a time.  A ctx owns one CUDA device, one stream
+ * and all device memory it allocates.  There is no CPU fallback: every render entry point
+ * fails with RT_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef RT_B200_H
+#define RT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_ABI_VERSION 1
+#define RT_MAX_LEVELS 32          /* reflection levels tracked in rt_stats.alive[]            */
+#define RT_SPHERE_STRIDE 10       /* cx cy cz r R G B metallic roughness shininess (file order)*/
+#define RT_LIGHT_STRIDE 7         /* x y z R G B intensity                         (file order)*/
+
+typedef enum rt_status {
+  RT_OK = 0,
+  RT_ERR_ARG = -1,      /* bad argument (NULL pointer, non-positive size, ...)                 */
+  RT_ERR_CUDA = -2,     /* CUDA runtime / driver error, or no usable sm_100 device             */
+  RT_ERR_STATE = -3,    /* call order violated (e.g. render before upload)                     */
+  RT_ERR_IO = -4,       /* file could not be opened / written                                  */
+  RT_ERR_NOMEM = -5,
+  RT_ERR_UNSUPPORTED = -6
+} rt_status;
+
+typedef struct rt_ctx rt_ctx;       /* opaque: device, stream, device-resident scene + buffers */
+typedef struct rt_scene rt_scene;   /* opaque: a parsed scene file (host memory only)          */
+
+/* Counters of one render.  Ray counts follow the oracle's definition:
+ * closest_queries = find_intersection calls issued by trace_ray (R_c), shadow_queries =
+ * in_shadow calls (R_s = lights x hits).  They are properties of (scene, W, H, depth).  */
+typedef struct rt_stats {
+  double ms_device;             /* CUDA-event time of the kernels of this call on the stream   */
+  double ms_host;               /* host wall-clock of the whole call, copies included          */
+  uint64_t closest_queries;
+  uint64_t hits;
+  uint64_t shadow_queries;
+  uint64_t occluded;
+  uint64_t alive[RT_MAX_LEVELS];/* closest queries per reflection level                        */
+  uint64_t fp64_intersections;  /* exact FP64 sphere evaluations the kernels needed            */
+  uint64_t sphere_tests;        /* FP32 (filter) or FP64 (exact mode) ray/sphere tests executed*/
+  int32_t kernel_launches;      /* kernels launched by this call                               */
+  int32_t rows_rendered;        /* image rows this call produced (all of H unless banded)      */
+} rt_stats;
+
+/* ---- library ------------------------------------------------------------------------- */
+int rt_abi_version(void);
+const char *rt_last_error(void);
+/* Number of CUDA devices usable by this library (0 when none; never fails). */
+int rt_device_count(void);
+
+/* ---- scene files (host only; usable without a GPU) -------------------------------------
+ * Same grammar and skip/warn behaviour as include/scene_loader.h:27-135: '#' comments,
+ * "sphere x y z r R G B metallic roughness shininess", "light x y z R G B intensity",
+ * "ambient R G B", "camera px py pz lx ly lz fov"; malformed or unknown lines are reported
+ * on stderr and skipped; a file that cannot be opened is RT_ERR_IO.  Defaults when a line
+ * type is absent: ambient (0,0,0), camera (0,0,0)->(0,0,-1) fov 60 (include/scene.h:22,31).
+ * If verbose != 0 prints "Loaded scene: N spheres, M lights" like scene_loader.h:131-132.  */
+int rt_scene_load(const char *path, int verbose, rt_scene **out);
+int rt_scene_counts(const rt_scene *s, int *nspheres, int *nlights, int *has_camera);
+/* Pointers stay valid until rt_scene_free.  spheres: N x RT_SPHERE_STRIDE, lights:
+ * L x RT_LIGHT_STRIDE, ambient[3], camera[7] = pos xyz, look_at xyz, fov (degrees).       */
+int rt_scene_data(const rt_scene *s, const double **spheres, const double **lights,
+                  const double **ambient, const double **camera);
+void rt_scene_free(rt_scene *s);
+
+/* ---- context ---------------------------------------------------------------------------- */
+int rt_create(int device, rt_ctx **out);
+void rt_destroy(rt_ctx *ctx);
+/* Integer options: "mode" 0 = fast FP32-filter kernels (default), 1 = exact FP64 brute force
+ * (diagnostic; same results, slower); "counters" 0/1 = collect ray counters (default 1).   */
+int rt_set_option(rt_ctx *ctx, const char *key, long long value);
+
+/* Copies the scene to the device (host -> device inside the call) and precomputes the
+ * per-origin sphere tables.  Arrays are in scene-file column order (see rt_scene_data).
+ * roughness and light intensity are accepted and ignored, as in the reference.            */
+int rt_upload_scene(rt_ctx *ctx, const double *spheres, int nspheres, const double *lights,
+                    int nlights, const double ambient[3], const double cam_pos[3],
+                    const double cam_look[3], double fov_deg);
+
+/* Renders the full frame and copies it to host_rgb: W*H*3 bytes, row j = 0 is the BOTTOM of
+ * the image (src/main.cpp:153-154), channel value int(255.99*min(1,c)).  stats may be NULL. */
+int rt_render(rt_ctx *ctx, int width, int height, int max_depth, uint8_t *host_rgb,
+              rt_stats *stats);
+
+/* As rt_render, additionally returning (each may be NULL), for every pixel p = j*W+i and
+ * reflection level k < max_depth: hit_idx[p*max_depth+k] = sphere index, -1 = miss,
+ * -2 = level not reached; shadow_mask[...] bit l = light l occluded at that hit.            */
+int rt_render_debug(rt_ctx *ctx, int width, int height, int max_depth, uint8_t *host_rgb,
+                    int32_t *hit_idx, uint32_t *shadow_mask, rt_stats *stats);
+
+/* Row-band sharded render into DEVICE memory (no host copy, asynchronous on `stream`).
+ * Bands are band_h rows tall; rank r of nranks owns bands b with b % nranks == r and writes
+ * its rows, in ascending j, compactly into dev_rgb (rt_band_rows()*W*3 bytes, 16-byte
+ * aligned).  nranks = 1 renders the whole frame.  stream is a cudaStream_t passed as void*
+ * (NULL = the ctx stream); dev_rgb must belong to the ctx's device.  stats (may be NULL) is
+ * filled after a stream synchronise only when counters are enabled.                        */
+int rt_render_bands(rt_ctx *ctx, int width, int height, int max_depth, int band_h, int rank,
+                    int nranks, void *dev_rgb, void *stream, rt_stats *stats);
+/* Rows owned by `rank` under the band rule above. */
+int rt_band_rows(int height, int band_h, int rank, int nranks);
+/* Writes the owned row indices (ascending) into rows[rt_band_rows()]. */
+int rt_band_row_list(int height, int band_h, int rank, int nranks, int32_t *rows);
+
+/* ---- pinned host memory -----------------------------------------------------------------
+ * Page-locked buffers so that the frame copy of rt_render runs at full host-link rate.
+ * (The reference does the same for its bulk copy: src/main_hybrid.cpp:524.)                 */
+int rt_host_alloc(size_t bytes, void **out);
+void rt_host_free(void *p);
+
+/* ---- PPM (host only) -------------------------------------------------------------------- */
+/* P3 text, byte-identical to src/main.cpp:69-91: "P3\nW H\n255\n", rows j = H-1 .. 0, one
+ * "r g b\n" per pixel.  rgb is bottom-row-first as produced by rt_render.                   */
+int rt_write_ppm(const char *path, const uint8_t *rgb, int width, int height);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_B200_H */

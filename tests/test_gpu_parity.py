@@ -1,0 +1,172 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the committed goldens.
+
+Bars (BASELINE.json north_star): hit / sphere index per reflection level and shadow booleans
+BIT-EXACT; 8-bit RGB within 1 LSB on >= 99.9 % of channel samples (scripts/compare_ppm.py rule
+with tolerance 0.5).  Needs a B200: run with -m gpu."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+MODES = ["exact", "fast"]
+
+
+@pytest.fixture(scope="module")
+def renderers(rt):
+    rs = {m: rt.Renderer(0, mode=m) for m in MODES}
+    yield rs
+    for r in rs.values():
+        r.close()
+
+
+def check(rt, oracle, renderer, scene, W, H, D, gold=None, rgb_exact_frac=None):
+    renderer.upload(scene)
+    rgb, hit, mask, st = renderer.render_debug(W, H, D)
+    if gold is None:
+        o = oracle.render(scene, W, H, D, want_idx=True)
+        gold = {"hit_idx": o["hit_idx"], "shadow_mask": o["shadow_mask"], "rgb": o["rgb"], "counters": o["counters"]}
+    if D > 0:
+        bad = np.argwhere(hit != gold["hit_idx"])
+        assert bad.size == 0, "hit index mismatch at (j,i,level) %s: got %s want %s" % (
+            bad[:5].tolist(), hit[tuple(bad[0])], gold["hit_idx"][tuple(bad[0])])
+        bad = np.argwhere(mask != gold["shadow_mask"])
+        assert bad.size == 0, "shadow mask mismatch at %s" % bad[:5].tolist()
+    ok, pct, mx = rt.compare_rgb(gold["rgb"], rgb, 0.5)
+    assert ok and mx <= 2, "rgb: %.4f %% of samples beyond 1 LSB, max diff %d" % (pct, mx)
+    for k in ("closest_queries", "hits", "shadow_queries", "occluded"):
+        assert getattr(st, k) == gold["counters"][k], k
+    return rgb, st
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("name", ["simple", "medium", "complex"])
+def test_small_goldens(rt, oracle, renderers, scenes, name, mode):
+    z = np.load(os.path.join(GOLDEN, "small_%s.npz" % name))
+    gold = {"hit_idx": z["hit_idx"], "shadow_mask": z["shadow_mask"], "rgb": z["rgb_top_first"][::-1],
+            "counters": json.loads(str(z["counters"]))}
+    check(rt, oracle, renderers[mode], scenes[name], 160, 90, 5, gold)
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("name,W,H,D", [("simple", 1280, 720, 10), ("medium", 1920, 1080, 5), ("complex", 1920, 1080, 5),
+                                        ("complex", 1280, 720, 10)])
+def test_baseline_configs_full_size(rt, oracle, renderers, scenes, golden, name, W, H, D, mode):
+    rgb, st = check(rt, oracle, renderers[mode], scenes[name], W, H, D)
+    g = [c for c in golden["counters"] if (c["scene"], c["W"], c["H"], c["depth"]) == (name, W, H, D)]
+    if g:
+        assert st.closest_queries == g[0]["closest_queries"] and st.shadow_queries == g[0]["shadow_queries"]
+        assert [int(x) for x in st.alive[:D]] == g[0]["alive"]
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("W,H,D", [(97, 61, 3), (2, 2, 1), (33, 7, 2), (640, 1, 2), (3, 500, 4), (130, 70, 0), (64, 64, 1), (200, 120, 32)])
+def test_ragged_sizes_and_depths(rt, oracle, renderers, scenes, W, H, D, mode):
+    check(rt, oracle, renderers[mode], scenes["medium"], W, H, D)
+
+
+def _scene(rt, spheres, lights=((5, 8, 2, 1, 1, 1, 1),), ambient=(0.1, 0.1, 0.1), camera=(0, 0, 5, 0, 0, -1, 60)):
+    return rt.Scene(np.array(spheres, dtype=np.float64).reshape(-1, 10), np.array(lights, dtype=np.float64).reshape(-1, 7),
+                    ambient, camera)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_empty_and_degenerate_scenes(rt, oracle, renderers, mode):
+    r = renderers[mode]
+    check(rt, oracle, r, _scene(rt, []), 64, 48, 3)                                    # no spheres: all sky
+    check(rt, oracle, r, _scene(rt, [(0, 0, -3, 1, 1, 0, 0, 0.5, 0.5, 20)], lights=[]), 64, 48, 3)   # no lights
+    check(rt, oracle, r, _scene(rt, [(0, 0, 0, 50, 1, 1, 1, 0.3, 0.5, 20)]), 64, 48, 4)   # camera inside a sphere
+    check(rt, oracle, r, _scene(rt, [(0, 0, -3, 1, 1, 0, 0, 1.0, 0.5, 0)]), 64, 48, 4)    # mirror, shininess 0
+    check(rt, oracle, r, _scene(rt, [(0, 0, -3, 1, 1, 0, 0, -0.2, 0.5, 8)]), 64, 48, 4)   # negative reflectivity
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_ties_go_to_lowest_index(rt, oracle, renderers, mode):
+    """include/scene.h:52 strict '<' (SURVEY F8): coincident / touching / nested spheres."""
+    s = (0.3, 0.2, -4, 1.25, 0.8, 0.3, 0.2, 0.4, 0.5, 30)
+    spheres = [s, s, (0.3, 0.2, -4, 1.25, 0.1, 0.9, 0.2, 0.0, 1, 5),        # three coincident spheres
+               (2.55, 0.2, -4, 1.0, 0.2, 0.3, 0.9, 0.6, 0.4, 50),           # touches the first (1.25 + 1.0 = 2.25 apart)
+               (0.3, 0.2, -4, 0.5, 1, 1, 1, 0.9, 0.1, 90),                  # nested inside
+               (0, -101.05, -4, 100, 0.5, 0.5, 0.5, 0.2, 1, 5)]             # ground touching
+    check(rt, oracle, renderers[mode], _scene(rt, spheres, lights=[(5, 8, 2, 1, 1, 1, 1), (-6, 3, 1, 1, 0.5, 0.5, 1)]), 320, 200, 6)
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("n,seed,W,H,D", [(300, 7, 320, 180, 5), (1000, 420, 240, 136, 5), (2001, 9, 160, 90, 4)])
+def test_synthetic_overlapping_spheres(rt, oracle, renderers, n, seed, W, H, D, mode):
+    import gen_scene
+    sph, lights, amb, cam = gen_scene.generate(n, seed, 0.3, 1.5)      # big radii: many overlaps
+    check(rt, oracle, renderers[mode], rt.Scene(sph, lights, amb, cam), W, H, D)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_far_from_origin_scene(rt, oracle, renderers, scenes, mode):
+    """Input rounding must be covered by the FP32 filter margins (SURVEY 7.3-H1 'M term')."""
+    sc = scenes["medium"]
+    off = np.array([1000.0, -2000.0, 500.0])
+    sph = sc.spheres.copy(); sph[:, :3] += off
+    lig = sc.lights.copy(); lig[:, :3] += off
+    cam = sc.camera.copy(); cam[:3] += off; cam[3:6] += off
+    check(rt, oracle, renderers[mode], rt.Scene(sph, lig, sc.ambient, cam), 320, 180, 5)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_deterministic_and_rerenderable(rt, renderers, scenes, mode):
+    r = renderers[mode]
+    r.upload(scenes["complex"])
+    a, _ = r.render(640, 360, 5)
+    b, _ = r.render(640, 360, 5)
+    r.upload(scenes["simple"])
+    c, _ = r.render(640, 360, 5)
+    r.upload(scenes["complex"])
+    d, _ = r.render(640, 360, 5)
+    assert np.array_equal(a, b) and np.array_equal(a, d) and not np.array_equal(a, c)
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("band_h,n", [(16, 2), (16, 8), (4, 3), (64, 5)])
+def test_row_bands_reassemble_to_the_full_frame(rt, renderers, scenes, band_h, n, mode):
+    import torch
+    r = renderers[mode]
+    r.upload(scenes["complex"])
+    W, H, D = 480, 270, 5
+    full, _ = r.render(W, H, D)
+    out = np.zeros_like(full)
+    for rank in range(n):
+        rows = rt.band_row_list(H, band_h, rank, n)
+        buf = torch.zeros(len(rows) * W * 3 + 16, dtype=torch.uint8, device="cuda:0")
+        st = r.render_bands_device(W, H, D, band_h, rank, n, buf.data_ptr(), None, want_stats=True)
+        assert st.rows_rendered == len(rows)
+        out[rows] = buf[:len(rows) * W * 3].cpu().numpy().reshape(len(rows), W, 3)
+    assert np.array_equal(out, full)
+
+
+def test_exact_and_fast_agree_on_large_synthetic(rt, renderers):
+    """BASELINE config 4 shape (10k spheres) at reduced resolution: the CPU oracle would need
+    minutes, so the FP64 brute-force kernel is the checker here (itself pinned to the oracle above)."""
+    import gen_scene
+    sc = rt.Scene(*gen_scene.generate(10000, 420))
+    out = {}
+    for m in MODES:
+        renderers[m].upload(sc)
+        out[m] = renderers[m].render_debug(480, 270, 5)
+    assert np.array_equal(out["exact"][1], out["fast"][1])
+    assert np.array_equal(out["exact"][2], out["fast"][2])
+    ok, pct, mx = rt.compare_rgb(out["exact"][0], out["fast"][0], 0.5)
+    assert ok and mx <= 2
+
+
+def test_errors(rt, renderers, scenes):
+    r = rt.Renderer(0)
+    with pytest.raises(rt.RtError, match="no scene uploaded"):
+        r.render(16, 16, 2)
+    r.upload(scenes["simple"])
+    with pytest.raises(rt.RtError):
+        r.render(0, 16, 2)
+    with pytest.raises(rt.RtError):
+        r.render(16, 16, 33)
+    r.close()

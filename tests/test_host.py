@@ -1,0 +1,150 @@
+"""Host-side logic of the product (no GPU compute): the C-ABI library loads and exports every
+symbol include/rt_b200.h declares, the scene loader behaves like include/scene_loader.h:27-135,
+the PPM writer is byte-identical to src/main.cpp:69-91, the comparison rule is the one of
+scripts/compare_ppm.py, and the row-band partition is a partition."""
+import ctypes
+import hashlib
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, scene_path
+
+
+def test_header_symbols_are_exported(rt):
+    hdr = open(os.path.join(ROOT, "include", "rt_b200.h")).read()
+    declared = set(re.findall(r"\b(rt_[a-z_0-9]+)\s*\(", hdr))
+    declared -= {"rt_ctx", "rt_scene", "rt_stats", "rt_status"}
+    assert declared == set(rt.ABI_SYMBOLS), declared ^ set(rt.ABI_SYMBOLS)
+    lib = rt.load_library()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.rt_abi_version() == 1
+    nm = subprocess.run(["nm", "-D", "--defined-only", rt.library_path()], stdout=subprocess.PIPE, text=True).stdout
+    for name in declared:
+        assert re.search(r"\bT %s\b" % name, nm), name
+
+
+def test_no_cpu_fallback_without_gpu(rt):
+    """On a box without a GPU every render entry point must fail loudly."""
+    lib = rt.load_library()
+    if lib.rt_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(rt.RtError, match="no CUDA device"):
+        rt.Renderer(0)
+
+
+def test_product_does_not_reference_the_oracle():
+    pkg = os.path.join(ROOT, "cs420-ray-tracer_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile")):
+                text = open(os.path.join(dp, f), errors="ignore").read()
+                assert "oracle_py" not in text and "librt_oracle" not in text and "rt_oracle" not in text, f
+
+
+def test_loader_matches_reference_on_repo_scenes(rt):
+    for name, ns, nl in (("simple", 5, 2), ("medium", 44, 3), ("complex", 154, 5)):
+        sc = rt.load_scene(scene_path(name))
+        assert (sc.nspheres, sc.nlights) == (ns, nl)
+        assert sc.has_camera
+    sc = rt.load_scene(scene_path("complex"))
+    assert list(sc.camera) == [0, 3, 12, 0, 0, -20, 65] and list(sc.ambient) == [0.1, 0.1, 0.12]
+    assert list(sc.spheres[-1]) == [0, -102, -20, 100, 0.3, 0.3, 0.3, 0.0, 1.0, 5]
+
+
+def test_loader_quirks_match_reference_dump(rt, capfd):
+    """tests/golden/quirks_dump.txt is what the reference's own load_scene parsed from the same file."""
+    sc = rt.load_scene(scene_path("quirks"))
+    err = capfd.readouterr().err
+    want = open(os.path.join(GOLDEN, "quirks_dump.txt")).read().split("\n")
+    lines = ["spheres %d" % sc.nspheres]
+    for s in sc.spheres:
+        lines.append(" ".join("%.17g" % v for v in (list(s[:8]) + [s[9]])))
+    lines.append("lights %d" % sc.nlights)
+    for li in sc.lights:
+        lines.append(" ".join("%.17g" % v for v in li))
+    lines.append("ambient " + " ".join("%.17g" % v for v in sc.ambient))
+    lines.append("camera " + " ".join("%.17g" % v for v in sc.camera) + " %d" % int(sc.has_camera))
+    assert lines == [w for w in want if w]
+    assert err == open(os.path.join(GOLDEN, "quirks_warnings.txt")).read()
+
+
+def test_loader_defaults_and_errors(rt, tmp_path, capfd):
+    p = tmp_path / "empty.txt"
+    p.write_text("# nothing\n\n")
+    sc = rt.load_scene(str(p), verbose=True)
+    assert sc.nspheres == 0 and sc.nlights == 0 and not sc.has_camera
+    assert list(sc.camera) == [0, 0, 0, 0, 0, -1, 60] and list(sc.ambient) == [0, 0, 0]   # include/scene.h:22,31
+    assert "Loaded scene: 0 spheres, 0 lights" in capfd.readouterr().out
+    with pytest.raises(rt.RtError, match="Could not open scene file"):
+        rt.load_scene(str(tmp_path / "missing.txt"))
+    crlf = tmp_path / "crlf.txt"
+    crlf.write_bytes(b"sphere 0 0 -5 1 1 1 1 0 1 10\r\nlight 1 2 3 1 1 1 1\r\n")
+    sc = rt.load_scene(str(crlf))
+    assert sc.nspheres == 1 and sc.nlights == 1
+
+
+def test_scene_text_roundtrip(rt, scenes, tmp_path):
+    p = tmp_path / "rt.txt"
+    p.write_text(scenes["medium"].to_text())
+    sc = rt.load_scene(str(p))
+    assert np.array_equal(sc.spheres, scenes["medium"].spheres)
+    assert np.array_equal(sc.lights, scenes["medium"].lights)
+
+
+def test_ppm_writer_is_byte_identical(rt, oracle, scenes, golden, tmp_path):
+    r = oracle.render(scenes["simple"], 160, 90, 5)
+    a, b = tmp_path / "a.ppm", tmp_path / "b.ppm"
+    rt.write_ppm(str(a), r["rgb"])
+    oracle.write_ppm(str(b), r["rgb"])
+    ta = a.read_bytes()
+    assert ta == b.read_bytes() == rt.ppm_text(r["rgb"]).encode()
+    want = [g["md5"] for g in golden["images"] if (g["scene"], g["W"], g["H"]) == ("simple", 160, 90)][0]
+    assert hashlib.md5(ta).hexdigest() == want           # == the reference's write_ppm output
+    W, H, mx, img = rt.read_ppm(str(a))
+    assert (W, H, mx) == (160, 90, 255) and np.array_equal(img[::-1], r["rgb"])
+    rng = np.random.default_rng(1)
+    x = rng.integers(0, 256, (7, 5, 3)).astype(np.uint8)
+    rt.write_ppm(str(a), x)
+    assert a.read_bytes() == rt.ppm_text(x).encode()
+    with pytest.raises(rt.RtError):
+        rt.write_ppm(str(tmp_path / "nodir" / "x.ppm"), x)
+
+
+def test_compare_rule_matches_reference_script(rt):
+    """scripts/compare_ppm.py:72-89: 0.5 -> 1 LSB, counts channel samples, pass < 0.1 %."""
+    a = np.zeros((10, 100, 3), dtype=np.uint8)
+    b = a.copy()
+    b[0, :, 0] = 1                         # 1 LSB everywhere in a row: within tolerance
+    assert rt.compare_rgb(a, b, 0.5) == (True, 0.0, 1)
+    b[0, 0:2, 1] = 2                       # 2 of 3000 samples off by 2 -> 0.0667 % < 0.1 %
+    ok, pct, mx = rt.compare_rgb(a, b, 0.5)
+    assert ok and abs(pct - 2 / 3000 * 100) < 1e-12 and mx == 2
+    b[0, 2, 1] = 2                         # 3 of 3000 -> 0.1 %: fails (strict <)
+    assert not rt.compare_rgb(a, b, 0.5)[0]
+    assert rt.compare_rgb(a, b, 1.0)[0]    # default tolerance 1.0 -> 2 LSB
+    assert not rt.compare_rgb(a, b[:5], 0.5)[0]
+
+
+@pytest.mark.parametrize("H,band_h,n", [(1080, 16, 1), (1080, 16, 2), (1080, 16, 8), (720, 8, 4), (61, 16, 8), (5, 16, 8), (2160, 4, 3)])
+def test_row_bands_partition_the_image(rt, H, band_h, n):
+    seen = np.zeros(H, dtype=np.int32)
+    sizes = []
+    for r in range(n):
+        rows = rt.band_row_list(H, band_h, r, n)
+        assert len(rows) == rt.band_rows(H, band_h, r, n)
+        assert np.all(np.diff(rows) > 0)
+        assert np.all((rows // band_h) % n == r)
+        seen[rows] += 1
+        sizes.append(len(rows))
+    assert np.all(seen == 1)
+    if H >= band_h * n:
+        assert max(sizes) - min(sizes) <= band_h
+    with pytest.raises(rt.RtError):
+        rt.band_rows(H, 0, 0, n)
+    with pytest.raises(rt.RtError):
+        rt.band_rows(H, band_h, n, n)
