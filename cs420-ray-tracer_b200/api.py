@@ -19,7 +19,7 @@ ABI_SYMBOLS = [
     "rt_scene_load", "rt_scene_counts", "rt_scene_data", "rt_scene_free",
     "rt_create", "rt_destroy", "rt_set_option", "rt_upload_scene",
     "rt_render", "rt_render_debug", "rt_render_bands", "rt_band_rows", "rt_band_row_list",
-    "rt_host_alloc", "rt_host_free", "rt_write_ppm",
+    "rt_host_alloc", "rt_host_free", "rt_write_ppm", "rt_measure_fp32_peak",
 ]
 
 
@@ -34,6 +34,7 @@ class RtStats(C.Structure):
         ("shadow_queries", C.c_uint64), ("occluded", C.c_uint64),
         ("alive", C.c_uint64 * RT_MAX_LEVELS),
         ("fp64_intersections", C.c_uint64), ("sphere_tests", C.c_uint64),
+        ("filter_violations", C.c_uint64),
         ("kernel_launches", C.c_int32), ("rows_rendered", C.c_int32),
     ]
 
@@ -84,6 +85,7 @@ def load_library():
     lib.rt_host_free.argtypes = [vp]
     lib.rt_host_free.restype = None
     lib.rt_write_ppm.argtypes = [C.c_char_p, vp, i, i]
+    lib.rt_measure_fp32_peak.argtypes = [i, dp, dp]
     for name in ABI_SYMBOLS:
         getattr(lib, name)
     _lib = lib
@@ -149,6 +151,13 @@ def write_ppm(path, rgb_bottom_first):
     a = np.ascontiguousarray(rgb_bottom_first, dtype=np.uint8)
     H, W, _ = a.shape
     _check(load_library().rt_write_ppm(os.fsencode(path), a.ctypes.data, W, H), "rt_write_ppm")
+
+
+def measure_fp32_peak(device=0):
+    """(FLOP/s, SM MHz) of the FFMA issue peak, measured live by the library."""
+    f, m = C.c_double(), C.c_double()
+    _check(load_library().rt_measure_fp32_peak(int(device), C.byref(f), C.byref(m)), "rt_measure_fp32_peak")
+    return f.value, m.value
 
 
 def band_rows(H, band_h, rank, nranks):

@@ -263,6 +263,7 @@ static void fill_stats(rt_stats *st, const unsigned long long *cnt) {
   st->occluded = cnt[RT_CNT_OCCLUDED];
   st->fp64_intersections = cnt[RT_CNT_FP64];
   st->sphere_tests = cnt[RT_CNT_TESTS];
+  st->filter_violations = cnt[RT_CNT_VIOLATIONS];
   for (int k = 0; k < RT_MAX_LEVELS; k++) st->alive[k] = cnt[RT_CNT_ALIVE0 + k];
 }
 
@@ -367,3 +368,13 @@ extern "C" int rt_host_alloc(size_t bytes, void **out) {
   return RT_OK;
 }
 extern "C" void rt_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+// FP32 FFMA issue peak of the device, measured live: the roofline denominator of bench.py.
+extern "C" int rt_measure_fp32_peak(int device, double *flops_per_s, double *sm_clock_mhz) {
+  if (!flops_per_s) return rt_fail(RT_ERR_ARG, "rt_measure_fp32_peak: NULL argument");
+  if (rt_device_count() <= device || device < 0) return rt_fail(RT_ERR_CUDA, "rt_measure_fp32_peak: no such CUDA device");
+  double v = rtk_measure_fp32_peak(device, sm_clock_mhz);
+  if (v < 0) return rt_fail(RT_ERR_CUDA, "rt_measure_fp32_peak: probe kernel failed");
+  *flops_per_s = v;
+  return RT_OK;
+}

@@ -44,6 +44,7 @@ enum {
   RT_CNT_OCCLUDED = 3,
   RT_CNT_FP64 = 4,
   RT_CNT_TESTS = 5,
+  RT_CNT_VIOLATIONS = 6,
   RT_CNT_ALIVE0 = 8,   // .. RT_CNT_ALIVE0 + 31
   RT_CNT_TOTAL = 40
 };

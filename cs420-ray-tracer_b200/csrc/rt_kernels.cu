@@ -1,10 +1,15 @@
 // rt_kernels.cu -- the single device translation unit of librt_b200.so (sm_100a only).
 #include "rt_kernels.h"
 
+#include <cmath>
+#include <cstring>
+#include <vector>
+
 // Camera basis, lights and ambient: one copy per device, refreshed by rt_upload_scene.
 __constant__ RtFrameConst g_frame;
 
 #include "kernels_exact.cuh"
+#include "kernels_fast.cuh"
 
 cudaError_t rtk_set_frame_const(const RtFrameConst *host_const, cudaStream_t stream) {
   return cudaMemcpyToSymbolAsync(g_frame, host_const, sizeof(RtFrameConst), 0, cudaMemcpyHostToDevice, stream);
@@ -18,9 +23,206 @@ int rtk_launch_exact(const RtRenderArgs &args, cudaStream_t stream) {
   return e == cudaSuccess ? 1 : -(int)e;
 }
 
-// ---- fast path: placeholder until kernels_fast.cuh lands (fails loudly, never falls back) ----
-int rtk_fast_init(int) { return 0; }
-int rtk_fast_build_scene(RtFastScene *fs, const double *, int N, const RtFrameConst *f, cudaStream_t) { fs->N = N; fs->L = f->nlights; return 0; }
-void rtk_fast_free_scene(RtFastScene *) {}
-void rtk_fast_free_work(RtFastWork *) {}
-int rtk_launch_fast(const RtRenderArgs &, const RtFastScene *, RtFastWork *, cudaStream_t) { return -(int)cudaErrorNotSupported; }
+// ---------------------------------------------------------------------------------------------
+// fast path, host side
+namespace {
+
+constexpr size_t kMaxSmemTables = 200 * 1024;   // stage tables in shared memory up to this size
+constexpr int kCtlWords = 128;                  // [0] tile counter, [1+k] chunk counter of level k, [64+k] rays entering level k
+
+inline float float_up(double x) {               // smallest float >= x
+  float f = (float)x;
+  if ((double)f < x) f = std::nextafterf(f, INFINITY);
+  return f;
+}
+
+#define RTK_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return -(int)e_; } while (0)
+
+}  // namespace
+
+int rtk_fast_init(int) {
+  const int big = 227 * 1024;
+  RTK_TRY(cudaFuncSetAttribute(rtf::k_primary<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  RTK_TRY(cudaFuncSetAttribute(rtf::k_bounce<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  return 0;
+}
+
+// Builds the FP32 filter tables on the host in double and rounds them conservatively
+// (DESIGN.md "filter margins"; error model in filter_math.cuh).
+//   shared-origin table for origin O (camera, each light), sphere i:
+//       oc = c_i - O (double -> nearest float), ncc = round_up(E_i - (|oc|^2 - r_i^2)),
+//       E_i = 2.01 * 2^-20 * |oc|^2 + delta64
+//   general table: c' = c_i - C0 (nearest float), rho' = round_up(r^2 (1+32u) + 8u S^2 + delta64)
+// Sphere PAIRS are interleaved for the packed FP32x2 test: (x0,x1,y0,y1) (z0,z1,w0,w1).
+int rtk_fast_build_scene(RtFastScene *fs, const double *sph, int N, const RtFrameConst *f, cudaStream_t stream) {
+  const int L = f->nlights;
+  int npairs = (N + 1) / 2;
+  npairs = ((npairs + rtf::kGroupPairs - 1) / rtf::kGroupPairs) * rtf::kGroupPairs;
+  if (npairs == 0) npairs = rtf::kGroupPairs;
+  fs->N = N; fs->L = L; fs->npairs = npairs;
+  const double u = std::ldexp(1.0, -24);
+
+  // absolute magnitude bound of every coordinate the reference touches -> delta64
+  double sabs = 0;
+  auto upd = [&](double x, double y, double z, double r) { sabs = std::fmax(sabs, std::sqrt(x * x + y * y + z * z) + r); };
+  upd(f->cam_pos[0], f->cam_pos[1], f->cam_pos[2], 0);
+  for (int l = 0; l < L; l++) upd(f->light_pos[l][0], f->light_pos[l][1], f->light_pos[l][2], 0);
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  for (int i = 0; i < N; i++) {
+    const double *s = sph + (size_t)i * 10;
+    upd(s[0], s[1], s[2], std::fabs(s[3]));
+    for (int k = 0; k < 3; k++) { lo[k] = std::fmin(lo[k], s[k]); hi[k] = std::fmax(hi[k], s[k]); }
+  }
+  const double delta64 = std::ldexp(4.0 * sabs * sabs, -40) + 1e-30;
+  fs->d64 = float_up(delta64);
+  for (int k = 0; k < 3; k++) fs->c0[k] = N > 0 ? 0.5 * (lo[k] + hi[k]) : 0.0;
+  double S = 0;
+  for (int i = 0; i < N; i++) {
+    const double *s = sph + (size_t)i * 10;
+    const double x = s[0] - fs->c0[0], y = s[1] - fs->c0[1], z = s[2] - fs->c0[2];
+    S = std::fmax(S, std::sqrt(x * x + y * y + z * z) + std::fabs(s[3]));
+  }
+  S += 0.01;
+  fs->gS2 = float_up(S * S * 1.0001);
+
+  const size_t per_table = (size_t)npairs * 2;
+  std::vector<float4> h((size_t)(L + 2) * per_table);
+  auto put = [&](size_t table, int i, float x, float y, float z, float w) {
+    float4 *A = &h[table * per_table + (size_t)(i >> 1) * 2], *B = A + 1;
+    if (i & 1) { A->y = x; A->w = y; B->y = z; B->w = w; } else { A->x = x; A->z = y; B->x = z; B->z = w; }
+  };
+  for (int t = 0; t <= L; t++) {
+    const double *O = t == 0 ? f->cam_pos : f->light_pos[t - 1];
+    for (int i = 0; i < 2 * npairs; i++) {
+      if (i >= N) { put(t, i, 0.f, 0.f, 0.f, -1.0f); continue; }       // padding: never a candidate
+      const double *s = sph + (size_t)i * 10;
+      const double x = s[0] - O[0], y = s[1] - O[1], z = s[2] - O[2];
+      const double oc2 = x * x + y * y + z * z;
+      const double E = 2.01 * std::ldexp(1.0, -20) * oc2 * (1 + 1e-9) + delta64;
+      put(t, i, (float)x, (float)y, (float)z, float_up(E - (oc2 - s[3] * s[3])));
+    }
+  }
+  for (int i = 0; i < 2 * npairs; i++) {
+    if (i >= N) { put(L + 1, i, 0.f, 0.f, 0.f, -1.0e30f); continue; }
+    const double *s = sph + (size_t)i * 10;
+    const double rho = s[3] * s[3] * (1 + 32 * u) + 8 * u * S * S + delta64;
+    put(L + 1, i, (float)(s[0] - fs->c0[0]), (float)(s[1] - fs->c0[1]), (float)(s[2] - fs->c0[2]), float_up(rho));
+  }
+  fs->table_bytes = (size_t)(L + 1) * per_table * sizeof(float4);
+  RTK_TRY(cudaMalloc(&fs->tabs, h.size() * sizeof(float4)));
+  RTK_TRY(cudaMemcpyAsync(fs->tabs, h.data(), h.size() * sizeof(float4), cudaMemcpyHostToDevice, stream));
+  RTK_TRY(cudaStreamSynchronize(stream));   // h goes out of scope
+  return 0;
+}
+
+void rtk_fast_free_scene(RtFastScene *fs) {
+  if (fs->tabs) cudaFree(fs->tabs);
+  fs->tabs = nullptr;
+}
+
+void rtk_fast_free_work(RtFastWork *w) {
+  cudaFree(w->queue[0]); cudaFree(w->queue[1]); cudaFree(w->ctl);
+  w->queue[0] = w->queue[1] = nullptr; w->ctl = nullptr; w->queue_cap = 0;
+}
+
+int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork *w, cudaStream_t stream) {
+  const size_t npix = (size_t)args.W * args.bands.local_rows;
+  if (!w->ctl) RTK_TRY(cudaMalloc(&w->ctl, kCtlWords * sizeof(unsigned int)));
+  if (args.max_depth > 1 && w->queue_cap < npix) {
+    RTK_TRY(cudaStreamSynchronize(stream));
+    cudaFree(w->queue[0]); cudaFree(w->queue[1]);
+    w->queue[0] = w->queue[1] = nullptr; w->queue_cap = 0;
+    RTK_TRY(cudaMalloc(&w->queue[0], npix * sizeof(rtf::RayRec)));
+    RTK_TRY(cudaMalloc(&w->queue[1], npix * sizeof(rtf::RayRec)));
+    w->queue_cap = npix;
+  }
+  RTK_TRY(cudaMemsetAsync(w->ctl, 0, kCtlWords * sizeof(unsigned int), stream));
+
+  rtf::FastArgs a;
+  memset(&a, 0, sizeof(a));
+  a.r = args;
+  a.otab = (const float4 *)fs->tabs;
+  a.gtab = a.otab + (size_t)(fs->L + 1) * fs->npairs * 2;
+  a.npairs = fs->npairs; a.N = fs->N; a.L = fs->L;
+  a.d64 = fs->d64; a.gS2 = fs->gS2;
+  for (int k = 0; k < 3; k++) a.c0[k] = fs->c0[k];
+  a.tiles_x = (args.W + rtf::kTileW - 1) / rtf::kTileW;
+  a.ntiles = a.tiles_x * ((args.bands.local_rows + rtf::kTileH - 1) / rtf::kTileH);
+  a.tile_counter = w->ctl;
+  a.table_bytes = (unsigned)fs->table_bytes;
+  a.tables_in_smem = fs->table_bytes <= kMaxSmemTables;
+  const size_t smem = rtf::kSmemHeader + (a.tables_in_smem ? fs->table_bytes : 0);
+  const int ctas_per_sm = (a.tables_in_smem && smem > 110 * 1024) ? 1 : 2;
+  const int max_grid = w->num_sms * ctas_per_sm;
+
+  a.level = 0;
+  a.q_out = (rtf::RayRec *)w->queue[0];
+  a.q_out_count = w->ctl + 64 + 1;
+  int grid = a.ntiles < max_grid ? a.ntiles : max_grid;
+  if (a.tables_in_smem) rtf::k_primary<true><<<grid, rtf::kThreads, smem, stream>>>(a);
+  else rtf::k_primary<false><<<grid, rtf::kThreads, smem, stream>>>(a);
+  int launches = 1;
+  for (int level = 1; level < args.max_depth; level++) {
+    a.level = level;
+    a.q_in = (const rtf::RayRec *)w->queue[(level - 1) & 1];
+    a.q_in_count = w->ctl + 64 + level;
+    a.q_out = (rtf::RayRec *)w->queue[level & 1];
+    a.q_out_count = w->ctl + 64 + level + 1;
+    a.chunk_counter = w->ctl + 1 + level;
+    if (a.tables_in_smem) rtf::k_bounce<true><<<max_grid, rtf::kThreads, smem, stream>>>(a);
+    else rtf::k_bounce<false><<<max_grid, rtf::kThreads, smem, stream>>>(a);
+    launches++;
+  }
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? launches : -(int)e;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP32 peak probe: 8 independent FFMA chains per thread, 8 CTAs x 256 threads per SM
+__global__ void k_fp32_peak(float *out, int iters, float a, float b, unsigned long long *clk) {
+  float x[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) x[i] = threadIdx.x * 0.001f + i;
+  unsigned long long c0 = clock64(), g0;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g0));
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int k = 0; k < 16; k++)
+#pragma unroll
+      for (int i = 0; i < 8; i++) x[i] = fmaf(x[i], a, b);
+  }
+  unsigned long long c1 = clock64(), g1;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g1));
+  float s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += x[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0 && blockIdx.x == 0) { clk[0] = c1 - c0; clk[1] = g1 - g0; }
+}
+
+double rtk_measure_fp32_peak(int device, double *sm_clock_mhz) {
+  cudaDeviceProp p;
+  if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&p, device) != cudaSuccess) return -1;
+  const int grid = p.multiProcessorCount * 8, block = 256, iters = 2048;
+  float *buf = nullptr; unsigned long long *clk = nullptr;
+  if (cudaMalloc(&buf, (size_t)grid * block * sizeof(float)) != cudaSuccess) return -2;
+  if (cudaMalloc(&clk, 16) != cudaSuccess) { cudaFree(buf); return -2; }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 6; rep++) {
+    cudaEventRecord(e0);
+    k_fp32_peak<<<grid, block>>>(buf, iters, 1.0001f, 0.5f, clk);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    if (rep >= 2 && ms < best) best = ms;
+  }
+  unsigned long long h[2] = {0, 1};
+  cudaMemcpy(h, clk, 16, cudaMemcpyDeviceToHost);
+  if (sm_clock_mhz) *sm_clock_mhz = (double)h[0] / (double)h[1] * 1e3;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(buf); cudaFree(clk);
+  if (cudaGetLastError() != cudaSuccess) return -3;
+  return 2.0 * grid * block * (double)iters * 16 * 8 / (best * 1e-3);
+}

@@ -9,29 +9,32 @@
 // Copies the frame constants into this device's __constant__ bank (async on `stream`).
 cudaError_t rtk_set_frame_const(const RtFrameConst *host_const, cudaStream_t stream);
 
-// mode 1: exact FP64 brute force.  Returns the number of kernels launched (or <0: cudaError).
+// mode 1: exact FP64 brute force.  Returns the number of kernels launched (or <0: -cudaError).
 int rtk_launch_exact(const RtRenderArgs &args, cudaStream_t stream);
-
 
 // mode 0: FP32-filter fast path (kernels_fast.cuh).
 struct RtFastScene {
   int N, L, npairs;
-  void *cam32;      // npairs x 2 float4 : camera-origin table
-  void *light32;    // L x npairs x 2 float4 : per-light tables
-  void *sph32;      // npairs x 3 float4 : general-origin table
+  void *tabs;            // device: (1+L) shared-origin tables, then the general table; npairs x 2 float4 each
+  size_t table_bytes;    // bytes one kernel stages into shared memory: (1+L) * npairs * 32
+  float d64;             // absolute FP64/geometry slack (delta64)
+  float gS2;             // squared radius bound of the recentred scene
+  double c0[3];          // recentring offset of the general table
 };
 struct RtFastWork {
   int num_sms;
-  void *queue[2];   // secondary-ray records, ping-pong
-  size_t queue_cap;
-  unsigned int *qcount;  // device: [2] record counts
-  void *accum;      // reserved
-  size_t accum_cap;
+  void *queue[2];        // reflected-ray records, ping-pong between levels
+  size_t queue_cap;      // records per queue
+  unsigned int *ctl;     // device control words: tile counter, per-level chunk counters, queue counts
 };
 int rtk_fast_init(int device);
 int rtk_fast_build_scene(RtFastScene *fs, const double *spheres, int N, const RtFrameConst *frame, cudaStream_t stream);
 void rtk_fast_free_scene(RtFastScene *fs);
 void rtk_fast_free_work(RtFastWork *w);
 int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork *w, cudaStream_t stream);
+
+// FP32 FFMA issue peak of `device`, measured live (FLOP/s); used by bench.py as the roofline
+// denominator because MEASURED_PEAKS.json carries no FP32 entry.  Returns <0: -cudaError.
+double rtk_measure_fp32_peak(int device, double *sm_clock_mhz);
 
 #endif

@@ -66,7 +66,8 @@ typedef struct rt_stats {
   uint64_t occluded;
   uint64_t alive[RT_MAX_LEVELS];/* closest queries per reflection level                        */
   uint64_t fp64_intersections;  /* exact FP64 sphere evaluations the kernels needed            */
-  uint64_t sphere_tests;        /* FP32 (filter) or FP64 (exact mode) ray/sphere tests executed*/
+  uint64_t sphere_tests;        /* ray/sphere tests of the brute-force algorithm: N x (R_c + R_s)*/
+  uint64_t filter_violations;   /* self-check of the FP32 filter; must be 0    */
   int32_t kernel_launches;      /* kernels launched by this call                               */
   int32_t rows_rendered;        /* image rows this call produced (all of H unless banded)      */
 } rt_stats;
@@ -135,6 +136,11 @@ int rt_band_row_list(int height, int band_h, int rank, int nranks, int32_t *rows
  * (The reference does the same for its bulk copy: src/main_hybrid.cpp:524.)                 */
 int rt_host_alloc(size_t bytes, void **out);
 void rt_host_free(void *p);
+
+/* ---- measurement -------------------------------------------------------------------------
+ * FP32 FFMA issue peak of `device` in FLOP/s (8 independent chains/thread, all SMs busy) and
+ * the SM clock seen while it ran.  bench.py divides the algorithmic FLOP/s by this.          */
+int rt_measure_fp32_peak(int device, double *flops_per_s, double *sm_clock_mhz);
 
 /* ---- PPM (host only) -------------------------------------------------------------------- */
 /* P3 text, byte-identical to src/main.cpp:69-91: "P3\nW H\n255\n", rows j = H-1 .. 0, one

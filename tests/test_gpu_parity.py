@@ -40,6 +40,8 @@ def check(rt, oracle, renderer, scene, W, H, D, gold=None, rgb_exact_frac=None):
     assert ok and mx <= 2, "rgb: %.4f %% of samples beyond 1 LSB, max diff %d" % (pct, mx)
     for k in ("closest_queries", "hits", "shadow_queries", "occluded"):
         assert getattr(st, k) == gold["counters"][k], k
+    assert st.filter_violations == 0           # the FP32 filter never contradicted the FP64 decider
+    assert st.sphere_tests == (st.closest_queries + st.shadow_queries) * scene.nspheres
     return rgb, st
 
 
