@@ -1,0 +1,347 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark: Mrays/s & ms/frame, complex.txt at 1920x1080 depth 5.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one full frame of the hot path (camera rays -> closest hit -> Phong + shadow rays
+-> reflection bounces -> 8-bit RGB).  The ray count of a frame is a property of (scene, W, H,
+depth) -- R_c + R_s in the oracle's definition -- so Mrays/s = rays / time.
+
+  value     frame already scheduled from device-resident scene tables, output into HBM; at N > 1
+            each rank renders its interleaved 16-row bands and the bands are gathered to rank 0
+            over NCCL inside the timed step.  CUDA events per step, L2 flushed between steps.
+  e2e       the same through the public C ABI with HOST buffers every step: rt_upload_scene
+            (host -> device) + render + frame copy into pinned host memory (device -> host).
+  roofline  FP32 FMA bound: algorithmic flops = 16 x N_spheres x rays.
+  cpu_baseline / --impl reference   the reference's own serial/OpenMP renderer (oracle/_ref,
+            built from the unmodified sources) on the host cores of the same box.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SCENE = os.path.join(ROOT, "tests", "golden", "scenes", "complex.txt")
+W, H, DEPTH, BAND_H = 1920, 1080, 5, 16
+WORKLOAD = "complex.txt (154 spheres, 5 lights) 1920x1080 depth 5"
+FLOP_PER_TEST = 16          # reduced form of include/sphere.h:29-34
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and clock-event (throttle) reasons of one GPU through NVML while the
+    timed regions run."""
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self.stop_flag = False
+        self.err = None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                getattr(nv, "nvmlClocksEventReasonGpuIdle", 0x1): "gpu_idle",
+                getattr(nv, "nvmlClocksEventReasonApplicationsClocksSetting", 0x2): "applications_clocks_setting",
+                getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+                getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+                getattr(nv, "nvmlClocksEventReasonSyncBoost", 0x10): "sync_boost",
+                getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+                getattr(nv, "nvmlClocksEventReasonDisplayClockSetting", 0x100): "display_clock_setting",
+            }
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                bits = get_reasons(h)
+                for b, n in names.items():
+                    if bits & b and n != "gpu_idle":
+                        self.reasons.add(n)
+                time.sleep(self.period)
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+
+    def summary(self):
+        s = sorted(self.samples)
+        # "under load": the upper half of the samples (idle gaps between regions pull clocks down)
+        load = s[len(s) // 2:] if s else []
+        med = load[len(load) // 2] if load else None
+        out = {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+        if self.err:
+            out["error"] = self.err
+        return out
+
+
+def physical_gpu_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except (ValueError, IndexError):
+            return local_rank
+    return local_rank
+
+
+# -------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own CPU renderer on this box's host cores
+def run_reference_frames(steps, warmup, budget_s=150.0):
+    """Times `steps` renders with oracle/_ref/ref_harness (the unmodified reference sources, OpenMP
+    loop of src/main.cpp:185 on all host threads).  Each step is a bounded sample of the frame
+    (every `pix_step`-th pixel) sized so the run fits the budget.  Falls back to the C port."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py
+    import rtb200
+    scene = rtb200.load_scene(SCENE)
+    cores = os.cpu_count() or 1
+    kind = "reference" if oracle_py.ref_available() else "port"
+
+    def one(pix_step):
+        if kind == "reference":
+            out = oracle_py.ref_harness("render", SCENE, W, H, DEPTH, "-", "omp", pix_step,
+                                        env={"OMP_NUM_THREADS": str(cores)})
+            return float([l for l in out.splitlines() if "time:" in l][0].split()[2])
+        t0 = time.perf_counter()
+        oracle_py.render(scene, W, H, DEPTH, pix_step=pix_step, nthreads=0)
+        return time.perf_counter() - t0
+
+    t_probe = one(16) * 16                       # estimate of a full frame
+    total = max(1, steps + warmup)
+    pix_step = 1
+    while t_probe / pix_step * total > budget_s and pix_step < 4096:
+        pix_step *= 2
+    rays = oracle_py.render(scene, W, H, DEPTH, pix_step=pix_step, nthreads=0)["counters"]["rays"]
+    for _ in range(warmup):
+        one(pix_step)
+    times = [one(pix_step) for _ in range(steps)]
+    sec = sum(times) / len(times)
+    return {"mrays_s": rays / sec * 1e-6, "ms_per_step": sec * 1e3, "cores": cores, "kind": kind,
+            "sample": "every %d-th pixel of the %s frame (%d rays/step), OpenMP schedule(dynamic) on %d threads, mean of %d"
+                      % (pix_step, WORKLOAD, rays, cores, steps),
+            "best_ms": min(times) * 1e3}
+
+
+def main_reference(args, rank):
+    if rank != 0:
+        return 0
+    steps = max(1, args.steps)
+    r = run_reference_frames(steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "Mrays/s", "value": round(r["mrays_s"], 3), "unit": "Mrays/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": round(r["ms_per_step"], 3),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "reference scene file (fixture)",
+        "config": {"workload": WORKLOAD, "parallelism": "openmp x%d host threads" % r["cores"]},
+        "cpu_baseline": {"value": round(r["mrays_s"], 3), "unit": "Mrays/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+        "e2e": {"value": round(r["mrays_s"], 3), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# -------------------------------------------------------------------------------------------------
+def main_b200(args, rank, local_rank, world):
+    import numpy as np
+    import torch
+    import rtb200
+
+    n = world
+    dist = None
+    if n > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    sampler.start()
+
+    scene = rtb200.load_scene(SCENE)
+    r = rtb200.Renderer(local_rank, mode="fast")
+    r.upload(scene)
+
+    my_rows = rtb200.band_row_list(H, BAND_H, rank, n)
+    max_rows = max(rtb200.band_rows(H, BAND_H, k, n) for k in range(n))
+    part = torch.zeros(max_rows * W * 3 + 16, dtype=torch.uint8, device=dev)
+    gathered = [torch.zeros_like(part) for _ in range(n)] if (n > 1 and rank == 0) else None
+    full = torch.zeros((H, W, 3), dtype=torch.uint8, device=dev) if rank == 0 else None
+    row_idx = [torch.from_numpy(rtb200.band_row_list(H, BAND_H, k, n).astype(np.int64)).to(dev) for k in range(n)] if rank == 0 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    # a real (non-default) stream: the library launches on the stream it is handed, and the
+    # CUDA events below are recorded on that same stream
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+
+    def step_device():
+        r.render_bands_device(W, H, DEPTH, BAND_H, rank, n, part.data_ptr(), stream.cuda_stream)
+        if n > 1:
+            dist.gather(part, gathered, dst=0)
+            if rank == 0:
+                for k in range(n):
+                    rows = row_idx[k]
+                    full[rows] = gathered[k][: rows.numel() * W * 3].view(rows.numel(), W, 3)
+
+    # ray counts of the frame (one counted render on rank 0's full frame, outside the timed region)
+    _, st = r.render(W, H, DEPTH)
+    rays = int(st.closest_queries + st.shadow_queries)
+    launches_per_step = int(st.kernel_launches)
+    assert st.filter_violations == 0
+
+    for _ in range(max(3, args.warmup)):
+        step_device()
+    torch.cuda.synchronize()
+    if n > 1:
+        dist.barrier()
+    K = max(1, args.steps)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    torch.cuda.synchronize()
+    for k in range(K):
+        flush.fill_(k & 0xff)                     # evict L2 between timed iterations (untimed)
+        ev[k][0].record(stream)
+        step_device()
+        ev[k][1].record(stream)
+    torch.cuda.synchronize()
+    if n > 1:
+        dist.barrier()
+    ms_total = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if n > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / K
+
+    # ---- e2e: public API with host buffers; scene upload (H2D) + render + frame to pinned host (D2H)
+    if n == 1:
+        host_frame = r.pinned_frame(W, H)
+
+        def step_e2e():
+            r.upload(scene)
+            r.render(W, H, DEPTH, out=host_frame, want_stats=False)
+        d2h = W * H * 3
+    else:
+        host_frame = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory() if rank == 0 else None
+
+        def step_e2e():
+            r.upload(scene)
+            step_device()
+            if rank == 0:
+                host_frame.copy_(full, non_blocking=True)
+            torch.cuda.synchronize()
+        d2h = W * H * 3
+    h2d = r.scene_bytes()
+    Ke = max(1, min(K, 200))
+    for _ in range(3):
+        step_e2e()
+    torch.cuda.synchronize()
+    if n > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        step_e2e()
+    torch.cuda.synchronize()
+    if n > 1:
+        dist.barrier()
+    te = torch.tensor([(time.perf_counter() - t0) / Ke], dtype=torch.float64, device=dev)
+    if n > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+
+    # ---- dominant kernel (level-0 k_primary) timed alone with the library's CUDA events
+    lvl0_ms, frame_ms, lvl0_rays = None, None, None
+    if rank == 0 and n == 1:
+        ms0, msf = [], []
+        for _ in range(30):
+            flush.fill_(1)
+            _, s2 = r.render(W, H, DEPTH)
+            ms0.append(s2.ms_level0); msf.append(s2.ms_device)
+        lvl0_ms, frame_ms = sum(ms0) / len(ms0), sum(msf) / len(msf)
+        _, _, mask1, s1 = r.render_debug(W, H, 1)          # level 0 only: pixels + L x primary hits
+        lvl0_rays = int(s1.closest_queries + s1.shadow_queries)
+
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    if rank == 0:
+        peak, peak_mhz = rtb200.measure_fp32_peak(local_rank)
+        nsph = scene.nspheres
+        frame_flops = FLOP_PER_TEST * nsph * rays
+        line = {
+            "metric": "Mrays/s", "value": round(rays / (ms_per_step * 1e-3) * 1e-6, 1), "unit": "Mrays/s",
+            "n_gpus": n, "steps": K, "warmup": max(3, args.warmup), "ms_per_step": round(ms_per_step, 5),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 filter / f64 decide",
+            "data": "reference scene file complex.txt (tests/golden fixture, identical doubles); no dataset involved",
+            "config": {"workload": WORKLOAD, "rays_per_frame": rays, "parallelism": "interleaved %d-row bands x %d GPU%s"
+                       % (BAND_H, n, "" if n == 1 else "s, NCCL gather to rank 0"), "band_h": BAND_H,
+                       "l2": "flushed between timed steps (256 MiB write, untimed)"},
+            "e2e": {"value": round(rays / e2e_s * 1e-6, 1), "unit": "Mrays/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_s * 1e3, 4), "steps": Ke,
+                    "path": "rt_upload_scene + rt_render into pinned host memory" if n == 1 else
+                            "rt_upload_scene + rt_render_bands + NCCL gather + copy to pinned host on rank 0"},
+            "gpu_launches": launches_per_step * K,
+            "clocks": sampler.summary(),
+        }
+        ach = frame_flops / (ms_per_step * 1e-3) * 1e-12
+        roof = {"bound": "fp32", "unit": "TFLOP/s", "peak": round(peak * 1e-12, 2),
+                "peak_source": "measured live: FFMA issue peak of this GPU (rt_measure_fp32_peak, SM clock %.0f MHz); "
+                               "MEASURED_PEAKS.json has no FP32 entry" % peak_mhz,
+                "flop_per_test": FLOP_PER_TEST, "traffic": None,
+                "frame": {"achieved": round(ach, 2), "frac": round(ach / (peak * 1e-12), 4), "flops": frame_flops}}
+        if lvl0_ms:
+            a0 = FLOP_PER_TEST * nsph * lvl0_rays / (lvl0_ms * 1e-3) * 1e-12
+            roof.update({"kernel": "k_primary (level 0: camera rays + their shadow rays)", "achieved": round(a0, 2),
+                         "frac": round(a0 / (peak * 1e-12), 4), "kernel_ms": round(lvl0_ms, 5),
+                         "kernel_rays": lvl0_rays, "kernel_share_of_frame": round(lvl0_ms / frame_ms, 4)})
+        else:
+            roof.update({"kernel": "whole frame (all levels)", "achieved": round(ach, 2), "frac": round(ach / (peak * 1e-12), 4)})
+        line["roofline"] = roof
+        if n == 1 and not args.no_cpu_baseline:
+            try:
+                cb = run_reference_frames(3, 1, budget_s=30.0)
+                line["cpu_baseline"] = {"value": round(cb["mrays_s"], 3), "unit": "Mrays/s", "cores": cb["cores"],
+                                        "kind": cb["kind"], "sample": cb["sample"]}
+            except Exception as e:  # noqa: BLE001
+                line["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "reference",
+                                        "sample": "failed: %r" % (e,)}
+        print(json.dumps(line), flush=True)
+    r.close()
+    if n > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return main_reference(args, rank)
+    if world == 1 and args.gpus > 1:
+        # convenience: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__),
+               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
+        return subprocess.call(cmd)
+    return main_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

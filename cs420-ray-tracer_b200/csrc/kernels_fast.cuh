@@ -1,15 +1,21 @@
 // kernels_fast.cuh -- "mode 0": the production path.  sm_100a only.
 //
-// Work decomposition (wavefront with compacted queues):
-//   k_primary   one persistent CTA per SM slot; tiles of 32x16 pixels, two pixels per thread.
-//               camera rays -> closest hit (FP32 filter over the CAMERA table, FP64 decide)
-//               -> Phong + one any-hit shadow query per light (FP32 filter over that LIGHT's
-//               table) -> final 8-bit pixel, or a reflected ray appended to the ray queue
-//               (warp-ballot compaction: only live rays reach the next level).
-//   k_bounce    one launch per reflection level >= 1: consumes the queue (two rays per thread),
-//               general-origin closest hit, same shading, appends to the other queue.
-// Sphere tables are staged once per CTA into shared memory with one TMA bulk copy
-// (cp.async.bulk + mbarrier) when they fit, otherwise read through L1/L2.
+// Work decomposition (wavefront with compacted queues, warps schedule themselves):
+//   k_primary   persistent CTAs; every WARP pulls 16x4-pixel tiles from an atomic counter (two
+//               vertically adjacent pixels per lane).  Camera rays -> closest hit (FP32 filter over
+//               the CAMERA table, FP64 decide) -> Phong + one any-hit shadow query per light (FP32
+//               filter over that LIGHT's table) -> final 8-bit pixel (staged per warp, 128-bit
+//               stores), or a reflected ray appended to the ray queue with warp-ballot compaction.
+//   k_bounce    level 1: consumes the queue, 64 rays per warp fetch, general-origin closest hit,
+//               same shading, appends survivors to the other queue.
+//               tail (levels >= 2, one launch): each lane follows its ray to termination, the
+//               queue record is updated in place instead of being re-queued.
+// Sphere tables are staged once per CTA into shared memory with ONE TMA bulk copy
+// (cp.async.bulk + mbarrier) when they fit, otherwise they are read through L1/L2.
+//
+// Shared-origin tables (camera, each light) are SORTED by the distance of the sphere's nearest
+// point from that origin; a query stops at the first 8-sphere group that lies entirely beyond
+// its cutoff (current best hit / distance to the shaded point), so "any hit" really is early out.
 //
 // What is FP32 and what is FP64:  every ray/sphere TEST is 4 packed-FP32 FMAs per sphere pair
 // (FFMA2; shared origin) or 10 (general origin).  The tests are conservative (filter_math.cuh);
@@ -29,36 +35,47 @@ namespace rtf {
 using rtx::d3;
 
 constexpr int kThreads = 256;
-constexpr int kTileW = 32, kTileH = 16;
-constexpr int kGroupPairs = 4;          // sphere pairs per fast-path group (8 spheres)
-constexpr int kSmemHeader = 2048;       // mbarrier, tile index, RGB staging
-constexpr float kEps = 0.001f;          // EPSILON, include/ray_math_constants.h:22
+constexpr int kWarps = kThreads / 32;
+constexpr int kWTileW = 16, kWTileH = 4;  // pixels per warp tile (32 lanes x 2 pixels)
+constexpr int kGroupPairs = 4;            // sphere pairs per fast-path group (8 spheres)
+constexpr int kSmemHeader = 2048;         // [0,8) mbarrier, [64, 64+8*192) per-warp RGB staging
+constexpr float kEps = 0.001f;            // EPSILON, include/ray_math_constants.h:22
+constexpr unsigned kSign = 0x80000000u;
+constexpr unsigned kFull = 0xffffffffu;
 
-struct __align__(16) RayRec {           // one queued reflected ray (80 bytes)
-  double ox, oy, oz, dx, dy, dz;        // exact FP64 origin / unit direction (src/main.cpp:45-48)
-  unsigned pix;                         // local pixel index lr*W + x
-  float wt;                             // product of reflectivities so far
-  float ar, ag, ab;                     // colour accumulated so far (front to back)
+struct __align__(16) RayRec {             // one queued reflected ray (80 bytes)
+  double ox, oy, oz, dx, dy, dz;          // exact FP64 origin / unit direction (src/main.cpp:45-48)
+  unsigned pix;                           // local pixel index lr*W + x
+  float wt;                               // product of reflectivities so far
+  float ar, ag, ab;                       // colour accumulated so far (front to back)
   unsigned pad;
 };
 
 struct FastArgs {
   RtRenderArgs r;
-  const float4 *otab;     // (1+L) tables x npairs x 2 float4; table 0 = camera, 1+l = light l
-  const float4 *gtab;     // general-origin table: npairs x 2 float4 (recentred centres, rho')
-  int npairs;             // padded to a multiple of kGroupPairs
+  const unsigned char *tabs;  // (1+L) shared-origin tables (tstride bytes each: pairs | gmin | perm), then the general table
+  int npairs, ngroups;        // npairs is a multiple of kGroupPairs; ngroups = npairs / kGroupPairs
   int N, L;
-  float d64;              // absolute slack covering FP64 rounding / geometry (delta64)
-  float gS2;              // squared radius bound of the recentred scene (general filter)
-  double c0[3];           // recentring offset of the general table
-  int tiles_x, ntiles;
+  unsigned tstride, gmin_off, perm_off;
+  unsigned stage_bytes;       // bytes this kernel stages into shared memory
+  float d64;                  // absolute slack covering FP64 rounding / geometry (delta64)
+  float gS2;                  // squared radius bound S^2 of the recentred scene (general filter)
+  float g_dtmax;              // 16u*S: bound of |fl32 dot - true| for the general filter
+  double c0[3];               // recentring offset of the general table
+  int wtiles_x, nwtiles;
   unsigned int *tile_counter;
   RayRec *q_out; unsigned int *q_out_count;
-  const RayRec *q_in; const unsigned int *q_in_count;
+  RayRec *q_in; const unsigned int *q_in_count;
   unsigned int *chunk_counter;
   int level;
   int tables_in_smem;
-  unsigned table_bytes;   // bytes staged into shared memory
+};
+
+// One shared-origin table: sphere pairs in sorted order, per-group minimum distance, original indices
+struct Tab {
+  const float4 *pairs;   // 2 float4 per pair: (x0,x1,y0,y1) (z0,z1,w0,w1)
+  const float *gmin;     // per group of 8 spheres: lower bound of |oc| - r over the group (ascending)
+  const int *perm;       // original sphere index per sorted slot, -1 = padding
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -74,10 +91,20 @@ __device__ __forceinline__ double4 ld_sph64(const double4 *p) {
 }
 __device__ __forceinline__ unsigned long long wsum(unsigned long long v) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ float wmaxf(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
   return v;
 }
 __device__ __forceinline__ unsigned quant8(float c) { return (unsigned)(int)(255.99f * fminf(1.0f, c)); }
+__device__ __forceinline__ int warp_fetch(unsigned int *counter) {
+  int v = 0;
+  if ((threadIdx.x & 31) == 0) v = (int)atomicAdd(counter, 1u);
+  return __shfl_sync(kFull, v, 0);
+}
 
 // mbarrier + TMA bulk copy (global -> shared), one phase, used once per CTA
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
@@ -105,6 +132,27 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t}" ::"r"(a), "r"(parity)
       : "memory");
+}
+
+// Stages `bytes` from gsrc into shared memory behind the header with ONE TMA bulk copy.
+__device__ __forceinline__ void stage_tables(unsigned char *smem, const unsigned char *gsrc, unsigned bytes) {
+  unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    mbar_expect_tx(bar, bytes);
+    tma_bulk_g2s(smem + kSmemHeader, gsrc, bytes, bar);
+  }
+  __syncthreads();
+  mbar_wait(bar, 0);
+}
+
+__device__ __forceinline__ Tab tab_at(const unsigned char *base, const FastArgs &a, int t) {
+  const unsigned char *p = base + (size_t)t * a.tstride;
+  Tab T;
+  T.pairs = reinterpret_cast<const float4 *>(p);
+  T.gmin = reinterpret_cast<const float *>(p + a.gmin_off);
+  T.perm = reinterpret_cast<const int *>(p + a.perm_off);
+  return T;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -140,7 +188,9 @@ __device__ __noinline__ int exact_bruteforce(const double4 *sph64, int n, d3 o, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// closest-hit bookkeeping: best candidate as an FP32 bracket, exact FP64 t only when needed
+// closest-hit bookkeeping: best candidate as an FP32 bracket, exact FP64 t only when needed.
+// All comparisons are order independent: (t, index) lexicographic, i.e. the reference's strict '<'
+// scan in ascending index order (include/scene.h:47-56), whatever order spheres are visited in.
 struct Best {
   float lo, hi;
   int idx;
@@ -152,18 +202,16 @@ __device__ __forceinline__ void best_set_exact(Best &b, int idx, double t) {
   b.idx = idx; b.t = t; b.exact = true; b.lo = f_rd(t); b.hi = f_ru(t);
 }
 
-// One candidate sphere `i` of a closest-hit query.  status/lo/hi from the FP32 brackets; `ray`
-// is only materialised (by the caller-supplied functor) when an FP64 decision is unavoidable.
 template <typename ExactRayFn>
 __device__ __forceinline__ void closest_consider(Best &b, int i, int status, float lo, float hi, const double4 *sph64,
                                                  ExactRayFn get_ray, unsigned &n_fp64) {
   if (status == RT_MISS) return;
   if (status == RT_HIT) {
     if (b.idx < 0) { b.lo = lo; b.hi = hi; b.idx = i; b.exact = false; return; }
-    if (lo >= b.hi) return;                       // cannot be strictly closer (include/scene.h:52)
+    if (lo > b.hi) return;                        // strictly farther
     if (hi < b.lo) { b.lo = lo; b.hi = hi; b.idx = i; b.exact = false; return; }
   }
-  // brackets overlap, or the sphere itself is ambiguous: decide in FP64, lowest index wins ties
+  // brackets touch, or the sphere itself is ambiguous: decide in FP64, lowest index wins ties
   ExactRay e = get_ray();
   double tn;
   n_fp64++;
@@ -171,7 +219,7 @@ __device__ __forceinline__ void closest_consider(Best &b, int i, int status, flo
   if (!hn || !(tn < 1e20)) return;                // INFINITY_DOUBLE init of include/scene.h:42
   if (b.idx >= 0 && !b.exact) {
     float tl = f_rd(tn), th = f_ru(tn);
-    if (tl >= b.hi) return;
+    if (tl > b.hi) return;
     if (th < b.lo) { best_set_exact(b, i, tn); return; }
     double tb;
     n_fp64++;
@@ -179,14 +227,6 @@ __device__ __forceinline__ void closest_consider(Best &b, int i, int status, flo
     if (hb) best_set_exact(b, b.idx, tb); else best_init(b);   // (else: filter violation, caught later)
   }
   if (b.idx < 0 || tn < b.t || (tn == b.t && i < b.idx)) best_set_exact(b, i, tn);
-}
-
-// ---------------------------------------------------------------------------------------------
-// table access: sphere pair p of a table = two float4: (x0,x1,y0,y1) (z0,z1,w0,w1)
-template <bool kSmem>
-__device__ __forceinline__ float4 tab_ld(const float4 *t, int i) {
-  if (kSmem) return t[i];
-  return __ldg(&t[i]);
 }
 
 // scalar re-evaluation of one sphere of a shared-origin table (same operations as the fast path)
@@ -198,8 +238,7 @@ __device__ __forceinline__ void shared_origin_eval(float ocx, float ocy, float o
   Dp = __fmaf_rn(tca, tca, ncc);
 }
 
-// Brackets the roots of sphere (oc, ncc) of a shared-origin table for direction d.
-// Returns false if the discriminant's sign is uncertain.
+// Brackets the roots of sphere (oc, ncc) of a shared-origin table.  False = discriminant sign uncertain.
 __device__ __forceinline__ bool shared_origin_roots(float ocx, float ocy, float ocz, float ncc, float tca, float Dp, float d64,
                                                     Roots &r) {
   float oc2 = __fmaf_ru(ocz, ocz, __fmaf_ru(ocy, ocy, __fmul_ru(ocx, ocx)));
@@ -212,110 +251,136 @@ __device__ __forceinline__ bool shared_origin_roots(float ocx, float ocy, float 
   return bracket_roots(tca, Dhi, E2, dt, r);
 }
 
+// The packed FP32 test of one group (4 pairs = 8 spheres) against two rays of a shared-origin table.
+// Bit 31 of acc stays set while no sphere of the group can be hit: D' = (oc.d)^2 + ncc < 0.
+__device__ __forceinline__ void group_test_shared(const float4 *__restrict__ pairs, int g, const float2 (&dx)[2],
+                                                  const float2 (&dy)[2], const float2 (&dz)[2], unsigned &acc0, unsigned &acc1) {
+  acc0 = kFull; acc1 = kFull;
+#pragma unroll
+  for (int k = 0; k < kGroupPairs; k++) {
+    const float4 A = pairs[2 * (g * kGroupPairs + k)], B = pairs[2 * (g * kGroupPairs + k) + 1];
+    const float2 X = make_float2(A.x, A.y), Y = make_float2(A.z, A.w), Z = make_float2(B.x, B.y), Wv = make_float2(B.z, B.w);
+    float2 t0 = __fmul2_rn(X, dx[0]); t0 = __ffma2_rn(Y, dy[0], t0); t0 = __ffma2_rn(Z, dz[0], t0);
+    float2 t1 = __fmul2_rn(X, dx[1]); t1 = __ffma2_rn(Y, dy[1], t1); t1 = __ffma2_rn(Z, dz[1], t1);
+    const float2 D0 = __ffma2_rn(t0, t0, Wv), D1 = __ffma2_rn(t1, t1, Wv);
+    acc0 &= fbits(D0.x) & fbits(D0.y);
+    acc1 &= fbits(D1.x) & fbits(D1.y);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
-// CLOSEST HIT, shared origin (camera table).  Two rays per thread.
-template <bool kSmem, typename ExactRayFn0, typename ExactRayFn1>
-__device__ __forceinline__ void closest_shared(const float4 *__restrict__ tab, int npairs, int N, const float (&dx)[2],
-                                               const float (&dy)[2], const float (&dz)[2], const bool (&live)[2], float d64,
-                                               const double4 *sph64, ExactRayFn0 ray0, ExactRayFn1 ray1, Best (&best)[2],
-                                               unsigned &n_fp64) {
-  const unsigned dead0 = live[0] ? 0u : 0x80000000u, dead1 = live[1] ? 0u : 0x80000000u;
-  const float2 dx0 = make_float2(dx[0], dx[0]), dy0 = make_float2(dy[0], dy[0]), dz0 = make_float2(dz[0], dz[0]);
-  const float2 dx1 = make_float2(dx[1], dx[1]), dy1 = make_float2(dy[1], dy[1]), dz1 = make_float2(dz[1], dz[1]);
-  for (int g = 0; g < npairs; g += kGroupPairs) {
-    unsigned acc0 = 0xffffffffu, acc1 = 0xffffffffu;
+// CLOSEST HIT, shared origin (camera table, sorted by nearest-point distance).  Two rays per lane.
+template <typename ExactRayFn0, typename ExactRayFn1>
+__device__ __forceinline__ void closest_shared(const Tab T, int ngroups, const float (&dx)[2], const float (&dy)[2],
+                                               const float (&dz)[2], const bool (&live)[2], float d64, const double4 *sph64,
+                                               ExactRayFn0 ray0, ExactRayFn1 ray1, Best (&best)[2], unsigned &n_fp64) {
+  unsigned dead[2] = {live[0] ? 0u : kSign, live[1] ? 0u : kSign};
+  const float2 dx2[2] = {make_float2(dx[0], dx[0]), make_float2(dx[1], dx[1])};
+  const float2 dy2[2] = {make_float2(dy[0], dy[0]), make_float2(dy[1], dy[1])};
+  const float2 dz2[2] = {make_float2(dz[0], dz[0]), make_float2(dz[1], dz[1])};
+  float wcut = 3.0e38f;                            // warp-uniform: farthest cutoff of any live ray
+  for (int g = 0; g < ngroups; g++) {
+    const float gm = T.gmin[g];
+    if (gm > wcut) break;                          // every remaining sphere is beyond every ray's best hit
+    if (gm > best[0].hi) dead[0] = kSign;
+    if (gm > best[1].hi) dead[1] = kSign;
+    unsigned acc0, acc1;
+    group_test_shared(T.pairs, g, dx2, dy2, dz2, acc0, acc1);
+    const bool flagged = (int)((acc0 | dead[0]) & (acc1 | dead[1])) >= 0;
+    if (__any_sync(kFull, flagged)) {
+      if (flagged) {
 #pragma unroll
-    for (int k = 0; k < kGroupPairs; k++) {
-      const float4 A = tab_ld<kSmem>(tab, 2 * (g + k)), B = tab_ld<kSmem>(tab, 2 * (g + k) + 1);
-      const float2 X = make_float2(A.x, A.y), Y = make_float2(A.z, A.w), Z = make_float2(B.x, B.y), W = make_float2(B.z, B.w);
-      float2 t0 = __fmul2_rn(X, dx0); t0 = __ffma2_rn(Y, dy0, t0); t0 = __ffma2_rn(Z, dz0, t0);
-      float2 t1 = __fmul2_rn(X, dx1); t1 = __ffma2_rn(Y, dy1, t1); t1 = __ffma2_rn(Z, dz1, t1);
-      float2 D0 = __ffma2_rn(t0, t0, W), D1 = __ffma2_rn(t1, t1, W);
-      acc0 &= fbits(D0.x) & fbits(D0.y);
-      acc1 &= fbits(D1.x) & fbits(D1.y);
-    }
-    if ((int)((acc0 | dead0) & (acc1 | dead1)) >= 0) {
-      // slow path: some sphere of this group may be hit by one of this thread's rays
-#pragma unroll
-      for (int r = 0; r < 2; r++) {
-        if ((int)((r ? acc1 : acc0) | (r ? dead1 : dead0)) < 0) continue;
-        for (int k = 0; k < 2 * kGroupPairs; k++) {
-          const int pi = g + (k >> 1), h = k & 1, i = 2 * pi + h;
-          if (i >= N) break;
-          const float4 A = tab_ld<kSmem>(tab, 2 * pi), B = tab_ld<kSmem>(tab, 2 * pi + 1);
-          const float ocx = h ? A.y : A.x, ocy = h ? A.w : A.z, ocz = h ? B.y : B.x, ncc = h ? B.w : B.z;
-          float tca, Dp;
-          shared_origin_eval(ocx, ocy, ocz, ncc, dx[r], dy[r], dz[r], tca, Dp);
-          if (!(Dp >= 0.0f)) continue;
-          Roots rt;
-          int status = RT_AMBIG;
-          float lo = 0, hi = 0;
-          if (shared_origin_roots(ocx, ocy, ocz, ncc, tca, Dp, d64, rt)) status = select_root(rt, lo, hi);
-          if (r == 0) closest_consider(best[0], i, status, lo, hi, sph64, ray0, n_fp64);
-          else closest_consider(best[1], i, status, lo, hi, sph64, ray1, n_fp64);
+        for (int r = 0; r < 2; r++) {
+          if ((int)((r ? acc1 : acc0) | dead[r]) < 0) continue;
+          for (int k = 0; k < 2 * kGroupPairs; k++) {
+            const int pi = g * kGroupPairs + (k >> 1), h = k & 1;
+            const int i = T.perm[2 * pi + h];
+            if (i < 0) continue;
+            const float4 A = T.pairs[2 * pi], B = T.pairs[2 * pi + 1];
+            const float ocx = h ? A.y : A.x, ocy = h ? A.w : A.z, ocz = h ? B.y : B.x, ncc = h ? B.w : B.z;
+            float tca, Dp;
+            shared_origin_eval(ocx, ocy, ocz, ncc, dx[r], dy[r], dz[r], tca, Dp);
+            if (!(Dp >= 0.0f)) continue;
+            Roots rt;
+            int status = RT_AMBIG;
+            float lo = 0, hi = 0;
+            if (shared_origin_roots(ocx, ocy, ocz, ncc, tca, Dp, d64, rt)) status = select_root(rt, lo, hi);
+            if (r == 0) closest_consider(best[0], i, status, lo, hi, sph64, ray0, n_fp64);
+            else closest_consider(best[1], i, status, lo, hi, sph64, ray1, n_fp64);
+          }
         }
       }
+      wcut = wmaxf(fmaxf(live[0] ? best[0].hi : -3.0e38f, live[1] ? best[1].hi : -3.0e38f));
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // CLOSEST HIT, general origin (bounce rays).  Table pair = (cx0,cx1,cy0,cy1) (cz0,cz1,rho0,rho1)
-// with recentred centres; o = recentred float origin, di = direction inflated by (1+16u).
-template <bool kSmem, typename ExactRayFn0, typename ExactRayFn1>
-__device__ __forceinline__ void closest_general(const float4 *__restrict__ tab, int npairs, int N, const float (&ox)[2],
+// with recentred centres, index order.  Per sphere: X = c - o, tu = X.d(1+16u) + dtmax (an UPPER
+// bound of the true centre projection), q = |X|^2 - rho' (> 0 => origin strictly outside),
+// D' = tu^2 - q.  A sphere is skipped when D' < 0, or when it lies behind an origin that is outside
+// it (tu < 0 and q > 0): that removes the sphere the ray just left without any extra arithmetic.
+template <typename ExactRayFn0, typename ExactRayFn1>
+__device__ __forceinline__ void closest_general(const float4 *__restrict__ pairs, int ngroups, int N, const float (&ox)[2],
                                                 const float (&oy)[2], const float (&oz)[2], const float (&dx)[2],
                                                 const float (&dy)[2], const float (&dz)[2], const bool (&live)[2], float d64,
-                                                float gS2, const double4 *sph64, ExactRayFn0 ray0, ExactRayFn1 ray1,
-                                                Best (&best)[2], unsigned &n_fp64) {
-  const unsigned dead0 = live[0] ? 0u : 0x80000000u, dead1 = live[1] ? 0u : 0x80000000u;
+                                                float gS2, float dtmax, const double4 *sph64, ExactRayFn0 ray0,
+                                                ExactRayFn1 ray1, Best (&best)[2], unsigned &n_fp64) {
+  const unsigned dead[2] = {live[0] ? 0u : kSign, live[1] ? 0u : kSign};
   const float kInfl = 1.0f + 16.0f * 5.9604645e-8f;
   float2 nox[2], noy[2], noz[2], idx2[2], idy2[2], idz2[2];
+  const float2 dtm = make_float2(dtmax, dtmax);
 #pragma unroll
   for (int r = 0; r < 2; r++) {
     nox[r] = make_float2(-ox[r], -ox[r]); noy[r] = make_float2(-oy[r], -oy[r]); noz[r] = make_float2(-oz[r], -oz[r]);
     float ix = __fmul_rn(dx[r], kInfl), iy = __fmul_rn(dy[r], kInfl), iz = __fmul_rn(dz[r], kInfl);
     idx2[r] = make_float2(ix, ix); idy2[r] = make_float2(iy, iy); idz2[r] = make_float2(iz, iz);
   }
-  for (int g = 0; g < npairs; g += kGroupPairs) {
-    unsigned acc[2] = {0xffffffffu, 0xffffffffu};
+  const float sS = __fsqrt_ru(gS2);
+  for (int g = 0; g < ngroups; g++) {
+    unsigned acc[2] = {kFull, kFull};
 #pragma unroll
     for (int k = 0; k < kGroupPairs; k++) {
-      const float4 A = tab_ld<kSmem>(tab, 2 * (g + k)), B = tab_ld<kSmem>(tab, 2 * (g + k) + 1);
+      const float4 A = pairs[2 * (g * kGroupPairs + k)], B = pairs[2 * (g * kGroupPairs + k) + 1];
       const float2 CX = make_float2(A.x, A.y), CY = make_float2(A.z, A.w), CZ = make_float2(B.x, B.y);
       const float2 NR = make_float2(-B.z, -B.w);
 #pragma unroll
       for (int r = 0; r < 2; r++) {
-        float2 x = __fadd2_rn(CX, nox[r]), y = __fadd2_rn(CY, noy[r]), z = __fadd2_rn(CZ, noz[r]);
-        float2 t = __fmul2_rn(x, idx2[r]); t = __ffma2_rn(y, idy2[r], t); t = __ffma2_rn(z, idz2[r], t);
+        const float2 x = __fadd2_rn(CX, nox[r]), y = __fadd2_rn(CY, noy[r]), z = __fadd2_rn(CZ, noz[r]);
+        float2 t = __ffma2_rn(x, idx2[r], dtm); t = __ffma2_rn(y, idy2[r], t); t = __ffma2_rn(z, idz2[r], t);
         float2 q = __ffma2_rn(x, x, NR); q = __ffma2_rn(y, y, q); q = __ffma2_rn(z, z, q);
-        float2 D = __ffma2_rn(t, t, make_float2(-q.x, -q.y));
-        acc[r] &= fbits(D.x) & fbits(D.y);
+        const float2 D = __ffma2_rn(t, t, make_float2(-q.x, -q.y));
+        // rejected  <=>  D' < 0  or  (tu < 0 and q >= 0)
+        acc[r] &= (fbits(D.x) | (fbits(t.x) & ~fbits(q.x))) & (fbits(D.y) | (fbits(t.y) & ~fbits(q.y)));
       }
     }
-    if ((int)((acc[0] | dead0) & (acc[1] | dead1)) >= 0) {
+    if ((int)((acc[0] | dead[0]) & (acc[1] | dead[1])) >= 0) {
 #pragma unroll
       for (int r = 0; r < 2; r++) {
-        if ((int)(acc[r] | (r ? dead1 : dead0)) < 0) continue;
+        if ((int)(acc[r] | dead[r]) < 0) continue;
         for (int k = 0; k < 2 * kGroupPairs; k++) {
-          const int pi = g + (k >> 1), h = k & 1, i = 2 * pi + h;
+          const int pi = g * kGroupPairs + (k >> 1), h = k & 1, i = 2 * pi + h;
           if (i >= N) break;
-          const float4 A = tab_ld<kSmem>(tab, 2 * pi), B = tab_ld<kSmem>(tab, 2 * pi + 1);
+          const float4 A = pairs[2 * pi], B = pairs[2 * pi + 1];
           const float cx = h ? A.y : A.x, cy = h ? A.w : A.z, cz = h ? B.y : B.x, rho = h ? B.w : B.z;
-          // explicit-margin evaluation (independent of the inflation trick of the fast path)
+          // explicit-margin evaluation (independent of the inflation tricks of the fast path)
           const float x = __fsub_rn(cx, ox[r]), y = __fsub_rn(cy, oy[r]), z = __fsub_rn(cz, oz[r]);
           float tca = __fmul_rn(x, dx[r]); tca = __fmaf_rn(y, dy[r], tca); tca = __fmaf_rn(z, dz[r], tca);
           const float oc2 = __fmaf_ru(z, z, __fmaf_ru(y, y, __fmul_ru(x, x)));
-          // |X - oc*| <= u(|c|+|o|+|oc|); D error <= 20u|oc|^2 + 4.1u S^2 + 3u r^2 + d64  
-          const float Eg = __fadd_ru(__fmul_ru(1.9073486e-6f, __fadd_ru(__fadd_ru(oc2, gS2), fabsf(rho))), d64);
-          const float Dc = __fmaf_rn(tca, tca, __fsub_rn(rho, oc2));      // rho ~ r^2 (+margins, harmless: covered by Eg)
+          // |X - oc*| <= u(2S + |oc|)  =>  D error <= u (8.1 S |oc| + 16 |oc|^2 + 4 rho) + d64   
+          const float ocn = __fsqrt_ru(oc2);
+          const float Eg = __fadd_ru(__fmul_ru(5.9604645e-8f, __fmaf_ru(8.2f * sS, ocn, __fmaf_ru(16.5f, oc2, 4.5f * fabsf(rho)))), d64);
+          const float Dc = __fmaf_rn(tca, tca, __fsub_rn(rho, oc2));      // rho = r^2 + margins (<= r^2 + Eg)
           const float Dhi = __fadd_ru(Dc, Eg);
           if (!(Dhi >= 0.0f)) continue;
           Roots rt;
           int status = RT_AMBIG;
           float lo = 0, hi = 0;
-          const float dt = __fmul_ru(RT_ETA * 1.001f, __fadd_ru(__fsqrt_ru(oc2), __fsqrt_ru(gS2)));
-          if (bracket_roots(tca, Dhi, __fmul_ru(3.0f, Eg), dt, rt)) status = select_root(rt, lo, hi);
+          const float dt = __fmul_ru(RT_ETA * 1.001f, __fadd_ru(ocn, sS));
+          // rho' - r^2 = 40u r^2 + 12u S r + 64u^2 S^2 + d64 (host), bounded here from rho' itself
+          const float rm = __fadd_ru(__fmul_ru(5.9604645e-8f, __fmaf_ru(12.5f * sS, __fsqrt_ru(fabsf(rho)), __fmaf_ru(41.0f, fabsf(rho), 1e-4f * gS2))), d64);
+          if (bracket_roots(tca, Dhi, __fadd_ru(__fmul_ru(2.0f, Eg), rm), dt, rt)) status = select_root(rt, lo, hi);
           if (r == 0) closest_consider(best[0], i, status, lo, hi, sph64, ray0, n_fp64);
           else closest_consider(best[1], i, status, lo, hi, sph64, ray1, n_fp64);
         }
@@ -325,65 +390,72 @@ __device__ __forceinline__ void closest_general(const float4 *__restrict__ tab, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// SHADOW (any hit, early out), light table.  Direction dl = unit vector FROM THE LIGHT TOWARDS the
-// shaded point, so = distance light -> shadow-ray origin (= |L-p| - EPS), both FP32 with known error.
-// Roots s are measured from the light; the reference's t = so - s (include/scene.h:70-85).
-//   occluded  <=>  (-EPS < s2 <= so)  or  (s2 > so and -EPS < s1 <= so)
-template <bool kSmem>
-__device__ __forceinline__ void shadow_light(const float4 *__restrict__ tab, int npairs, int N, int light,
-                                             const float (&dx)[2], const float (&dy)[2], const float (&dz)[2],
-                                             const float (&so)[2], const bool (&want)[2], const d3 (&p64)[2], float d64,
+// SHADOW (any hit, early out), light table sorted by distance from the light.  dl = unit vector FROM
+// THE LIGHT TOWARDS the shaded point, so = distance light -> shadow-ray origin (= |L-p| - EPS), both
+// FP32 with known error.  Roots s are measured from the light; the reference's t = so - s
+// (include/scene.h:70-85):   occluded  <=>  (-EPS < s2 <= so)  or  (s2 > so and -EPS < s1 <= so).
+// self[r] / cosl[r]: the sphere the point lies on and n.light_dir there -- on its lit side that
+// sphere cannot occlude (the shadow origin is outside it and moving away), so it is skipped cheaply.
+__device__ __forceinline__ void shadow_light(const Tab T, int ngroups, int light, const float (&dx)[2], const float (&dy)[2],
+                                             const float (&dz)[2], const float (&so)[2], const bool (&want)[2],
+                                             const int (&self)[2], const float (&cosl)[2], const d3 (&p64)[2], float d64,
                                              const double4 *sph64, bool (&occ)[2], unsigned &n_fp64) {
-  unsigned dead[2] = {want[0] ? 0u : 0x80000000u, want[1] ? 0u : 0x80000000u};
+  unsigned dead[2] = {want[0] ? 0u : kSign, want[1] ? 0u : kSign};
   occ[0] = occ[1] = false;
-  const float2 dx0 = make_float2(dx[0], dx[0]), dy0 = make_float2(dy[0], dy[0]), dz0 = make_float2(dz[0], dz[0]);
-  const float2 dx1 = make_float2(dx[1], dx[1]), dy1 = make_float2(dy[1], dy[1]), dz1 = make_float2(dz[1], dz[1]);
-  for (int g = 0; g < npairs; g += kGroupPairs) {
-    unsigned acc0 = 0xffffffffu, acc1 = 0xffffffffu;
+  const float2 dx2[2] = {make_float2(dx[0], dx[0]), make_float2(dx[1], dx[1])};
+  const float2 dy2[2] = {make_float2(dy[0], dy[0]), make_float2(dy[1], dy[1])};
+  const float2 dz2[2] = {make_float2(dz[0], dz[0]), make_float2(dz[1], dz[1])};
+  float m[2], cut[2];
 #pragma unroll
-    for (int k = 0; k < kGroupPairs; k++) {
-      const float4 A = tab_ld<kSmem>(tab, 2 * (g + k)), B = tab_ld<kSmem>(tab, 2 * (g + k) + 1);
-      const float2 X = make_float2(A.x, A.y), Y = make_float2(A.z, A.w), Z = make_float2(B.x, B.y), W = make_float2(B.z, B.w);
-      float2 t0 = __fmul2_rn(X, dx0); t0 = __ffma2_rn(Y, dy0, t0); t0 = __ffma2_rn(Z, dz0, t0);
-      float2 t1 = __fmul2_rn(X, dx1); t1 = __ffma2_rn(Y, dy1, t1); t1 = __ffma2_rn(Z, dz1, t1);
-      float2 D0 = __ffma2_rn(t0, t0, W), D1 = __ffma2_rn(t1, t1, W);
-      acc0 &= fbits(D0.x) & fbits(D0.y);
-      acc1 &= fbits(D1.x) & fbits(D1.y);
-    }
+  for (int r = 0; r < 2; r++) {
+    m[r] = __fmaf_ru(1.9073486e-6f, so[r] + kEps, 1e-7f);     // 2^-19 |L-p|: covers the FP32 length error
+    cut[r] = want[r] ? so[r] + m[r] : -3.0e38f;               // nothing farther from the light can matter
+  }
+  const float wcut = wmaxf(fmaxf(cut[0], cut[1]));
+  for (int g = 0; g < ngroups; g++) {
+    const float gm = T.gmin[g];
+    if (gm > wcut) break;
+    if (gm > cut[0]) dead[0] = kSign;
+    if (gm > cut[1]) dead[1] = kSign;
+    unsigned acc0, acc1;
+    group_test_shared(T.pairs, g, dx2, dy2, dz2, acc0, acc1);
     const bool flagged = (int)((acc0 | dead[0]) & (acc1 | dead[1])) >= 0;
-    if (__any_sync(0xffffffffu, flagged)) {          // warp-uniform: the vote below needs every lane
+    if (__any_sync(kFull, flagged)) {                 // warp-uniform: the vote below needs every lane
+      if (flagged) {
 #pragma unroll
-      for (int r = 0; r < 2; r++) {
-        if (!flagged || (int)((r ? acc1 : acc0) | dead[r]) < 0) continue;
-        const float m = __fmaf_ru(1.9073486e-6f, so[r] + kEps, 1e-7f);      // 2^-19 * |L-p|: covers the FP32 length error
-        const float so_lo = so[r] - m, so_hi = so[r] + m, e_lo = -kEps - m, e_hi = -kEps + m;
-        for (int k = 0; k < 2 * kGroupPairs && !occ[r]; k++) {
-          const int pi = g + (k >> 1), h = k & 1, i = 2 * pi + h;
-          if (i >= N) break;
-          const float4 A = tab_ld<kSmem>(tab, 2 * pi), B = tab_ld<kSmem>(tab, 2 * pi + 1);
-          const float ocx = h ? A.y : A.x, ocy = h ? A.w : A.z, ocz = h ? B.y : B.x, ncc = h ? B.w : B.z;
-          float tca, Dp;
-          shared_origin_eval(ocx, ocy, ocz, ncc, dx[r], dy[r], dz[r], tca, Dp);
-          if (!(Dp >= 0.0f)) continue;
-          Roots rt;
-          bool decided = false;
-          if (shared_origin_roots(ocx, ocy, ocz, ncc, tca, Dp, d64, rt)) {
-            const bool no = (rt.n_lo > so_hi) || (rt.f_hi < e_lo) || (rt.n_hi < e_lo && rt.f_lo > so_hi);
-            const bool yes = (rt.f_lo > e_hi && rt.f_hi < so_lo) ||
-                             (rt.f_lo > so_hi && rt.n_lo > e_hi && rt.n_hi < so_lo);
-            if (no) decided = true;
-            else if (yes) { decided = true; occ[r] = true; }
+        for (int r = 0; r < 2; r++) {
+          if ((int)((r ? acc1 : acc0) | dead[r]) < 0) continue;
+          const float so_lo = so[r] - m[r], so_hi = so[r] + m[r], e_lo = -kEps - m[r], e_hi = -kEps + m[r];
+          for (int k = 0; k < 2 * kGroupPairs && !occ[r]; k++) {
+            const int pi = g * kGroupPairs + (k >> 1), h = k & 1;
+            const int i = T.perm[2 * pi + h];
+            if (i < 0) continue;
+            if (i == self[r] && cosl[r] > 1e-3f) continue;
+            const float4 A = T.pairs[2 * pi], B = T.pairs[2 * pi + 1];
+            const float ocx = h ? A.y : A.x, ocy = h ? A.w : A.z, ocz = h ? B.y : B.x, ncc = h ? B.w : B.z;
+            float tca, Dp;
+            shared_origin_eval(ocx, ocy, ocz, ncc, dx[r], dy[r], dz[r], tca, Dp);
+            if (!(Dp >= 0.0f)) continue;
+            Roots rt;
+            bool decided = false;
+            if (shared_origin_roots(ocx, ocy, ocz, ncc, tca, Dp, d64, rt)) {
+              const bool no = (rt.n_lo > so_hi) || (rt.f_hi < e_lo) || (rt.n_hi < e_lo && rt.f_lo > so_hi);
+              const bool yes = (rt.f_lo > e_hi && rt.f_hi < so_lo) ||
+                               (rt.f_lo > so_hi && rt.n_lo > e_hi && rt.n_hi < so_lo);
+              if (no) decided = true;
+              else if (yes) { decided = true; occ[r] = true; }
+            }
+            if (!decided) {       // the reference's own formula on the reference's own shadow ray
+              double ldist, tt;
+              ExactRay e = exact_shadow_ray(p64[r], light, ldist);
+              n_fp64++;
+              if (exact_sphere(sph64, i, e.o, e.d, e.a, tt) && tt < 1e20 && tt < ldist) occ[r] = true;
+            }
           }
-          if (!decided) {       // the reference's own formula on the reference's own shadow ray
-            double ldist, tt;
-            ExactRay e = exact_shadow_ray(p64[r], light, ldist);
-            n_fp64++;
-            if (exact_sphere(sph64, i, e.o, e.d, e.a, tt) && tt < 1e20 && tt < ldist) occ[r] = true;
-          }
+          if (occ[r]) dead[r] = kSign;
         }
-        if (occ[r]) dead[r] = 0x80000000u;
       }
-      if (__all_sync(0xffffffffu, (dead[0] & dead[1]) != 0u)) break;     // every ray of the warp is done
+      if (__all_sync(kFull, (dead[0] & dead[1]) != 0u)) break;     // every ray of the warp is decided
     }
   }
 }
@@ -391,13 +463,13 @@ __device__ __forceinline__ void shadow_light(const float4 *__restrict__ tab, int
 // ---------------------------------------------------------------------------------------------
 // warp-ballot compaction: rays still alive are appended densely to the next level's queue
 __device__ __forceinline__ void queue_push(bool want, const RayRec &rec, RayRec *q, unsigned int *count) {
-  const unsigned m = __ballot_sync(0xffffffffu, want);
-  if (m == 0) return;
-  const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+  const unsigned mk = __ballot_sync(kFull, want);
+  if (mk == 0) return;
+  const int lane = threadIdx.x & 31, leader = __ffs(mk) - 1;
   unsigned base = 0;
-  if (lane == leader) base = atomicAdd(count, (unsigned)__popc(m));
-  base = __shfl_sync(0xffffffffu, base, leader);
-  if (want) q[base + __popc(m & ((1u << lane) - 1u))] = rec;
+  if (lane == leader) base = atomicAdd(count, (unsigned)__popc(mk));
+  base = __shfl_sync(kFull, base, leader);
+  if (want) q[base + __popc(mk & ((1u << lane) - 1u))] = rec;
 }
 
 struct Counters {
@@ -405,15 +477,14 @@ struct Counters {
 };
 
 // ---------------------------------------------------------------------------------------------
-// Shading of up to two hits per thread + continuation (shared by both kernels).
-//   in : hit[r], sphere index, exact FP64 ray (o, d) and t of the hit, float view = -d, carried acc/wt
-//   out: final[r] (pixel finished, colour in fr/fg/fb) or a pushed reflected ray.
-template <bool kSmem>
-__device__ __forceinline__ void shade_and_continue(const FastArgs &a, const float4 *__restrict__ ltabs, const bool (&hit)[2],
-                                                   const int (&idx)[2], const d3 (&o64)[2], const d3 (&d64v)[2],
-                                                   const double (&t64)[2], const unsigned (&pix)[2], float (&wt)[2],
-                                                   float (&cr)[2], float (&cg)[2], float (&cb)[2], bool (&final_)[2],
-                                                   int level, Counters &cnt, unsigned &n_fp64) {
+// Shading of up to two hits per lane (shared by both kernels).
+//   in : hit[r], sphere index, exact FP64 ray (o, d) and t of the hit, carried acc/wt
+//   out: final[r] (pixel finished, colour in cr/cg/cb) or cont[r] + rec[r] (reflected ray).
+__device__ __forceinline__ void shade_hits(const FastArgs &a, const unsigned char *tabs_base, int first_light_table,
+                                           const bool (&hit)[2], const int (&idx)[2], const d3 (&o64)[2], const d3 (&d64v)[2],
+                                           const double (&t64)[2], const unsigned (&pix)[2], float (&wt)[2], float (&cr)[2],
+                                           float (&cg)[2], float (&cb)[2], bool (&final_)[2], bool (&cont)[2], RayRec (&rec)[2],
+                                           int level, Counters &cnt, unsigned &n_fp64) {
   d3 p[2], n[2];
   float nx[2], ny[2], nz[2], vx[2], vy[2], vz[2];
   float4 m[2]; float2 mx[2];
@@ -424,6 +495,7 @@ __device__ __forceinline__ void shade_and_continue(const FastArgs &a, const floa
     p[r] = rtx::mk(0, 0, 0); n[r] = p[r];
     m[r] = make_float4(0, 0, 0, 0); mx[r] = make_float2(0, 0);
     nx[r] = ny[r] = nz[r] = vx[r] = vy[r] = vz[r] = 0.f; sr[r] = sg[r] = sb[r] = 0.f;
+    cont[r] = false;
     if (hit[r]) {
       const double4 s = ld_sph64(&a.r.sph64[idx[r]]);
       p[r] = rtx::hit_point(o64[r], d64v[r], t64[r]);                     // src/main.cpp:32
@@ -436,14 +508,14 @@ __device__ __forceinline__ void shade_and_continue(const FastArgs &a, const floa
     }
   }
   const int L = a.L;
-  if (__any_sync(0xffffffffu, hit[0] || hit[1])) {
+  if (__any_sync(kFull, hit[0] || hit[1])) {
     for (int l = 0; l < L; l++) {
-      float dx[2], dy[2], dz[2], so[2];
+      float dx[2], dy[2], dz[2], so[2], cosl[2];
       bool occ[2];
       const d3 lp = ldc3(g_frame.light_pos[l]);
 #pragma unroll
       for (int r = 0; r < 2; r++) {
-        dx[r] = dy[r] = dz[r] = 0.f; so[r] = 0.f;
+        dx[r] = dy[r] = dz[r] = 0.f; so[r] = 0.f; cosl[r] = 0.f;
         if (hit[r]) {
           // direction light -> point: FP64 difference, FP32 normalisation (error <= 12u, see filter_math.cuh)
           const d3 w = rtx::sub(p[r], lp);
@@ -452,19 +524,20 @@ __device__ __forceinline__ void shade_and_continue(const FastArgs &a, const floa
           const float inv = rsqrtf(l2);
           dx[r] = wx * inv; dy[r] = wy * inv; dz[r] = wz * inv;
           so[r] = l2 * inv - kEps;
+          cosl[r] = -(nx[r] * dx[r] + ny[r] * dy[r] + nz[r] * dz[r]);         // n . light_dir
         }
       }
-      shadow_light<kSmem>(ltabs + (size_t)l * a.npairs * 2, a.npairs, a.N, l, dx, dy, dz, so, hit, p, a.d64, a.r.sph64, occ,
-                          n_fp64);
+      shadow_light(tab_at(tabs_base, a, first_light_table + l), a.ngroups, l, dx, dy, dz, so, hit, idx, cosl, p, a.d64,
+                   a.r.sph64, occ, n_fp64);
 #pragma unroll
       for (int r = 0; r < 2; r++) {
         if (!hit[r]) continue;
         cnt.shadow++;
         if (occ[r]) { cnt.occluded++; if (l < 32) smask[r] |= 1u << l; continue; }
         // include/scene.h:104-117 in FP32; light_dir = -(dx,dy,dz)
-        const float ndl = fmaxf(0.0f, -(nx[r] * dx[r] + ny[r] * dy[r] + nz[r] * dz[r]));
+        const float ndl = fmaxf(0.0f, cosl[r]);
         const float kd = (1.0f - m[r].w) * ndl;
-        const float dn = dx[r] * nx[r] + dy[r] * ny[r] + dz[r] * nz[r];          // dot(-light_dir, n)
+        const float dn = -cosl[r];                                                // dot(-light_dir, n)
         const float rx = dx[r] - 2.0f * nx[r] * dn, ry = dy[r] - 2.0f * ny[r] * dn, rz = dz[r] - 2.0f * nz[r] * dn;
         const float rdv = fmaxf(0.0f, rx * vx[r] + ry * vy[r] + rz * vz[r]);
         const float spec = 0.5f * (mx[r].x == 0.0f ? 1.0f : __powf(rdv, mx[r].x));
@@ -477,33 +550,29 @@ __device__ __forceinline__ void shade_and_continue(const FastArgs &a, const floa
   // continuation: src/main.cpp:43-55 unrolled front to back
 #pragma unroll
   for (int r = 0; r < 2; r++) {
-    bool push = false;
-    RayRec rec;
-    if (hit[r]) {
-      if (a.r.shadow_mask) a.r.shadow_mask[(size_t)pix[r] * a.r.max_depth + level] = smask[r];
-      if (mx[r].y > 0.5f) {                       // reflectivity > 0, decided in double on the host
-        const float refl = m[r].w, k = wt[r] * (1.0f - refl);
-        cr[r] += k * sr[r]; cg[r] += k * sg[r]; cb[r] += k * sb[r];
-        wt[r] *= refl;
-        if (level + 1 < a.r.max_depth) {
-          d3 o2, d2;
-          rtx::reflect_ray(d64v[r], p[r], n[r], 0.001, o2, d2);
-          rec.ox = o2.x; rec.oy = o2.y; rec.oz = o2.z; rec.dx = d2.x; rec.dy = d2.y; rec.dz = d2.z;
-          rec.pix = pix[r]; rec.wt = wt[r]; rec.ar = cr[r]; rec.ag = cg[r]; rec.ab = cb[r]; rec.pad = 0;
-          push = true;
-        } else {
-          final_[r] = true;                       // depth exhausted: the child contributes black
-        }
+    if (!hit[r]) continue;
+    if (a.r.shadow_mask) a.r.shadow_mask[(size_t)pix[r] * a.r.max_depth + level] = smask[r];
+    if (mx[r].y > 0.5f) {                         // reflectivity > 0, decided in double on the host
+      const float refl = m[r].w, k = wt[r] * (1.0f - refl);
+      cr[r] += k * sr[r]; cg[r] += k * sg[r]; cb[r] += k * sb[r];
+      wt[r] *= refl;
+      if (level + 1 < a.r.max_depth) {
+        d3 o2, d2;
+        rtx::reflect_ray(d64v[r], p[r], n[r], 0.001, o2, d2);
+        rec[r].ox = o2.x; rec[r].oy = o2.y; rec[r].oz = o2.z; rec[r].dx = d2.x; rec[r].dy = d2.y; rec[r].dz = d2.z;
+        rec[r].pix = pix[r]; rec[r].wt = wt[r]; rec[r].ar = cr[r]; rec[r].ag = cg[r]; rec[r].ab = cb[r]; rec[r].pad = 0;
+        cont[r] = true;
       } else {
-        cr[r] += wt[r] * sr[r]; cg[r] += wt[r] * sg[r]; cb[r] += wt[r] * sb[r];
-        final_[r] = true;
+        final_[r] = true;                         // depth exhausted: the child contributes black
       }
+    } else {
+      cr[r] += wt[r] * sr[r]; cg[r] += wt[r] * sg[r]; cb[r] += wt[r] * sb[r];
+      final_[r] = true;
     }
-    queue_push(push, rec, a.q_out, a.q_out_count);
   }
 }
 
-__device__ __forceinline__ void flush_counters(const FastArgs &a, Counters &c, unsigned n_fp64, int level) {
+__device__ __forceinline__ void flush_counters(const FastArgs &a, Counters &c, unsigned &n_fp64, int level) {
   if (!a.r.counters) return;
   c.fp64 += n_fp64;
   unsigned long long v[6] = {c.closest, c.hits, c.shadow, c.occluded, c.fp64, c.violations};
@@ -519,52 +588,47 @@ __device__ __forceinline__ void flush_counters(const FastArgs &a, Counters &c, u
     atomicAdd(&a.r.counters[RT_CNT_TESTS], (v[0] + v[2]) * (unsigned long long)a.N);
     if (level < 32) atomicAdd(&a.r.counters[RT_CNT_ALIVE0 + level], v[0]);
   }
+  c.closest = c.hits = c.shadow = c.occluded = c.fp64 = c.violations = 0;
+  n_fp64 = 0;
 }
 
-// Stages the sphere tables of this kernel into shared memory with ONE TMA bulk copy.
-__device__ __forceinline__ const float4 *stage_tables(const FastArgs &a, unsigned char *smem, const float4 *gsrc) {
-  if (!a.tables_in_smem) return gsrc;
-  unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem);
-  float4 *dst = reinterpret_cast<float4 *>(smem + kSmemHeader);
-  if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
-    mbar_expect_tx(bar, a.table_bytes);
-    tma_bulk_g2s(dst, gsrc, a.table_bytes, bar);
-  }
-  __syncthreads();
-  mbar_wait(bar, 0);
-  return dst;
+// Exact FP64 t of the winner (or the brute-force safety net if the filter contradicted itself).
+__device__ __forceinline__ void finish_closest(const FastArgs &a, const Best &b, const ExactRay &e, bool &hit, int &idx, double &t64,
+                                               Counters &cnt, unsigned &n_fp64) {
+  double t = b.t;
+  bool ok = b.exact;
+  if (!ok) { n_fp64++; ok = exact_sphere(a.r.sph64, b.idx, e.o, e.d, e.a, t) && t < 1e20; }
+  int bi = b.idx;
+  if (!ok) { cnt.violations++; bi = exact_bruteforce(a.r.sph64, a.N, e.o, e.d, e.a, t); }
+  if (bi >= 0) { hit = true; idx = bi; t64 = t; cnt.hits++; }
 }
 
 // ---------------------------------------------------------------------------------------------
-// LEVEL 0: camera rays.  Persistent CTAs pull 32x16-pixel tiles from an atomic counter.
-// Thread layout inside a tile: warp w covers an 8x8 block (wx = w&3, wy = w>>2), lane = (lx, ly)
-// = (lane&7, lane>>3) owns the two vertically adjacent pixels (x, 2*ly) and (x, 2*ly+1).
+// LEVEL 0: camera rays.  Each warp pulls 16x4-pixel tiles; lane = (lx, ly) = (lane & 15, lane >> 4)
+// owns the two vertically adjacent pixels (x, 2*ly) and (x, 2*ly + 1) of the tile.
 template <bool kSmem>
 __global__ void __launch_bounds__(kThreads, 2) k_primary(const FastArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
-  int *s_tile = reinterpret_cast<int *>(smem + 16);
-  unsigned char *s_rgb = smem + 64;                                  // kTileH x kTileW x 3 = 1536 bytes
-  const float4 *tabs = stage_tables(a, smem, a.otab);
-  const float4 *cam = tabs, *ltabs = tabs + (size_t)a.npairs * 2;
+  const unsigned char *tabs = a.tabs;
+  if (kSmem) { stage_tables(smem, a.tabs, a.stage_bytes); tabs = smem + kSmemHeader; }
+  const Tab cam = tab_at(tabs, a, 0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char *s_rgb = smem + 64 + warp * (kWTileH * kWTileW * 3);
   const int W = a.r.W, rows = a.r.bands.local_rows, depth = a.r.max_depth;
   Counters cnt = {0, 0, 0, 0, 0, 0};
   unsigned n_fp64 = 0;
   for (;;) {
-    if (threadIdx.x == 0) *s_tile = (int)atomicAdd(a.tile_counter, 1u);
-    __syncthreads();
-    const int tile = *s_tile;
-    if (tile >= a.ntiles) break;
-    const int tx0 = (tile % a.tiles_x) * kTileW, ty0 = (tile / a.tiles_x) * kTileH;
-    const int x = tx0 + (warp & 3) * 8 + (lane & 7);
+    const int tile = warp_fetch(a.tile_counter);
+    if (tile >= a.nwtiles) break;
+    const int tx0 = (tile % a.wtiles_x) * kWTileW, ty0 = (tile / a.wtiles_x) * kWTileH;
+    const int x = tx0 + (lane & 15);
     int lr[2], j[2];
     unsigned pix[2];
     bool live[2];
     float dx[2], dy[2], dz[2];
 #pragma unroll
     for (int r = 0; r < 2; r++) {
-      lr[r] = ty0 + (warp >> 2) * 8 + (lane >> 3) * 2 + r;
+      lr[r] = ty0 + (lane >> 4) * 2 + r;
       live[r] = x < W && lr[r] < rows && depth > 0;
       j[r] = 0; pix[r] = 0; dx[r] = dy[r] = dz[r] = 0.f;
       if (x < W && lr[r] < rows) {
@@ -588,12 +652,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_primary(const FastArgs a) {
     const int j0 = j[0], j1 = j[1];
     auto ray0 = [&]() { return exact_primary_ray(su, sv, x, j0); };
     auto ray1 = [&]() { return exact_primary_ray(su, sv, x, j1); };
-    closest_shared<kSmem>(cam, a.npairs, a.N, dx, dy, dz, live, a.d64, a.r.sph64, ray0, ray1, best, n_fp64);
+    closest_shared(cam, a.ngroups, dx, dy, dz, live, a.d64, a.r.sph64, ray0, ray1, best, n_fp64);
 
-    bool hit[2], final_[2];
+    bool hit[2], final_[2], cont[2];
     int idx[2];
     d3 o64[2], d64v[2];
     double t64[2];
+    RayRec rec[2];
     float wt[2] = {1.f, 1.f}, cr[2] = {0.f, 0.f}, cg[2] = {0.f, 0.f}, cb[2] = {0.f, 0.f};
 #pragma unroll
     for (int r = 0; r < 2; r++) {
@@ -602,13 +667,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_primary(const FastArgs a) {
       if (!live[r]) continue;
       cnt.closest++;
       if (best[r].idx >= 0) {
-        ExactRay e = exact_primary_ray(su, sv, x, j[r]);
-        double t = best[r].t;
-        bool ok = best[r].exact;
-        if (!ok) { n_fp64++; ok = exact_sphere(a.r.sph64, best[r].idx, e.o, e.d, e.a, t) && t < 1e20; }
-        int bi = best[r].idx;
-        if (!ok) { cnt.violations++; bi = exact_bruteforce(a.r.sph64, a.N, e.o, e.d, e.a, t); }
-        if (bi >= 0) { hit[r] = true; idx[r] = bi; t64[r] = t; o64[r] = e.o; d64v[r] = e.d; cnt.hits++; }
+        const ExactRay e = exact_primary_ray(su, sv, x, j[r]);
+        finish_closest(a, best[r], e, hit[r], idx[r], t64[r], cnt, n_fp64);
+        o64[r] = e.o; d64v[r] = e.d;
       }
       if (a.r.hit_idx) a.r.hit_idx[(size_t)pix[r] * depth] = idx[r];
       if (!hit[r]) {                               // sky, src/main.cpp:26-30
@@ -617,88 +678,81 @@ __global__ void __launch_bounds__(kThreads, 2) k_primary(const FastArgs a) {
         final_[r] = true;
       }
     }
-    shade_and_continue<kSmem>(a, ltabs, hit, idx, o64, d64v, t64, pix, wt, cr, cg, cb, final_, 0, cnt, n_fp64);
+    shade_hits(a, tabs, 1, hit, idx, o64, d64v, t64, pix, wt, cr, cg, cb, final_, cont, rec, 0, cnt, n_fp64);
+#pragma unroll
+    for (int r = 0; r < 2; r++) queue_push(cont[r], rec[r], a.q_out, a.q_out_count);
 
-    // ---- 8-bit quantise (src/main.cpp:84-86) into the tile staging buffer, then 128-bit row stores
+    // ---- 8-bit quantise (src/main.cpp:84-86) into the warp's staging buffer, then 128-bit row stores
 #pragma unroll
     for (int r = 0; r < 2; r++) {
-      const int ty = (warp >> 2) * 8 + (lane >> 3) * 2 + r, txx = (warp & 3) * 8 + (lane & 7);
-      unsigned char *q = s_rgb + (ty * kTileW + txx) * 3;
-      const bool blackout = x < W && lr[r] < rows && depth <= 0;
-      const bool fin = final_[r] || blackout;
+      unsigned char *q = s_rgb + (((lane >> 4) * 2 + r) * kWTileW + (lane & 15)) * 3;
+      const bool fin = final_[r] || (x < W && lr[r] < rows && depth <= 0);
       q[0] = (unsigned char)quant8(fin ? cr[r] : 0.f); q[1] = (unsigned char)quant8(fin ? cg[r] : 0.f);
       q[2] = (unsigned char)quant8(fin ? cb[r] : 0.f);
     }
-    __syncthreads();
-    {
-      const bool full_w = tx0 + kTileW <= W && (W & 15) == 0;
-      if (full_w) {
-        // 6 x 16-byte stores per 96-byte row segment; pixels still in flight are overwritten by k_bounce
-        if (threadIdx.x < kTileH * 6) {
-          const int ty = threadIdx.x / 6, seg = threadIdx.x % 6;
-          if (ty0 + ty < rows) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(s_rgb + ty * kTileW * 3 + seg * 16);
-            *reinterpret_cast<uint4 *>(a.r.rgb + ((size_t)(ty0 + ty) * W + tx0) * 3 + seg * 16) = v;
-          }
-        }
-      } else {
-        for (int k = threadIdx.x; k < kTileH * kTileW; k += kThreads) {
-          const int ty = k / kTileW, txx = k % kTileW;
-          if (tx0 + txx < W && ty0 + ty < rows) {
-            unsigned char *o = a.r.rgb + ((size_t)(ty0 + ty) * W + tx0 + txx) * 3;
-            const unsigned char *q = s_rgb + k * 3;
-            o[0] = q[0]; o[1] = q[1]; o[2] = q[2];
-          }
+    __syncwarp();
+    if (tx0 + kWTileW <= W && (W & 15) == 0) {
+      // 3 x 16-byte stores per 48-byte row segment; pixels still in flight are overwritten by k_bounce
+      if (lane < kWTileH * 3) {
+        const int ty = lane / 3, seg = lane % 3;
+        if (ty0 + ty < rows)
+          *reinterpret_cast<uint4 *>(a.r.rgb + ((size_t)(ty0 + ty) * W + tx0) * 3 + seg * 16) =
+              *reinterpret_cast<const uint4 *>(s_rgb + ty * kWTileW * 3 + seg * 16);
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        if (x < W && lr[r] < rows) {
+          const unsigned char *q = s_rgb + (((lane >> 4) * 2 + r) * kWTileW + (lane & 15)) * 3;
+          unsigned char *o = a.r.rgb + (size_t)pix[r] * 3;
+          o[0] = q[0]; o[1] = q[1]; o[2] = q[2];
         }
       }
     }
-    __syncthreads();
+    __syncwarp();
   }
   flush_counters(a, cnt, n_fp64, 0);
 }
 
 // ---------------------------------------------------------------------------------------------
-// LEVEL >= 1: reflected rays from the queue, two per thread, 512 per CTA chunk.
-template <bool kSmem>
+// LEVEL >= 1: reflected rays from the queue, two per lane, 64 per warp fetch.
+// kTail = false: one level, survivors are compacted into q_out.
+// kTail = true : every lane follows its ray to termination; the record is updated in place.
+template <bool kSmem, bool kTail>
 __global__ void __launch_bounds__(kThreads, 2) k_bounce(const FastArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
-  int *s_chunk = reinterpret_cast<int *>(smem + 16);
-  if (*a.q_in_count == 0u) return;                  // nothing survived to this level
-  // tables: [L light tables][general table], contiguous in global memory in that order
-  const float4 *tabs = stage_tables(a, smem, a.otab + (size_t)a.npairs * 2);
-  const float4 *ltabs = tabs, *gen = tabs + (size_t)a.L * a.npairs * 2;
   const unsigned nq = *a.q_in_count;
-  const int nchunks = (int)((nq + 2 * kThreads - 1) / (2 * kThreads));
-  const int depth = a.r.max_depth, level = a.level;
+  if (nq == 0u) return;                             // nothing survived to this level
+  // staged: [L light tables][general table], contiguous in global memory in that order
+  const unsigned char *tabs = a.tabs + a.tstride;
+  if (kSmem) { stage_tables(smem, tabs, a.stage_bytes); tabs = smem + kSmemHeader; }
+  const float4 *gen = reinterpret_cast<const float4 *>(tabs + (size_t)a.L * a.tstride);
+  const int lane = threadIdx.x & 31;
+  const int depth = a.r.max_depth;
   Counters cnt = {0, 0, 0, 0, 0, 0};
   unsigned n_fp64 = 0;
+  RayRec *qin = a.q_in;
   for (;;) {
-    if (threadIdx.x == 0) *s_chunk = (int)atomicAdd(a.chunk_counter, 1u);
-    __syncthreads();
-    const int chunk = *s_chunk;
-    __syncthreads();
-    if (chunk >= nchunks) break;
+    const int chunk = warp_fetch(a.chunk_counter);
+    if ((unsigned)chunk * 64u >= nq) break;
     bool live[2];
     unsigned qi[2], pix[2];
     float ox[2], oy[2], oz[2], dx[2], dy[2], dz[2];
     float wt[2], cr[2], cg[2], cb[2];
 #pragma unroll
     for (int r = 0; r < 2; r++) {
-      // interleave so that the two rays of a thread are neighbours in the queue (coherent)
-      qi[r] = (unsigned)chunk * 2u * kThreads + 2u * threadIdx.x + r;
+      // the two rays of a lane are neighbours in the queue (coherent)
+      qi[r] = (unsigned)chunk * 64u + 2u * lane + r;
       live[r] = qi[r] < nq;
       ox[r] = oy[r] = oz[r] = dx[r] = dy[r] = dz[r] = 0.f; wt[r] = cr[r] = cg[r] = cb[r] = 0.f; pix[r] = 0;
       if (live[r]) {
-        const RayRec &q = a.q_in[qi[r]];
+        const RayRec &q = qin[qi[r]];
         // recentred FP32 origin and FP32 direction for the filter (exact values stay in the record)
         ox[r] = (float)(q.ox - a.c0[0]); oy[r] = (float)(q.oy - a.c0[1]); oz[r] = (float)(q.oz - a.c0[2]);
         dx[r] = (float)q.dx; dy[r] = (float)q.dy; dz[r] = (float)q.dz;
         pix[r] = q.pix; wt[r] = q.wt; cr[r] = q.ar; cg[r] = q.ag; cb[r] = q.ab;
       }
     }
-    Best best[2];
-    best_init(best[0]); best_init(best[1]);
-    const RayRec *qin = a.q_in;
     const unsigned q0 = qi[0], q1 = qi[1];
     auto mkray = [&](unsigned k) {
       ExactRay e;
@@ -708,44 +762,61 @@ __global__ void __launch_bounds__(kThreads, 2) k_bounce(const FastArgs a) {
     };
     auto ray0 = [&]() { return mkray(q0); };
     auto ray1 = [&]() { return mkray(q1); };
-    closest_general<kSmem>(gen, a.npairs, a.N, ox, oy, oz, dx, dy, dz, live, a.d64, a.gS2, a.r.sph64, ray0, ray1, best, n_fp64);
-
-    bool hit[2], final_[2];
-    int idx[2];
-    d3 o64[2], d64v[2];
-    double t64[2];
+    for (int level = a.level;; level++) {
+      Best best[2];
+      best_init(best[0]); best_init(best[1]);
+      closest_general(gen, a.ngroups, a.N, ox, oy, oz, dx, dy, dz, live, a.d64, a.gS2, a.g_dtmax, a.r.sph64, ray0, ray1, best,
+                      n_fp64);
+      bool hit[2], final_[2], cont[2];
+      int idx[2];
+      d3 o64[2], d64v[2];
+      double t64[2];
+      RayRec rec[2];
 #pragma unroll
-    for (int r = 0; r < 2; r++) {
-      hit[r] = false; final_[r] = false; idx[r] = -1; t64[r] = 0;
-      o64[r] = rtx::mk(0, 0, 0); d64v[r] = o64[r];
-      if (!live[r]) continue;
-      cnt.closest++;
-      if (best[r].idx >= 0) {
-        ExactRay e = mkray(qi[r]);
-        double t = best[r].t;
-        bool ok = best[r].exact;
-        if (!ok) { n_fp64++; ok = exact_sphere(a.r.sph64, best[r].idx, e.o, e.d, e.a, t) && t < 1e20; }
-        int bi = best[r].idx;
-        if (!ok) { cnt.violations++; bi = exact_bruteforce(a.r.sph64, a.N, e.o, e.d, e.a, t); }
-        if (bi >= 0) { hit[r] = true; idx[r] = bi; t64[r] = t; o64[r] = e.o; d64v[r] = e.d; cnt.hits++; }
+      for (int r = 0; r < 2; r++) {
+        hit[r] = false; final_[r] = false; idx[r] = -1; t64[r] = 0;
+        o64[r] = rtx::mk(0, 0, 0); d64v[r] = o64[r];
+        if (!live[r]) continue;
+        cnt.closest++;
+        if (best[r].idx >= 0) {
+          const ExactRay e = mkray(qi[r]);
+          finish_closest(a, best[r], e, hit[r], idx[r], t64[r], cnt, n_fp64);
+          o64[r] = e.o; d64v[r] = e.d;
+        }
+        if (a.r.hit_idx) a.r.hit_idx[(size_t)pix[r] * depth + level] = idx[r];
+        if (!hit[r]) {
+          const float ts = 0.5f * (dy[r] + 1.0f);
+          cr[r] += wt[r] * ((1.0f - ts) + 0.5f * ts); cg[r] += wt[r] * ((1.0f - ts) + 0.7f * ts); cb[r] += wt[r] * ((1.0f - ts) + ts);
+          final_[r] = true;
+        }
       }
-      if (a.r.hit_idx) a.r.hit_idx[(size_t)pix[r] * depth + level] = idx[r];
-      if (!hit[r]) {
-        const float ts = 0.5f * (dy[r] + 1.0f);
-        cr[r] += wt[r] * ((1.0f - ts) + 0.5f * ts); cg[r] += wt[r] * ((1.0f - ts) + 0.7f * ts); cb[r] += wt[r] * ((1.0f - ts) + ts);
-        final_[r] = true;
-      }
-    }
-    shade_and_continue<kSmem>(a, ltabs, hit, idx, o64, d64v, t64, pix, wt, cr, cg, cb, final_, level, cnt, n_fp64);
+      shade_hits(a, tabs, 0, hit, idx, o64, d64v, t64, pix, wt, cr, cg, cb, final_, cont, rec, level, cnt, n_fp64);
 #pragma unroll
-    for (int r = 0; r < 2; r++) {
-      if (live[r] && final_[r]) {
-        unsigned char *o = a.r.rgb + (size_t)pix[r] * 3;
-        o[0] = (unsigned char)quant8(cr[r]); o[1] = (unsigned char)quant8(cg[r]); o[2] = (unsigned char)quant8(cb[r]);
+      for (int r = 0; r < 2; r++) {
+        if (live[r] && final_[r]) {
+          unsigned char *o = a.r.rgb + (size_t)pix[r] * 3;
+          o[0] = (unsigned char)quant8(cr[r]); o[1] = (unsigned char)quant8(cg[r]); o[2] = (unsigned char)quant8(cb[r]);
+        }
       }
+      if (!kTail) {
+#pragma unroll
+        for (int r = 0; r < 2; r++) queue_push(cont[r], rec[r], a.q_out, a.q_out_count);
+        break;
+      }
+      if (a.r.counters) flush_counters(a, cnt, n_fp64, level);
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        live[r] = cont[r];
+        if (cont[r]) {
+          qin[qi[r]] = rec[r];                    // in place: the exact ray is re-read from here
+          ox[r] = (float)(rec[r].ox - a.c0[0]); oy[r] = (float)(rec[r].oy - a.c0[1]); oz[r] = (float)(rec[r].oz - a.c0[2]);
+          dx[r] = (float)rec[r].dx; dy[r] = (float)rec[r].dy; dz[r] = (float)rec[r].dz;
+        }
+      }
+      if (!__any_sync(kFull, live[0] || live[1])) break;
     }
   }
-  flush_counters(a, cnt, n_fp64, level);
+  if (!kTail) flush_counters(a, cnt, n_fp64, a.level);
 }
 
 }  // namespace rtf

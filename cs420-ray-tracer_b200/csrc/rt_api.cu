@@ -46,7 +46,7 @@ extern "C" int rt_device_count(void) {
 struct rt_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm = nullptr;
   int mode = 0;          // 0 fast, 1 exact
   int counters_on = 1;
   // scene
@@ -101,6 +101,7 @@ extern "C" int rt_create(int device, rt_ctx **out) {
   RT_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   RT_CUDA(cudaEventCreate(&c->ev0));
   RT_CUDA(cudaEventCreate(&c->ev1));
+  RT_CUDA(cudaEventCreate(&c->evm));
   RT_CUDA(cudaMalloc(&c->d_counters, RT_CNT_TOTAL * sizeof(unsigned long long)));
   int r = rtk_fast_init(c->device);
   if (r != 0) return rt_fail(RT_ERR_CUDA, std::string("rt_create: kernel attribute setup failed: ") + cudaGetErrorString((cudaError_t)-r));
@@ -128,7 +129,7 @@ extern "C" void rt_destroy(rt_ctx *c) {
   rtk_fast_free_work(&c->work);
   cudaFree(c->d_su); cudaFree(c->d_sv);
   cudaFree(c->d_rgb); cudaFree(c->d_hit); cudaFree(c->d_mask); cudaFree(c->d_counters);
-  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->evm);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -301,7 +302,7 @@ static int render_common(rt_ctx *c, int W, int H, int depth, int band_h, int ran
   int launches = 0;
   if (rows > 0) {
     if (c->mode == 1) launches = rtk_launch_exact(a, stream);
-    else launches = rtk_launch_fast(a, &c->fast, &c->work, stream);
+    else launches = rtk_launch_fast(a, &c->fast, &c->work, stream, stats ? c->evm : nullptr);
     if (launches < 0) return rt_fail(RT_ERR_CUDA, std::string("render: launch failed: ") + cudaGetErrorString((cudaError_t)-launches));
   }
   if (stats) {
@@ -311,6 +312,8 @@ static int render_common(rt_ctx *c, int W, int H, int depth, int band_h, int ran
     RT_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     memset(stats, 0, sizeof(*stats));
     stats->ms_device = ms;
+    stats->ms_level0 = ms;
+    if (rows > 0 && c->mode == 0) { float m0 = 0; RT_CUDA(cudaEventElapsedTime(&m0, c->ev0, c->evm)); stats->ms_level0 = m0; }
     stats->kernel_launches = launches;
     stats->rows_rendered = rows;
     if (want_counters) {
@@ -345,9 +348,8 @@ extern "C" int rt_render_debug(rt_ctx *c, int W, int H, int depth, uint8_t *host
   const size_t nlev = npx * (size_t)(depth > 0 ? depth : 1);
   if (hit_idx && (rc = ensure_cap(c->d_hit, c->hit_cap, nlev))) return rc;
   if (shadow_mask && (rc = ensure_cap(c->d_mask, c->mask_cap, nlev))) return rc;
-  rt_stats local;
   rc = render_common(c, W, H, depth, H, 0, 1, c->d_rgb, hit_idx ? c->d_hit : nullptr,
-                     shadow_mask ? c->d_mask : nullptr, c->stream, stats ? stats : &local);
+                     shadow_mask ? c->d_mask : nullptr, c->stream, stats);
   if (rc) return rc;
   RT_CUDA(cudaMemcpyAsync(host_rgb, c->d_rgb, npx * 3, cudaMemcpyDeviceToHost, c->stream));
   if (hit_idx && depth > 0) RT_CUDA(cudaMemcpyAsync(hit_idx, c->d_hit, nlev * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));

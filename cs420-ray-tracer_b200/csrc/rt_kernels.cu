@@ -1,6 +1,7 @@
 // rt_kernels.cu -- the single device translation unit of librt_b200.so (sm_100a only).
 #include "rt_kernels.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -35,6 +36,11 @@ inline float float_up(double x) {               // smallest float >= x
   if ((double)f < x) f = std::nextafterf(f, INFINITY);
   return f;
 }
+inline float float_down(double x) {             // largest float <= x
+  float f = (float)x;
+  if ((double)f > x) f = std::nextafterf(f, -INFINITY);
+  return f;
+}
 
 #define RTK_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return -(int)e_; } while (0)
 
@@ -43,23 +49,27 @@ inline float float_up(double x) {               // smallest float >= x
 int rtk_fast_init(int) {
   const int big = 227 * 1024;
   RTK_TRY(cudaFuncSetAttribute(rtf::k_primary<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  RTK_TRY(cudaFuncSetAttribute(rtf::k_bounce<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  RTK_TRY(cudaFuncSetAttribute(rtf::k_bounce<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  RTK_TRY(cudaFuncSetAttribute(rtf::k_bounce<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   return 0;
 }
 
 // Builds the FP32 filter tables on the host in double and rounds them conservatively
 // (DESIGN.md "filter margins"; error model in filter_math.cuh).
-//   shared-origin table for origin O (camera, each light), sphere i:
+//   shared-origin table for origin O (camera, each light), spheres SORTED by key = |oc| - r:
 //       oc = c_i - O (double -> nearest float), ncc = round_up(E_i - (|oc|^2 - r_i^2)),
-//       E_i = 2.01 * 2^-20 * |oc|^2 + delta64
-//   general table: c' = c_i - C0 (nearest float), rho' = round_up(r^2 (1+32u) + 8u S^2 + delta64)
+//       E_i = 2.01 * 2^-20 * |oc|^2 + delta64;  gmin[g] = round_down(key of the group's first sphere)
+//       perm[slot] = original sphere index (-1 = padding)
+//   general table (index order): c' = c_i - C0 (nearest float),
+//       rho' = round_up(r^2 (1+40u) + 12u S r + 64u^2 S^2 + delta64)
 // Sphere PAIRS are interleaved for the packed FP32x2 test: (x0,x1,y0,y1) (z0,z1,w0,w1).
 int rtk_fast_build_scene(RtFastScene *fs, const double *sph, int N, const RtFrameConst *f, cudaStream_t stream) {
   const int L = f->nlights;
   int npairs = (N + 1) / 2;
   npairs = ((npairs + rtf::kGroupPairs - 1) / rtf::kGroupPairs) * rtf::kGroupPairs;
   if (npairs == 0) npairs = rtf::kGroupPairs;
-  fs->N = N; fs->L = L; fs->npairs = npairs;
+  const int ngroups = npairs / rtf::kGroupPairs, nslots = 2 * npairs;
+  fs->N = N; fs->L = L; fs->npairs = npairs; fs->ngroups = ngroups;
   const double u = std::ldexp(1.0, -24);
 
   // absolute magnitude bound of every coordinate the reference touches -> delta64
@@ -84,33 +94,66 @@ int rtk_fast_build_scene(RtFastScene *fs, const double *sph, int N, const RtFram
   }
   S += 0.01;
   fs->gS2 = float_up(S * S * 1.0001);
+  fs->g_dtmax = float_up(80.0 * u * S);
 
-  const size_t per_table = (size_t)npairs * 2;
-  std::vector<float4> h((size_t)(L + 2) * per_table);
-  auto put = [&](size_t table, int i, float x, float y, float z, float w) {
-    float4 *A = &h[table * per_table + (size_t)(i >> 1) * 2], *B = A + 1;
-    if (i & 1) { A->y = x; A->w = y; B->y = z; B->w = w; } else { A->x = x; A->z = y; B->x = z; B->z = w; }
+  // byte layout of one shared-origin table
+  const unsigned pairs_bytes = (unsigned)npairs * 32u;
+  const unsigned gmin_bytes = ((unsigned)ngroups * 4u + 15u) & ~15u;
+  const unsigned perm_bytes = (unsigned)nslots * 4u;
+  fs->gmin_off = pairs_bytes; fs->perm_off = pairs_bytes + gmin_bytes;
+  fs->tstride = pairs_bytes + gmin_bytes + perm_bytes;
+  fs->bytes_primary = (size_t)(L + 1) * fs->tstride;
+  fs->bytes_bounce = (size_t)L * fs->tstride + pairs_bytes;
+  const size_t total = (size_t)(L + 1) * fs->tstride + pairs_bytes;
+  std::vector<unsigned char> h(total, 0);
+  auto put = [&](float4 *pairs, int slot, float x, float y, float z, float w) {
+    float4 *A = pairs + (size_t)(slot >> 1) * 2, *B = A + 1;
+    if (slot & 1) { A->y = x; A->w = y; B->y = z; B->w = w; } else { A->x = x; A->z = y; B->x = z; B->z = w; }
   };
+  std::vector<int> order((size_t)(N > 0 ? N : 1));
+  std::vector<double> key((size_t)(N > 0 ? N : 1));
   for (int t = 0; t <= L; t++) {
+    unsigned char *base = h.data() + (size_t)t * fs->tstride;
+    float4 *pairs = reinterpret_cast<float4 *>(base);
+    float *gmin = reinterpret_cast<float *>(base + fs->gmin_off);
+    int *perm = reinterpret_cast<int *>(base + fs->perm_off);
     const double *O = t == 0 ? f->cam_pos : f->light_pos[t - 1];
-    for (int i = 0; i < 2 * npairs; i++) {
-      if (i >= N) { put(t, i, 0.f, 0.f, 0.f, -1.0f); continue; }       // padding: never a candidate
+    for (int i = 0; i < N; i++) {
+      const double *s = sph + (size_t)i * 10;
+      const double x = s[0] - O[0], y = s[1] - O[1], z = s[2] - O[2];
+      key[i] = std::sqrt(x * x + y * y + z * z) - std::fabs(s[3]);
+      order[i] = i;
+    }
+    std::stable_sort(order.begin(), order.begin() + N, [&](int p, int q) { return key[p] < key[q]; });
+    for (int slot = 0; slot < nslots; slot++) {
+      if (slot >= N) { put(pairs, slot, 0.f, 0.f, 0.f, -1.0f); perm[slot] = -1; continue; }   // padding: never a candidate
+      const int i = order[slot];
       const double *s = sph + (size_t)i * 10;
       const double x = s[0] - O[0], y = s[1] - O[1], z = s[2] - O[2];
       const double oc2 = x * x + y * y + z * z;
       const double E = 2.01 * std::ldexp(1.0, -20) * oc2 * (1 + 1e-9) + delta64;
-      put(t, i, (float)x, (float)y, (float)z, float_up(E - (oc2 - s[3] * s[3])));
+      put(pairs, slot, (float)x, (float)y, (float)z, float_up(E - (oc2 - s[3] * s[3])));
+      perm[slot] = i;
+    }
+    for (int g = 0; g < ngroups; g++) {
+      const int slot = g * 2 * rtf::kGroupPairs;
+      if (slot >= N) { gmin[g] = 3.0e38f; continue; }
+      const double k = key[order[slot]];
+      gmin[g] = float_down(k - std::fabs(k) * 1e-6 - 1e-6 - delta64);
     }
   }
-  for (int i = 0; i < 2 * npairs; i++) {
-    if (i >= N) { put(L + 1, i, 0.f, 0.f, 0.f, -1.0e30f); continue; }
-    const double *s = sph + (size_t)i * 10;
-    const double rho = s[3] * s[3] * (1 + 32 * u) + 8 * u * S * S + delta64;
-    put(L + 1, i, (float)(s[0] - fs->c0[0]), (float)(s[1] - fs->c0[1]), (float)(s[2] - fs->c0[2]), float_up(rho));
+  {
+    float4 *pairs = reinterpret_cast<float4 *>(h.data() + (size_t)(L + 1) * fs->tstride);
+    for (int i = 0; i < nslots; i++) {
+      if (i >= N) { put(pairs, i, 0.f, 0.f, 0.f, -1.0e30f); continue; }
+      const double *s = sph + (size_t)i * 10;
+      const double r = std::fabs(s[3]);
+      const double rho = r * r * (1 + 40 * u) + 12 * u * S * r + 64 * u * u * S * S + delta64;
+      put(pairs, i, (float)(s[0] - fs->c0[0]), (float)(s[1] - fs->c0[1]), (float)(s[2] - fs->c0[2]), float_up(rho));
+    }
   }
-  fs->table_bytes = (size_t)(L + 1) * per_table * sizeof(float4);
-  RTK_TRY(cudaMalloc(&fs->tabs, h.size() * sizeof(float4)));
-  RTK_TRY(cudaMemcpyAsync(fs->tabs, h.data(), h.size() * sizeof(float4), cudaMemcpyHostToDevice, stream));
+  RTK_TRY(cudaMalloc(&fs->tabs, total));
+  RTK_TRY(cudaMemcpyAsync(fs->tabs, h.data(), total, cudaMemcpyHostToDevice, stream));
   RTK_TRY(cudaStreamSynchronize(stream));   // h goes out of scope
   return 0;
 }
@@ -125,7 +168,8 @@ void rtk_fast_free_work(RtFastWork *w) {
   w->queue[0] = w->queue[1] = nullptr; w->ctl = nullptr; w->queue_cap = 0;
 }
 
-int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork *w, cudaStream_t stream) {
+int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork *w, cudaStream_t stream,
+                    cudaEvent_t after_level0) {
   const size_t npix = (size_t)args.W * args.bands.local_rows;
   if (!w->ctl) RTK_TRY(cudaMalloc(&w->ctl, kCtlWords * sizeof(unsigned int)));
   if (args.max_depth > 1 && w->queue_cap < npix) {
@@ -141,36 +185,47 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
   rtf::FastArgs a;
   memset(&a, 0, sizeof(a));
   a.r = args;
-  a.otab = (const float4 *)fs->tabs;
-  a.gtab = a.otab + (size_t)(fs->L + 1) * fs->npairs * 2;
-  a.npairs = fs->npairs; a.N = fs->N; a.L = fs->L;
-  a.d64 = fs->d64; a.gS2 = fs->gS2;
+  a.tabs = (const unsigned char *)fs->tabs;
+  a.npairs = fs->npairs; a.ngroups = fs->ngroups; a.N = fs->N; a.L = fs->L;
+  a.tstride = fs->tstride; a.gmin_off = fs->gmin_off; a.perm_off = fs->perm_off;
+  a.d64 = fs->d64; a.gS2 = fs->gS2; a.g_dtmax = fs->g_dtmax;
   for (int k = 0; k < 3; k++) a.c0[k] = fs->c0[k];
-  a.tiles_x = (args.W + rtf::kTileW - 1) / rtf::kTileW;
-  a.ntiles = a.tiles_x * ((args.bands.local_rows + rtf::kTileH - 1) / rtf::kTileH);
+  a.wtiles_x = (args.W + rtf::kWTileW - 1) / rtf::kWTileW;
+  a.nwtiles = a.wtiles_x * ((args.bands.local_rows + rtf::kWTileH - 1) / rtf::kWTileH);
   a.tile_counter = w->ctl;
-  a.table_bytes = (unsigned)fs->table_bytes;
-  a.tables_in_smem = fs->table_bytes <= kMaxSmemTables;
-  const size_t smem = rtf::kSmemHeader + (a.tables_in_smem ? fs->table_bytes : 0);
-  const int ctas_per_sm = (a.tables_in_smem && smem > 110 * 1024) ? 1 : 2;
+  const size_t big = fs->bytes_primary > fs->bytes_bounce ? fs->bytes_primary : fs->bytes_bounce;
+  a.tables_in_smem = big <= kMaxSmemTables;
+  const int ctas_per_sm = (a.tables_in_smem && rtf::kSmemHeader + big > 110 * 1024) ? 1 : 2;
   const int max_grid = w->num_sms * ctas_per_sm;
 
   a.level = 0;
   a.q_out = (rtf::RayRec *)w->queue[0];
   a.q_out_count = w->ctl + 64 + 1;
-  int grid = a.ntiles < max_grid ? a.ntiles : max_grid;
+  a.stage_bytes = (unsigned)fs->bytes_primary;
+  size_t smem = rtf::kSmemHeader + (a.tables_in_smem ? fs->bytes_primary : 0);
+  const int cta_tiles = (a.nwtiles + rtf::kWarps - 1) / rtf::kWarps;
+  int grid = cta_tiles < max_grid ? cta_tiles : max_grid;
   if (a.tables_in_smem) rtf::k_primary<true><<<grid, rtf::kThreads, smem, stream>>>(a);
   else rtf::k_primary<false><<<grid, rtf::kThreads, smem, stream>>>(a);
   int launches = 1;
-  for (int level = 1; level < args.max_depth; level++) {
+  if (after_level0) RTK_TRY(cudaEventRecord(after_level0, stream));
+  a.stage_bytes = (unsigned)fs->bytes_bounce;
+  smem = rtf::kSmemHeader + (a.tables_in_smem ? fs->bytes_bounce : 0);
+  // level 1: one compacted wavefront; levels >= 2: one tail launch that follows rays to termination
+  for (int level = 1; level < args.max_depth && level <= 2; level++) {
     a.level = level;
-    a.q_in = (const rtf::RayRec *)w->queue[(level - 1) & 1];
+    a.q_in = (rtf::RayRec *)w->queue[(level - 1) & 1];
     a.q_in_count = w->ctl + 64 + level;
     a.q_out = (rtf::RayRec *)w->queue[level & 1];
     a.q_out_count = w->ctl + 64 + level + 1;
     a.chunk_counter = w->ctl + 1 + level;
-    if (a.tables_in_smem) rtf::k_bounce<true><<<max_grid, rtf::kThreads, smem, stream>>>(a);
-    else rtf::k_bounce<false><<<max_grid, rtf::kThreads, smem, stream>>>(a);
+    if (level == 1) {
+      if (a.tables_in_smem) rtf::k_bounce<true, false><<<max_grid, rtf::kThreads, smem, stream>>>(a);
+      else rtf::k_bounce<false, false><<<max_grid, rtf::kThreads, smem, stream>>>(a);
+    } else {
+      if (a.tables_in_smem) rtf::k_bounce<true, true><<<max_grid, rtf::kThreads, smem, stream>>>(a);
+      else rtf::k_bounce<false, true><<<max_grid, rtf::kThreads, smem, stream>>>(a);
+    }
     launches++;
   }
   cudaError_t e = cudaGetLastError();

@@ -14,12 +14,16 @@ int rtk_launch_exact(const RtRenderArgs &args, cudaStream_t stream);
 
 // mode 0: FP32-filter fast path (kernels_fast.cuh).
 struct RtFastScene {
-  int N, L, npairs;
-  void *tabs;            // device: (1+L) shared-origin tables, then the general table; npairs x 2 float4 each
-  size_t table_bytes;    // bytes one kernel stages into shared memory: (1+L) * npairs * 32
-  float d64;             // absolute FP64/geometry slack (delta64)
-  float gS2;             // squared radius bound of the recentred scene
-  double c0[3];          // recentring offset of the general table
+  int N, L, npairs, ngroups;
+  void *tabs;             // device: (1+L) shared-origin tables (pairs | gmin | perm), then the general table
+  unsigned tstride;       // bytes per shared-origin table
+  unsigned gmin_off, perm_off;
+  size_t bytes_primary;   // staged by k_primary: (1+L) * tstride
+  size_t bytes_bounce;    // staged by k_bounce : L * tstride + npairs * 32
+  float d64;              // absolute FP64/geometry slack (delta64)
+  float gS2;              // squared radius bound of the recentred scene
+  float g_dtmax;          // additive bound of the general filter's centre projection
+  double c0[3];           // recentring offset of the general table
 };
 struct RtFastWork {
   int num_sms;
@@ -31,7 +35,9 @@ int rtk_fast_init(int device);
 int rtk_fast_build_scene(RtFastScene *fs, const double *spheres, int N, const RtFrameConst *frame, cudaStream_t stream);
 void rtk_fast_free_scene(RtFastScene *fs);
 void rtk_fast_free_work(RtFastWork *w);
-int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork *w, cudaStream_t stream);
+// `after_level0` (may be null) is recorded right after the level-0 kernel.
+int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork *w, cudaStream_t stream,
+                    cudaEvent_t after_level0);
 
 // FP32 FFMA issue peak of `device`, measured live (FLOP/s); used by bench.py as the roofline
 // denominator because MEASURED_PEAKS.json carries no FP32 entry.  Returns <0: -cudaError.

@@ -60,6 +60,7 @@ typedef struct rt_scene rt_scene;   /* opaque: a parsed scene file (host memory 
 typedef struct rt_stats {
   double ms_device;             /* CUDA-event time of the kernels of this call on the stream   */
   double ms_host;               /* host wall-clock of the whole call, copies included          */
+  double ms_level0;             /* device time of the level-0 (camera-ray) kernel alone        */
   uint64_t closest_queries;
   uint64_t hits;
   uint64_t shadow_queries;

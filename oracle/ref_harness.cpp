@@ -73,11 +73,14 @@ int main(int argc, char **argv) {
   Camera camera(scene.camera.position, scene.camera.look_at, scene.camera.fov);  // src/main.cpp:132
   if (mode == "render") {
     const bool use_omp = argc > 7 && std::string(argv[7]) == "omp";
+    // optional bounded sample: only pixels whose linear index is a multiple of `step` (bench.py)
+    const size_t step = argc > 8 ? (size_t)std::atoll(argv[8]) : 1;
     std::vector<Vec3> fb((size_t)W * H);
     auto t0 = std::chrono::high_resolution_clock::now();
     if (!use_omp) {
       for (int j = 0; j < H; j++)  // src/main.cpp:146-157
         for (int i = 0; i < W; i++) {
+          if (step > 1 && ((size_t)j * W + i) % step) continue;
           double u = double(i) / (W - 1), v = double(j) / (H - 1);
           fb[(size_t)j * W + i] = trace_ray(camera.get_ray(u, v), scene, D);
         }
@@ -85,6 +88,7 @@ int main(int argc, char **argv) {
 #pragma omp parallel for schedule(dynamic) collapse(2)  // src/main.cpp:185
       for (int j = 0; j < H; j++)
         for (int i = 0; i < W; i++) {
+          if (step > 1 && ((size_t)j * W + i) % step) continue;
           double u = double(i) / (W - 1), v = double(j) / (H - 1);
           fb[(size_t)j * W + i] = trace_ray(camera.get_ray(u, v), scene, D);
         }
