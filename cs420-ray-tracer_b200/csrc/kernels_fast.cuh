@@ -156,25 +156,35 @@ __device__ __forceinline__ Tab tab_at(const unsigned char *base, const FastArgs 
 }
 
 // ---------------------------------------------------------------------------------------------
-// exact (FP64) deciders, kept out of line: they are rare and register hungry
+// exact (FP64) deciders.  Everything here is OUT OF LINE on purpose: it is rare, register hungry
+// and large (IEEE double sqrt / div expand to dozens of instructions); one copy per kernel keeps
+// the instruction footprint of the kernels inside the instruction cache.
 struct ExactRay { d3 o, d; double a; };
 
-__device__ __noinline__ ExactRay exact_primary_ray(const double *su, const double *sv, int x, int j) {
+// Where a query's exact FP64 ray comes from: the camera (pixel x, row j) or a queue record.
+struct RaySrc { const double *su, *sv; int x, j; const RayRec *rec; };
+
+__device__ __noinline__ ExactRay exact_ray(RaySrc s) {
   ExactRay e;
-  e.o = ldc3(g_frame.cam_pos);
-  e.d = rtx::camera_dir(ldc3(g_frame.fwd), ldc3(g_frame.right), ldc3(g_frame.up), su[x], sv[j]);
-  e.a = rtx::dot(e.d, e.d);
-  return e;
-}
-__device__ __noinline__ ExactRay exact_shadow_ray(d3 p, int light, double &ldist) {
-  ExactRay e;
-  rtx::shadow_ray(p, ldc3(g_frame.light_pos[light]), 0.001, e.o, e.d, ldist);
+  if (s.rec) {
+    e.o = rtx::mk(s.rec->ox, s.rec->oy, s.rec->oz);
+    e.d = rtx::mk(s.rec->dx, s.rec->dy, s.rec->dz);
+  } else {
+    e.o = ldc3(g_frame.cam_pos);
+    e.d = rtx::camera_dir(ldc3(g_frame.fwd), ldc3(g_frame.right), ldc3(g_frame.up), s.su[s.x], s.sv[s.j]);
+  }
   e.a = rtx::dot(e.d, e.d);
   return e;
 }
 __device__ __noinline__ bool exact_sphere(const double4 *sph64, int idx, d3 o, d3 d, double a, double &t) {
   double4 s = ld_sph64(&sph64[idx]);
   return rtx::intersect(o, d, a, rtx::mk(s.x, s.y, s.z), s.w, t);
+}
+// include/scene.h:70-85 for ONE sphere: the reference's own formula on the reference's own shadow ray
+__device__ __noinline__ bool exact_shadow_sphere(const double4 *sph64, int idx, d3 p, int light) {
+  d3 o, d; double ldist, tt;
+  rtx::shadow_ray(p, ldc3(g_frame.light_pos[light]), 0.001, o, d, ldist);
+  return exact_sphere(sph64, idx, o, d, rtx::dot(d, d), tt) && tt < 1e20 && tt < ldist;
 }
 // safety net only: full FP64 brute force for one ray (a filter violation was detected)
 __device__ __noinline__ int exact_bruteforce(const double4 *sph64, int n, d3 o, d3 d, double a, double &tbest) {
@@ -186,6 +196,21 @@ __device__ __noinline__ int exact_bruteforce(const double4 *sph64, int n, d3 o, 
   tbest = t;
   return idx;
 }
+// src/main.cpp:32,35 : hit point and unit normal
+struct HitGeom { d3 p, n; };
+__device__ __noinline__ HitGeom hit_geometry(const double4 *sph64, int idx, d3 o, d3 d, double t) {
+  const double4 s = ld_sph64(&sph64[idx]);
+  HitGeom h;
+  h.p = rtx::hit_point(o, d, t);
+  h.n = rtx::normal_at(h.p, rtx::mk(s.x, s.y, s.z));
+  return h;
+}
+// src/main.cpp:45-48 : the reflected ray as the Ray ctor stores it
+__device__ __noinline__ void reflected_ray(d3 d, d3 p, d3 n, RayRec *rec) {
+  d3 o2, d2;
+  rtx::reflect_ray(d, p, n, 0.001, o2, d2);
+  rec->ox = o2.x; rec->oy = o2.y; rec->oz = o2.z; rec->dx = d2.x; rec->dy = d2.y; rec->dz = d2.z;
+}
 
 // ---------------------------------------------------------------------------------------------
 // closest-hit bookkeeping: best candidate as an FP32 bracket, exact FP64 t only when needed.
@@ -194,39 +219,39 @@ __device__ __noinline__ int exact_bruteforce(const double4 *sph64, int n, d3 o, 
 struct Best {
   float lo, hi;
   int idx;
+  int nfp64;      // FP64 sphere evaluations spent on this query
   double t;       // valid iff exact
   bool exact;
 };
-__device__ __forceinline__ void best_init(Best &b) { b.lo = 3.0e38f; b.hi = 3.0e38f; b.idx = -1; b.t = 1e20; b.exact = false; }
+__device__ __forceinline__ void best_init(Best &b) { b.lo = 3.0e38f; b.hi = 3.0e38f; b.idx = -1; b.t = 1e20; b.exact = false; b.nfp64 = 0; }
 __device__ __forceinline__ void best_set_exact(Best &b, int idx, double t) {
   b.idx = idx; b.t = t; b.exact = true; b.lo = f_rd(t); b.hi = f_ru(t);
 }
 
-template <typename ExactRayFn>
-__device__ __forceinline__ void closest_consider(Best &b, int i, int status, float lo, float hi, const double4 *sph64,
-                                                 ExactRayFn get_ray, unsigned &n_fp64) {
-  if (status == RT_MISS) return;
+__device__ __noinline__ Best closest_consider(Best b, int i, int status, float lo, float hi, const double4 *sph64, RaySrc src) {
+  if (status == RT_MISS) return b;
   if (status == RT_HIT) {
-    if (b.idx < 0) { b.lo = lo; b.hi = hi; b.idx = i; b.exact = false; return; }
-    if (lo > b.hi) return;                        // strictly farther
-    if (hi < b.lo) { b.lo = lo; b.hi = hi; b.idx = i; b.exact = false; return; }
+    if (b.idx < 0) { b.lo = lo; b.hi = hi; b.idx = i; b.exact = false; return b; }
+    if (lo > b.hi) return b;                      // strictly farther
+    if (hi < b.lo) { b.lo = lo; b.hi = hi; b.idx = i; b.exact = false; return b; }
   }
   // brackets touch, or the sphere itself is ambiguous: decide in FP64, lowest index wins ties
-  ExactRay e = get_ray();
+  const ExactRay e = exact_ray(src);
   double tn;
-  n_fp64++;
-  bool hn = exact_sphere(sph64, i, e.o, e.d, e.a, tn);
-  if (!hn || !(tn < 1e20)) return;                // INFINITY_DOUBLE init of include/scene.h:42
+  b.nfp64++;
+  const bool hn = exact_sphere(sph64, i, e.o, e.d, e.a, tn);
+  if (!hn || !(tn < 1e20)) return b;              // INFINITY_DOUBLE init of include/scene.h:42
   if (b.idx >= 0 && !b.exact) {
-    float tl = f_rd(tn), th = f_ru(tn);
-    if (tl > b.hi) return;
-    if (th < b.lo) { best_set_exact(b, i, tn); return; }
+    const float tl = f_rd(tn), th = f_ru(tn);
+    if (tl > b.hi) return b;
+    if (th < b.lo) { best_set_exact(b, i, tn); return b; }
     double tb;
-    n_fp64++;
-    bool hb = exact_sphere(sph64, b.idx, e.o, e.d, e.a, tb);
-    if (hb) best_set_exact(b, b.idx, tb); else best_init(b);   // (else: filter violation, caught later)
+    b.nfp64++;
+    const bool hb = exact_sphere(sph64, b.idx, e.o, e.d, e.a, tb);
+    if (hb) best_set_exact(b, b.idx, tb); else { const int k = b.nfp64; best_init(b); b.nfp64 = k; }   // (else: filter violation, caught later)
   }
   if (b.idx < 0 || tn < b.t || (tn == b.t && i < b.idx)) best_set_exact(b, i, tn);
+  return b;
 }
 
 // scalar re-evaluation of one sphere of a shared-origin table (same operations as the fast path)
@@ -251,6 +276,88 @@ __device__ __forceinline__ bool shared_origin_roots(float ocx, float ocy, float 
   return bracket_roots(tca, Dhi, E2, dt, r);
 }
 
+// ---- slow paths: one flagged group (8 spheres) for ONE ray, out of line ---------------------------
+__device__ __noinline__ Best slow_closest_shared(Best b, const float4 *pairs, const int *perm, int g, float dx, float dy, float dz,
+                                                 float d64, const double4 *sph64, RaySrc src) {
+#pragma unroll 1
+  for (int k = 0; k < 2 * kGroupPairs; k++) {
+    const int pi = g * kGroupPairs + (k >> 1), h = k & 1;
+    const int i = perm[2 * pi + h];
+    if (i < 0) continue;
+    const float4 A = pairs[2 * pi], B = pairs[2 * pi + 1];
+    const float ocx = h ? A.y : A.x, ocy = h ? A.w : A.z, ocz = h ? B.y : B.x, ncc = h ? B.w : B.z;
+    float tca, Dp;
+    shared_origin_eval(ocx, ocy, ocz, ncc, dx, dy, dz, tca, Dp);
+    if (!(Dp >= 0.0f)) continue;
+    Roots rt;
+    int status = RT_AMBIG;
+    float lo = 0, hi = 0;
+    if (shared_origin_roots(ocx, ocy, ocz, ncc, tca, Dp, d64, rt)) status = select_root(rt, lo, hi);
+    b = closest_consider(b, i, status, lo, hi, sph64, src);
+  }
+  return b;
+}
+
+// returns bit 0 = an occluder was found in this group, bits 1.. = FP64 evaluations spent
+__device__ __noinline__ int slow_shadow(const float4 *pairs, const int *perm, int g, float dx, float dy, float dz, float so, float m,
+                                        int self, float cosl, d3 p64, int light, float d64, const double4 *sph64) {
+  const float so_lo = so - m, so_hi = so + m, e_lo = -kEps - m, e_hi = -kEps + m;
+  int n64 = 0, found = 0;
+#pragma unroll 1
+  for (int k = 0; k < 2 * kGroupPairs; k++) {
+    const int pi = g * kGroupPairs + (k >> 1), h = k & 1;
+    const int i = perm[2 * pi + h];
+    if (i < 0) continue;
+    if (i == self && cosl > 1e-3f) continue;
+    const float4 A = pairs[2 * pi], B = pairs[2 * pi + 1];
+    const float ocx = h ? A.y : A.x, ocy = h ? A.w : A.z, ocz = h ? B.y : B.x, ncc = h ? B.w : B.z;
+    float tca, Dp;
+    shared_origin_eval(ocx, ocy, ocz, ncc, dx, dy, dz, tca, Dp);
+    if (!(Dp >= 0.0f)) continue;
+    Roots rt;
+    if (shared_origin_roots(ocx, ocy, ocz, ncc, tca, Dp, d64, rt)) {
+      const bool no = (rt.n_lo > so_hi) || (rt.f_hi < e_lo) || (rt.n_hi < e_lo && rt.f_lo > so_hi);
+      const bool yes = (rt.f_lo > e_hi && rt.f_hi < so_lo) || (rt.f_lo > so_hi && rt.n_lo > e_hi && rt.n_hi < so_lo);
+      if (no) continue;
+      if (yes) { found = 1; break; }
+    }
+    n64++;
+    if (exact_shadow_sphere(sph64, i, p64, light)) { found = 1; break; }
+  }
+  return found | (n64 << 1);
+}
+
+__device__ __noinline__ Best slow_closest_general(Best b, const float4 *pairs, int g, int N, float ox, float oy, float oz, float dx,
+                                                  float dy, float dz, float d64, float gS2, const double4 *sph64, RaySrc src) {
+  const float sS = __fsqrt_ru(gS2);
+#pragma unroll 1
+  for (int k = 0; k < 2 * kGroupPairs; k++) {
+    const int pi = g * kGroupPairs + (k >> 1), h = k & 1, i = 2 * pi + h;
+    if (i >= N) break;
+    const float4 A = pairs[2 * pi], B = pairs[2 * pi + 1];
+    const float cx = h ? A.y : A.x, cy = h ? A.w : A.z, cz = h ? B.y : B.x, rho = h ? B.w : B.z;
+    // explicit-margin evaluation (independent of the inflation tricks of the fast path)
+    const float x = __fsub_rn(cx, ox), y = __fsub_rn(cy, oy), z = __fsub_rn(cz, oz);
+    float tca = __fmul_rn(x, dx); tca = __fmaf_rn(y, dy, tca); tca = __fmaf_rn(z, dz, tca);
+    const float oc2 = __fmaf_ru(z, z, __fmaf_ru(y, y, __fmul_ru(x, x)));
+    // |X - oc*| <= u(2S + |oc|)  =>  D error <= u (8.1 S |oc| + 16 |oc|^2 + 4 rho) + d64   
+    const float ocn = __fsqrt_ru(oc2);
+    const float Eg = __fadd_ru(__fmul_ru(5.9604645e-8f, __fmaf_ru(8.2f * sS, ocn, __fmaf_ru(16.5f, oc2, 4.5f * fabsf(rho)))), d64);
+    const float Dc = __fmaf_rn(tca, tca, __fsub_rn(rho, oc2));      // rho = r^2 + margins
+    const float Dhi = __fadd_ru(Dc, Eg);
+    if (!(Dhi >= 0.0f)) continue;
+    Roots rt;
+    int status = RT_AMBIG;
+    float lo = 0, hi = 0;
+    const float dt = __fmul_ru(RT_ETA * 1.001f, __fadd_ru(ocn, sS));
+    // rho' - r^2 = 40u r^2 + 12u S r + 64u^2 S^2 + d64 (host), bounded here from rho' itself
+    const float rm = __fadd_ru(__fmul_ru(5.9604645e-8f, __fmaf_ru(12.5f * sS, __fsqrt_ru(fabsf(rho)), __fmaf_ru(41.0f, fabsf(rho), 1e-4f * gS2))), d64);
+    if (bracket_roots(tca, Dhi, __fadd_ru(__fmul_ru(2.0f, Eg), rm), dt, rt)) status = select_root(rt, lo, hi);
+    b = closest_consider(b, i, status, lo, hi, sph64, src);
+  }
+  return b;
+}
+
 // The packed FP32 test of one group (4 pairs = 8 spheres) against two rays of a shared-origin table.
 // Bit 31 of acc stays set while no sphere of the group can be hit: D' = (oc.d)^2 + ncc < 0.
 __device__ __forceinline__ void group_test_shared(const float4 *__restrict__ pairs, int g, const float2 (&dx)[2],
@@ -270,15 +377,15 @@ __device__ __forceinline__ void group_test_shared(const float4 *__restrict__ pai
 
 // ---------------------------------------------------------------------------------------------
 // CLOSEST HIT, shared origin (camera table, sorted by nearest-point distance).  Two rays per lane.
-template <typename ExactRayFn0, typename ExactRayFn1>
 __device__ __forceinline__ void closest_shared(const Tab T, int ngroups, const float (&dx)[2], const float (&dy)[2],
                                                const float (&dz)[2], const bool (&live)[2], float d64, const double4 *sph64,
-                                               ExactRayFn0 ray0, ExactRayFn1 ray1, Best (&best)[2], unsigned &n_fp64) {
+                                               const RaySrc (&src)[2], Best (&best)[2]) {
   unsigned dead[2] = {live[0] ? 0u : kSign, live[1] ? 0u : kSign};
   const float2 dx2[2] = {make_float2(dx[0], dx[0]), make_float2(dx[1], dx[1])};
   const float2 dy2[2] = {make_float2(dy[0], dy[0]), make_float2(dy[1], dy[1])};
   const float2 dz2[2] = {make_float2(dz[0], dz[0]), make_float2(dz[1], dz[1])};
   float wcut = 3.0e38f;                            // warp-uniform: farthest cutoff of any live ray
+#pragma unroll 1
   for (int g = 0; g < ngroups; g++) {
     const float gm = T.gmin[g];
     if (gm > wcut) break;                          // every remaining sphere is beyond every ray's best hit
@@ -286,30 +393,10 @@ __device__ __forceinline__ void closest_shared(const Tab T, int ngroups, const f
     if (gm > best[1].hi) dead[1] = kSign;
     unsigned acc0, acc1;
     group_test_shared(T.pairs, g, dx2, dy2, dz2, acc0, acc1);
-    const bool flagged = (int)((acc0 | dead[0]) & (acc1 | dead[1])) >= 0;
-    if (__any_sync(kFull, flagged)) {
-      if (flagged) {
-#pragma unroll
-        for (int r = 0; r < 2; r++) {
-          if ((int)((r ? acc1 : acc0) | dead[r]) < 0) continue;
-          for (int k = 0; k < 2 * kGroupPairs; k++) {
-            const int pi = g * kGroupPairs + (k >> 1), h = k & 1;
-            const int i = T.perm[2 * pi + h];
-            if (i < 0) continue;
-            const float4 A = T.pairs[2 * pi], B = T.pairs[2 * pi + 1];
-            const float ocx = h ? A.y : A.x, ocy = h ? A.w : A.z, ocz = h ? B.y : B.x, ncc = h ? B.w : B.z;
-            float tca, Dp;
-            shared_origin_eval(ocx, ocy, ocz, ncc, dx[r], dy[r], dz[r], tca, Dp);
-            if (!(Dp >= 0.0f)) continue;
-            Roots rt;
-            int status = RT_AMBIG;
-            float lo = 0, hi = 0;
-            if (shared_origin_roots(ocx, ocy, ocz, ncc, tca, Dp, d64, rt)) status = select_root(rt, lo, hi);
-            if (r == 0) closest_consider(best[0], i, status, lo, hi, sph64, ray0, n_fp64);
-            else closest_consider(best[1], i, status, lo, hi, sph64, ray1, n_fp64);
-          }
-        }
-      }
+    const bool f0 = (int)(acc0 | dead[0]) >= 0, f1 = (int)(acc1 | dead[1]) >= 0;
+    if (__any_sync(kFull, f0 || f1)) {
+      if (f0) best[0] = slow_closest_shared(best[0], T.pairs, T.perm, g, dx[0], dy[0], dz[0], d64, sph64, src[0]);
+      if (f1) best[1] = slow_closest_shared(best[1], T.pairs, T.perm, g, dx[1], dy[1], dz[1], d64, sph64, src[1]);
       wcut = wmaxf(fmaxf(live[0] ? best[0].hi : -3.0e38f, live[1] ? best[1].hi : -3.0e38f));
     }
   }
@@ -317,18 +404,17 @@ __device__ __forceinline__ void closest_shared(const Tab T, int ngroups, const f
 
 // ---------------------------------------------------------------------------------------------
 // CLOSEST HIT, general origin (bounce rays).  Table pair = (cx0,cx1,cy0,cy1) (cz0,cz1,rho0,rho1)
-// with recentred centres, index order.  Per sphere: X = c - o, tu = X.d(1+16u) + dtmax (an UPPER
-// bound of the true centre projection), q = |X|^2 - rho' (> 0 => origin strictly outside),
+// with recentred centres, index order.  Per sphere: X = c - o, tu = X.d(1+24u) + dtmax (an UPPER
+// bound of the true centre projection), q = |X|^2 - rho' (>= 0 => origin strictly outside),
 // D' = tu^2 - q.  A sphere is skipped when D' < 0, or when it lies behind an origin that is outside
-// it (tu < 0 and q > 0): that removes the sphere the ray just left without any extra arithmetic.
-template <typename ExactRayFn0, typename ExactRayFn1>
+// it (tu < 0 and q >= 0): that removes the sphere the ray just left without any extra arithmetic.
 __device__ __forceinline__ void closest_general(const float4 *__restrict__ pairs, int ngroups, int N, const float (&ox)[2],
                                                 const float (&oy)[2], const float (&oz)[2], const float (&dx)[2],
                                                 const float (&dy)[2], const float (&dz)[2], const bool (&live)[2], float d64,
-                                                float gS2, float dtmax, const double4 *sph64, ExactRayFn0 ray0,
-                                                ExactRayFn1 ray1, Best (&best)[2], unsigned &n_fp64) {
+                                                float gS2, float dtmax, const double4 *sph64, const RaySrc (&src)[2],
+                                                Best (&best)[2]) {
   const unsigned dead[2] = {live[0] ? 0u : kSign, live[1] ? 0u : kSign};
-  const float kInfl = 1.0f + 16.0f * 5.9604645e-8f;
+  const float kInfl = 1.0f + 24.0f * 5.9604645e-8f;
   float2 nox[2], noy[2], noz[2], idx2[2], idy2[2], idz2[2];
   const float2 dtm = make_float2(dtmax, dtmax);
 #pragma unroll
@@ -337,7 +423,7 @@ __device__ __forceinline__ void closest_general(const float4 *__restrict__ pairs
     float ix = __fmul_rn(dx[r], kInfl), iy = __fmul_rn(dy[r], kInfl), iz = __fmul_rn(dz[r], kInfl);
     idx2[r] = make_float2(ix, ix); idy2[r] = make_float2(iy, iy); idz2[r] = make_float2(iz, iz);
   }
-  const float sS = __fsqrt_ru(gS2);
+#pragma unroll 1
   for (int g = 0; g < ngroups; g++) {
     unsigned acc[2] = {kFull, kFull};
 #pragma unroll
@@ -355,36 +441,10 @@ __device__ __forceinline__ void closest_general(const float4 *__restrict__ pairs
         acc[r] &= (fbits(D.x) | (fbits(t.x) & ~fbits(q.x))) & (fbits(D.y) | (fbits(t.y) & ~fbits(q.y)));
       }
     }
-    if ((int)((acc[0] | dead[0]) & (acc[1] | dead[1])) >= 0) {
-#pragma unroll
-      for (int r = 0; r < 2; r++) {
-        if ((int)(acc[r] | dead[r]) < 0) continue;
-        for (int k = 0; k < 2 * kGroupPairs; k++) {
-          const int pi = g * kGroupPairs + (k >> 1), h = k & 1, i = 2 * pi + h;
-          if (i >= N) break;
-          const float4 A = pairs[2 * pi], B = pairs[2 * pi + 1];
-          const float cx = h ? A.y : A.x, cy = h ? A.w : A.z, cz = h ? B.y : B.x, rho = h ? B.w : B.z;
-          // explicit-margin evaluation (independent of the inflation tricks of the fast path)
-          const float x = __fsub_rn(cx, ox[r]), y = __fsub_rn(cy, oy[r]), z = __fsub_rn(cz, oz[r]);
-          float tca = __fmul_rn(x, dx[r]); tca = __fmaf_rn(y, dy[r], tca); tca = __fmaf_rn(z, dz[r], tca);
-          const float oc2 = __fmaf_ru(z, z, __fmaf_ru(y, y, __fmul_ru(x, x)));
-          // |X - oc*| <= u(2S + |oc|)  =>  D error <= u (8.1 S |oc| + 16 |oc|^2 + 4 rho) + d64   
-          const float ocn = __fsqrt_ru(oc2);
-          const float Eg = __fadd_ru(__fmul_ru(5.9604645e-8f, __fmaf_ru(8.2f * sS, ocn, __fmaf_ru(16.5f, oc2, 4.5f * fabsf(rho)))), d64);
-          const float Dc = __fmaf_rn(tca, tca, __fsub_rn(rho, oc2));      // rho = r^2 + margins (<= r^2 + Eg)
-          const float Dhi = __fadd_ru(Dc, Eg);
-          if (!(Dhi >= 0.0f)) continue;
-          Roots rt;
-          int status = RT_AMBIG;
-          float lo = 0, hi = 0;
-          const float dt = __fmul_ru(RT_ETA * 1.001f, __fadd_ru(ocn, sS));
-          // rho' - r^2 = 40u r^2 + 12u S r + 64u^2 S^2 + d64 (host), bounded here from rho' itself
-          const float rm = __fadd_ru(__fmul_ru(5.9604645e-8f, __fmaf_ru(12.5f * sS, __fsqrt_ru(fabsf(rho)), __fmaf_ru(41.0f, fabsf(rho), 1e-4f * gS2))), d64);
-          if (bracket_roots(tca, Dhi, __fadd_ru(__fmul_ru(2.0f, Eg), rm), dt, rt)) status = select_root(rt, lo, hi);
-          if (r == 0) closest_consider(best[0], i, status, lo, hi, sph64, ray0, n_fp64);
-          else closest_consider(best[1], i, status, lo, hi, sph64, ray1, n_fp64);
-        }
-      }
+    const bool f0 = (int)(acc[0] | dead[0]) >= 0, f1 = (int)(acc[1] | dead[1]) >= 0;
+    if (f0 || f1) {
+      if (f0) best[0] = slow_closest_general(best[0], pairs, g, N, ox[0], oy[0], oz[0], dx[0], dy[0], dz[0], d64, gS2, sph64, src[0]);
+      if (f1) best[1] = slow_closest_general(best[1], pairs, g, N, ox[1], oy[1], oz[1], dx[1], dy[1], dz[1], d64, gS2, sph64, src[1]);
     }
   }
 }
@@ -399,7 +459,7 @@ __device__ __forceinline__ void closest_general(const float4 *__restrict__ pairs
 __device__ __forceinline__ void shadow_light(const Tab T, int ngroups, int light, const float (&dx)[2], const float (&dy)[2],
                                              const float (&dz)[2], const float (&so)[2], const bool (&want)[2],
                                              const int (&self)[2], const float (&cosl)[2], const d3 (&p64)[2], float d64,
-                                             const double4 *sph64, bool (&occ)[2], unsigned &n_fp64) {
+                                             const double4 *sph64, bool (&occ)[2], int &n_fp64) {
   unsigned dead[2] = {want[0] ? 0u : kSign, want[1] ? 0u : kSign};
   occ[0] = occ[1] = false;
   const float2 dx2[2] = {make_float2(dx[0], dx[0]), make_float2(dx[1], dx[1])};
@@ -412,6 +472,7 @@ __device__ __forceinline__ void shadow_light(const Tab T, int ngroups, int light
     cut[r] = want[r] ? so[r] + m[r] : -3.0e38f;               // nothing farther from the light can matter
   }
   const float wcut = wmaxf(fmaxf(cut[0], cut[1]));
+#pragma unroll 1
   for (int g = 0; g < ngroups; g++) {
     const float gm = T.gmin[g];
     if (gm > wcut) break;
@@ -419,41 +480,17 @@ __device__ __forceinline__ void shadow_light(const Tab T, int ngroups, int light
     if (gm > cut[1]) dead[1] = kSign;
     unsigned acc0, acc1;
     group_test_shared(T.pairs, g, dx2, dy2, dz2, acc0, acc1);
-    const bool flagged = (int)((acc0 | dead[0]) & (acc1 | dead[1])) >= 0;
-    if (__any_sync(kFull, flagged)) {                 // warp-uniform: the vote below needs every lane
-      if (flagged) {
-#pragma unroll
-        for (int r = 0; r < 2; r++) {
-          if ((int)((r ? acc1 : acc0) | dead[r]) < 0) continue;
-          const float so_lo = so[r] - m[r], so_hi = so[r] + m[r], e_lo = -kEps - m[r], e_hi = -kEps + m[r];
-          for (int k = 0; k < 2 * kGroupPairs && !occ[r]; k++) {
-            const int pi = g * kGroupPairs + (k >> 1), h = k & 1;
-            const int i = T.perm[2 * pi + h];
-            if (i < 0) continue;
-            if (i == self[r] && cosl[r] > 1e-3f) continue;
-            const float4 A = T.pairs[2 * pi], B = T.pairs[2 * pi + 1];
-            const float ocx = h ? A.y : A.x, ocy = h ? A.w : A.z, ocz = h ? B.y : B.x, ncc = h ? B.w : B.z;
-            float tca, Dp;
-            shared_origin_eval(ocx, ocy, ocz, ncc, dx[r], dy[r], dz[r], tca, Dp);
-            if (!(Dp >= 0.0f)) continue;
-            Roots rt;
-            bool decided = false;
-            if (shared_origin_roots(ocx, ocy, ocz, ncc, tca, Dp, d64, rt)) {
-              const bool no = (rt.n_lo > so_hi) || (rt.f_hi < e_lo) || (rt.n_hi < e_lo && rt.f_lo > so_hi);
-              const bool yes = (rt.f_lo > e_hi && rt.f_hi < so_lo) ||
-                               (rt.f_lo > so_hi && rt.n_lo > e_hi && rt.n_hi < so_lo);
-              if (no) decided = true;
-              else if (yes) { decided = true; occ[r] = true; }
-            }
-            if (!decided) {       // the reference's own formula on the reference's own shadow ray
-              double ldist, tt;
-              ExactRay e = exact_shadow_ray(p64[r], light, ldist);
-              n_fp64++;
-              if (exact_sphere(sph64, i, e.o, e.d, e.a, tt) && tt < 1e20 && tt < ldist) occ[r] = true;
-            }
-          }
-          if (occ[r]) dead[r] = kSign;
-        }
+    const bool f0 = (int)(acc0 | dead[0]) >= 0, f1 = (int)(acc1 | dead[1]) >= 0;
+    if (__any_sync(kFull, f0 || f1)) {                // warp-uniform: the vote below needs every lane
+      if (f0) {
+        const int rc = slow_shadow(T.pairs, T.perm, g, dx[0], dy[0], dz[0], so[0], m[0], self[0], cosl[0], p64[0], light, d64, sph64);
+        n_fp64 += rc >> 1;
+        if (rc & 1) { occ[0] = true; dead[0] = kSign; }
+      }
+      if (f1) {
+        const int rc = slow_shadow(T.pairs, T.perm, g, dx[1], dy[1], dz[1], so[1], m[1], self[1], cosl[1], p64[1], light, d64, sph64);
+        n_fp64 += rc >> 1;
+        if (rc & 1) { occ[1] = true; dead[1] = kSign; }
       }
       if (__all_sync(kFull, (dead[0] & dead[1]) != 0u)) break;     // every ray of the warp is decided
     }
@@ -484,7 +521,7 @@ __device__ __forceinline__ void shade_hits(const FastArgs &a, const unsigned cha
                                            const bool (&hit)[2], const int (&idx)[2], const d3 (&o64)[2], const d3 (&d64v)[2],
                                            const double (&t64)[2], const unsigned (&pix)[2], float (&wt)[2], float (&cr)[2],
                                            float (&cg)[2], float (&cb)[2], bool (&final_)[2], bool (&cont)[2], RayRec (&rec)[2],
-                                           int level, Counters &cnt, unsigned &n_fp64) {
+                                           int level, Counters &cnt, int &n_fp64) {
   d3 p[2], n[2];
   float nx[2], ny[2], nz[2], vx[2], vy[2], vz[2];
   float4 m[2]; float2 mx[2];
@@ -497,9 +534,8 @@ __device__ __forceinline__ void shade_hits(const FastArgs &a, const unsigned cha
     nx[r] = ny[r] = nz[r] = vx[r] = vy[r] = vz[r] = 0.f; sr[r] = sg[r] = sb[r] = 0.f;
     cont[r] = false;
     if (hit[r]) {
-      const double4 s = ld_sph64(&a.r.sph64[idx[r]]);
-      p[r] = rtx::hit_point(o64[r], d64v[r], t64[r]);                     // src/main.cpp:32
-      n[r] = rtx::normal_at(p[r], rtx::mk(s.x, s.y, s.z));               // src/main.cpp:35
+      const HitGeom hg = hit_geometry(a.r.sph64, idx[r], o64[r], d64v[r], t64[r]);   // src/main.cpp:32,35
+      p[r] = hg.p; n[r] = hg.n;
       m[r] = __ldg(&a.r.mat[idx[r]]); mx[r] = __ldg(&a.r.matx[idx[r]]);
       nx[r] = (float)n[r].x; ny[r] = (float)n[r].y; nz[r] = (float)n[r].z;
       // view_dir = normalized(origin - hit) = -d up to rounding (src/main.cpp:38); colour only
@@ -557,9 +593,7 @@ __device__ __forceinline__ void shade_hits(const FastArgs &a, const unsigned cha
       cr[r] += k * sr[r]; cg[r] += k * sg[r]; cb[r] += k * sb[r];
       wt[r] *= refl;
       if (level + 1 < a.r.max_depth) {
-        d3 o2, d2;
-        rtx::reflect_ray(d64v[r], p[r], n[r], 0.001, o2, d2);
-        rec[r].ox = o2.x; rec[r].oy = o2.y; rec[r].oz = o2.z; rec[r].dx = d2.x; rec[r].dy = d2.y; rec[r].dz = d2.z;
+        reflected_ray(d64v[r], p[r], n[r], &rec[r]);
         rec[r].pix = pix[r]; rec[r].wt = wt[r]; rec[r].ar = cr[r]; rec[r].ag = cg[r]; rec[r].ab = cb[r]; rec[r].pad = 0;
         cont[r] = true;
       } else {
@@ -572,9 +606,9 @@ __device__ __forceinline__ void shade_hits(const FastArgs &a, const unsigned cha
   }
 }
 
-__device__ __forceinline__ void flush_counters(const FastArgs &a, Counters &c, unsigned &n_fp64, int level) {
+__device__ __forceinline__ void flush_counters(const FastArgs &a, Counters &c, int &n_fp64, int level) {
   if (!a.r.counters) return;
-  c.fp64 += n_fp64;
+  c.fp64 += (unsigned long long)n_fp64;
   unsigned long long v[6] = {c.closest, c.hits, c.shadow, c.occluded, c.fp64, c.violations};
 #pragma unroll
   for (int k = 0; k < 6; k++) v[k] = wsum(v[k]);
@@ -594,7 +628,7 @@ __device__ __forceinline__ void flush_counters(const FastArgs &a, Counters &c, u
 
 // Exact FP64 t of the winner (or the brute-force safety net if the filter contradicted itself).
 __device__ __forceinline__ void finish_closest(const FastArgs &a, const Best &b, const ExactRay &e, bool &hit, int &idx, double &t64,
-                                               Counters &cnt, unsigned &n_fp64) {
+                                               Counters &cnt, int &n_fp64) {
   double t = b.t;
   bool ok = b.exact;
   if (!ok) { n_fp64++; ok = exact_sphere(a.r.sph64, b.idx, e.o, e.d, e.a, t) && t < 1e20; }
@@ -616,7 +650,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_primary(const FastArgs a) {
   unsigned char *s_rgb = smem + 64 + warp * (kWTileH * kWTileW * 3);
   const int W = a.r.W, rows = a.r.bands.local_rows, depth = a.r.max_depth;
   Counters cnt = {0, 0, 0, 0, 0, 0};
-  unsigned n_fp64 = 0;
+  int n_fp64 = 0;
   for (;;) {
     const int tile = warp_fetch(a.tile_counter);
     if (tile >= a.nwtiles) break;
@@ -648,11 +682,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_primary(const FastArgs a) {
     }
     Best best[2];
     best_init(best[0]); best_init(best[1]);
-    const double *su = a.r.su, *sv = a.r.sv;
-    const int j0 = j[0], j1 = j[1];
-    auto ray0 = [&]() { return exact_primary_ray(su, sv, x, j0); };
-    auto ray1 = [&]() { return exact_primary_ray(su, sv, x, j1); };
-    closest_shared(cam, a.ngroups, dx, dy, dz, live, a.d64, a.r.sph64, ray0, ray1, best, n_fp64);
+    const RaySrc src[2] = {{a.r.su, a.r.sv, x, j[0], nullptr}, {a.r.su, a.r.sv, x, j[1], nullptr}};
+    closest_shared(cam, a.ngroups, dx, dy, dz, live, a.d64, a.r.sph64, src, best);
 
     bool hit[2], final_[2], cont[2];
     int idx[2];
@@ -666,8 +697,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_primary(const FastArgs a) {
       o64[r] = rtx::mk(0, 0, 0); d64v[r] = o64[r];
       if (!live[r]) continue;
       cnt.closest++;
+      n_fp64 += best[r].nfp64;
       if (best[r].idx >= 0) {
-        const ExactRay e = exact_primary_ray(su, sv, x, j[r]);
+        const ExactRay e = exact_ray(src[r]);
         finish_closest(a, best[r], e, hit[r], idx[r], t64[r], cnt, n_fp64);
         o64[r] = e.o; d64v[r] = e.d;
       }
@@ -730,7 +762,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_bounce(const FastArgs a) {
   const int lane = threadIdx.x & 31;
   const int depth = a.r.max_depth;
   Counters cnt = {0, 0, 0, 0, 0, 0};
-  unsigned n_fp64 = 0;
+  int n_fp64 = 0;
   RayRec *qin = a.q_in;
   for (;;) {
     const int chunk = warp_fetch(a.chunk_counter);
@@ -753,20 +785,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_bounce(const FastArgs a) {
         pix[r] = q.pix; wt[r] = q.wt; cr[r] = q.ar; cg[r] = q.ag; cb[r] = q.ab;
       }
     }
-    const unsigned q0 = qi[0], q1 = qi[1];
-    auto mkray = [&](unsigned k) {
-      ExactRay e;
-      const RayRec &q = qin[k];
-      e.o = rtx::mk(q.ox, q.oy, q.oz); e.d = rtx::mk(q.dx, q.dy, q.dz); e.a = rtx::dot(e.d, e.d);
-      return e;
-    };
-    auto ray0 = [&]() { return mkray(q0); };
-    auto ray1 = [&]() { return mkray(q1); };
+    const RaySrc src[2] = {{nullptr, nullptr, 0, 0, qin + qi[0]}, {nullptr, nullptr, 0, 0, qin + qi[1]}};
     for (int level = a.level;; level++) {
       Best best[2];
       best_init(best[0]); best_init(best[1]);
-      closest_general(gen, a.ngroups, a.N, ox, oy, oz, dx, dy, dz, live, a.d64, a.gS2, a.g_dtmax, a.r.sph64, ray0, ray1, best,
-                      n_fp64);
+      closest_general(gen, a.ngroups, a.N, ox, oy, oz, dx, dy, dz, live, a.d64, a.gS2, a.g_dtmax, a.r.sph64, src, best);
       bool hit[2], final_[2], cont[2];
       int idx[2];
       d3 o64[2], d64v[2];
@@ -778,8 +801,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_bounce(const FastArgs a) {
         o64[r] = rtx::mk(0, 0, 0); d64v[r] = o64[r];
         if (!live[r]) continue;
         cnt.closest++;
+        n_fp64 += best[r].nfp64;
         if (best[r].idx >= 0) {
-          const ExactRay e = mkray(qi[r]);
+          const ExactRay e = exact_ray(src[r]);
           finish_closest(a, best[r], e, hit[r], idx[r], t64[r], cnt, n_fp64);
           o64[r] = e.o; d64v[r] = e.d;
         }
