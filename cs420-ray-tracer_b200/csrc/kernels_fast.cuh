@@ -276,15 +276,14 @@ __device__ __forceinline__ bool shared_origin_roots(float ocx, float ocy, float 
   return bracket_roots(tca, Dhi, E2, dt, r);
 }
 
-// ---- slow paths: one flagged group (8 spheres) for ONE ray, out of line ---------------------------
-__device__ __noinline__ Best slow_closest_shared(Best b, const float4 *pairs, const int *perm, int g, float dx, float dy, float dz,
+// ---- slow paths: one flagged sphere PAIR for ONE ray, out of line --------------------------------
+__device__ __noinline__ Best slow_closest_shared(Best b, const float4 *pairs, const int *perm, int pi, float dx, float dy, float dz,
                                                  float d64, const double4 *sph64, RaySrc src) {
+  const float4 A = pairs[2 * pi], B = pairs[2 * pi + 1];
 #pragma unroll 1
-  for (int k = 0; k < 2 * kGroupPairs; k++) {
-    const int pi = g * kGroupPairs + (k >> 1), h = k & 1;
+  for (int h = 0; h < 2; h++) {
     const int i = perm[2 * pi + h];
     if (i < 0) continue;
-    const float4 A = pairs[2 * pi], B = pairs[2 * pi + 1];
     const float ocx = h ? A.y : A.x, ocy = h ? A.w : A.z, ocz = h ? B.y : B.x, ncc = h ? B.w : B.z;
     float tca, Dp;
     shared_origin_eval(ocx, ocy, ocz, ncc, dx, dy, dz, tca, Dp);
@@ -298,18 +297,17 @@ __device__ __noinline__ Best slow_closest_shared(Best b, const float4 *pairs, co
   return b;
 }
 
-// returns bit 0 = an occluder was found in this group, bits 1.. = FP64 evaluations spent
-__device__ __noinline__ int slow_shadow(const float4 *pairs, const int *perm, int g, float dx, float dy, float dz, float so, float m,
+// returns bit 0 = an occluder was found in this pair, bits 1.. = FP64 evaluations spent
+__device__ __noinline__ int slow_shadow(const float4 *pairs, const int *perm, int pi, float dx, float dy, float dz, float so, float m,
                                         int self, float cosl, d3 p64, int light, float d64, const double4 *sph64) {
   const float so_lo = so - m, so_hi = so + m, e_lo = -kEps - m, e_hi = -kEps + m;
+  const float4 A = pairs[2 * pi], B = pairs[2 * pi + 1];
   int n64 = 0, found = 0;
 #pragma unroll 1
-  for (int k = 0; k < 2 * kGroupPairs; k++) {
-    const int pi = g * kGroupPairs + (k >> 1), h = k & 1;
+  for (int h = 0; h < 2; h++) {
     const int i = perm[2 * pi + h];
     if (i < 0) continue;
     if (i == self && cosl > 1e-3f) continue;
-    const float4 A = pairs[2 * pi], B = pairs[2 * pi + 1];
     const float ocx = h ? A.y : A.x, ocy = h ? A.w : A.z, ocz = h ? B.y : B.x, ncc = h ? B.w : B.z;
     float tca, Dp;
     shared_origin_eval(ocx, ocy, ocz, ncc, dx, dy, dz, tca, Dp);
@@ -327,14 +325,14 @@ __device__ __noinline__ int slow_shadow(const float4 *pairs, const int *perm, in
   return found | (n64 << 1);
 }
 
-__device__ __noinline__ Best slow_closest_general(Best b, const float4 *pairs, int g, int N, float ox, float oy, float oz, float dx,
+__device__ __noinline__ Best slow_closest_general(Best b, const float4 *pairs, int pi, int N, float ox, float oy, float oz, float dx,
                                                   float dy, float dz, float d64, float gS2, const double4 *sph64, RaySrc src) {
   const float sS = __fsqrt_ru(gS2);
+  const float4 A = pairs[2 * pi], B = pairs[2 * pi + 1];
 #pragma unroll 1
-  for (int k = 0; k < 2 * kGroupPairs; k++) {
-    const int pi = g * kGroupPairs + (k >> 1), h = k & 1, i = 2 * pi + h;
+  for (int h = 0; h < 2; h++) {
+    const int i = 2 * pi + h;
     if (i >= N) break;
-    const float4 A = pairs[2 * pi], B = pairs[2 * pi + 1];
     const float cx = h ? A.y : A.x, cy = h ? A.w : A.z, cz = h ? B.y : B.x, rho = h ? B.w : B.z;
     // explicit-margin evaluation (independent of the inflation tricks of the fast path)
     const float x = __fsub_rn(cx, ox), y = __fsub_rn(cy, oy), z = __fsub_rn(cz, oz);
@@ -358,45 +356,70 @@ __device__ __noinline__ Best slow_closest_general(Best b, const float4 *pairs, i
   return b;
 }
 
-// The packed FP32 test of one group (4 pairs = 8 spheres) against two rays of a shared-origin table.
-// Bit 31 of acc stays set while no sphere of the group can be hit: D' = (oc.d)^2 + ncc < 0.
-__device__ __forceinline__ void group_test_shared(const float4 *__restrict__ pairs, int g, const float2 (&dx)[2],
-                                                  const float2 (&dy)[2], const float2 (&dz)[2], unsigned &acc0, unsigned &acc1) {
-  acc0 = kFull; acc1 = kFull;
+// The packed FP32 test of up to 32 sphere PAIRS (one "chunk") of a shared-origin table against the
+// two rays of a lane.  For every pair and ray one bit is shifted into a history word: 1 = neither
+// sphere of the pair can be hit (D' = (oc.d)^2 + ncc < 0 for both), 0 = flagged.  No branch, no vote:
+// flagged pairs are resolved afterwards, all lanes together (see the drain loops below).
+constexpr int kChunkPairs = 32;
+__device__ __forceinline__ unsigned push_sign(unsigned hist, unsigned v) { return __funnelshift_l(v, hist, 1); }
+
+__device__ __forceinline__ void chunk_test_shared(const float4 *__restrict__ pairs, int p0, int np, const float2 (&dx)[2],
+                                                  const float2 (&dy)[2], const float2 (&dz)[2], unsigned &h0, unsigned &h1) {
+  h0 = kFull; h1 = kFull;
+#pragma unroll 1
+  for (int p = p0; p < p0 + np; p += kGroupPairs) {
 #pragma unroll
-  for (int k = 0; k < kGroupPairs; k++) {
-    const float4 A = pairs[2 * (g * kGroupPairs + k)], B = pairs[2 * (g * kGroupPairs + k) + 1];
-    const float2 X = make_float2(A.x, A.y), Y = make_float2(A.z, A.w), Z = make_float2(B.x, B.y), Wv = make_float2(B.z, B.w);
-    float2 t0 = __fmul2_rn(X, dx[0]); t0 = __ffma2_rn(Y, dy[0], t0); t0 = __ffma2_rn(Z, dz[0], t0);
-    float2 t1 = __fmul2_rn(X, dx[1]); t1 = __ffma2_rn(Y, dy[1], t1); t1 = __ffma2_rn(Z, dz[1], t1);
-    const float2 D0 = __ffma2_rn(t0, t0, Wv), D1 = __ffma2_rn(t1, t1, Wv);
-    acc0 &= fbits(D0.x) & fbits(D0.y);
-    acc1 &= fbits(D1.x) & fbits(D1.y);
+    for (int k = 0; k < kGroupPairs; k++) {
+      const float4 A = pairs[2 * (p + k)], B = pairs[2 * (p + k) + 1];
+      const float2 X = make_float2(A.x, A.y), Y = make_float2(A.z, A.w), Z = make_float2(B.x, B.y), Wv = make_float2(B.z, B.w);
+      float2 t0 = __fmul2_rn(X, dx[0]); t0 = __ffma2_rn(Y, dy[0], t0); t0 = __ffma2_rn(Z, dz[0], t0);
+      float2 t1 = __fmul2_rn(X, dx[1]); t1 = __ffma2_rn(Y, dy[1], t1); t1 = __ffma2_rn(Z, dz[1], t1);
+      const float2 D0 = __ffma2_rn(t0, t0, Wv), D1 = __ffma2_rn(t1, t1, Wv);
+      h0 = push_sign(h0, fbits(D0.x) & fbits(D0.y));
+      h1 = push_sign(h1, fbits(D1.x) & fbits(D1.y));
+    }
   }
 }
+// history word -> flagged-pair bits (bit i <-> pair p0 + np - 1 - i)
+__device__ __forceinline__ unsigned flagged_bits(unsigned hist, int np, bool live) {
+  const unsigned pm = np >= 32 ? kFull : ((1u << np) - 1u);
+  return live ? (~hist & pm) : 0u;
+}
+
+#define RT_SEL(r, a) ((r) ? a[1] : a[0])
 
 // ---------------------------------------------------------------------------------------------
 // CLOSEST HIT, shared origin (camera table, sorted by nearest-point distance).  Two rays per lane.
-__device__ __forceinline__ void closest_shared(const Tab T, int ngroups, const float (&dx)[2], const float (&dy)[2],
+__device__ __forceinline__ void closest_shared(const Tab T, int npairs, const float (&dx)[2], const float (&dy)[2],
                                                const float (&dz)[2], const bool (&live)[2], float d64, const double4 *sph64,
                                                const RaySrc (&src)[2], Best (&best)[2]) {
-  unsigned dead[2] = {live[0] ? 0u : kSign, live[1] ? 0u : kSign};
   const float2 dx2[2] = {make_float2(dx[0], dx[0]), make_float2(dx[1], dx[1])};
   const float2 dy2[2] = {make_float2(dy[0], dy[0]), make_float2(dy[1], dy[1])};
   const float2 dz2[2] = {make_float2(dz[0], dz[0]), make_float2(dz[1], dz[1])};
   float wcut = 3.0e38f;                            // warp-uniform: farthest cutoff of any live ray
 #pragma unroll 1
-  for (int g = 0; g < ngroups; g++) {
-    const float gm = T.gmin[g];
-    if (gm > wcut) break;                          // every remaining sphere is beyond every ray's best hit
-    if (gm > best[0].hi) dead[0] = kSign;
-    if (gm > best[1].hi) dead[1] = kSign;
-    unsigned acc0, acc1;
-    group_test_shared(T.pairs, g, dx2, dy2, dz2, acc0, acc1);
-    const bool f0 = (int)(acc0 | dead[0]) >= 0, f1 = (int)(acc1 | dead[1]) >= 0;
-    if (__any_sync(kFull, f0 || f1)) {
-      if (f0) best[0] = slow_closest_shared(best[0], T.pairs, T.perm, g, dx[0], dy[0], dz[0], d64, sph64, src[0]);
-      if (f1) best[1] = slow_closest_shared(best[1], T.pairs, T.perm, g, dx[1], dy[1], dz[1], d64, sph64, src[1]);
+  for (int p0 = 0; p0 < npairs; p0 += kChunkPairs) {
+    if (T.gmin[p0 / kGroupPairs] > wcut) break;    // every remaining sphere is beyond every ray's best hit
+    const int np = min(kChunkPairs, npairs - p0);
+    unsigned h0, h1;
+    chunk_test_shared(T.pairs, p0, np, dx2, dy2, dz2, h0, h1);
+    unsigned f[2] = {flagged_bits(h0, np, live[0]), flagged_bits(h1, np, live[1])};
+    if (__any_sync(kFull, (f[0] | f[1]) != 0u)) {
+      // drain: every lane resolves its own flagged pairs, nearest first, one per iteration
+      while (__any_sync(kFull, (f[0] | f[1]) != 0u)) {
+        if ((f[0] | f[1]) != 0u) {
+          const int r = f[0] ? 0 : 1;
+          const unsigned fr = RT_SEL(r, f);
+          const int bit = 31 - __clz(fr);
+          const int pi = p0 + np - 1 - bit;
+          if (r) f[1] = fr & ~(1u << bit); else f[0] = fr & ~(1u << bit);
+          Best b = RT_SEL(r, best);
+          if (!(T.gmin[pi / kGroupPairs] > b.hi)) {
+            b = slow_closest_shared(b, T.pairs, T.perm, pi, RT_SEL(r, dx), RT_SEL(r, dy), RT_SEL(r, dz), d64, sph64, RT_SEL(r, src));
+            if (r) best[1] = b; else best[0] = b;
+          }
+        }
+      }
       wcut = wmaxf(fmaxf(live[0] ? best[0].hi : -3.0e38f, live[1] ? best[1].hi : -3.0e38f));
     }
   }
@@ -408,12 +431,11 @@ __device__ __forceinline__ void closest_shared(const Tab T, int ngroups, const f
 // bound of the true centre projection), q = |X|^2 - rho' (>= 0 => origin strictly outside),
 // D' = tu^2 - q.  A sphere is skipped when D' < 0, or when it lies behind an origin that is outside
 // it (tu < 0 and q >= 0): that removes the sphere the ray just left without any extra arithmetic.
-__device__ __forceinline__ void closest_general(const float4 *__restrict__ pairs, int ngroups, int N, const float (&ox)[2],
+__device__ __forceinline__ void closest_general(const float4 *__restrict__ pairs, int npairs, int N, const float (&ox)[2],
                                                 const float (&oy)[2], const float (&oz)[2], const float (&dx)[2],
                                                 const float (&dy)[2], const float (&dz)[2], const bool (&live)[2], float d64,
                                                 float gS2, float dtmax, const double4 *sph64, const RaySrc (&src)[2],
                                                 Best (&best)[2]) {
-  const unsigned dead[2] = {live[0] ? 0u : kSign, live[1] ? 0u : kSign};
   const float kInfl = 1.0f + 24.0f * 5.9604645e-8f;
   float2 nox[2], noy[2], noz[2], idx2[2], idy2[2], idz2[2];
   const float2 dtm = make_float2(dtmax, dtmax);
@@ -424,27 +446,39 @@ __device__ __forceinline__ void closest_general(const float4 *__restrict__ pairs
     idx2[r] = make_float2(ix, ix); idy2[r] = make_float2(iy, iy); idz2[r] = make_float2(iz, iz);
   }
 #pragma unroll 1
-  for (int g = 0; g < ngroups; g++) {
-    unsigned acc[2] = {kFull, kFull};
+  for (int p0 = 0; p0 < npairs; p0 += kChunkPairs) {
+    const int np = min(kChunkPairs, npairs - p0);
+    unsigned h[2] = {kFull, kFull};
+#pragma unroll 1
+    for (int p = p0; p < p0 + np; p += 2) {
 #pragma unroll
-    for (int k = 0; k < kGroupPairs; k++) {
-      const float4 A = pairs[2 * (g * kGroupPairs + k)], B = pairs[2 * (g * kGroupPairs + k) + 1];
-      const float2 CX = make_float2(A.x, A.y), CY = make_float2(A.z, A.w), CZ = make_float2(B.x, B.y);
-      const float2 NR = make_float2(-B.z, -B.w);
+      for (int k = 0; k < 2; k++) {
+        const float4 A = pairs[2 * (p + k)], B = pairs[2 * (p + k) + 1];
+        const float2 CX = make_float2(A.x, A.y), CY = make_float2(A.z, A.w), CZ = make_float2(B.x, B.y);
+        const float2 NR = make_float2(-B.z, -B.w);
 #pragma unroll
-      for (int r = 0; r < 2; r++) {
-        const float2 x = __fadd2_rn(CX, nox[r]), y = __fadd2_rn(CY, noy[r]), z = __fadd2_rn(CZ, noz[r]);
-        float2 t = __ffma2_rn(x, idx2[r], dtm); t = __ffma2_rn(y, idy2[r], t); t = __ffma2_rn(z, idz2[r], t);
-        float2 q = __ffma2_rn(x, x, NR); q = __ffma2_rn(y, y, q); q = __ffma2_rn(z, z, q);
-        const float2 D = __ffma2_rn(t, t, make_float2(-q.x, -q.y));
-        // rejected  <=>  D' < 0  or  (tu < 0 and q >= 0)
-        acc[r] &= (fbits(D.x) | (fbits(t.x) & ~fbits(q.x))) & (fbits(D.y) | (fbits(t.y) & ~fbits(q.y)));
+        for (int r = 0; r < 2; r++) {
+          const float2 x = __fadd2_rn(CX, nox[r]), y = __fadd2_rn(CY, noy[r]), z = __fadd2_rn(CZ, noz[r]);
+          float2 t = __ffma2_rn(x, idx2[r], dtm); t = __ffma2_rn(y, idy2[r], t); t = __ffma2_rn(z, idz2[r], t);
+          float2 q = __ffma2_rn(x, x, NR); q = __ffma2_rn(y, y, q); q = __ffma2_rn(z, z, q);
+          const float2 D = __ffma2_rn(t, t, make_float2(-q.x, -q.y));
+          // rejected  <=>  D' < 0  or  (tu < 0 and q >= 0)
+          h[r] = push_sign(h[r], (fbits(D.x) | (fbits(t.x) & ~fbits(q.x))) & (fbits(D.y) | (fbits(t.y) & ~fbits(q.y))));
+        }
       }
     }
-    const bool f0 = (int)(acc[0] | dead[0]) >= 0, f1 = (int)(acc[1] | dead[1]) >= 0;
-    if (f0 || f1) {
-      if (f0) best[0] = slow_closest_general(best[0], pairs, g, N, ox[0], oy[0], oz[0], dx[0], dy[0], dz[0], d64, gS2, sph64, src[0]);
-      if (f1) best[1] = slow_closest_general(best[1], pairs, g, N, ox[1], oy[1], oz[1], dx[1], dy[1], dz[1], d64, gS2, sph64, src[1]);
+    unsigned f[2] = {flagged_bits(h[0], np, live[0]), flagged_bits(h[1], np, live[1])};
+    while (__any_sync(kFull, (f[0] | f[1]) != 0u)) {
+      if ((f[0] | f[1]) != 0u) {
+        const int r = f[0] ? 0 : 1;
+        const unsigned fr = RT_SEL(r, f);
+        const int bit = 31 - __clz(fr);
+        const int pi = p0 + np - 1 - bit;
+        if (r) f[1] = fr & ~(1u << bit); else f[0] = fr & ~(1u << bit);
+        const Best b = slow_closest_general(RT_SEL(r, best), pairs, pi, N, RT_SEL(r, ox), RT_SEL(r, oy), RT_SEL(r, oz), RT_SEL(r, dx),
+                                            RT_SEL(r, dy), RT_SEL(r, dz), d64, gS2, sph64, RT_SEL(r, src));
+        if (r) best[1] = b; else best[0] = b;
+      }
     }
   }
 }
@@ -456,11 +490,11 @@ __device__ __forceinline__ void closest_general(const float4 *__restrict__ pairs
 // (include/scene.h:70-85):   occluded  <=>  (-EPS < s2 <= so)  or  (s2 > so and -EPS < s1 <= so).
 // self[r] / cosl[r]: the sphere the point lies on and n.light_dir there -- on its lit side that
 // sphere cannot occlude (the shadow origin is outside it and moving away), so it is skipped cheaply.
-__device__ __forceinline__ void shadow_light(const Tab T, int ngroups, int light, const float (&dx)[2], const float (&dy)[2],
+__device__ __forceinline__ void shadow_light(const Tab T, int npairs, int light, const float (&dx)[2], const float (&dy)[2],
                                              const float (&dz)[2], const float (&so)[2], const bool (&want)[2],
                                              const int (&self)[2], const float (&cosl)[2], const d3 (&p64)[2], float d64,
                                              const double4 *sph64, bool (&occ)[2], int &n_fp64) {
-  unsigned dead[2] = {want[0] ? 0u : kSign, want[1] ? 0u : kSign};
+  bool open[2] = {want[0], want[1]};                 // still undecided
   occ[0] = occ[1] = false;
   const float2 dx2[2] = {make_float2(dx[0], dx[0]), make_float2(dx[1], dx[1])};
   const float2 dy2[2] = {make_float2(dy[0], dy[0]), make_float2(dy[1], dy[1])};
@@ -471,28 +505,34 @@ __device__ __forceinline__ void shadow_light(const Tab T, int ngroups, int light
     m[r] = __fmaf_ru(1.9073486e-6f, so[r] + kEps, 1e-7f);     // 2^-19 |L-p|: covers the FP32 length error
     cut[r] = want[r] ? so[r] + m[r] : -3.0e38f;               // nothing farther from the light can matter
   }
-  const float wcut = wmaxf(fmaxf(cut[0], cut[1]));
+  float wcut = wmaxf(fmaxf(cut[0], cut[1]));
 #pragma unroll 1
-  for (int g = 0; g < ngroups; g++) {
-    const float gm = T.gmin[g];
-    if (gm > wcut) break;
-    if (gm > cut[0]) dead[0] = kSign;
-    if (gm > cut[1]) dead[1] = kSign;
-    unsigned acc0, acc1;
-    group_test_shared(T.pairs, g, dx2, dy2, dz2, acc0, acc1);
-    const bool f0 = (int)(acc0 | dead[0]) >= 0, f1 = (int)(acc1 | dead[1]) >= 0;
-    if (__any_sync(kFull, f0 || f1)) {                // warp-uniform: the vote below needs every lane
-      if (f0) {
-        const int rc = slow_shadow(T.pairs, T.perm, g, dx[0], dy[0], dz[0], so[0], m[0], self[0], cosl[0], p64[0], light, d64, sph64);
-        n_fp64 += rc >> 1;
-        if (rc & 1) { occ[0] = true; dead[0] = kSign; }
+  for (int p0 = 0; p0 < npairs; p0 += kChunkPairs) {
+    if (T.gmin[p0 / kGroupPairs] > wcut) break;
+    const int np = min(kChunkPairs, npairs - p0);
+    unsigned h0, h1;
+    chunk_test_shared(T.pairs, p0, np, dx2, dy2, dz2, h0, h1);
+    unsigned f[2] = {flagged_bits(h0, np, open[0]), flagged_bits(h1, np, open[1])};
+    if (__any_sync(kFull, (f[0] | f[1]) != 0u)) {
+      while (__any_sync(kFull, (f[0] | f[1]) != 0u)) {
+        if ((f[0] | f[1]) != 0u) {
+          const int r = f[0] ? 0 : 1;
+          const unsigned fr = RT_SEL(r, f);
+          const int bit = 31 - __clz(fr);
+          const int pi = p0 + np - 1 - bit;
+          unsigned rest = fr & ~(1u << bit);
+          if (!(T.gmin[pi / kGroupPairs] > RT_SEL(r, cut))) {
+            const int rc = slow_shadow(T.pairs, T.perm, pi, RT_SEL(r, dx), RT_SEL(r, dy), RT_SEL(r, dz), RT_SEL(r, so), RT_SEL(r, m),
+                                       RT_SEL(r, self), RT_SEL(r, cosl), RT_SEL(r, p64), light, d64, sph64);
+            n_fp64 += rc >> 1;
+            if (rc & 1) { rest = 0u; if (r) { occ[1] = true; open[1] = false; } else { occ[0] = true; open[0] = false; } }
+          } else {
+            rest = 0u;                                // sorted: everything after this pair is farther still
+          }
+          if (r) f[1] = rest; else f[0] = rest;
+        }
       }
-      if (f1) {
-        const int rc = slow_shadow(T.pairs, T.perm, g, dx[1], dy[1], dz[1], so[1], m[1], self[1], cosl[1], p64[1], light, d64, sph64);
-        n_fp64 += rc >> 1;
-        if (rc & 1) { occ[1] = true; dead[1] = kSign; }
-      }
-      if (__all_sync(kFull, (dead[0] & dead[1]) != 0u)) break;     // every ray of the warp is decided
+      wcut = wmaxf(fmaxf(open[0] ? cut[0] : -3.0e38f, open[1] ? cut[1] : -3.0e38f));   // decided rays stop holding the warp
     }
   }
 }
@@ -563,7 +603,7 @@ __device__ __forceinline__ void shade_hits(const FastArgs &a, const unsigned cha
           cosl[r] = -(nx[r] * dx[r] + ny[r] * dy[r] + nz[r] * dz[r]);         // n . light_dir
         }
       }
-      shadow_light(tab_at(tabs_base, a, first_light_table + l), a.ngroups, l, dx, dy, dz, so, hit, idx, cosl, p, a.d64,
+      shadow_light(tab_at(tabs_base, a, first_light_table + l), a.npairs, l, dx, dy, dz, so, hit, idx, cosl, p, a.d64,
                    a.r.sph64, occ, n_fp64);
 #pragma unroll
       for (int r = 0; r < 2; r++) {
@@ -683,7 +723,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_primary(const FastArgs a) {
     Best best[2];
     best_init(best[0]); best_init(best[1]);
     const RaySrc src[2] = {{a.r.su, a.r.sv, x, j[0], nullptr}, {a.r.su, a.r.sv, x, j[1], nullptr}};
-    closest_shared(cam, a.ngroups, dx, dy, dz, live, a.d64, a.r.sph64, src, best);
+    closest_shared(cam, a.npairs, dx, dy, dz, live, a.d64, a.r.sph64, src, best);
 
     bool hit[2], final_[2], cont[2];
     int idx[2];
@@ -789,7 +829,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_bounce(const FastArgs a) {
     for (int level = a.level;; level++) {
       Best best[2];
       best_init(best[0]); best_init(best[1]);
-      closest_general(gen, a.ngroups, a.N, ox, oy, oz, dx, dy, dz, live, a.d64, a.gS2, a.g_dtmax, a.r.sph64, src, best);
+      closest_general(gen, a.npairs, a.N, ox, oy, oz, dx, dy, dz, live, a.d64, a.gS2, a.g_dtmax, a.r.sph64, src, best);
       bool hit[2], final_[2], cont[2];
       int idx[2];
       d3 o64[2], d64v[2];
