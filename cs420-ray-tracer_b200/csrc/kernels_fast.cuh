@@ -522,7 +522,21 @@ __device__ __forceinline__ void shadow_light(const Tab T, int npairs, int light,
           const int pi = p0 + np - 1 - bit;
           unsigned rest = fr & ~(1u << bit);
           if (!(T.gmin[pi / kGroupPairs] > RT_SEL(r, cut))) {
-            const int rc = slow_shadow(T.pairs, T.perm, pi, RT_SEL(r, dx), RT_SEL(r, dy), RT_SEL(r, dz), RT_SEL(r, so), RT_SEL(r, m),
+            // The sphere the point lies on is flagged by nearly every query (its surface passes through
+            // the point).  On its lit side it cannot occlude: then only its pair partner matters, and
+            // that one is re-tested here, inline, before paying for the out-of-line refinement.
+            const int i0 = T.perm[2 * pi], i1 = T.perm[2 * pi + 1], sf = RT_SEL(r, self);
+            bool need = true;
+            if ((i0 == sf || i1 == sf) && RT_SEL(r, cosl) > 1e-3f) {
+              const bool h = i0 == sf;               // partner = the other half of the pair
+              const float4 A = T.pairs[2 * pi], B = T.pairs[2 * pi + 1];
+              float tca, Dp;
+              shared_origin_eval(h ? A.y : A.x, h ? A.w : A.z, h ? B.y : B.x, h ? B.w : B.z, RT_SEL(r, dx), RT_SEL(r, dy),
+                                 RT_SEL(r, dz), tca, Dp);
+              need = (h ? i1 : i0) >= 0 && Dp >= 0.0f;
+            }
+            int rc = 0;
+            if (need) rc = slow_shadow(T.pairs, T.perm, pi, RT_SEL(r, dx), RT_SEL(r, dy), RT_SEL(r, dz), RT_SEL(r, so), RT_SEL(r, m),
                                        RT_SEL(r, self), RT_SEL(r, cosl), RT_SEL(r, p64), light, d64, sph64);
             n_fp64 += rc >> 1;
             if (rc & 1) { rest = 0u; if (r) { occ[1] = true; open[1] = false; } else { occ[0] = true; open[0] = false; } }
@@ -805,8 +819,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_bounce(const FastArgs a) {
   int n_fp64 = 0;
   RayRec *qin = a.q_in;
   for (;;) {
+    // level 1: 64 rays per fetch (two per lane); tail: 32 (one per lane -- it is latency bound, the
+    // SMs are mostly empty there, so shorter per-warp chains beat packed arithmetic)
+    constexpr unsigned kRaysPerFetch = kTail ? 32u : 64u;
     const int chunk = warp_fetch(a.chunk_counter);
-    if ((unsigned)chunk * 64u >= nq) break;
+    if ((unsigned)chunk * kRaysPerFetch >= nq) break;
     bool live[2];
     unsigned qi[2], pix[2];
     float ox[2], oy[2], oz[2], dx[2], dy[2], dz[2];
@@ -814,8 +831,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_bounce(const FastArgs a) {
 #pragma unroll
     for (int r = 0; r < 2; r++) {
       // the two rays of a lane are neighbours in the queue (coherent)
-      qi[r] = (unsigned)chunk * 64u + 2u * lane + r;
-      live[r] = qi[r] < nq;
+      qi[r] = kTail ? (unsigned)chunk * 32u + lane : (unsigned)chunk * 64u + 2u * lane + r;
+      live[r] = qi[r] < nq && !(kTail && r == 1);
       ox[r] = oy[r] = oz[r] = dx[r] = dy[r] = dz[r] = 0.f; wt[r] = cr[r] = cg[r] = cb[r] = 0.f; pix[r] = 0;
       if (live[r]) {
         const RayRec &q = qin[qi[r]];
