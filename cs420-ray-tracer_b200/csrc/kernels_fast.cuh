@@ -56,7 +56,7 @@ struct FastArgs {
   const unsigned char *tabs;  // (1+L) shared-origin tables (tstride bytes each: pairs | gmin | perm), then the general table
   int npairs, ngroups;        // npairs is a multiple of kGroupPairs; ngroups = npairs / kGroupPairs
   int N, L;
-  unsigned tstride, gmin_off, perm_off;
+  unsigned tstride, gmin_off, perm_off, inv_off;
   unsigned stage_bytes;       // bytes this kernel stages into shared memory
   float d64;                  // absolute slack covering FP64 rounding / geometry (delta64)
   float gS2;                  // squared radius bound S^2 of the recentred scene (general filter)
@@ -76,6 +76,7 @@ struct Tab {
   const float4 *pairs;   // 2 float4 per pair: (x0,x1,y0,y1) (z0,z1,w0,w1)
   const float *gmin;     // per group of 8 spheres: lower bound of |oc| - r over the group (ascending)
   const int *perm;       // original sphere index per sorted slot, -1 = padding
+  const int *inv;        // sorted slot of each original sphere index
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -152,6 +153,7 @@ __device__ __forceinline__ Tab tab_at(const unsigned char *base, const FastArgs 
   T.pairs = reinterpret_cast<const float4 *>(p);
   T.gmin = reinterpret_cast<const float *>(p + a.gmin_off);
   T.perm = reinterpret_cast<const int *>(p + a.perm_off);
+  T.inv = reinterpret_cast<const int *>(p + a.inv_off);
   return T;
 }
 
@@ -299,7 +301,7 @@ __device__ __noinline__ Best slow_closest_shared(Best b, const float4 *pairs, co
 
 // returns bit 0 = an occluder was found in this pair, bits 1.. = FP64 evaluations spent
 __device__ __noinline__ int slow_shadow(const float4 *pairs, const int *perm, int pi, float dx, float dy, float dz, float so, float m,
-                                        int self, float cosl, d3 p64, int light, float d64, const double4 *sph64) {
+                                        int self, float cosl, const double *p3, int light, float d64, const double4 *sph64) {
   const float so_lo = so - m, so_hi = so + m, e_lo = -kEps - m, e_hi = -kEps + m;
   const float4 A = pairs[2 * pi], B = pairs[2 * pi + 1];
   int n64 = 0, found = 0;
@@ -320,7 +322,7 @@ __device__ __noinline__ int slow_shadow(const float4 *pairs, const int *perm, in
       if (yes) { found = 1; break; }
     }
     n64++;
-    if (exact_shadow_sphere(sph64, i, p64, light)) { found = 1; break; }
+    if (exact_shadow_sphere(sph64, i, rtx::mk(p3[0], p3[1], p3[2]), light)) { found = 1; break; }
   }
   return found | (n64 << 1);
 }
@@ -386,8 +388,6 @@ __device__ __forceinline__ unsigned flagged_bits(unsigned hist, int np, bool liv
   return live ? (~hist & pm) : 0u;
 }
 
-#define RT_SEL(r, a) ((r) ? a[1] : a[0])
-
 // ---------------------------------------------------------------------------------------------
 // CLOSEST HIT, shared origin (camera table, sorted by nearest-point distance).  Two rays per lane.
 __device__ __forceinline__ void closest_shared(const Tab T, int npairs, const float (&dx)[2], const float (&dy)[2],
@@ -403,20 +403,19 @@ __device__ __forceinline__ void closest_shared(const Tab T, int npairs, const fl
     const int np = min(kChunkPairs, npairs - p0);
     unsigned h0, h1;
     chunk_test_shared(T.pairs, p0, np, dx2, dy2, dz2, h0, h1);
-    unsigned f[2] = {flagged_bits(h0, np, live[0]), flagged_bits(h1, np, live[1])};
+    const unsigned f[2] = {flagged_bits(h0, np, live[0]), flagged_bits(h1, np, live[1])};
     if (__any_sync(kFull, (f[0] | f[1]) != 0u)) {
       // drain: every lane resolves its own flagged pairs, nearest first, one per iteration
-      while (__any_sync(kFull, (f[0] | f[1]) != 0u)) {
-        if ((f[0] | f[1]) != 0u) {
-          const int r = f[0] ? 0 : 1;
-          const unsigned fr = RT_SEL(r, f);
-          const int bit = 31 - __clz(fr);
-          const int pi = p0 + np - 1 - bit;
-          if (r) f[1] = fr & ~(1u << bit); else f[0] = fr & ~(1u << bit);
-          Best b = RT_SEL(r, best);
-          if (!(T.gmin[pi / kGroupPairs] > b.hi)) {
-            b = slow_closest_shared(b, T.pairs, T.perm, pi, RT_SEL(r, dx), RT_SEL(r, dy), RT_SEL(r, dz), d64, sph64, RT_SEL(r, src));
-            if (r) best[1] = b; else best[0] = b;
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        unsigned fr = f[r];
+        while (__any_sync(kFull, fr != 0u)) {
+          if (fr != 0u) {
+            const int bit = 31 - __clz(fr);
+            const int pi = p0 + np - 1 - bit;
+            fr &= ~(1u << bit);
+            if (T.gmin[pi / kGroupPairs] > best[r].hi) fr = 0u;       // sorted: the rest is farther still
+            else best[r] = slow_closest_shared(best[r], T.pairs, T.perm, pi, dx[r], dy[r], dz[r], d64, sph64, src[r]);
           }
         }
       }
@@ -467,17 +466,16 @@ __device__ __forceinline__ void closest_general(const float4 *__restrict__ pairs
         }
       }
     }
-    unsigned f[2] = {flagged_bits(h[0], np, live[0]), flagged_bits(h[1], np, live[1])};
-    while (__any_sync(kFull, (f[0] | f[1]) != 0u)) {
-      if ((f[0] | f[1]) != 0u) {
-        const int r = f[0] ? 0 : 1;
-        const unsigned fr = RT_SEL(r, f);
-        const int bit = 31 - __clz(fr);
-        const int pi = p0 + np - 1 - bit;
-        if (r) f[1] = fr & ~(1u << bit); else f[0] = fr & ~(1u << bit);
-        const Best b = slow_closest_general(RT_SEL(r, best), pairs, pi, N, RT_SEL(r, ox), RT_SEL(r, oy), RT_SEL(r, oz), RT_SEL(r, dx),
-                                            RT_SEL(r, dy), RT_SEL(r, dz), d64, gS2, sph64, RT_SEL(r, src));
-        if (r) best[1] = b; else best[0] = b;
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      unsigned fr = flagged_bits(h[r], np, live[r]);
+      while (__any_sync(kFull, fr != 0u)) {
+        if (fr != 0u) {
+          const int bit = 31 - __clz(fr);
+          const int pi = p0 + np - 1 - bit;
+          fr &= ~(1u << bit);
+          best[r] = slow_closest_general(best[r], pairs, pi, N, ox[r], oy[r], oz[r], dx[r], dy[r], dz[r], d64, gS2, sph64, src[r]);
+        }
       }
     }
   }
@@ -488,11 +486,13 @@ __device__ __forceinline__ void closest_general(const float4 *__restrict__ pairs
 // THE LIGHT TOWARDS the shaded point, so = distance light -> shadow-ray origin (= |L-p| - EPS), both
 // FP32 with known error.  Roots s are measured from the light; the reference's t = so - s
 // (include/scene.h:70-85):   occluded  <=>  (-EPS < s2 <= so)  or  (s2 > so and -EPS < s1 <= so).
-// self[r] / cosl[r]: the sphere the point lies on and n.light_dir there -- on its lit side that
-// sphere cannot occlude (the shadow origin is outside it and moving away), so it is skipped cheaply.
+// self[r] / cosl[r]: the sphere the point lies on and n.light_dir there.  Its surface passes through
+// the point, so the filter flags it for every query; on its lit side it cannot occlude (the shadow
+// origin is outside it and moving away), so its flag is cleared up front unless its pair partner
+// is a candidate too.  p64[r] points at the exact hit point (only read if FP64 is needed).
 __device__ __forceinline__ void shadow_light(const Tab T, int npairs, int light, const float (&dx)[2], const float (&dy)[2],
                                              const float (&dz)[2], const float (&so)[2], const bool (&want)[2],
-                                             const int (&self)[2], const float (&cosl)[2], const d3 (&p64)[2], float d64,
+                                             const int (&self)[2], const float (&cosl)[2], const double *const (&p64)[2], float d64,
                                              const double4 *sph64, bool (&occ)[2], int &n_fp64) {
   bool open[2] = {want[0], want[1]};                 // still undecided
   occ[0] = occ[1] = false;
@@ -500,10 +500,12 @@ __device__ __forceinline__ void shadow_light(const Tab T, int npairs, int light,
   const float2 dy2[2] = {make_float2(dy[0], dy[0]), make_float2(dy[1], dy[1])};
   const float2 dz2[2] = {make_float2(dz[0], dz[0]), make_float2(dz[1], dz[1])};
   float m[2], cut[2];
+  int sslot[2];
 #pragma unroll
   for (int r = 0; r < 2; r++) {
     m[r] = __fmaf_ru(1.9073486e-6f, so[r] + kEps, 1e-7f);     // 2^-19 |L-p|: covers the FP32 length error
     cut[r] = want[r] ? so[r] + m[r] : -3.0e38f;               // nothing farther from the light can matter
+    sslot[r] = (want[r] && cosl[r] > 1e-3f) ? T.inv[self[r]] : -1;
   }
   float wcut = wmaxf(fmaxf(cut[0], cut[1]));
 #pragma unroll 1
@@ -513,37 +515,34 @@ __device__ __forceinline__ void shadow_light(const Tab T, int npairs, int light,
     unsigned h0, h1;
     chunk_test_shared(T.pairs, p0, np, dx2, dy2, dz2, h0, h1);
     unsigned f[2] = {flagged_bits(h0, np, open[0]), flagged_bits(h1, np, open[1])};
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      const int sp = sslot[r] >> 1;                  // pair of the lit self sphere (or -1)
+      if (sp >= p0 && sp < p0 + np) {
+        const int ph = (sslot[r] & 1) ^ 1;           // partner = the other half of the pair
+        const float4 A = T.pairs[2 * sp], B = T.pairs[2 * sp + 1];
+        float tca, Dp;
+        shared_origin_eval(ph ? A.y : A.x, ph ? A.w : A.z, ph ? B.y : B.x, ph ? B.w : B.z, dx[r], dy[r], dz[r], tca, Dp);
+        if (!(Dp >= 0.0f)) f[r] &= ~(1u << (p0 + np - 1 - sp));
+      }
+    }
     if (__any_sync(kFull, (f[0] | f[1]) != 0u)) {
-      while (__any_sync(kFull, (f[0] | f[1]) != 0u)) {
-        if ((f[0] | f[1]) != 0u) {
-          const int r = f[0] ? 0 : 1;
-          const unsigned fr = RT_SEL(r, f);
-          const int bit = 31 - __clz(fr);
-          const int pi = p0 + np - 1 - bit;
-          unsigned rest = fr & ~(1u << bit);
-          if (!(T.gmin[pi / kGroupPairs] > RT_SEL(r, cut))) {
-            // The sphere the point lies on is flagged by nearly every query (its surface passes through
-            // the point).  On its lit side it cannot occlude: then only its pair partner matters, and
-            // that one is re-tested here, inline, before paying for the out-of-line refinement.
-            const int i0 = T.perm[2 * pi], i1 = T.perm[2 * pi + 1], sf = RT_SEL(r, self);
-            bool need = true;
-            if ((i0 == sf || i1 == sf) && RT_SEL(r, cosl) > 1e-3f) {
-              const bool h = i0 == sf;               // partner = the other half of the pair
-              const float4 A = T.pairs[2 * pi], B = T.pairs[2 * pi + 1];
-              float tca, Dp;
-              shared_origin_eval(h ? A.y : A.x, h ? A.w : A.z, h ? B.y : B.x, h ? B.w : B.z, RT_SEL(r, dx), RT_SEL(r, dy),
-                                 RT_SEL(r, dz), tca, Dp);
-              need = (h ? i1 : i0) >= 0 && Dp >= 0.0f;
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        unsigned fr = f[r];
+        while (__any_sync(kFull, fr != 0u)) {
+          if (fr != 0u) {
+            const int bit = 31 - __clz(fr);
+            const int pi = p0 + np - 1 - bit;
+            fr &= ~(1u << bit);
+            if (T.gmin[pi / kGroupPairs] > cut[r]) {
+              fr = 0u;                                // sorted: everything after this pair is farther still
+            } else {
+              const int rc = slow_shadow(T.pairs, T.perm, pi, dx[r], dy[r], dz[r], so[r], m[r], self[r], cosl[r], p64[r], light, d64, sph64);
+              n_fp64 += rc >> 1;
+              if (rc & 1) { occ[r] = true; open[r] = false; fr = 0u; }
             }
-            int rc = 0;
-            if (need) rc = slow_shadow(T.pairs, T.perm, pi, RT_SEL(r, dx), RT_SEL(r, dy), RT_SEL(r, dz), RT_SEL(r, so), RT_SEL(r, m),
-                                       RT_SEL(r, self), RT_SEL(r, cosl), RT_SEL(r, p64), light, d64, sph64);
-            n_fp64 += rc >> 1;
-            if (rc & 1) { rest = 0u; if (r) { occ[1] = true; open[1] = false; } else { occ[0] = true; open[0] = false; } }
-          } else {
-            rest = 0u;                                // sorted: everything after this pair is farther still
           }
-          if (r) f[1] = rest; else f[0] = rest;
         }
       }
       wcut = wmaxf(fmaxf(open[0] ? cut[0] : -3.0e38f, open[1] ? cut[1] : -3.0e38f));   // decided rays stop holding the warp
@@ -617,7 +616,8 @@ __device__ __forceinline__ void shade_hits(const FastArgs &a, const unsigned cha
           cosl[r] = -(nx[r] * dx[r] + ny[r] * dy[r] + nz[r] * dz[r]);         // n . light_dir
         }
       }
-      shadow_light(tab_at(tabs_base, a, first_light_table + l), a.npairs, l, dx, dy, dz, so, hit, idx, cosl, p, a.d64,
+      const double *const pp[2] = {&p[0].x, &p[1].x};
+      shadow_light(tab_at(tabs_base, a, first_light_table + l), a.npairs, l, dx, dy, dz, so, hit, idx, cosl, pp, a.d64,
                    a.r.sph64, occ, n_fp64);
 #pragma unroll
       for (int r = 0; r < 2; r++) {

@@ -1,0 +1,378 @@
+// kernels_wave.cuh -- the phase-separated wavefront used for reflection levels 0 and 1.
+//
+// Profiling the fused per-warp pipeline (kernels_fast.cuh) showed that the packed FP32 sphere
+// loops were only ~30 % of its time: the rest was FP64 geometry, shading and slow-path code that
+// is latency bound at 16 warps/SM and too large for the instruction cache.  Here every phase is its
+// own lean kernel, so the loops run at high occupancy with a few-hundred-instruction footprint and
+// every warp is full because each phase consumes a COMPACTED queue:
+//
+//   k_closest0   pixels      -> camera-table loop -> exact t -> hit point / normal -> HitRec queue
+//                               (sky pixels are final: staged per warp, 128-bit stores)
+//   k_closest1   RayRec queue-> general-origin loop -> same, for reflected rays (misses are final)
+//   k_shadow     HitRec x light items (light-major, two hits per lane) -> light-table loop ->
+//                               one occlusion byte per (light, hit)
+//   k_shade      HitRec      -> Phong (include/scene.h:89-121) -> final pixel, or the reflected
+//                               ray appended to the RayRec queue (warp-ballot compaction)
+// Levels >= 2 hold a few percent of the rays; they run in the fused tail kernel of
+// kernels_fast.cuh (k_bounce<.., true>), one launch for all remaining levels.
+#ifndef RT_KERNELS_WAVE_CUH
+#define RT_KERNELS_WAVE_CUH
+
+#include "kernels_fast.cuh"
+
+namespace rtf {
+
+struct __align__(16) HitRec {      // 80 bytes
+  double px, py, pz;               // exact FP64 hit point (src/main.cpp:32)
+  float nx, ny, nz;                // unit normal, FP32 copy (colour + lit-side test only)
+  float vx, vy, vz;                // view direction = -ray direction, FP32 (colour only)
+  int idx;                         // sphere index
+  unsigned pix;                    // local pixel index lr*W + x
+  unsigned src;                    // level >= 1: index of the ray in the level's RayRec queue
+  float wt, ar, ag, ab;            // carried weight / colour (front to back)
+  unsigned pad;
+};
+
+struct WaveArgs {
+  FastArgs f;
+  HitRec *hits; unsigned int *hit_count; unsigned hit_cap;
+  unsigned char *occ;              // [L][hit_cap] occlusion bytes
+  unsigned int *work_counter;      // per-launch chunk counter
+};
+
+__device__ __forceinline__ void hit_push(bool want, const HitRec &rec, HitRec *q, unsigned int *count) {
+  const unsigned mk = __ballot_sync(kFull, want);
+  if (mk == 0) return;
+  const int lane = threadIdx.x & 31, leader = __ffs(mk) - 1;
+  unsigned base = 0;
+  if (lane == leader) base = atomicAdd(count, (unsigned)__popc(mk));
+  base = __shfl_sync(kFull, base, leader);
+  if (want) q[base + __popc(mk & ((1u << lane) - 1u))] = rec;
+}
+
+// 32-bit per-thread counters, reduced once per warp at kernel end (cold path, out of line)
+__device__ __noinline__ void flush_counts(unsigned long long *counters, int level, unsigned closest, unsigned hits, unsigned shadow,
+                                          unsigned occluded, unsigned fp64, unsigned violations, unsigned long long n_spheres) {
+  unsigned v[6] = {closest, hits, shadow, occluded, fp64, violations};
+#pragma unroll
+  for (int k = 0; k < 6; k++) v[k] = __reduce_add_sync(kFull, v[k]);
+  if ((threadIdx.x & 31) == 0) {
+    if (v[0]) { atomicAdd(&counters[RT_CNT_CLOSEST], (unsigned long long)v[0]); if (level < 32) atomicAdd(&counters[RT_CNT_ALIVE0 + level], (unsigned long long)v[0]); }
+    if (v[1]) atomicAdd(&counters[RT_CNT_HITS], (unsigned long long)v[1]);
+    if (v[2]) atomicAdd(&counters[RT_CNT_SHADOW], (unsigned long long)v[2]);
+    if (v[3]) atomicAdd(&counters[RT_CNT_OCCLUDED], (unsigned long long)v[3]);
+    if (v[4]) atomicAdd(&counters[RT_CNT_FP64], (unsigned long long)v[4]);
+    if (v[5]) atomicAdd(&counters[RT_CNT_VIOLATIONS], (unsigned long long)v[5]);
+    if (v[0] + v[2]) atomicAdd(&counters[RT_CNT_TESTS], (unsigned long long)(v[0] + v[2]) * n_spheres);
+  }
+}
+
+// src/main.cpp:35,45-48 from the exact hit point and the sphere centre
+__device__ __noinline__ void reflected_ray_from_center(d3 d, d3 p, d3 c, RayRec *rec) {
+  const d3 n = rtx::normal_at(p, c);
+  d3 o2, d2;
+  rtx::reflect_ray(d, p, n, 0.001, o2, d2);
+  rec->ox = o2.x; rec->oy = o2.y; rec->oz = o2.z; rec->dx = d2.x; rec->dy = d2.y; rec->dz = d2.z;
+}
+
+// Exact t of the winner + hit record (out of line: FP64 heavy, once per hit ray)
+__device__ __noinline__ bool finish_hit(const FastArgs &a, Best b, RaySrc src, unsigned pix, unsigned srcidx, float wt, float ar, float ag,
+                                        float ab, HitRec *out, unsigned *viol, unsigned *nfp64) {
+  const ExactRay e = exact_ray(src);
+  double t = b.t;
+  bool ok = b.exact;
+  if (!ok) { (*nfp64)++; ok = exact_sphere(a.r.sph64, b.idx, e.o, e.d, e.a, t) && t < 1e20; }
+  int bi = b.idx;
+  if (!ok) { (*viol)++; bi = exact_bruteforce(a.r.sph64, a.N, e.o, e.d, e.a, t); }
+  if (bi < 0) return false;
+  const HitGeom g = hit_geometry(a.r.sph64, bi, e.o, e.d, t);
+  out->px = g.p.x; out->py = g.p.y; out->pz = g.p.z;
+  out->nx = (float)g.n.x; out->ny = (float)g.n.y; out->nz = (float)g.n.z;
+  out->vx = -(float)e.d.x; out->vy = -(float)e.d.y; out->vz = -(float)e.d.z;   // view_dir = -d up to rounding (src/main.cpp:38)
+  out->idx = bi; out->pix = pix; out->src = srcidx; out->wt = wt; out->ar = ar; out->ag = ag; out->ab = ab; out->pad = 0;
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LEVEL 0 closest hit: each warp pulls 16x4-pixel tiles, two vertically adjacent pixels per lane.
+template <bool kSmem>
+__global__ void __launch_bounds__(kThreads, 3) k_closest0(const WaveArgs w) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const FastArgs &a = w.f;
+  const unsigned char *tabs = a.tabs;
+  if (kSmem) { stage_tables(smem, a.tabs, a.stage_bytes); tabs = smem + kSmemHeader; }
+  const Tab cam = tab_at(tabs, a, 0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char *s_rgb = smem + 64 + warp * (kWTileH * kWTileW * 3);
+  const int W = a.r.W, rows = a.r.bands.local_rows, depth = a.r.max_depth;
+  unsigned c_closest = 0, c_hits = 0, c_fp64 = 0, c_viol = 0;
+  for (;;) {
+    const int tile = warp_fetch(a.tile_counter);
+    if (tile >= a.nwtiles) break;
+    const int tx0 = (tile % a.wtiles_x) * kWTileW, ty0 = (tile / a.wtiles_x) * kWTileH;
+    const int x = tx0 + (lane & 15);
+    int lr[2], j[2];
+    unsigned pix[2];
+    bool live[2];
+    float dx[2], dy[2], dz[2];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      lr[r] = ty0 + (lane >> 4) * 2 + r;
+      live[r] = x < W && lr[r] < rows && depth > 0;
+      j[r] = 0; pix[r] = 0; dx[r] = dy[r] = dz[r] = 0.f;
+      if (x < W && lr[r] < rows) {
+        j[r] = rt_local_to_global_row(a.r.bands, lr[r]);
+        pix[r] = (unsigned)lr[r] * (unsigned)W + (unsigned)x;
+      }
+      if (live[r]) {
+        // include/camera.h:21-22 in FP64 (un-normalised), then an FP32 unit vector for the filter
+        const d3 v = rtx::add(rtx::add(ldc3(g_frame.fwd), rtx::scale(ldc3(g_frame.right), a.r.su[x])),
+                              rtx::scale(ldc3(g_frame.up), a.r.sv[j[r]]));
+        const float fx = (float)v.x, fy = (float)v.y, fz = (float)v.z;
+        const float inv = rsqrtf(fmaf(fz, fz, fmaf(fy, fy, fx * fx)));
+        dx[r] = fx * inv; dy[r] = fy * inv; dz[r] = fz * inv;
+        if (a.r.hit_idx) for (int k = 0; k < depth; k++) a.r.hit_idx[(size_t)pix[r] * depth + k] = -2;
+        if (a.r.shadow_mask) for (int k = 0; k < depth; k++) a.r.shadow_mask[(size_t)pix[r] * depth + k] = 0u;
+      }
+    }
+    Best best[2];
+    best_init(best[0]); best_init(best[1]);
+    const RaySrc src[2] = {{a.r.su, a.r.sv, x, j[0], nullptr}, {a.r.su, a.r.sv, x, j[1], nullptr}};
+    closest_shared(cam, a.npairs, dx, dy, dz, live, a.d64, a.r.sph64, src, best);
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      bool hit = false;
+      HitRec rec;
+      if (live[r]) {
+        c_closest++; c_fp64 += best[r].nfp64;
+        if (best[r].idx >= 0) hit = finish_hit(a, best[r], src[r], pix[r], 0u, 1.0f, 0.f, 0.f, 0.f, &rec, &c_viol, &c_fp64);
+        if (a.r.hit_idx) a.r.hit_idx[(size_t)pix[r] * depth] = hit ? rec.idx : -1;
+      }
+      c_hits += hit;
+      hit_push(hit, rec, w.hits, w.hit_count);
+      // sky (src/main.cpp:26-30) is final now; hit pixels are written by k_shade / later levels
+      const float ts = 0.5f * (dy[r] + 1.0f);
+      const bool sky = live[r] && !hit;
+      unsigned char *q = s_rgb + (((lane >> 4) * 2 + r) * kWTileW + (lane & 15)) * 3;
+      q[0] = (unsigned char)quant8(sky ? (1.0f - ts) + 0.5f * ts : 0.f);
+      q[1] = (unsigned char)quant8(sky ? (1.0f - ts) + 0.7f * ts : 0.f);
+      q[2] = (unsigned char)quant8(sky ? (1.0f - ts) + ts : 0.f);
+    }
+    __syncwarp();
+    if (tx0 + kWTileW <= W && (W & 15) == 0) {
+      // 3 x 16-byte stores per 48-byte row segment (src/main.cpp:84-86 quantiser applied above)
+      if (lane < kWTileH * 3) {
+        const int ty = lane / 3, seg = lane % 3;
+        if (ty0 + ty < rows)
+          *reinterpret_cast<uint4 *>(a.r.rgb + ((size_t)(ty0 + ty) * W + tx0) * 3 + seg * 16) =
+              *reinterpret_cast<const uint4 *>(s_rgb + ty * kWTileW * 3 + seg * 16);
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        if (x < W && lr[r] < rows) {
+          const unsigned char *q = s_rgb + (((lane >> 4) * 2 + r) * kWTileW + (lane & 15)) * 3;
+          unsigned char *o = a.r.rgb + (size_t)pix[r] * 3;
+          o[0] = q[0]; o[1] = q[1]; o[2] = q[2];
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (a.r.counters) flush_counts(a.r.counters, 0, c_closest, c_hits, 0, 0, c_fp64, c_viol, (unsigned long long)a.N);
+}
+
+// ---------------------------------------------------------------------------------------------
+// LEVEL >= 1 closest hit: reflected rays from the RayRec queue, 64 per warp fetch, two per lane.
+template <bool kSmem>
+__global__ void __launch_bounds__(kThreads, 3) k_closest1(const WaveArgs w) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const FastArgs &a = w.f;
+  const unsigned nq = *a.q_in_count;
+  if (nq == 0u) return;
+  // staged: the general table only (it follows the (1+L) shared-origin tables)
+  const unsigned char *tabs = a.tabs + (size_t)(a.L + 1) * a.tstride;
+  if (kSmem) { stage_tables(smem, tabs, a.stage_bytes); tabs = smem + kSmemHeader; }
+  const float4 *gen = reinterpret_cast<const float4 *>(tabs);
+  const int lane = threadIdx.x & 31, depth = a.r.max_depth, level = a.level;
+  unsigned c_closest = 0, c_hits = 0, c_fp64 = 0, c_viol = 0;
+  const RayRec *qin = a.q_in;
+  for (;;) {
+    const int chunk = warp_fetch(w.work_counter);
+    if ((unsigned)chunk * 64u >= nq) break;
+    bool live[2];
+    unsigned qi[2], pix[2];
+    float ox[2], oy[2], oz[2], dx[2], dy[2], dz[2], wt[2], cr[2], cg[2], cb[2];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      qi[r] = (unsigned)chunk * 64u + 2u * lane + r;
+      live[r] = qi[r] < nq;
+      ox[r] = oy[r] = oz[r] = dx[r] = dy[r] = dz[r] = 0.f; wt[r] = cr[r] = cg[r] = cb[r] = 0.f; pix[r] = 0;
+      if (live[r]) {
+        const RayRec &q = qin[qi[r]];
+        ox[r] = (float)(q.ox - a.c0[0]); oy[r] = (float)(q.oy - a.c0[1]); oz[r] = (float)(q.oz - a.c0[2]);
+        dx[r] = (float)q.dx; dy[r] = (float)q.dy; dz[r] = (float)q.dz;
+        pix[r] = q.pix; wt[r] = q.wt; cr[r] = q.ar; cg[r] = q.ag; cb[r] = q.ab;
+      }
+    }
+    Best best[2];
+    best_init(best[0]); best_init(best[1]);
+    const RaySrc src[2] = {{nullptr, nullptr, 0, 0, qin + qi[0]}, {nullptr, nullptr, 0, 0, qin + qi[1]}};
+    closest_general(gen, a.npairs, a.N, ox, oy, oz, dx, dy, dz, live, a.d64, a.gS2, a.g_dtmax, a.r.sph64, src, best);
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      bool hit = false;
+      HitRec rec;
+      if (live[r]) {
+        c_closest++; c_fp64 += best[r].nfp64;
+        if (best[r].idx >= 0) hit = finish_hit(a, best[r], src[r], pix[r], qi[r], wt[r], cr[r], cg[r], cb[r], &rec, &c_viol, &c_fp64);
+        if (a.r.hit_idx) a.r.hit_idx[(size_t)pix[r] * depth + level] = hit ? rec.idx : -1;
+        if (!hit) {                                // sky through the mirror(s): the pixel is final
+          const float ts = 0.5f * (dy[r] + 1.0f);
+          unsigned char *o = a.r.rgb + (size_t)pix[r] * 3;
+          o[0] = (unsigned char)quant8(cr[r] + wt[r] * ((1.0f - ts) + 0.5f * ts));
+          o[1] = (unsigned char)quant8(cg[r] + wt[r] * ((1.0f - ts) + 0.7f * ts));
+          o[2] = (unsigned char)quant8(cb[r] + wt[r] * ((1.0f - ts) + ts));
+        }
+      }
+      c_hits += hit;
+      hit_push(hit, rec, w.hits, w.hit_count);
+    }
+  }
+  if (a.r.counters) flush_counts(a.r.counters, level, c_closest, c_hits, 0, 0, c_fp64, c_viol, (unsigned long long)a.N);
+}
+
+// ---------------------------------------------------------------------------------------------
+// SHADOW: items = (light, hit), light-major.  A warp fetch is 64 consecutive hits of ONE light; a
+// lane owns hits 2*lane and 2*lane+1 of the chunk.  Output: one occlusion byte per item.
+template <bool kSmem>
+__global__ void __launch_bounds__(kThreads, 3) k_shadow(const WaveArgs w) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const FastArgs &a = w.f;
+  const unsigned nh = *w.hit_count;
+  if (nh == 0u || a.L == 0) return;
+  // staged: the L light tables
+  const unsigned char *tabs = a.tabs + a.tstride;
+  if (kSmem) { stage_tables(smem, tabs, a.stage_bytes); tabs = smem + kSmemHeader; }
+  const int lane = threadIdx.x & 31;
+  const unsigned chunks_per_light = (nh + 63u) / 64u, nchunks = chunks_per_light * (unsigned)a.L;
+  unsigned c_fp64 = 0;
+  for (;;) {
+    const unsigned chunk = (unsigned)warp_fetch(w.work_counter);
+    if (chunk >= nchunks) break;
+    const int l = (int)(chunk / chunks_per_light);
+    const unsigned h0 = (chunk % chunks_per_light) * 64u + 2u * lane;
+    const d3 lp = ldc3(g_frame.light_pos[l]);
+    bool want[2], occ[2];
+    int self[2];
+    float dx[2], dy[2], dz[2], so[2], cosl[2];
+    const double *pp[2];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      want[r] = h0 + r < nh;
+      dx[r] = dy[r] = dz[r] = 0.f; so[r] = 0.f; cosl[r] = 0.f; self[r] = -1; pp[r] = &w.hits[0].px;
+      if (want[r]) {
+        const HitRec &hr = w.hits[h0 + r];
+        pp[r] = &hr.px;
+        self[r] = hr.idx;
+        // direction light -> point: FP64 difference, FP32 normalisation (error <= 12u, see filter_math.cuh)
+        const d3 wv = rtx::sub(rtx::mk(hr.px, hr.py, hr.pz), lp);
+        const float wx = (float)wv.x, wy = (float)wv.y, wz = (float)wv.z;
+        const float l2 = fmaf(wz, wz, fmaf(wy, wy, wx * wx));
+        const float inv = rsqrtf(l2);
+        dx[r] = wx * inv; dy[r] = wy * inv; dz[r] = wz * inv;
+        so[r] = l2 * inv - kEps;
+        cosl[r] = -(hr.nx * dx[r] + hr.ny * dy[r] + hr.nz * dz[r]);       // n . light_dir
+      }
+    }
+    int n64 = 0;
+    const double *const ppc[2] = {pp[0], pp[1]};
+    shadow_light(tab_at(tabs, a, l), a.npairs, l, dx, dy, dz, so, want, self, cosl, ppc, a.d64, a.r.sph64, occ, n64);
+    c_fp64 += (unsigned)n64;
+    // two adjacent bytes per lane -> one 16-bit store when both exist
+    unsigned char *o = w.occ + (size_t)l * w.hit_cap + h0;
+    if (want[1]) *reinterpret_cast<unsigned short *>(o) = (unsigned short)((occ[0] ? 1u : 0u) | (occ[1] ? 256u : 0u));
+    else if (want[0]) o[0] = occ[0] ? 1 : 0;
+  }
+  if (a.r.counters) flush_counts(a.r.counters, 99, 0, 0, 0, 0, c_fp64, 0, 0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// SHADE: one hit per lane.  include/scene.h:89-121 in FP32 with the occlusion bytes of k_shadow, then
+// src/main.cpp:43-55: final pixel, or the reflected ray (exact FP64) appended to the RayRec queue.
+__global__ void __launch_bounds__(kThreads, 4) k_shade(const WaveArgs w) {
+  const FastArgs &a = w.f;
+  const unsigned nh = *w.hit_count;
+  if (nh == 0u) return;
+  const int lane = threadIdx.x & 31, level = a.level, L = a.L, W = a.r.W;
+  unsigned c_shadow = 0, c_occ = 0;
+  for (;;) {
+    const unsigned chunk = (unsigned)warp_fetch(w.work_counter);
+    if (chunk * 32u >= nh) break;
+    const unsigned h = chunk * 32u + lane;
+    const bool live = h < nh;
+    bool cont = false;
+    RayRec rec;
+    if (live) {
+      const HitRec hr = w.hits[h];
+      const float4 m = __ldg(&a.r.mat[hr.idx]);
+      const float2 mx = __ldg(&a.r.matx[hr.idx]);
+      float sr = g_frame.ambient[0] * m.x, sg = g_frame.ambient[1] * m.y, sb = g_frame.ambient[2] * m.z;
+      unsigned smask = 0;
+      for (int l = 0; l < L; l++) {
+        c_shadow++;
+        if (w.occ[(size_t)l * w.hit_cap + h]) { c_occ++; if (l < 32) smask |= 1u << l; continue; }
+        // light_dir = normalized(light - point): FP64 difference, FP32 normalisation (colour only)
+        const float wx = (float)(g_frame.light_pos[l][0] - hr.px), wy = (float)(g_frame.light_pos[l][1] - hr.py),
+                    wz = (float)(g_frame.light_pos[l][2] - hr.pz);
+        const float inv = rsqrtf(fmaf(wz, wz, fmaf(wy, wy, wx * wx)));
+        const float lx = wx * inv, ly = wy * inv, lz = wz * inv;
+        const float nl = hr.nx * lx + hr.ny * ly + hr.nz * lz;
+        const float kd = (1.0f - m.w) * fmaxf(0.0f, nl);
+        // reflect(-light_dir, n) = -l + 2 (l.n) n   (include/vec3.h:31-33)
+        const float rx = 2.0f * nl * hr.nx - lx, ry = 2.0f * nl * hr.ny - ly, rz = 2.0f * nl * hr.nz - lz;
+        const float rdv = fmaxf(0.0f, rx * hr.vx + ry * hr.vy + rz * hr.vz);
+        const float spec = 0.5f * (mx.x == 0.0f ? 1.0f : __powf(rdv, mx.x));
+        sr += g_frame.light_col[l][0] * spec + m.x * kd;
+        sg += g_frame.light_col[l][1] * spec + m.y * kd;
+        sb += g_frame.light_col[l][2] * spec + m.z * kd;
+      }
+      if (a.r.shadow_mask) a.r.shadow_mask[(size_t)hr.pix * a.r.max_depth + level] = smask;
+      float cr = hr.ar, cg = hr.ag, cb = hr.ab, wt = hr.wt;
+      bool final_ = true;
+      if (mx.y > 0.5f) {                          // reflectivity > 0, decided in double on the host
+        const float refl = m.w, k = wt * (1.0f - refl);
+        cr += k * sr; cg += k * sg; cb += k * sb;
+        wt *= refl;
+        if (level + 1 < a.r.max_depth) {
+          // exact reflected ray: the incoming direction is re-derived from its source, the normal from
+          // the exact hit point (src/main.cpp:35,45-48)
+          RaySrc src;
+          if (level == 0) {
+            const int lr = (int)(hr.pix / (unsigned)W), x = (int)(hr.pix - (unsigned)lr * (unsigned)W);
+            src = RaySrc{a.r.su, a.r.sv, x, rt_local_to_global_row(a.r.bands, lr), nullptr};
+          } else {
+            src = RaySrc{nullptr, nullptr, 0, 0, a.q_in + hr.src};
+          }
+          const ExactRay e = exact_ray(src);
+          const double4 s = ld_sph64(&a.r.sph64[hr.idx]);
+          const d3 p = rtx::mk(hr.px, hr.py, hr.pz);
+          reflected_ray_from_center(e.d, p, rtx::mk(s.x, s.y, s.z), &rec);
+          rec.pix = hr.pix; rec.wt = wt; rec.ar = cr; rec.ag = cg; rec.ab = cb; rec.pad = 0;
+          cont = true; final_ = false;
+        }
+      } else {
+        cr += wt * sr; cg += wt * sg; cb += wt * sb;
+      }
+      if (final_) {
+        unsigned char *o = a.r.rgb + (size_t)hr.pix * 3;
+        o[0] = (unsigned char)quant8(cr); o[1] = (unsigned char)quant8(cg); o[2] = (unsigned char)quant8(cb);
+      }
+    }
+    queue_push(cont, rec, a.q_out, a.q_out_count);
+  }
+  if (a.r.counters) flush_counts(a.r.counters, 99, 0, 0, c_shadow, c_occ, 0, 0, (unsigned long long)a.N);
+}
+
+}  // namespace rtf
+#endif

@@ -11,6 +11,7 @@ __constant__ RtFrameConst g_frame;
 
 #include "kernels_exact.cuh"
 #include "kernels_fast.cuh"
+#include "kernels_wave.cuh"
 
 cudaError_t rtk_set_frame_const(const RtFrameConst *host_const, cudaStream_t stream) {
   return cudaMemcpyToSymbolAsync(g_frame, host_const, sizeof(RtFrameConst), 0, cudaMemcpyHostToDevice, stream);
@@ -48,9 +49,10 @@ inline float float_down(double x) {             // largest float <= x
 
 int rtk_fast_init(int) {
   const int big = 227 * 1024;
-  RTK_TRY(cudaFuncSetAttribute(rtf::k_primary<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  RTK_TRY(cudaFuncSetAttribute(rtf::k_bounce<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   RTK_TRY(cudaFuncSetAttribute(rtf::k_bounce<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  RTK_TRY(cudaFuncSetAttribute(rtf::k_closest0<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  RTK_TRY(cudaFuncSetAttribute(rtf::k_closest1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  RTK_TRY(cudaFuncSetAttribute(rtf::k_shadow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   return 0;
 }
 
@@ -100,8 +102,9 @@ int rtk_fast_build_scene(RtFastScene *fs, const double *sph, int N, const RtFram
   const unsigned pairs_bytes = (unsigned)npairs * 32u;
   const unsigned gmin_bytes = ((unsigned)ngroups * 4u + 15u) & ~15u;
   const unsigned perm_bytes = (unsigned)nslots * 4u;
-  fs->gmin_off = pairs_bytes; fs->perm_off = pairs_bytes + gmin_bytes;
-  fs->tstride = pairs_bytes + gmin_bytes + perm_bytes;
+  const unsigned inv_bytes = (((unsigned)(N > 0 ? N : 1)) * 4u + 15u) & ~15u;
+  fs->gmin_off = pairs_bytes; fs->perm_off = pairs_bytes + gmin_bytes; fs->inv_off = fs->perm_off + perm_bytes;
+  fs->tstride = pairs_bytes + gmin_bytes + perm_bytes + inv_bytes;
   fs->bytes_primary = (size_t)(L + 1) * fs->tstride;
   fs->bytes_bounce = (size_t)L * fs->tstride + pairs_bytes;
   const size_t total = (size_t)(L + 1) * fs->tstride + pairs_bytes;
@@ -117,6 +120,7 @@ int rtk_fast_build_scene(RtFastScene *fs, const double *sph, int N, const RtFram
     float4 *pairs = reinterpret_cast<float4 *>(base);
     float *gmin = reinterpret_cast<float *>(base + fs->gmin_off);
     int *perm = reinterpret_cast<int *>(base + fs->perm_off);
+    int *inv = reinterpret_cast<int *>(base + fs->inv_off);
     const double *O = t == 0 ? f->cam_pos : f->light_pos[t - 1];
     for (int i = 0; i < N; i++) {
       const double *s = sph + (size_t)i * 10;
@@ -134,6 +138,7 @@ int rtk_fast_build_scene(RtFastScene *fs, const double *sph, int N, const RtFram
       const double E = 2.01 * std::ldexp(1.0, -20) * oc2 * (1 + 1e-9) + delta64;
       put(pairs, slot, (float)x, (float)y, (float)z, float_up(E - (oc2 - s[3] * s[3])));
       perm[slot] = i;
+      inv[i] = slot;
     }
     for (int g = 0; g < ngroups; g++) {
       const int slot = g * 2 * rtf::kGroupPairs;
@@ -164,68 +169,115 @@ void rtk_fast_free_scene(RtFastScene *fs) {
 }
 
 void rtk_fast_free_work(RtFastWork *w) {
-  cudaFree(w->queue[0]); cudaFree(w->queue[1]); cudaFree(w->ctl);
-  w->queue[0] = w->queue[1] = nullptr; w->ctl = nullptr; w->queue_cap = 0;
+  cudaFree(w->queue[0]); cudaFree(w->queue[1]); cudaFree(w->ctl); cudaFree(w->hits); cudaFree(w->occ);
+  w->queue[0] = w->queue[1] = nullptr; w->ctl = nullptr; w->hits = nullptr; w->occ = nullptr;
+  w->queue_cap = w->hit_cap = w->occ_bytes = 0;
 }
+
+namespace {
+// persistent grid: as many CTAs as can be resident
+template <typename K>
+int resident_grid(K kernel, size_t smem, int num_sms) {
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, rtf::kThreads, smem) != cudaSuccess || nb < 1) nb = 1;
+  return nb * num_sms;
+}
+// control words (u32): [0] tile counter; per level k: [1+k] tail chunk counter, [8+k] shadow, [16+k] shade,
+// [24+k] closest work counters, [32+k] hits of level k, [64+k] rays entering level k
+enum { CTL_TILE = 0, CTL_TAIL = 1, CTL_SHADOW = 8, CTL_SHADE = 16, CTL_CLOSEST = 24, CTL_HITS = 32, CTL_RAYS = 64 };
+}  // namespace
 
 int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork *w, cudaStream_t stream,
                     cudaEvent_t after_level0) {
   const size_t npix = (size_t)args.W * args.bands.local_rows;
   if (!w->ctl) RTK_TRY(cudaMalloc(&w->ctl, kCtlWords * sizeof(unsigned int)));
-  if (args.max_depth > 1 && w->queue_cap < npix) {
+  const size_t hit_cap = (npix + 63) & ~(size_t)63;
+  if (w->hit_cap < hit_cap || w->occ_bytes < hit_cap * (size_t)(fs->L > 0 ? fs->L : 1) || (args.max_depth > 1 && w->queue_cap < npix)) {
     RTK_TRY(cudaStreamSynchronize(stream));
-    cudaFree(w->queue[0]); cudaFree(w->queue[1]);
-    w->queue[0] = w->queue[1] = nullptr; w->queue_cap = 0;
-    RTK_TRY(cudaMalloc(&w->queue[0], npix * sizeof(rtf::RayRec)));
-    RTK_TRY(cudaMalloc(&w->queue[1], npix * sizeof(rtf::RayRec)));
-    w->queue_cap = npix;
+    cudaFree(w->queue[0]); cudaFree(w->queue[1]); cudaFree(w->hits); cudaFree(w->occ);
+    w->queue[0] = w->queue[1] = nullptr; w->hits = nullptr; w->occ = nullptr; w->queue_cap = w->hit_cap = w->occ_bytes = 0;
+    RTK_TRY(cudaMalloc(&w->hits, hit_cap * sizeof(rtf::HitRec)));
+    w->occ_bytes = hit_cap * (size_t)(fs->L > 0 ? fs->L : 1);
+    RTK_TRY(cudaMalloc(&w->occ, w->occ_bytes));
+    w->hit_cap = hit_cap;
+    if (args.max_depth > 1) {
+      RTK_TRY(cudaMalloc(&w->queue[0], npix * sizeof(rtf::RayRec)));
+      RTK_TRY(cudaMalloc(&w->queue[1], npix * sizeof(rtf::RayRec)));
+      w->queue_cap = npix;
+    }
   }
   RTK_TRY(cudaMemsetAsync(w->ctl, 0, kCtlWords * sizeof(unsigned int), stream));
+  if (args.max_depth <= 0) RTK_TRY(cudaMemsetAsync(args.rgb, 0, npix * 3, stream));   // src/main.cpp:17-18: black
 
-  rtf::FastArgs a;
-  memset(&a, 0, sizeof(a));
+  rtf::WaveArgs wa;
+  memset(&wa, 0, sizeof(wa));
+  rtf::FastArgs &a = wa.f;
   a.r = args;
   a.tabs = (const unsigned char *)fs->tabs;
   a.npairs = fs->npairs; a.ngroups = fs->ngroups; a.N = fs->N; a.L = fs->L;
-  a.tstride = fs->tstride; a.gmin_off = fs->gmin_off; a.perm_off = fs->perm_off;
+  a.tstride = fs->tstride; a.gmin_off = fs->gmin_off; a.perm_off = fs->perm_off; a.inv_off = fs->inv_off;
   a.d64 = fs->d64; a.gS2 = fs->gS2; a.g_dtmax = fs->g_dtmax;
   for (int k = 0; k < 3; k++) a.c0[k] = fs->c0[k];
   a.wtiles_x = (args.W + rtf::kWTileW - 1) / rtf::kWTileW;
   a.nwtiles = a.wtiles_x * ((args.bands.local_rows + rtf::kWTileH - 1) / rtf::kWTileH);
-  a.tile_counter = w->ctl;
-  const size_t big = fs->bytes_primary > fs->bytes_bounce ? fs->bytes_primary : fs->bytes_bounce;
-  a.tables_in_smem = big <= kMaxSmemTables;
-  const int ctas_per_sm = (a.tables_in_smem && rtf::kSmemHeader + big > 110 * 1024) ? 1 : 2;
-  const int max_grid = w->num_sms * ctas_per_sm;
+  a.tile_counter = w->ctl + CTL_TILE;
+  wa.hits = (rtf::HitRec *)w->hits; wa.hit_cap = (unsigned)w->hit_cap; wa.occ = w->occ;
+  const size_t pairs_bytes = (size_t)fs->npairs * 32;
+  const size_t light_bytes = (size_t)fs->L * fs->tstride;
+  const bool in_smem = fs->bytes_bounce <= kMaxSmemTables && fs->bytes_primary <= kMaxSmemTables;
+  a.tables_in_smem = in_smem;
+  int launches = 0;
 
-  a.level = 0;
-  a.q_out = (rtf::RayRec *)w->queue[0];
-  a.q_out_count = w->ctl + 64 + 1;
-  a.stage_bytes = (unsigned)fs->bytes_primary;
-  size_t smem = rtf::kSmemHeader + (a.tables_in_smem ? fs->bytes_primary : 0);
-  const int cta_tiles = (a.nwtiles + rtf::kWarps - 1) / rtf::kWarps;
-  int grid = cta_tiles < max_grid ? cta_tiles : max_grid;
-  if (a.tables_in_smem) rtf::k_primary<true><<<grid, rtf::kThreads, smem, stream>>>(a);
-  else rtf::k_primary<false><<<grid, rtf::kThreads, smem, stream>>>(a);
-  int launches = 1;
-  if (after_level0) RTK_TRY(cudaEventRecord(after_level0, stream));
-  a.stage_bytes = (unsigned)fs->bytes_bounce;
-  smem = rtf::kSmemHeader + (a.tables_in_smem ? fs->bytes_bounce : 0);
-  // level 1: one compacted wavefront; levels >= 2: one tail launch that follows rays to termination
-  for (int level = 1; level < args.max_depth && level <= 2; level++) {
+  for (int level = 0; level < args.max_depth && level < 2; level++) {
+    a.level = level;
+    wa.hit_count = w->ctl + CTL_HITS + level;
+    // ---- closest hit
+    if (level == 0) {
+      a.stage_bytes = fs->tstride;
+      const size_t smem = rtf::kSmemHeader + (in_smem ? a.stage_bytes : 0);
+      const int cta_tiles = (a.nwtiles + rtf::kWarps - 1) / rtf::kWarps;
+      if (in_smem) { int g = resident_grid(rtf::k_closest0<true>, smem, w->num_sms); rtf::k_closest0<true><<<g < cta_tiles ? g : cta_tiles, rtf::kThreads, smem, stream>>>(wa); }
+      else { int g = resident_grid(rtf::k_closest0<false>, smem, w->num_sms); rtf::k_closest0<false><<<g < cta_tiles ? g : cta_tiles, rtf::kThreads, smem, stream>>>(wa); }
+    } else {
+      a.q_in = (rtf::RayRec *)w->queue[(level - 1) & 1];
+      a.q_in_count = w->ctl + CTL_RAYS + level;
+      wa.work_counter = w->ctl + CTL_CLOSEST + level;
+      a.stage_bytes = (unsigned)pairs_bytes;
+      const size_t smem = rtf::kSmemHeader + (in_smem ? a.stage_bytes : 0);
+      if (in_smem) rtf::k_closest1<true><<<resident_grid(rtf::k_closest1<true>, smem, w->num_sms), rtf::kThreads, smem, stream>>>(wa);
+      else rtf::k_closest1<false><<<resident_grid(rtf::k_closest1<false>, smem, w->num_sms), rtf::kThreads, smem, stream>>>(wa);
+    }
+    launches++;
+    // ---- shadow queries: (light, hit) items
+    if (fs->L > 0) {
+      wa.work_counter = w->ctl + CTL_SHADOW + level;
+      a.stage_bytes = (unsigned)light_bytes;
+      const size_t smem = rtf::kSmemHeader + (in_smem ? a.stage_bytes : 0);
+      if (in_smem) rtf::k_shadow<true><<<resident_grid(rtf::k_shadow<true>, smem, w->num_sms), rtf::kThreads, smem, stream>>>(wa);
+      else rtf::k_shadow<false><<<resident_grid(rtf::k_shadow<false>, smem, w->num_sms), rtf::kThreads, smem, stream>>>(wa);
+      launches++;
+    }
+    // ---- shade + continuation
+    wa.work_counter = w->ctl + CTL_SHADE + level;
+    a.q_out = (rtf::RayRec *)w->queue[level & 1];
+    a.q_out_count = w->ctl + CTL_RAYS + level + 1;
+    rtf::k_shade<<<resident_grid(rtf::k_shade, 0, w->num_sms), rtf::kThreads, 0, stream>>>(wa);
+    launches++;
+    if (level == 0 && after_level0) RTK_TRY(cudaEventRecord(after_level0, stream));
+  }
+  // ---- levels >= 2: one fused launch that follows every remaining ray to termination
+  if (args.max_depth > 2) {
+    const int level = 2;
     a.level = level;
     a.q_in = (rtf::RayRec *)w->queue[(level - 1) & 1];
-    a.q_in_count = w->ctl + 64 + level;
+    a.q_in_count = w->ctl + CTL_RAYS + level;
     a.q_out = (rtf::RayRec *)w->queue[level & 1];
-    a.q_out_count = w->ctl + 64 + level + 1;
-    a.chunk_counter = w->ctl + 1 + level;
-    if (level == 1) {
-      if (a.tables_in_smem) rtf::k_bounce<true, false><<<max_grid, rtf::kThreads, smem, stream>>>(a);
-      else rtf::k_bounce<false, false><<<max_grid, rtf::kThreads, smem, stream>>>(a);
-    } else {
-      if (a.tables_in_smem) rtf::k_bounce<true, true><<<max_grid, rtf::kThreads, smem, stream>>>(a);
-      else rtf::k_bounce<false, true><<<max_grid, rtf::kThreads, smem, stream>>>(a);
-    }
+    a.q_out_count = w->ctl + CTL_RAYS + level + 1;
+    a.chunk_counter = w->ctl + CTL_TAIL + level;
+    a.stage_bytes = (unsigned)fs->bytes_bounce;
+    const size_t smem = rtf::kSmemHeader + (in_smem ? fs->bytes_bounce : 0);
+    if (in_smem) rtf::k_bounce<true, true><<<resident_grid(rtf::k_bounce<true, true>, smem, w->num_sms), rtf::kThreads, smem, stream>>>(a);
+    else rtf::k_bounce<false, true><<<resident_grid(rtf::k_bounce<false, true>, smem, w->num_sms), rtf::kThreads, smem, stream>>>(a);
     launches++;
   }
   cudaError_t e = cudaGetLastError();

@@ -17,7 +17,7 @@ struct RtFastScene {
   int N, L, npairs, ngroups;
   void *tabs;             // device: (1+L) shared-origin tables (pairs | gmin | perm), then the general table
   unsigned tstride;       // bytes per shared-origin table
-  unsigned gmin_off, perm_off;
+  unsigned gmin_off, perm_off, inv_off;
   size_t bytes_primary;   // staged by k_primary: (1+L) * tstride
   size_t bytes_bounce;    // staged by k_bounce : L * tstride + npairs * 32
   float d64;              // absolute FP64/geometry slack (delta64)
@@ -30,6 +30,9 @@ struct RtFastWork {
   void *queue[2];        // reflected-ray records, ping-pong between levels
   size_t queue_cap;      // records per queue
   unsigned int *ctl;     // device control words: tile counter, per-level chunk counters, queue counts
+  void *hits;            // HitRec queue of the current level (kernels_wave.cuh)
+  unsigned char *occ;    // [L][hit_cap] occlusion bytes of the current level
+  size_t hit_cap, occ_bytes;
 };
 int rtk_fast_init(int device);
 int rtk_fast_build_scene(RtFastScene *fs, const double *spheres, int N, const RtFrameConst *frame, cudaStream_t stream);
