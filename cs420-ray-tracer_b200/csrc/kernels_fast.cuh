@@ -76,7 +76,7 @@ struct Tab {
   const float4 *pairs;   // 2 float4 per pair: (x0,x1,y0,y1) (z0,z1,w0,w1)
   const float *gmin;     // per group of 8 spheres: lower bound of |oc| - r over the group (ascending)
   const int *perm;       // original sphere index per sorted slot, -1 = padding
-  const int *inv;        // sorted slot of each original sphere index
+  const int *inv;        // sorted slot of each original sphere index; bit 30: the origin is strictly outside it
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -505,7 +505,7 @@ __device__ __forceinline__ void shadow_light(const Tab T, int npairs, int light,
   for (int r = 0; r < 2; r++) {
     m[r] = __fmaf_ru(1.9073486e-6f, so[r] + kEps, 1e-7f);     // 2^-19 |L-p|: covers the FP32 length error
     cut[r] = want[r] ? so[r] + m[r] : -3.0e38f;               // nothing farther from the light can matter
-    sslot[r] = (want[r] && cosl[r] > 1e-3f) ? T.inv[self[r]] : -1;
+    sslot[r] = (want[r] && cosl[r] > 1e-3f) ? (T.inv[self[r]] & 0x3fffffff) : -1;
   }
   float wcut = wmaxf(fmaxf(cut[0], cut[1]));
 #pragma unroll 1

@@ -243,8 +243,14 @@ __global__ void __launch_bounds__(kThreads, 3) k_closest1(const WaveArgs w) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// SHADOW: items = (light, hit), light-major.  A warp fetch is 64 consecutive hits of ONE light; a
-// lane owns hits 2*lane and 2*lane+1 of the chunk.  Output: one occlusion byte per item.
+// SHADOW: a warp fetch is 64 consecutive hits; a lane owns hits 2*lane and 2*lane+1 of the chunk and
+// runs their shadow queries against every light in turn (the hit records are read once).
+// Output: one occlusion byte per (light, hit).
+//
+// Self-shadow shortcut: if the point faces away from the light (n.l < -4 EPS / r) the shadow-ray
+// origin p + l*EPS lies strictly inside the sphere the point is on, so the reference's query returns
+// that sphere's exit distance, which is shorter than the distance to any light outside that sphere
+// (flag bit 30 of Tab::inv, set on the host): occluded, no table walk needed.
 template <bool kSmem>
 __global__ void __launch_bounds__(kThreads, 3) k_shadow(const WaveArgs w) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -255,44 +261,63 @@ __global__ void __launch_bounds__(kThreads, 3) k_shadow(const WaveArgs w) {
   const unsigned char *tabs = a.tabs + a.tstride;
   if (kSmem) { stage_tables(smem, tabs, a.stage_bytes); tabs = smem + kSmemHeader; }
   const int lane = threadIdx.x & 31;
-  const unsigned chunks_per_light = (nh + 63u) / 64u, nchunks = chunks_per_light * (unsigned)a.L;
+  const unsigned nchunks = (nh + 63u) / 64u;
   unsigned c_fp64 = 0;
   for (;;) {
     const unsigned chunk = (unsigned)warp_fetch(w.work_counter);
     if (chunk >= nchunks) break;
-    const int l = (int)(chunk / chunks_per_light);
-    const unsigned h0 = (chunk % chunks_per_light) * 64u + 2u * lane;
-    const d3 lp = ldc3(g_frame.light_pos[l]);
-    bool want[2], occ[2];
+    const unsigned h0 = chunk * 64u + 2u * lane;
+    bool have[2];
     int self[2];
-    float dx[2], dy[2], dz[2], so[2], cosl[2];
+    float nx[2], ny[2], nz[2], backthr[2];
+    d3 p[2];
     const double *pp[2];
 #pragma unroll
     for (int r = 0; r < 2; r++) {
-      want[r] = h0 + r < nh;
-      dx[r] = dy[r] = dz[r] = 0.f; so[r] = 0.f; cosl[r] = 0.f; self[r] = -1; pp[r] = &w.hits[0].px;
-      if (want[r]) {
+      have[r] = h0 + r < nh;
+      self[r] = -1; nx[r] = ny[r] = nz[r] = 0.f; backthr[r] = 0.f; p[r] = rtx::mk(0, 0, 0); pp[r] = &w.hits[0].px;
+      if (have[r]) {
         const HitRec &hr = w.hits[h0 + r];
         pp[r] = &hr.px;
+        p[r] = rtx::mk(hr.px, hr.py, hr.pz);
         self[r] = hr.idx;
-        // direction light -> point: FP64 difference, FP32 normalisation (error <= 12u, see filter_math.cuh)
-        const d3 wv = rtx::sub(rtx::mk(hr.px, hr.py, hr.pz), lp);
-        const float wx = (float)wv.x, wy = (float)wv.y, wz = (float)wv.z;
-        const float l2 = fmaf(wz, wz, fmaf(wy, wy, wx * wx));
-        const float inv = rsqrtf(l2);
-        dx[r] = wx * inv; dy[r] = wy * inv; dz[r] = wz * inv;
-        so[r] = l2 * inv - kEps;
-        cosl[r] = -(hr.nx * dx[r] + hr.ny * dy[r] + hr.nz * dz[r]);       // n . light_dir
+        nx[r] = hr.nx; ny[r] = hr.ny; nz[r] = hr.nz;
+        backthr[r] = -fmaxf(4.0f * kEps * rsqrtf((float)a.r.sph64[hr.idx].w), 1e-4f);     // -4 EPS / r
       }
     }
-    int n64 = 0;
     const double *const ppc[2] = {pp[0], pp[1]};
-    shadow_light(tab_at(tabs, a, l), a.npairs, l, dx, dy, dz, so, want, self, cosl, ppc, a.d64, a.r.sph64, occ, n64);
-    c_fp64 += (unsigned)n64;
-    // two adjacent bytes per lane -> one 16-bit store when both exist
-    unsigned char *o = w.occ + (size_t)l * w.hit_cap + h0;
-    if (want[1]) *reinterpret_cast<unsigned short *>(o) = (unsigned short)((occ[0] ? 1u : 0u) | (occ[1] ? 256u : 0u));
-    else if (want[0]) o[0] = occ[0] ? 1 : 0;
+    for (int l = 0; l < a.L; l++) {
+      const Tab T = tab_at(tabs, a, l);
+      const d3 lp = ldc3(g_frame.light_pos[l]);
+      bool want[2], occ[2], shortcut[2];
+      float dx[2], dy[2], dz[2], so[2], cosl[2];
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        dx[r] = dy[r] = dz[r] = 0.f; so[r] = 0.f; cosl[r] = 0.f; shortcut[r] = false;
+        if (have[r]) {
+          // direction light -> point: FP64 difference, FP32 normalisation (error <= 12u, see filter_math.cuh)
+          const d3 wv = rtx::sub(p[r], lp);
+          const float wx = (float)wv.x, wy = (float)wv.y, wz = (float)wv.z;
+          const float l2 = fmaf(wz, wz, fmaf(wy, wy, wx * wx));
+          const float inv = rsqrtf(l2);
+          dx[r] = wx * inv; dy[r] = wy * inv; dz[r] = wz * inv;
+          so[r] = l2 * inv - kEps;
+          cosl[r] = -(nx[r] * dx[r] + ny[r] * dy[r] + nz[r] * dz[r]);       // n . light_dir
+          shortcut[r] = cosl[r] < backthr[r] && (T.inv[self[r]] & 0x40000000) != 0;
+        }
+        want[r] = have[r] && !shortcut[r];
+      }
+      int n64 = 0;
+      if (__any_sync(kFull, want[0] || want[1]))
+        shadow_light(T, a.npairs, l, dx, dy, dz, so, want, self, cosl, ppc, a.d64, a.r.sph64, occ, n64);
+      else occ[0] = occ[1] = false;
+      c_fp64 += (unsigned)n64;
+      // two adjacent bytes per lane -> one 16-bit store when both exist
+      const unsigned o0 = (occ[0] || shortcut[0]) ? 1u : 0u, o1 = (occ[1] || shortcut[1]) ? 256u : 0u;
+      unsigned char *o = w.occ + (size_t)l * w.hit_cap + h0;
+      if (have[1]) *reinterpret_cast<unsigned short *>(o) = (unsigned short)(o0 | o1);
+      else if (have[0]) o[0] = (unsigned char)o0;
+    }
   }
   if (a.r.counters) flush_counts(a.r.counters, 99, 0, 0, 0, 0, c_fp64, 0, 0);
 }

@@ -138,7 +138,8 @@ int rtk_fast_build_scene(RtFastScene *fs, const double *sph, int N, const RtFram
       const double E = 2.01 * std::ldexp(1.0, -20) * oc2 * (1 + 1e-9) + delta64;
       put(pairs, slot, (float)x, (float)y, (float)z, float_up(E - (oc2 - s[3] * s[3])));
       perm[slot] = i;
-      inv[i] = slot;
+      // bit 30: the table origin (camera / light) is strictly outside sphere i, with a generous margin
+      inv[i] = slot | ((oc2 - s[3] * s[3] > 1e-6 * (oc2 + s[3] * s[3]) + 4.0 * delta64) ? 0x40000000 : 0);
     }
     for (int g = 0; g < ngroups; g++) {
       const int slot = g * 2 * rtf::kGroupPairs;
