@@ -29,7 +29,7 @@ class RtError(RuntimeError):
 
 class RtStats(C.Structure):
     _fields_ = [
-        ("ms_device", C.c_double), ("ms_host", C.c_double), ("ms_level0", C.c_double),
+        ("ms_device", C.c_double), ("ms_host", C.c_double), ("ms_level0", C.c_double), ("ms_closest0", C.c_double), ("ms_shadow0", C.c_double),
         ("closest_queries", C.c_uint64), ("hits", C.c_uint64),
         ("shadow_queries", C.c_uint64), ("occluded", C.c_uint64),
         ("alive", C.c_uint64 * RT_MAX_LEVELS),

@@ -46,7 +46,7 @@ extern "C" int rt_device_count(void) {
 struct rt_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm[3] = {nullptr, nullptr, nullptr};
   int mode = 0;          // 0 fast, 1 exact
   int counters_on = 1;
   // scene
@@ -101,7 +101,7 @@ extern "C" int rt_create(int device, rt_ctx **out) {
   RT_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   RT_CUDA(cudaEventCreate(&c->ev0));
   RT_CUDA(cudaEventCreate(&c->ev1));
-  RT_CUDA(cudaEventCreate(&c->evm));
+  for (int k = 0; k < 3; k++) RT_CUDA(cudaEventCreate(&c->evm[k]));
   RT_CUDA(cudaMalloc(&c->d_counters, RT_CNT_TOTAL * sizeof(unsigned long long)));
   int r = rtk_fast_init(c->device);
   if (r != 0) return rt_fail(RT_ERR_CUDA, std::string("rt_create: kernel attribute setup failed: ") + cudaGetErrorString((cudaError_t)-r));
@@ -129,7 +129,7 @@ extern "C" void rt_destroy(rt_ctx *c) {
   rtk_fast_free_work(&c->work);
   cudaFree(c->d_su); cudaFree(c->d_sv);
   cudaFree(c->d_rgb); cudaFree(c->d_hit); cudaFree(c->d_mask); cudaFree(c->d_counters);
-  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->evm);
+  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); for (int k = 0; k < 3; k++) cudaEventDestroy(c->evm[k]);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -302,7 +302,7 @@ static int render_common(rt_ctx *c, int W, int H, int depth, int band_h, int ran
   int launches = 0;
   if (rows > 0) {
     if (c->mode == 1) launches = rtk_launch_exact(a, stream);
-    else launches = rtk_launch_fast(a, &c->fast, &c->work, stream, stats ? c->evm : nullptr);
+    else launches = rtk_launch_fast(a, &c->fast, &c->work, stream, (stats && depth > 0) ? c->evm : nullptr);
     if (launches < 0) return rt_fail(RT_ERR_CUDA, std::string("render: launch failed: ") + cudaGetErrorString((cudaError_t)-launches));
   }
   if (stats) {
@@ -313,7 +313,14 @@ static int render_common(rt_ctx *c, int W, int H, int depth, int band_h, int ran
     memset(stats, 0, sizeof(*stats));
     stats->ms_device = ms;
     stats->ms_level0 = ms;
-    if (rows > 0 && c->mode == 0) { float m0 = 0; RT_CUDA(cudaEventElapsedTime(&m0, c->ev0, c->evm)); stats->ms_level0 = m0; }
+    stats->ms_closest0 = ms; stats->ms_shadow0 = 0;
+    if (rows > 0 && c->mode == 0 && depth > 0) {
+      float m0 = 0, m1 = 0, m2 = 0;
+      RT_CUDA(cudaEventElapsedTime(&m0, c->ev0, c->evm[0]));
+      RT_CUDA(cudaEventElapsedTime(&m1, c->evm[0], c->evm[1]));
+      RT_CUDA(cudaEventElapsedTime(&m2, c->ev0, c->evm[2]));
+      stats->ms_closest0 = m0; stats->ms_shadow0 = m1; stats->ms_level0 = m2;
+    }
     stats->kernel_launches = launches;
     stats->rows_rendered = rows;
     if (want_counters) {

@@ -189,7 +189,7 @@ enum { CTL_TILE = 0, CTL_TAIL = 1, CTL_SHADOW = 8, CTL_SHADE = 16, CTL_CLOSEST =
 }  // namespace
 
 int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork *w, cudaStream_t stream,
-                    cudaEvent_t after_level0) {
+                    const cudaEvent_t *marks) {
   const size_t npix = (size_t)args.W * args.bands.local_rows;
   if (!w->ctl) RTK_TRY(cudaMalloc(&w->ctl, kCtlWords * sizeof(unsigned int)));
   const size_t hit_cap = (npix + 63) & ~(size_t)63;
@@ -249,6 +249,7 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
       else rtf::k_closest1<false><<<resident_grid(rtf::k_closest1<false>, smem, w->num_sms), rtf::kThreads, smem, stream>>>(wa);
     }
     launches++;
+    if (level == 0 && marks) RTK_TRY(cudaEventRecord(marks[0], stream));
     // ---- shadow queries: (light, hit) items
     if (fs->L > 0) {
       wa.work_counter = w->ctl + CTL_SHADOW + level;
@@ -258,13 +259,14 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
       else rtf::k_shadow<false><<<resident_grid(rtf::k_shadow<false>, smem, w->num_sms), rtf::kThreads, smem, stream>>>(wa);
       launches++;
     }
+    if (level == 0 && marks) RTK_TRY(cudaEventRecord(marks[1], stream));
     // ---- shade + continuation
     wa.work_counter = w->ctl + CTL_SHADE + level;
     a.q_out = (rtf::RayRec *)w->queue[level & 1];
     a.q_out_count = w->ctl + CTL_RAYS + level + 1;
     rtf::k_shade<<<resident_grid(rtf::k_shade, 0, w->num_sms), rtf::kThreads, 0, stream>>>(wa);
     launches++;
-    if (level == 0 && after_level0) RTK_TRY(cudaEventRecord(after_level0, stream));
+    if (level == 0 && marks) RTK_TRY(cudaEventRecord(marks[2], stream));
   }
   // ---- levels >= 2: one fused launch that follows every remaining ray to termination
   if (args.max_depth > 2) {

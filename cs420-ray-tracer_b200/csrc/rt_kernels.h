@@ -38,9 +38,9 @@ int rtk_fast_init(int device);
 int rtk_fast_build_scene(RtFastScene *fs, const double *spheres, int N, const RtFrameConst *frame, cudaStream_t stream);
 void rtk_fast_free_scene(RtFastScene *fs);
 void rtk_fast_free_work(RtFastWork *w);
-// `after_level0` (may be null) is recorded right after the level-0 kernel.
+// marks (may be null): 3 events recorded after the level-0 closest-hit, shadow and shade kernels.
 int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork *w, cudaStream_t stream,
-                    cudaEvent_t after_level0);
+                    const cudaEvent_t *marks);
 
 // FP32 FFMA issue peak of `device`, measured live (FLOP/s); used by bench.py as the roofline
 // denominator because MEASURED_PEAKS.json carries no FP32 entry.  Returns <0: -cudaError.

@@ -60,7 +60,9 @@ typedef struct rt_scene rt_scene;   /* opaque: a parsed scene file (host memory 
 typedef struct rt_stats {
   double ms_device;             /* CUDA-event time of the kernels of this call on the stream   */
   double ms_host;               /* host wall-clock of the whole call, copies included          */
-  double ms_level0;             /* device time of the level-0 (camera-ray) kernel alone        */
+  double ms_level0;             /* device time of reflection level 0 (camera rays + their shadows + shading) */
+  double ms_closest0;           /* ... of which: the camera-ray closest-hit kernel             */
+  double ms_shadow0;            /* ... of which: the level-0 shadow kernel (the dominant one)  */
   uint64_t closest_queries;
   uint64_t hits;
   uint64_t shadow_queries;
