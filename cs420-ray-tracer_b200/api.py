@@ -49,7 +49,8 @@ _lib = None
 
 
 def library_path():
-    return os.path.join(HERE, "librt_b200.so")
+    # RTB200_LIB: A/B testing of alternative builds of the same library (never a different backend)
+    return os.environ.get("RTB200_LIB") or os.path.join(HERE, "librt_b200.so")
 
 
 def load_library():

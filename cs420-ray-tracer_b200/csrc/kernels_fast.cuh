@@ -390,19 +390,29 @@ __device__ __forceinline__ unsigned flagged_bits(unsigned hist, int np, bool liv
 
 // ---------------------------------------------------------------------------------------------
 // CLOSEST HIT, shared origin (camera table, sorted by nearest-point distance).  Two rays per lane.
-__device__ __forceinline__ void closest_shared(const Tab T, int npairs, const float (&dx)[2], const float (&dy)[2],
-                                               const float (&dz)[2], const bool (&live)[2], float d64, const double4 *sph64,
-                                               const RaySrc (&src)[2], Best (&best)[2]) {
+// The query is resumable over pair ranges so that a table larger than shared memory can be streamed
+// through it tile by tile: `pairs` is indexed with ABSOLUTE pair numbers (a tile buffer is passed as
+// buffer - 2*first_pair), gmin / perm may live in global memory.
+struct ClosestQ {
+  Best best[2];
+  float wcut;                                        // warp-uniform: farthest cutoff of any live ray
+};
+__device__ __forceinline__ void closest_begin(ClosestQ &q) { best_init(q.best[0]); best_init(q.best[1]); q.wcut = 3.0e38f; }
+
+// returns false once every remaining sphere of the (sorted) table is beyond every ray's best hit
+__device__ __forceinline__ bool closest_shared_range(ClosestQ &q, const float4 *__restrict__ pairs, const float *gmin, const int *perm,
+                                                     int pbeg, int pend, const float (&dx)[2], const float (&dy)[2],
+                                                     const float (&dz)[2], const bool (&live)[2], float d64, const double4 *sph64,
+                                                     const RaySrc (&src)[2]) {
   const float2 dx2[2] = {make_float2(dx[0], dx[0]), make_float2(dx[1], dx[1])};
   const float2 dy2[2] = {make_float2(dy[0], dy[0]), make_float2(dy[1], dy[1])};
   const float2 dz2[2] = {make_float2(dz[0], dz[0]), make_float2(dz[1], dz[1])};
-  float wcut = 3.0e38f;                            // warp-uniform: farthest cutoff of any live ray
 #pragma unroll 1
-  for (int p0 = 0; p0 < npairs; p0 += kChunkPairs) {
-    if (T.gmin[p0 / kGroupPairs] > wcut) break;    // every remaining sphere is beyond every ray's best hit
-    const int np = min(kChunkPairs, npairs - p0);
+  for (int p0 = pbeg; p0 < pend; p0 += kChunkPairs) {
+    if (gmin[p0 / kGroupPairs] > q.wcut) return false;
+    const int np = min(kChunkPairs, pend - p0);
     unsigned h0, h1;
-    chunk_test_shared(T.pairs, p0, np, dx2, dy2, dz2, h0, h1);
+    chunk_test_shared(pairs, p0, np, dx2, dy2, dz2, h0, h1);
     const unsigned f[2] = {flagged_bits(h0, np, live[0]), flagged_bits(h1, np, live[1])};
     if (__any_sync(kFull, (f[0] | f[1]) != 0u)) {
       // drain: every lane resolves its own flagged pairs, nearest first, one per iteration
@@ -414,14 +424,24 @@ __device__ __forceinline__ void closest_shared(const Tab T, int npairs, const fl
             const int bit = 31 - __clz(fr);
             const int pi = p0 + np - 1 - bit;
             fr &= ~(1u << bit);
-            if (T.gmin[pi / kGroupPairs] > best[r].hi) fr = 0u;       // sorted: the rest is farther still
-            else best[r] = slow_closest_shared(best[r], T.pairs, T.perm, pi, dx[r], dy[r], dz[r], d64, sph64, src[r]);
+            if (gmin[pi / kGroupPairs] > q.best[r].hi) fr = 0u;       // sorted: the rest is farther still
+            else q.best[r] = slow_closest_shared(q.best[r], pairs, perm, pi, dx[r], dy[r], dz[r], d64, sph64, src[r]);
           }
         }
       }
-      wcut = wmaxf(fmaxf(live[0] ? best[0].hi : -3.0e38f, live[1] ? best[1].hi : -3.0e38f));
+      q.wcut = wmaxf(fmaxf(live[0] ? q.best[0].hi : -3.0e38f, live[1] ? q.best[1].hi : -3.0e38f));
     }
   }
+  return true;
+}
+
+__device__ __forceinline__ void closest_shared(const Tab T, int npairs, const float (&dx)[2], const float (&dy)[2],
+                                               const float (&dz)[2], const bool (&live)[2], float d64, const double4 *sph64,
+                                               const RaySrc (&src)[2], Best (&best)[2]) {
+  ClosestQ q;
+  closest_begin(q);
+  closest_shared_range(q, T.pairs, T.gmin, T.perm, 0, npairs, dx, dy, dz, live, d64, sph64, src);
+  best[0] = q.best[0]; best[1] = q.best[1];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -490,37 +510,44 @@ __device__ __forceinline__ void closest_general(const float4 *__restrict__ pairs
 // the point, so the filter flags it for every query; on its lit side it cannot occlude (the shadow
 // origin is outside it and moving away), so its flag is cleared up front unless its pair partner
 // is a candidate too.  p64[r] points at the exact hit point (only read if FP64 is needed).
-__device__ __forceinline__ void shadow_light(const Tab T, int npairs, int light, const float (&dx)[2], const float (&dy)[2],
-                                             const float (&dz)[2], const float (&so)[2], const bool (&want)[2],
-                                             const int (&self)[2], const float (&cosl)[2], const double *const (&p64)[2], float d64,
-                                             const double4 *sph64, bool (&occ)[2], int &n_fp64) {
-  bool open[2] = {want[0], want[1]};                 // still undecided
-  occ[0] = occ[1] = false;
+struct ShadowQ {
+  bool open[2], occ[2];                              // still undecided / found an occluder
+  float m[2], cut[2], wcut;
+  int sslot[2];                                      // slot of the lit self sphere in this light's table, or -1
+};
+__device__ __forceinline__ void shadow_begin(ShadowQ &q, const int *inv, const float (&so)[2], const bool (&want)[2],
+                                             const int (&self)[2], const float (&cosl)[2]) {
+#pragma unroll
+  for (int r = 0; r < 2; r++) {
+    q.open[r] = want[r]; q.occ[r] = false;
+    q.m[r] = __fmaf_ru(1.9073486e-6f, so[r] + kEps, 1e-7f);   // 2^-19 |L-p|: covers the FP32 length error
+    q.cut[r] = want[r] ? so[r] + q.m[r] : -3.0e38f;           // nothing farther from the light can matter
+    q.sslot[r] = (want[r] && cosl[r] > 1e-3f) ? (inv[self[r]] & 0x3fffffff) : -1;
+  }
+  q.wcut = wmaxf(fmaxf(q.cut[0], q.cut[1]));
+}
+
+// returns false once the warp needs nothing further from this (sorted) table
+__device__ __forceinline__ bool shadow_range(ShadowQ &q, const float4 *__restrict__ pairs, const float *gmin, const int *perm, int pbeg,
+                                             int pend, int light, const float (&dx)[2], const float (&dy)[2], const float (&dz)[2],
+                                             const float (&so)[2], const int (&self)[2], const float (&cosl)[2],
+                                             const double *const (&p64)[2], float d64, const double4 *sph64, int &n_fp64) {
   const float2 dx2[2] = {make_float2(dx[0], dx[0]), make_float2(dx[1], dx[1])};
   const float2 dy2[2] = {make_float2(dy[0], dy[0]), make_float2(dy[1], dy[1])};
   const float2 dz2[2] = {make_float2(dz[0], dz[0]), make_float2(dz[1], dz[1])};
-  float m[2], cut[2];
-  int sslot[2];
-#pragma unroll
-  for (int r = 0; r < 2; r++) {
-    m[r] = __fmaf_ru(1.9073486e-6f, so[r] + kEps, 1e-7f);     // 2^-19 |L-p|: covers the FP32 length error
-    cut[r] = want[r] ? so[r] + m[r] : -3.0e38f;               // nothing farther from the light can matter
-    sslot[r] = (want[r] && cosl[r] > 1e-3f) ? (T.inv[self[r]] & 0x3fffffff) : -1;
-  }
-  float wcut = wmaxf(fmaxf(cut[0], cut[1]));
 #pragma unroll 1
-  for (int p0 = 0; p0 < npairs; p0 += kChunkPairs) {
-    if (T.gmin[p0 / kGroupPairs] > wcut) break;
-    const int np = min(kChunkPairs, npairs - p0);
+  for (int p0 = pbeg; p0 < pend; p0 += kChunkPairs) {
+    if (gmin[p0 / kGroupPairs] > q.wcut) return false;
+    const int np = min(kChunkPairs, pend - p0);
     unsigned h0, h1;
-    chunk_test_shared(T.pairs, p0, np, dx2, dy2, dz2, h0, h1);
-    unsigned f[2] = {flagged_bits(h0, np, open[0]), flagged_bits(h1, np, open[1])};
+    chunk_test_shared(pairs, p0, np, dx2, dy2, dz2, h0, h1);
+    unsigned f[2] = {flagged_bits(h0, np, q.open[0]), flagged_bits(h1, np, q.open[1])};
 #pragma unroll
     for (int r = 0; r < 2; r++) {
-      const int sp = sslot[r] >> 1;                  // pair of the lit self sphere (or -1)
+      const int sp = q.sslot[r] >> 1;                // pair of the lit self sphere (or -1)
       if (sp >= p0 && sp < p0 + np) {
-        const int ph = (sslot[r] & 1) ^ 1;           // partner = the other half of the pair
-        const float4 A = T.pairs[2 * sp], B = T.pairs[2 * sp + 1];
+        const int ph = (q.sslot[r] & 1) ^ 1;         // partner = the other half of the pair
+        const float4 A = pairs[2 * sp], B = pairs[2 * sp + 1];
         float tca, Dp;
         shared_origin_eval(ph ? A.y : A.x, ph ? A.w : A.z, ph ? B.y : B.x, ph ? B.w : B.z, dx[r], dy[r], dz[r], tca, Dp);
         if (!(Dp >= 0.0f)) f[r] &= ~(1u << (p0 + np - 1 - sp));
@@ -535,19 +562,31 @@ __device__ __forceinline__ void shadow_light(const Tab T, int npairs, int light,
             const int bit = 31 - __clz(fr);
             const int pi = p0 + np - 1 - bit;
             fr &= ~(1u << bit);
-            if (T.gmin[pi / kGroupPairs] > cut[r]) {
+            if (gmin[pi / kGroupPairs] > q.cut[r]) {
               fr = 0u;                                // sorted: everything after this pair is farther still
             } else {
-              const int rc = slow_shadow(T.pairs, T.perm, pi, dx[r], dy[r], dz[r], so[r], m[r], self[r], cosl[r], p64[r], light, d64, sph64);
+              const int rc = slow_shadow(pairs, perm, pi, dx[r], dy[r], dz[r], so[r], q.m[r], self[r], cosl[r], p64[r], light, d64, sph64);
               n_fp64 += rc >> 1;
-              if (rc & 1) { occ[r] = true; open[r] = false; fr = 0u; }
+              if (rc & 1) { q.occ[r] = true; q.open[r] = false; fr = 0u; }
             }
           }
         }
       }
-      wcut = wmaxf(fmaxf(open[0] ? cut[0] : -3.0e38f, open[1] ? cut[1] : -3.0e38f));   // decided rays stop holding the warp
+      q.wcut = wmaxf(fmaxf(q.open[0] ? q.cut[0] : -3.0e38f, q.open[1] ? q.cut[1] : -3.0e38f));   // decided rays stop holding the warp
+      if (q.wcut < -1.0e38f) return false;
     }
   }
+  return true;
+}
+
+__device__ __forceinline__ void shadow_light(const Tab T, int npairs, int light, const float (&dx)[2], const float (&dy)[2],
+                                             const float (&dz)[2], const float (&so)[2], const bool (&want)[2],
+                                             const int (&self)[2], const float (&cosl)[2], const double *const (&p64)[2], float d64,
+                                             const double4 *sph64, bool (&occ)[2], int &n_fp64) {
+  ShadowQ q;
+  shadow_begin(q, T.inv, so, want, self, cosl);
+  shadow_range(q, T.pairs, T.gmin, T.perm, 0, npairs, light, dx, dy, dz, so, self, cosl, p64, d64, sph64, n_fp64);
+  occ[0] = q.occ[0]; occ[1] = q.occ[1];
 }
 
 // ---------------------------------------------------------------------------------------------

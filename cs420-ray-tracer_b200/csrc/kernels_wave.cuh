@@ -20,6 +20,9 @@
 
 #include "kernels_fast.cuh"
 
+#ifndef RT_SHADOW_CTAS
+#define RT_SHADOW_CTAS 3
+#endif
 namespace rtf {
 
 struct __align__(16) HitRec {      // 80 bytes
@@ -94,21 +97,74 @@ __device__ __noinline__ bool finish_hit(const FastArgs &a, Best b, RaySrc src, u
 }
 
 // ---------------------------------------------------------------------------------------------
+// Table modes of the two table-walking kernels of level 0:
+//   kTabGlobal  tables read through L1/L2 (no staging)
+//   kTabSmem    the kernel's tables staged once per CTA with one TMA bulk copy (they fit)
+//   kTabStream  tables larger than shared memory: every CTA streams the (sorted) table through a
+//               two-stage ring of 32 KB tiles -- cp.async.bulk into stage k+1 while the eight warps
+//               test their rays against stage k (full barriers = mbarriers with expect_tx, the
+//               "stage is free again" edge = the CTA barrier that also votes on early termination).
+enum { kTabGlobal = 0, kTabSmem = 1, kTabStream = 2 };
+constexpr int kTilePairs = 1024;                                   // sphere pairs per streamed tile
+constexpr unsigned kTileBytes = kTilePairs * 32u;                  // 32 KB per stage
+
+__device__ __forceinline__ void ring_init(unsigned char *smem) {
+  unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem);
+  if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); }
+  __syncthreads();
+}
+__device__ __forceinline__ float4 *ring_stage(unsigned char *smem, int st) {
+  return reinterpret_cast<float4 *>(smem + kSmemHeader + (unsigned)st * kTileBytes);
+}
+// thread 0 only: arm the stage's barrier and start the bulk copy of `npairs_tile` pairs
+__device__ __forceinline__ void ring_issue(unsigned char *smem, int st, const float4 *gsrc, int npairs_tile) {
+  unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem) + st;
+  const unsigned bytes = (unsigned)npairs_tile * 32u;
+  mbar_expect_tx(bar, bytes);
+  tma_bulk_g2s(ring_stage(smem, st), gsrc, bytes, bar);
+}
+// all threads: wait until the stage's copy has landed; phase bit per stage flips per use
+__device__ __forceinline__ void ring_wait(unsigned char *smem, int st, unsigned &phase) {
+  mbar_wait(reinterpret_cast<unsigned long long *>(smem) + st, (phase >> st) & 1u);
+  phase ^= 1u << st;
+}
+// CTA-uniform work fetch (streamed kernels walk a table together, so the CTA takes 8 items at once)
+__device__ __forceinline__ int cta_fetch(unsigned int *counter, unsigned char *smem) {
+  int *slot = reinterpret_cast<int *>(smem + 32);
+  if (threadIdx.x == 0) *slot = (int)atomicAdd(counter, 1u);
+  __syncthreads();
+  const int v = *slot;
+  __syncthreads();
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
 // LEVEL 0 closest hit: each warp pulls 16x4-pixel tiles, two vertically adjacent pixels per lane.
-template <bool kSmem>
+template <int kMode>
 __global__ void __launch_bounds__(kThreads, 3) k_closest0(const WaveArgs w) {
   extern __shared__ __align__(128) unsigned char smem[];
   const FastArgs &a = w.f;
   const unsigned char *tabs = a.tabs;
-  if (kSmem) { stage_tables(smem, a.tabs, a.stage_bytes); tabs = smem + kSmemHeader; }
+  if (kMode == kTabSmem) { stage_tables(smem, a.tabs, a.stage_bytes); tabs = smem + kSmemHeader; }
+  if (kMode == kTabStream) ring_init(smem);
+  const Tab camg = tab_at(a.tabs, a, 0);             // global view (gmin / perm of the streamed mode)
   const Tab cam = tab_at(tabs, a, 0);
+  unsigned ring_phase = 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char *s_rgb = smem + 64 + warp * (kWTileH * kWTileW * 3);
   const int W = a.r.W, rows = a.r.bands.local_rows, depth = a.r.max_depth;
   unsigned c_closest = 0, c_hits = 0, c_fp64 = 0, c_viol = 0;
   for (;;) {
-    const int tile = warp_fetch(a.tile_counter);
-    if (tile >= a.nwtiles) break;
+    int tile;
+    if (kMode == kTabStream) {
+      const int ct = cta_fetch(a.tile_counter, smem);
+      if (ct * kWarps >= a.nwtiles) break;
+      tile = ct * kWarps + warp;
+    } else {
+      tile = warp_fetch(a.tile_counter);
+      if (tile >= a.nwtiles) break;
+    }
+    const bool tile_ok = tile < a.nwtiles;
     const int tx0 = (tile % a.wtiles_x) * kWTileW, ty0 = (tile / a.wtiles_x) * kWTileH;
     const int x = tx0 + (lane & 15);
     int lr[2], j[2];
@@ -118,9 +174,9 @@ __global__ void __launch_bounds__(kThreads, 3) k_closest0(const WaveArgs w) {
 #pragma unroll
     for (int r = 0; r < 2; r++) {
       lr[r] = ty0 + (lane >> 4) * 2 + r;
-      live[r] = x < W && lr[r] < rows && depth > 0;
+      live[r] = tile_ok && x < W && lr[r] < rows && depth > 0;
       j[r] = 0; pix[r] = 0; dx[r] = dy[r] = dz[r] = 0.f;
-      if (x < W && lr[r] < rows) {
+      if (tile_ok && x < W && lr[r] < rows) {
         j[r] = rt_local_to_global_row(a.r.bands, lr[r]);
         pix[r] = (unsigned)lr[r] * (unsigned)W + (unsigned)x;
       }
@@ -138,7 +194,27 @@ __global__ void __launch_bounds__(kThreads, 3) k_closest0(const WaveArgs w) {
     Best best[2];
     best_init(best[0]); best_init(best[1]);
     const RaySrc src[2] = {{a.r.su, a.r.sv, x, j[0], nullptr}, {a.r.su, a.r.sv, x, j[1], nullptr}};
-    closest_shared(cam, a.npairs, dx, dy, dz, live, a.d64, a.r.sph64, src, best);
+    if (kMode != kTabStream) {
+      closest_shared(cam, a.npairs, dx, dy, dz, live, a.d64, a.r.sph64, src, best);
+    } else {
+      // the eight warps of the CTA walk the sorted camera table together, tile by tile
+      ClosestQ q;
+      closest_begin(q);
+      bool need = true;
+      const int ntiles = (a.npairs + kTilePairs - 1) / kTilePairs;
+      if (threadIdx.x == 0) ring_issue(smem, 0, camg.pairs, min(kTilePairs, a.npairs));
+      for (int k = 0; k < ntiles; k++) {
+        const int st = k & 1, p0 = k * kTilePairs, np = min(kTilePairs, a.npairs - p0);
+        if (threadIdx.x == 0 && k + 1 < ntiles)
+          ring_issue(smem, st ^ 1, camg.pairs + (size_t)(p0 + kTilePairs) * 2, min(kTilePairs, a.npairs - p0 - kTilePairs));
+        ring_wait(smem, st, ring_phase);
+        if (need) need = closest_shared_range(q, ring_stage(smem, st) - (size_t)p0 * 2, camg.gmin, camg.perm, p0, p0 + np, dx, dy, dz,
+                                              live, a.d64, a.r.sph64, src);
+        const int more = __syncthreads_or(need ? 1 : 0);        // also: stage st is free again
+        if (!more || k + 1 == ntiles) { if (k + 1 < ntiles) ring_wait(smem, st ^ 1, ring_phase); break; }
+      }
+      best[0] = q.best[0]; best[1] = q.best[1];
+    }
 #pragma unroll
     for (int r = 0; r < 2; r++) {
       bool hit = false;
@@ -159,6 +235,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_closest0(const WaveArgs w) {
       q[2] = (unsigned char)quant8(sky ? (1.0f - ts) + ts : 0.f);
     }
     __syncwarp();
+    if (!tile_ok) { __syncwarp(); continue; }
     if (tx0 + kWTileW <= W && (W & 15) == 0) {
       // 3 x 16-byte stores per 48-byte row segment (src/main.cpp:84-86 quantiser applied above)
       if (lane < kWTileH * 3) {
@@ -251,21 +328,31 @@ __global__ void __launch_bounds__(kThreads, 3) k_closest1(const WaveArgs w) {
 // origin p + l*EPS lies strictly inside the sphere the point is on, so the reference's query returns
 // that sphere's exit distance, which is shorter than the distance to any light outside that sphere
 // (flag bit 30 of Tab::inv, set on the host): occluded, no table walk needed.
-template <bool kSmem>
-__global__ void __launch_bounds__(kThreads, 3) k_shadow(const WaveArgs w) {
+template <int kMode>
+__global__ void __launch_bounds__(kThreads, RT_SHADOW_CTAS) k_shadow(const WaveArgs w) {
   extern __shared__ __align__(128) unsigned char smem[];
   const FastArgs &a = w.f;
   const unsigned nh = *w.hit_count;
   if (nh == 0u || a.L == 0) return;
   // staged: the L light tables
-  const unsigned char *tabs = a.tabs + a.tstride;
-  if (kSmem) { stage_tables(smem, tabs, a.stage_bytes); tabs = smem + kSmemHeader; }
-  const int lane = threadIdx.x & 31;
+  const unsigned char *gtabs = a.tabs + a.tstride;
+  const unsigned char *tabs = gtabs;
+  if (kMode == kTabSmem) { stage_tables(smem, tabs, a.stage_bytes); tabs = smem + kSmemHeader; }
+  if (kMode == kTabStream) ring_init(smem);
+  unsigned ring_phase = 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned nchunks = (nh + 63u) / 64u;
   unsigned c_fp64 = 0;
   for (;;) {
-    const unsigned chunk = (unsigned)warp_fetch(w.work_counter);
-    if (chunk >= nchunks) break;
+    unsigned chunk;
+    if (kMode == kTabStream) {
+      const unsigned cc = (unsigned)cta_fetch(w.work_counter, smem);
+      if (cc * kWarps >= nchunks) break;
+      chunk = cc * kWarps + warp;
+    } else {
+      chunk = (unsigned)warp_fetch(w.work_counter);
+      if (chunk >= nchunks) break;
+    }
     const unsigned h0 = chunk * 64u + 2u * lane;
     bool have[2];
     int self[2];
@@ -287,7 +374,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_shadow(const WaveArgs w) {
     }
     const double *const ppc[2] = {pp[0], pp[1]};
     for (int l = 0; l < a.L; l++) {
-      const Tab T = tab_at(tabs, a, l);
+      const Tab T = tab_at(kMode == kTabStream ? gtabs : tabs, a, l);
       const d3 lp = ldc3(g_frame.light_pos[l]);
       bool want[2], occ[2], shortcut[2];
       float dx[2], dy[2], dz[2], so[2], cosl[2];
@@ -308,9 +395,32 @@ __global__ void __launch_bounds__(kThreads, 3) k_shadow(const WaveArgs w) {
         want[r] = have[r] && !shortcut[r];
       }
       int n64 = 0;
-      if (__any_sync(kFull, want[0] || want[1]))
-        shadow_light(T, a.npairs, l, dx, dy, dz, so, want, self, cosl, ppc, a.d64, a.r.sph64, occ, n64);
-      else occ[0] = occ[1] = false;
+      if (kMode != kTabStream) {
+        if (__any_sync(kFull, want[0] || want[1]))
+          shadow_light(T, a.npairs, l, dx, dy, dz, so, want, self, cosl, ppc, a.d64, a.r.sph64, occ, n64);
+        else occ[0] = occ[1] = false;
+      } else {
+        // the eight warps of the CTA walk this light's sorted table together, tile by tile
+        const Tab TG = tab_at(gtabs, a, l);
+        ShadowQ q;
+        shadow_begin(q, TG.inv, so, want, self, cosl);
+        bool need = q.wcut > -1.0e38f;
+        if (__syncthreads_or(need ? 1 : 0)) {
+          const int ntiles = (a.npairs + kTilePairs - 1) / kTilePairs;
+          if (threadIdx.x == 0) ring_issue(smem, 0, TG.pairs, min(kTilePairs, a.npairs));
+          for (int k = 0; k < ntiles; k++) {
+            const int st = k & 1, p0 = k * kTilePairs, np = min(kTilePairs, a.npairs - p0);
+            if (threadIdx.x == 0 && k + 1 < ntiles)
+              ring_issue(smem, st ^ 1, TG.pairs + (size_t)(p0 + kTilePairs) * 2, min(kTilePairs, a.npairs - p0 - kTilePairs));
+            ring_wait(smem, st, ring_phase);
+            if (need) need = shadow_range(q, ring_stage(smem, st) - (size_t)p0 * 2, TG.gmin, TG.perm, p0, p0 + np, l, dx, dy, dz, so, self,
+                                          cosl, ppc, a.d64, a.r.sph64, n64);
+            const int more = __syncthreads_or(need ? 1 : 0);      // also: stage st is free again
+            if (!more || k + 1 == ntiles) { if (k + 1 < ntiles) ring_wait(smem, st ^ 1, ring_phase); break; }
+          }
+        }
+        occ[0] = q.occ[0]; occ[1] = q.occ[1];
+      }
       c_fp64 += (unsigned)n64;
       // two adjacent bytes per lane -> one 16-bit store when both exist
       const unsigned o0 = (occ[0] || shortcut[0]) ? 1u : 0u, o1 = (occ[1] || shortcut[1]) ? 256u : 0u;

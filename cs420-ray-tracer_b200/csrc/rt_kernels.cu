@@ -29,7 +29,7 @@ int rtk_launch_exact(const RtRenderArgs &args, cudaStream_t stream) {
 // fast path, host side
 namespace {
 
-constexpr size_t kMaxSmemTables = 200 * 1024;   // stage tables in shared memory up to this size
+constexpr size_t kMaxSmemTables = 72 * 1024;    // stage a kernel's tables in shared memory up to this size (3 CTAs/SM stay resident)
 constexpr int kCtlWords = 128;                  // [0] tile counter, [1+k] chunk counter of level k, [64+k] rays entering level k
 
 inline float float_up(double x) {               // smallest float >= x
@@ -50,9 +50,11 @@ inline float float_down(double x) {             // largest float <= x
 int rtk_fast_init(int) {
   const int big = 227 * 1024;
   RTK_TRY(cudaFuncSetAttribute(rtf::k_bounce<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  RTK_TRY(cudaFuncSetAttribute(rtf::k_closest0<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  RTK_TRY(cudaFuncSetAttribute(rtf::k_closest0<rtf::kTabSmem>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  RTK_TRY(cudaFuncSetAttribute(rtf::k_closest0<rtf::kTabStream>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   RTK_TRY(cudaFuncSetAttribute(rtf::k_closest1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  RTK_TRY(cudaFuncSetAttribute(rtf::k_shadow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  RTK_TRY(cudaFuncSetAttribute(rtf::k_shadow<rtf::kTabSmem>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  RTK_TRY(cudaFuncSetAttribute(rtf::k_shadow<rtf::kTabStream>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   return 0;
 }
 
@@ -225,8 +227,12 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
   wa.hits = (rtf::HitRec *)w->hits; wa.hit_cap = (unsigned)w->hit_cap; wa.occ = w->occ;
   const size_t pairs_bytes = (size_t)fs->npairs * 32;
   const size_t light_bytes = (size_t)fs->L * fs->tstride;
-  const bool in_smem = fs->bytes_bounce <= kMaxSmemTables && fs->bytes_primary <= kMaxSmemTables;
+  // per kernel: its tables are staged whole when they fit, else streamed (shared-origin tables) or read through L1/L2 (general table)
+  const bool cam_smem = fs->tstride <= kMaxSmemTables, light_smem = light_bytes <= kMaxSmemTables;
+  const bool gen_smem = pairs_bytes <= kMaxSmemTables, in_smem = fs->bytes_bounce <= kMaxSmemTables;
   a.tables_in_smem = in_smem;
+  // larger tables are streamed through a two-stage ring of TMA tiles (kernels_wave.cuh, kTabStream)
+  const size_t stream_smem = rtf::kSmemHeader + 2 * (size_t)rtf::kTileBytes;
   int launches = 0;
 
   for (int level = 0; level < args.max_depth && level < 2; level++) {
@@ -235,17 +241,17 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
     // ---- closest hit
     if (level == 0) {
       a.stage_bytes = fs->tstride;
-      const size_t smem = rtf::kSmemHeader + (in_smem ? a.stage_bytes : 0);
+      const size_t smem = cam_smem ? rtf::kSmemHeader + a.stage_bytes : stream_smem;
       const int cta_tiles = (a.nwtiles + rtf::kWarps - 1) / rtf::kWarps;
-      if (in_smem) { int g = resident_grid(rtf::k_closest0<true>, smem, w->num_sms); rtf::k_closest0<true><<<g < cta_tiles ? g : cta_tiles, rtf::kThreads, smem, stream>>>(wa); }
-      else { int g = resident_grid(rtf::k_closest0<false>, smem, w->num_sms); rtf::k_closest0<false><<<g < cta_tiles ? g : cta_tiles, rtf::kThreads, smem, stream>>>(wa); }
+      if (cam_smem) { int g = resident_grid(rtf::k_closest0<rtf::kTabSmem>, smem, w->num_sms); rtf::k_closest0<rtf::kTabSmem><<<g < cta_tiles ? g : cta_tiles, rtf::kThreads, smem, stream>>>(wa); }
+      else { int g = resident_grid(rtf::k_closest0<rtf::kTabStream>, smem, w->num_sms); rtf::k_closest0<rtf::kTabStream><<<g < cta_tiles ? g : cta_tiles, rtf::kThreads, smem, stream>>>(wa); }
     } else {
       a.q_in = (rtf::RayRec *)w->queue[(level - 1) & 1];
       a.q_in_count = w->ctl + CTL_RAYS + level;
       wa.work_counter = w->ctl + CTL_CLOSEST + level;
       a.stage_bytes = (unsigned)pairs_bytes;
-      const size_t smem = rtf::kSmemHeader + (in_smem ? a.stage_bytes : 0);
-      if (in_smem) rtf::k_closest1<true><<<resident_grid(rtf::k_closest1<true>, smem, w->num_sms), rtf::kThreads, smem, stream>>>(wa);
+      const size_t smem = rtf::kSmemHeader + (gen_smem ? a.stage_bytes : 0);
+      if (gen_smem) rtf::k_closest1<true><<<resident_grid(rtf::k_closest1<true>, smem, w->num_sms), rtf::kThreads, smem, stream>>>(wa);
       else rtf::k_closest1<false><<<resident_grid(rtf::k_closest1<false>, smem, w->num_sms), rtf::kThreads, smem, stream>>>(wa);
     }
     launches++;
@@ -254,9 +260,9 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
     if (fs->L > 0) {
       wa.work_counter = w->ctl + CTL_SHADOW + level;
       a.stage_bytes = (unsigned)light_bytes;
-      const size_t smem = rtf::kSmemHeader + (in_smem ? a.stage_bytes : 0);
-      if (in_smem) rtf::k_shadow<true><<<resident_grid(rtf::k_shadow<true>, smem, w->num_sms), rtf::kThreads, smem, stream>>>(wa);
-      else rtf::k_shadow<false><<<resident_grid(rtf::k_shadow<false>, smem, w->num_sms), rtf::kThreads, smem, stream>>>(wa);
+      const size_t smem = light_smem ? rtf::kSmemHeader + a.stage_bytes : stream_smem;
+      if (light_smem) rtf::k_shadow<rtf::kTabSmem><<<resident_grid(rtf::k_shadow<rtf::kTabSmem>, smem, w->num_sms), rtf::kThreads, smem, stream>>>(wa);
+      else rtf::k_shadow<rtf::kTabStream><<<resident_grid(rtf::k_shadow<rtf::kTabStream>, smem, w->num_sms), rtf::kThreads, smem, stream>>>(wa);
       launches++;
     }
     if (level == 0 && marks) RTK_TRY(cudaEventRecord(marks[1], stream));
