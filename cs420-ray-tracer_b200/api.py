@@ -36,6 +36,7 @@ class RtStats(C.Structure):
         ("fp64_intersections", C.c_uint64), ("sphere_tests", C.c_uint64),
         ("filter_violations", C.c_uint64),
         ("kernel_launches", C.c_int32), ("rows_rendered", C.c_int32),
+        ("bundle_walks", C.c_uint64), ("bundle_candidates", C.c_uint64),
     ]
 
     def as_dict(self):
@@ -211,6 +212,9 @@ class Renderer:
 
     def set_counters(self, on):
         _check(self._lib.rt_set_option(self._h, b"counters", int(bool(on))), "rt_set_option")
+
+    def set_option(self, key, value):
+        _check(self._lib.rt_set_option(self._h, key.encode(), int(value)), "rt_set_option")
 
     def upload(self, scene):
         self.scene = scene

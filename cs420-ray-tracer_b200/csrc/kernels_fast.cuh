@@ -1,21 +1,23 @@
 // kernels_fast.cuh -- "mode 0": the production path.  sm_100a only.
 //
 // Work decomposition (wavefront with compacted queues, warps schedule themselves):
-//   k_primary   persistent CTAs; every WARP pulls 16x4-pixel tiles from an atomic counter (two
-//               vertically adjacent pixels per lane).  Camera rays -> closest hit (FP32 filter over
-//               the CAMERA table, FP64 decide) -> Phong + one any-hit shadow query per light (FP32
-//               filter over that LIGHT's table) -> final 8-bit pixel (staged per warp, 128-bit
-//               stores), or a reflected ray appended to the ray queue with warp-ballot compaction.
-//   k_bounce    level 1: consumes the queue, 64 rays per warp fetch, general-origin closest hit,
-//               same shading, appends survivors to the other queue.
-//               tail (levels >= 2, one launch): each lane follows its ray to termination, the
-//               queue record is updated in place instead of being re-queued.
+//   levels 0 and 1 run as phase-separated wavefront kernels (kernels_wave.cuh); this file holds the
+//   query primitives they share and
+//   k_bounce    the tail (levels >= 2, one launch): consumes the ray queue, 32 rays per warp fetch,
+//               general-origin closest hit, Phong + one any-hit shadow query per light; each lane
+//               follows its ray to termination, the queue record is updated in place.
 // Sphere tables are staged once per CTA into shared memory with ONE TMA bulk copy
 // (cp.async.bulk + mbarrier) when they fit, otherwise they are read through L1/L2.
 //
 // Shared-origin tables (camera, each light) are SORTED by the distance of the sphere's nearest
 // point from that origin; a query stops at the first 8-sphere group that lies entirely beyond
 // its cutoff (current best hit / distance to the shaded point), so "any hit" really is early out.
+//
+// Bundle culling (tables staged in shared memory): the rays a warp works on at one time share their
+// origin (camera / one light) and form a narrow bundle.  The warp bounds them by a cone, tests every
+// sphere of the table against that cone ONCE (one sphere per lane, warp ballot), compacts the
+// survivors into a per-warp shared-memory table and runs the per-ray tests over that table only:
+// a handful of spheres instead of all N.  The cone test is conservative (see cull_round).
 //
 // What is FP32 and what is FP64:  every ray/sphere TEST is 4 packed-FP32 FMAs per sphere pair
 // (FFMA2; shared origin) or 10 (general origin).  The tests are conservative (filter_math.cuh);
@@ -34,7 +36,10 @@ namespace rtf {
 
 using rtx::d3;
 
-constexpr int kThreads = 256;
+#ifndef RT_THREADS
+#define RT_THREADS 256
+#endif
+constexpr int kThreads = RT_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kWTileW = 16, kWTileH = 4;  // pixels per warp tile (32 lanes x 2 pixels)
 constexpr int kGroupPairs = 4;            // sphere pairs per fast-path group (8 spheres)
@@ -56,7 +61,7 @@ struct FastArgs {
   const unsigned char *tabs;  // (1+L) shared-origin tables (tstride bytes each: pairs | gmin | perm), then the general table
   int npairs, ngroups;        // npairs is a multiple of kGroupPairs; ngroups = npairs / kGroupPairs
   int N, L;
-  unsigned tstride, gmin_off, perm_off, inv_off;
+  unsigned tstride, gmin_off, perm_off, inv_off, cullA_off, cullB_off;
   unsigned stage_bytes;       // bytes this kernel stages into shared memory
   float d64;                  // absolute slack covering FP64 rounding / geometry (delta64)
   float gS2;                  // squared radius bound S^2 of the recentred scene (general filter)
@@ -77,6 +82,8 @@ struct Tab {
   const float *gmin;     // per group of 8 spheres: lower bound of |oc| - r over the group (ascending)
   const int *perm;       // original sphere index per sorted slot, -1 = padding
   const int *inv;        // sorted slot of each original sphere index; bit 30: the origin is strictly outside it
+  const float4 *cullA;   // per slot: unit vector origin -> centre, cos(alpha); alpha = angular radius seen from the origin
+  const float *cullB;    // per slot: sin(alpha)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -154,6 +161,8 @@ __device__ __forceinline__ Tab tab_at(const unsigned char *base, const FastArgs 
   T.gmin = reinterpret_cast<const float *>(p + a.gmin_off);
   T.perm = reinterpret_cast<const int *>(p + a.perm_off);
   T.inv = reinterpret_cast<const int *>(p + a.inv_off);
+  T.cullA = reinterpret_cast<const float4 *>(p + a.cullA_off);
+  T.cullB = reinterpret_cast<const float *>(p + a.cullB_off);
   return T;
 }
 
@@ -230,14 +239,8 @@ __device__ __forceinline__ void best_set_exact(Best &b, int idx, double t) {
   b.idx = idx; b.t = t; b.exact = true; b.lo = f_rd(t); b.hi = f_ru(t);
 }
 
-__device__ __noinline__ Best closest_consider(Best b, int i, int status, float lo, float hi, const double4 *sph64, RaySrc src) {
-  if (status == RT_MISS) return b;
-  if (status == RT_HIT) {
-    if (b.idx < 0) { b.lo = lo; b.hi = hi; b.idx = i; b.exact = false; return b; }
-    if (lo > b.hi) return b;                      // strictly farther
-    if (hi < b.lo) { b.lo = lo; b.hi = hi; b.idx = i; b.exact = false; return b; }
-  }
-  // brackets touch, or the sphere itself is ambiguous: decide in FP64, lowest index wins ties
+// brackets touch, or the sphere itself is ambiguous: decide in FP64, lowest index wins ties (rare, out of line)
+__device__ __noinline__ Best closest_consider_exact(Best b, int i, const double4 *sph64, RaySrc src) {
   const ExactRay e = exact_ray(src);
   double tn;
   b.nfp64++;
@@ -254,6 +257,16 @@ __device__ __noinline__ Best closest_consider(Best b, int i, int status, float l
   }
   if (b.idx < 0 || tn < b.t || (tn == b.t && i < b.idx)) best_set_exact(b, i, tn);
   return b;
+}
+// the common outcomes are decided inline on the FP32 brackets
+__device__ __forceinline__ void closest_consider(Best &b, int i, int status, float lo, float hi, const double4 *sph64, RaySrc src) {
+  if (status == RT_MISS) return;
+  if (status == RT_HIT) {
+    if (b.idx < 0) { b.lo = lo; b.hi = hi; b.idx = i; b.exact = false; return; }
+    if (lo > b.hi) return;                        // strictly farther
+    if (hi < b.lo) { b.lo = lo; b.hi = hi; b.idx = i; b.exact = false; return; }
+  }
+  b = closest_consider_exact(b, i, sph64, src);
 }
 
 // scalar re-evaluation of one sphere of a shared-origin table (same operations as the fast path)
@@ -278,8 +291,12 @@ __device__ __forceinline__ bool shared_origin_roots(float ocx, float ocy, float 
   return bracket_roots(tca, Dhi, E2, dt, r);
 }
 
-// ---- slow paths: one flagged sphere PAIR for ONE ray, out of line --------------------------------
-__device__ __noinline__ Best slow_closest_shared(Best b, const float4 *pairs, const int *perm, int pi, float dx, float dy, float dz,
+// ---- slow paths: one flagged sphere PAIR for ONE ray.  The FP32 bracketing is inline (a call would
+// spill the caller's registers to local memory around it); only the FP64 deciders are out of line.
+#ifndef RT_SLOW
+#define RT_SLOW __forceinline__
+#endif
+__device__ RT_SLOW Best slow_closest_shared(Best b, const float4 *pairs, const int *perm, int pi, float dx, float dy, float dz,
                                                  float d64, const double4 *sph64, RaySrc src) {
   const float4 A = pairs[2 * pi], B = pairs[2 * pi + 1];
 #pragma unroll 1
@@ -294,13 +311,13 @@ __device__ __noinline__ Best slow_closest_shared(Best b, const float4 *pairs, co
     int status = RT_AMBIG;
     float lo = 0, hi = 0;
     if (shared_origin_roots(ocx, ocy, ocz, ncc, tca, Dp, d64, rt)) status = select_root(rt, lo, hi);
-    b = closest_consider(b, i, status, lo, hi, sph64, src);
+    closest_consider(b, i, status, lo, hi, sph64, src);
   }
   return b;
 }
 
 // returns bit 0 = an occluder was found in this pair, bits 1.. = FP64 evaluations spent
-__device__ __noinline__ int slow_shadow(const float4 *pairs, const int *perm, int pi, float dx, float dy, float dz, float so, float m,
+__device__ RT_SLOW int slow_shadow(const float4 *pairs, const int *perm, int pi, float dx, float dy, float dz, float so, float m,
                                         int self, float cosl, const double *p3, int light, float d64, const double4 *sph64) {
   const float so_lo = so - m, so_hi = so + m, e_lo = -kEps - m, e_hi = -kEps + m;
   const float4 A = pairs[2 * pi], B = pairs[2 * pi + 1];
@@ -327,7 +344,7 @@ __device__ __noinline__ int slow_shadow(const float4 *pairs, const int *perm, in
   return found | (n64 << 1);
 }
 
-__device__ __noinline__ Best slow_closest_general(Best b, const float4 *pairs, int pi, int N, float ox, float oy, float oz, float dx,
+__device__ RT_SLOW Best slow_closest_general(Best b, const float4 *pairs, int pi, int N, float ox, float oy, float oz, float dx,
                                                   float dy, float dz, float d64, float gS2, const double4 *sph64, RaySrc src) {
   const float sS = __fsqrt_ru(gS2);
   const float4 A = pairs[2 * pi], B = pairs[2 * pi + 1];
@@ -353,32 +370,35 @@ __device__ __noinline__ Best slow_closest_general(Best b, const float4 *pairs, i
     // rho' - r^2 = 40u r^2 + 12u S r + 64u^2 S^2 + d64 (host), bounded here from rho' itself
     const float rm = __fadd_ru(__fmul_ru(5.9604645e-8f, __fmaf_ru(12.5f * sS, __fsqrt_ru(fabsf(rho)), __fmaf_ru(41.0f, fabsf(rho), 1e-4f * gS2))), d64);
     if (bracket_roots(tca, Dhi, __fadd_ru(__fmul_ru(2.0f, Eg), rm), dt, rt)) status = select_root(rt, lo, hi);
-    b = closest_consider(b, i, status, lo, hi, sph64, src);
+    closest_consider(b, i, status, lo, hi, sph64, src);
   }
   return b;
 }
 
 // The packed FP32 test of up to 32 sphere PAIRS (one "chunk") of a shared-origin table against the
-// two rays of a lane.  For every pair and ray one bit is shifted into a history word: 1 = neither
+// NR rays of a lane.  For every pair and ray one bit is shifted into a history word: 1 = neither
 // sphere of the pair can be hit (D' = (oc.d)^2 + ncc < 0 for both), 0 = flagged.  No branch, no vote:
 // flagged pairs are resolved afterwards, all lanes together (see the drain loops below).
 constexpr int kChunkPairs = 32;
 __device__ __forceinline__ unsigned push_sign(unsigned hist, unsigned v) { return __funnelshift_l(v, hist, 1); }
 
-__device__ __forceinline__ void chunk_test_shared(const float4 *__restrict__ pairs, int p0, int np, const float2 (&dx)[2],
-                                                  const float2 (&dy)[2], const float2 (&dz)[2], unsigned &h0, unsigned &h1) {
-  h0 = kFull; h1 = kFull;
+template <int NR>
+__device__ __forceinline__ void chunk_test_shared(const float4 *__restrict__ pairs, int p0, int np, const float2 (&dx)[NR],
+                                                  const float2 (&dy)[NR], const float2 (&dz)[NR], unsigned (&h)[NR]) {
+#pragma unroll
+  for (int r = 0; r < NR; r++) h[r] = kFull;
 #pragma unroll 1
   for (int p = p0; p < p0 + np; p += kGroupPairs) {
 #pragma unroll
     for (int k = 0; k < kGroupPairs; k++) {
       const float4 A = pairs[2 * (p + k)], B = pairs[2 * (p + k) + 1];
       const float2 X = make_float2(A.x, A.y), Y = make_float2(A.z, A.w), Z = make_float2(B.x, B.y), Wv = make_float2(B.z, B.w);
-      float2 t0 = __fmul2_rn(X, dx[0]); t0 = __ffma2_rn(Y, dy[0], t0); t0 = __ffma2_rn(Z, dz[0], t0);
-      float2 t1 = __fmul2_rn(X, dx[1]); t1 = __ffma2_rn(Y, dy[1], t1); t1 = __ffma2_rn(Z, dz[1], t1);
-      const float2 D0 = __ffma2_rn(t0, t0, Wv), D1 = __ffma2_rn(t1, t1, Wv);
-      h0 = push_sign(h0, fbits(D0.x) & fbits(D0.y));
-      h1 = push_sign(h1, fbits(D1.x) & fbits(D1.y));
+#pragma unroll
+      for (int r = 0; r < NR; r++) {
+        float2 t = __fmul2_rn(X, dx[r]); t = __ffma2_rn(Y, dy[r], t); t = __ffma2_rn(Z, dz[r], t);
+        const float2 D = __ffma2_rn(t, t, Wv);
+        h[r] = push_sign(h[r], fbits(D.x) & fbits(D.y));
+      }
     }
   }
 }
@@ -389,35 +409,133 @@ __device__ __forceinline__ unsigned flagged_bits(unsigned hist, int np, bool liv
 }
 
 // ---------------------------------------------------------------------------------------------
-// CLOSEST HIT, shared origin (camera table, sorted by nearest-point distance).  Two rays per lane.
+// Bundle culling.
+//
+// Cone of a warp's rays: axis a = normalised sum of the (FP32, unit) directions, cos(theta) = the
+// smallest d.a over the active rays, lowered by 2e-6 (FP32 rounding of the dot products and of |a|).
+// A ray of the bundle -- extended to a LINE, because include/sphere.h:37 also reports tangent hits
+// behind the origin -- can meet a sphere whose centre direction is u and whose angular radius is
+// alpha only if |u.a| >= cos(theta + alpha).  Spheres failing that by more than 2e-5 are culled:
+// that margin is >= 10x every FP32 error involved (direction 12u, dot 4u, table entries 1u; the
+// host rounds cos(alpha) down and sin(alpha) up and inflates r by 1e-6) and ~1e9 x the FP64 rounding
+// of the reference's own discriminant, so a culled sphere is a certain miss for the reference.
+// Spheres containing the origin carry cos(alpha) = -4 (never culled), padding slots +4 (always).
+// Bundles wider than 60 degrees are not culled at all (the caller walks the whole table).
+struct Cone { float ax, ay, az, cth, sth; bool ok; };
+
+template <int NR>
+__device__ __forceinline__ Cone warp_cone(const float (&dx)[NR], const float (&dy)[NR], const float (&dz)[NR], const bool (&act)[NR]) {
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+#pragma unroll
+  for (int r = 0; r < NR; r++)
+    if (act[r]) { sx += dx[r]; sy += dy[r]; sz += dz[r]; }
+  // any axis is valid (cos(theta) is measured against it), so a fixed-point integer reduction will do
+  const float ax = (float)__reduce_add_sync(kFull, __float2int_rn(sx * 65536.f));
+  const float ay = (float)__reduce_add_sync(kFull, __float2int_rn(sy * 65536.f));
+  const float az = (float)__reduce_add_sync(kFull, __float2int_rn(sz * 65536.f));
+  const float l2 = fmaf(az, az, fmaf(ay, ay, ax * ax));
+  const float inv = rsqrtf(fmaxf(l2, 1.0f));
+  Cone c;
+  c.ax = ax * inv; c.ay = ay * inv; c.az = az * inv;
+  float mn = 1.0f;
+#pragma unroll
+  for (int r = 0; r < NR; r++)
+    if (act[r]) mn = fminf(mn, fmaf(dz[r], c.az, fmaf(dy[r], c.ay, dx[r] * c.ax)));
+  mn = fmaxf(mn, 0.0f);                              // non-negative floats order like their bit patterns
+  c.cth = __uint_as_float(__reduce_min_sync(kFull, __float_as_uint(mn))) - 2e-6f;
+  c.ok = l2 >= 1.0f && c.cth >= 0.5f;
+  c.sth = fmaf(sqrtf(fmaxf(0.0f, fmaf(-c.cth, c.cth, 1.0f))), 1.0001f, 1e-4f);
+  return c;
+}
+
+// Per-warp compacted table in shared memory: same layout as a shared-origin table, so the chunk test
+// and the slow paths run on it unchanged.  kCandMax candidates = one 32-pair chunk per fill.
+constexpr int kCandMax = 64;
+constexpr unsigned kWarpBufBytes = kCandMax * 16 + kCandMax * 4 + 32 + 96;   // pairs | perm | gmin | pad -> 1408 (multiple of 128)
+struct WarpBuf { float4 *pairs; int *perm; float *gmin; };
+__device__ __forceinline__ WarpBuf warp_buf(unsigned char *base) {
+  unsigned char *p = base + (threadIdx.x >> 5) * kWarpBufBytes;
+  WarpBuf b;
+  b.pairs = reinterpret_cast<float4 *>(p);
+  b.perm = reinterpret_cast<int *>(p + kCandMax * 16);
+  b.gmin = reinterpret_cast<float *>(p + kCandMax * 16 + kCandMax * 4);
+  return b;
+}
+
+// One culling round: lane l looks at slot base + l of table T.  Survivors (ballot order = table order,
+// so the compacted table stays sorted) are copied to positions ncand.. of the warp's table.  `wcut`:
+// spheres whose group lies beyond it are dropped as well.  Returns the survivors' ballot mask.
+__device__ __forceinline__ unsigned cull_round(const Tab &T, int base, int nslots, const Cone &c, float wcut, const WarpBuf &wb,
+                                               int ncand) {
+  const int lane = threadIdx.x & 31, slot = base + lane;
+  bool keep = false;
+  if (slot < nslots) {
+    const float4 u = T.cullA[slot];
+    const float sA = T.cullB[slot];
+    const float dotv = fabsf(fmaf(u.z, c.az, fmaf(u.y, c.ay, u.x * c.ax)));
+    keep = !(dotv < fmaf(c.cth, u.w, -fmaf(c.sth, sA, 2e-5f))) && !(T.gmin[slot >> 3] > wcut);
+  }
+  const unsigned mk = __ballot_sync(kFull, keep);
+  if (keep) {
+    const int rank = ncand + __popc(mk & ((1u << lane) - 1u));
+    const float *src = reinterpret_cast<const float *>(T.pairs) + (slot >> 1) * 8 + (slot & 1);
+    float *dst = reinterpret_cast<float *>(wb.pairs) + (rank >> 1) * 8 + (rank & 1);
+    dst[0] = src[0]; dst[2] = src[2]; dst[4] = src[4]; dst[6] = src[6];
+    wb.perm[rank] = T.perm[slot];
+    if ((rank & 7) == 0) wb.gmin[rank >> 3] = T.gmin[slot >> 3];    // lower bound of this and every later key
+  }
+  return mk;
+}
+// Pads the warp's table to a whole group of 8 spheres with never-hit entries; returns its pair count.
+__device__ __forceinline__ int cull_finish(const WarpBuf &wb, int ncand) {
+  const int lane = threadIdx.x & 31, padded = (ncand + 7) & ~7, rank = ncand + lane;
+  if (rank < padded) {
+    float *dst = reinterpret_cast<float *>(wb.pairs) + (rank >> 1) * 8 + (rank & 1);
+    dst[0] = 0.f; dst[2] = 0.f; dst[4] = 0.f; dst[6] = -1.0f;
+    wb.perm[rank] = -1;
+  }
+  __syncwarp();
+  return padded >> 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// CLOSEST HIT, shared origin (camera table, sorted by nearest-point distance).  NR rays per lane.
 // The query is resumable over pair ranges so that a table larger than shared memory can be streamed
 // through it tile by tile: `pairs` is indexed with ABSOLUTE pair numbers (a tile buffer is passed as
 // buffer - 2*first_pair), gmin / perm may live in global memory.
+template <int NR>
 struct ClosestQ {
-  Best best[2];
+  Best best[NR];
   float wcut;                                        // warp-uniform: farthest cutoff of any live ray
 };
-__device__ __forceinline__ void closest_begin(ClosestQ &q) { best_init(q.best[0]); best_init(q.best[1]); q.wcut = 3.0e38f; }
+template <int NR>
+__device__ __forceinline__ void closest_begin(ClosestQ<NR> &q) {
+#pragma unroll
+  for (int r = 0; r < NR; r++) best_init(q.best[r]);
+  q.wcut = 3.0e38f;
+}
 
 // returns false once every remaining sphere of the (sorted) table is beyond every ray's best hit
-__device__ __forceinline__ bool closest_shared_range(ClosestQ &q, const float4 *__restrict__ pairs, const float *gmin, const int *perm,
-                                                     int pbeg, int pend, const float (&dx)[2], const float (&dy)[2],
-                                                     const float (&dz)[2], const bool (&live)[2], float d64, const double4 *sph64,
-                                                     const RaySrc (&src)[2]) {
-  const float2 dx2[2] = {make_float2(dx[0], dx[0]), make_float2(dx[1], dx[1])};
-  const float2 dy2[2] = {make_float2(dy[0], dy[0]), make_float2(dy[1], dy[1])};
-  const float2 dz2[2] = {make_float2(dz[0], dz[0]), make_float2(dz[1], dz[1])};
+template <int NR>
+__device__ __forceinline__ bool closest_shared_range(ClosestQ<NR> &q, const float4 *__restrict__ pairs, const float *gmin, const int *perm,
+                                                     int pbeg, int pend, const float (&dx)[NR], const float (&dy)[NR],
+                                                     const float (&dz)[NR], const bool (&live)[NR], float d64, const double4 *sph64,
+                                                     const RaySrc (&src)[NR]) {
+  float2 dx2[NR], dy2[NR], dz2[NR];
+#pragma unroll
+  for (int r = 0; r < NR; r++) { dx2[r] = make_float2(dx[r], dx[r]); dy2[r] = make_float2(dy[r], dy[r]); dz2[r] = make_float2(dz[r], dz[r]); }
 #pragma unroll 1
   for (int p0 = pbeg; p0 < pend; p0 += kChunkPairs) {
     if (gmin[p0 / kGroupPairs] > q.wcut) return false;
     const int np = min(kChunkPairs, pend - p0);
-    unsigned h0, h1;
-    chunk_test_shared(pairs, p0, np, dx2, dy2, dz2, h0, h1);
-    const unsigned f[2] = {flagged_bits(h0, np, live[0]), flagged_bits(h1, np, live[1])};
-    if (__any_sync(kFull, (f[0] | f[1]) != 0u)) {
+    unsigned h[NR], f[NR], any = 0u;
+    chunk_test_shared<NR>(pairs, p0, np, dx2, dy2, dz2, h);
+#pragma unroll
+    for (int r = 0; r < NR; r++) { f[r] = flagged_bits(h[r], np, live[r]); any |= f[r]; }
+    if (__any_sync(kFull, any != 0u)) {
       // drain: every lane resolves its own flagged pairs, nearest first, one per iteration
 #pragma unroll
-      for (int r = 0; r < 2; r++) {
+      for (int r = 0; r < NR; r++) {
         unsigned fr = f[r];
         while (__any_sync(kFull, fr != 0u)) {
           if (fr != 0u) {
@@ -429,19 +547,56 @@ __device__ __forceinline__ bool closest_shared_range(ClosestQ &q, const float4 *
           }
         }
       }
-      q.wcut = wmaxf(fmaxf(live[0] ? q.best[0].hi : -3.0e38f, live[1] ? q.best[1].hi : -3.0e38f));
+      float c = -3.0e38f;
+#pragma unroll
+      for (int r = 0; r < NR; r++) c = fmaxf(c, live[r] ? q.best[r].hi : -3.0e38f);
+      q.wcut = wmaxf(c);
     }
   }
   return true;
 }
 
-__device__ __forceinline__ void closest_shared(const Tab T, int npairs, const float (&dx)[2], const float (&dy)[2],
-                                               const float (&dz)[2], const bool (&live)[2], float d64, const double4 *sph64,
-                                               const RaySrc (&src)[2], Best (&best)[2]) {
-  ClosestQ q;
+template <int NR>
+__device__ __forceinline__ void closest_shared(const Tab T, int npairs, const float (&dx)[NR], const float (&dy)[NR],
+                                               const float (&dz)[NR], const bool (&live)[NR], float d64, const double4 *sph64,
+                                               const RaySrc (&src)[NR], Best (&best)[NR]) {
+  ClosestQ<NR> q;
   closest_begin(q);
-  closest_shared_range(q, T.pairs, T.gmin, T.perm, 0, npairs, dx, dy, dz, live, d64, sph64, src);
-  best[0] = q.best[0]; best[1] = q.best[1];
+  closest_shared_range<NR>(q, T.pairs, T.gmin, T.perm, 0, npairs, dx, dy, dz, live, d64, sph64, src);
+#pragma unroll
+  for (int r = 0; r < NR; r++) best[r] = q.best[r];
+}
+
+// The same query with bundle culling (T staged in shared memory, wb = this warp's compacted table).
+template <int NR>
+__device__ __forceinline__ void closest_shared_culled(const Tab T, int npairs, const WarpBuf &wb, const float (&dx)[NR],
+                                                      const float (&dy)[NR], const float (&dz)[NR], const bool (&live)[NR], float d64,
+                                                      const double4 *sph64, const RaySrc (&src)[NR], Best (&best)[NR],
+                                                      unsigned &c_cand, unsigned &c_walks) {
+  const Cone cone = warp_cone<NR>(dx, dy, dz, live);
+  if (!cone.ok) { closest_shared<NR>(T, npairs, dx, dy, dz, live, d64, sph64, src, best); return; }
+  c_walks++;
+  ClosestQ<NR> q;
+  closest_begin(q);
+  const int nslots = 2 * npairs;
+  int ncand = 0;
+  bool more = true;
+#pragma unroll 1
+  for (int base = 0; base < nslots && more; base += 32) {
+    if (T.gmin[base >> 3] > q.wcut) break;           // the rest of the table is beyond every ray's best hit
+    ncand += __popc(cull_round(T, base, nslots, cone, q.wcut, wb, ncand));
+    if (ncand > kCandMax - 32 || base + 32 >= nslots) {
+      if (ncand > 0) {
+        c_cand += (unsigned)ncand;
+        const int np = cull_finish(wb, ncand);
+        more = closest_shared_range<NR>(q, wb.pairs, wb.gmin, wb.perm, 0, np, dx, dy, dz, live, d64, sph64, src);
+        __syncwarp();
+        ncand = 0;
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < NR; r++) best[r] = q.best[r];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -450,16 +605,17 @@ __device__ __forceinline__ void closest_shared(const Tab T, int npairs, const fl
 // bound of the true centre projection), q = |X|^2 - rho' (>= 0 => origin strictly outside),
 // D' = tu^2 - q.  A sphere is skipped when D' < 0, or when it lies behind an origin that is outside
 // it (tu < 0 and q >= 0): that removes the sphere the ray just left without any extra arithmetic.
-__device__ __forceinline__ void closest_general(const float4 *__restrict__ pairs, int npairs, int N, const float (&ox)[2],
-                                                const float (&oy)[2], const float (&oz)[2], const float (&dx)[2],
-                                                const float (&dy)[2], const float (&dz)[2], const bool (&live)[2], float d64,
-                                                float gS2, float dtmax, const double4 *sph64, const RaySrc (&src)[2],
-                                                Best (&best)[2]) {
+template <int NR>
+__device__ __forceinline__ void closest_general(const float4 *__restrict__ pairs, int npairs, int N, const float (&ox)[NR],
+                                                const float (&oy)[NR], const float (&oz)[NR], const float (&dx)[NR],
+                                                const float (&dy)[NR], const float (&dz)[NR], const bool (&live)[NR], float d64,
+                                                float gS2, float dtmax, const double4 *sph64, const RaySrc (&src)[NR],
+                                                Best (&best)[NR]) {
   const float kInfl = 1.0f + 24.0f * 5.9604645e-8f;
-  float2 nox[2], noy[2], noz[2], idx2[2], idy2[2], idz2[2];
+  float2 nox[NR], noy[NR], noz[NR], idx2[NR], idy2[NR], idz2[NR];
   const float2 dtm = make_float2(dtmax, dtmax);
 #pragma unroll
-  for (int r = 0; r < 2; r++) {
+  for (int r = 0; r < NR; r++) {
     nox[r] = make_float2(-ox[r], -ox[r]); noy[r] = make_float2(-oy[r], -oy[r]); noz[r] = make_float2(-oz[r], -oz[r]);
     float ix = __fmul_rn(dx[r], kInfl), iy = __fmul_rn(dy[r], kInfl), iz = __fmul_rn(dz[r], kInfl);
     idx2[r] = make_float2(ix, ix); idy2[r] = make_float2(iy, iy); idz2[r] = make_float2(iz, iz);
@@ -467,19 +623,21 @@ __device__ __forceinline__ void closest_general(const float4 *__restrict__ pairs
 #pragma unroll 1
   for (int p0 = 0; p0 < npairs; p0 += kChunkPairs) {
     const int np = min(kChunkPairs, npairs - p0);
-    unsigned h[2] = {kFull, kFull};
+    unsigned h[NR];
+#pragma unroll
+    for (int r = 0; r < NR; r++) h[r] = kFull;
 #pragma unroll 1
     for (int p = p0; p < p0 + np; p += 2) {
 #pragma unroll
       for (int k = 0; k < 2; k++) {
         const float4 A = pairs[2 * (p + k)], B = pairs[2 * (p + k) + 1];
         const float2 CX = make_float2(A.x, A.y), CY = make_float2(A.z, A.w), CZ = make_float2(B.x, B.y);
-        const float2 NR = make_float2(-B.z, -B.w);
+        const float2 NR_ = make_float2(-B.z, -B.w);
 #pragma unroll
-        for (int r = 0; r < 2; r++) {
+        for (int r = 0; r < NR; r++) {
           const float2 x = __fadd2_rn(CX, nox[r]), y = __fadd2_rn(CY, noy[r]), z = __fadd2_rn(CZ, noz[r]);
           float2 t = __ffma2_rn(x, idx2[r], dtm); t = __ffma2_rn(y, idy2[r], t); t = __ffma2_rn(z, idz2[r], t);
-          float2 q = __ffma2_rn(x, x, NR); q = __ffma2_rn(y, y, q); q = __ffma2_rn(z, z, q);
+          float2 q = __ffma2_rn(x, x, NR_); q = __ffma2_rn(y, y, q); q = __ffma2_rn(z, z, q);
           const float2 D = __ffma2_rn(t, t, make_float2(-q.x, -q.y));
           // rejected  <=>  D' < 0  or  (tu < 0 and q >= 0)
           h[r] = push_sign(h[r], (fbits(D.x) | (fbits(t.x) & ~fbits(q.x))) & (fbits(D.y) | (fbits(t.y) & ~fbits(q.y))));
@@ -487,7 +645,7 @@ __device__ __forceinline__ void closest_general(const float4 *__restrict__ pairs
       }
     }
 #pragma unroll
-    for (int r = 0; r < 2; r++) {
+    for (int r = 0; r < NR; r++) {
       unsigned fr = flagged_bits(h[r], np, live[r]);
       while (__any_sync(kFull, fr != 0u)) {
         if (fr != 0u) {
@@ -510,40 +668,47 @@ __device__ __forceinline__ void closest_general(const float4 *__restrict__ pairs
 // the point, so the filter flags it for every query; on its lit side it cannot occlude (the shadow
 // origin is outside it and moving away), so its flag is cleared up front unless its pair partner
 // is a candidate too.  p64[r] points at the exact hit point (only read if FP64 is needed).
+template <int NR>
 struct ShadowQ {
-  bool open[2], occ[2];                              // still undecided / found an occluder
-  float m[2], cut[2], wcut;
-  int sslot[2];                                      // slot of the lit self sphere in this light's table, or -1
+  bool open[NR], occ[NR];                            // still undecided / found an occluder
+  float m[NR], cut[NR], wcut;
+  int tslot[NR];                                     // slot of the lit self sphere in this light's table, or -1
+  int sslot[NR];                                     // ... its position in the table shadow_range is walking, or -1
 };
-__device__ __forceinline__ void shadow_begin(ShadowQ &q, const int *inv, const float (&so)[2], const bool (&want)[2],
-                                             const int (&self)[2], const float (&cosl)[2]) {
+template <int NR>
+__device__ __forceinline__ void shadow_begin(ShadowQ<NR> &q, const int *inv, const float (&so)[NR], const bool (&want)[NR],
+                                             const int (&self)[NR], const float (&cosl)[NR]) {
+  float c = -3.0e38f;
 #pragma unroll
-  for (int r = 0; r < 2; r++) {
+  for (int r = 0; r < NR; r++) {
     q.open[r] = want[r]; q.occ[r] = false;
     q.m[r] = __fmaf_ru(1.9073486e-6f, so[r] + kEps, 1e-7f);   // 2^-19 |L-p|: covers the FP32 length error
     q.cut[r] = want[r] ? so[r] + q.m[r] : -3.0e38f;           // nothing farther from the light can matter
-    q.sslot[r] = (want[r] && cosl[r] > 1e-3f) ? (inv[self[r]] & 0x3fffffff) : -1;
+    q.tslot[r] = (want[r] && cosl[r] > 1e-3f) ? (inv[self[r]] & 0x3fffffff) : -1;
+    q.sslot[r] = q.tslot[r];
+    c = fmaxf(c, q.cut[r]);
   }
-  q.wcut = wmaxf(fmaxf(q.cut[0], q.cut[1]));
+  q.wcut = wmaxf(c);
 }
 
 // returns false once the warp needs nothing further from this (sorted) table
-__device__ __forceinline__ bool shadow_range(ShadowQ &q, const float4 *__restrict__ pairs, const float *gmin, const int *perm, int pbeg,
-                                             int pend, int light, const float (&dx)[2], const float (&dy)[2], const float (&dz)[2],
-                                             const float (&so)[2], const int (&self)[2], const float (&cosl)[2],
-                                             const double *const (&p64)[2], float d64, const double4 *sph64, int &n_fp64) {
-  const float2 dx2[2] = {make_float2(dx[0], dx[0]), make_float2(dx[1], dx[1])};
-  const float2 dy2[2] = {make_float2(dy[0], dy[0]), make_float2(dy[1], dy[1])};
-  const float2 dz2[2] = {make_float2(dz[0], dz[0]), make_float2(dz[1], dz[1])};
+template <int NR>
+__device__ __forceinline__ bool shadow_range(ShadowQ<NR> &q, const float4 *__restrict__ pairs, const float *gmin, const int *perm, int pbeg,
+                                             int pend, int light, const float (&dx)[NR], const float (&dy)[NR], const float (&dz)[NR],
+                                             const float (&so)[NR], const int (&self)[NR], const float (&cosl)[NR],
+                                             const double *const (&p64)[NR], float d64, const double4 *sph64, int &n_fp64) {
+  float2 dx2[NR], dy2[NR], dz2[NR];
+#pragma unroll
+  for (int r = 0; r < NR; r++) { dx2[r] = make_float2(dx[r], dx[r]); dy2[r] = make_float2(dy[r], dy[r]); dz2[r] = make_float2(dz[r], dz[r]); }
 #pragma unroll 1
   for (int p0 = pbeg; p0 < pend; p0 += kChunkPairs) {
     if (gmin[p0 / kGroupPairs] > q.wcut) return false;
     const int np = min(kChunkPairs, pend - p0);
-    unsigned h0, h1;
-    chunk_test_shared(pairs, p0, np, dx2, dy2, dz2, h0, h1);
-    unsigned f[2] = {flagged_bits(h0, np, q.open[0]), flagged_bits(h1, np, q.open[1])};
+    unsigned h[NR], f[NR], any = 0u;
+    chunk_test_shared<NR>(pairs, p0, np, dx2, dy2, dz2, h);
 #pragma unroll
-    for (int r = 0; r < 2; r++) {
+    for (int r = 0; r < NR; r++) {
+      f[r] = flagged_bits(h[r], np, q.open[r]);
       const int sp = q.sslot[r] >> 1;                // pair of the lit self sphere (or -1)
       if (sp >= p0 && sp < p0 + np) {
         const int ph = (q.sslot[r] & 1) ^ 1;         // partner = the other half of the pair
@@ -552,10 +717,11 @@ __device__ __forceinline__ bool shadow_range(ShadowQ &q, const float4 *__restric
         shared_origin_eval(ph ? A.y : A.x, ph ? A.w : A.z, ph ? B.y : B.x, ph ? B.w : B.z, dx[r], dy[r], dz[r], tca, Dp);
         if (!(Dp >= 0.0f)) f[r] &= ~(1u << (p0 + np - 1 - sp));
       }
+      any |= f[r];
     }
-    if (__any_sync(kFull, (f[0] | f[1]) != 0u)) {
+    if (__any_sync(kFull, any != 0u)) {
 #pragma unroll
-      for (int r = 0; r < 2; r++) {
+      for (int r = 0; r < NR; r++) {
         unsigned fr = f[r];
         while (__any_sync(kFull, fr != 0u)) {
           if (fr != 0u) {
@@ -572,21 +738,72 @@ __device__ __forceinline__ bool shadow_range(ShadowQ &q, const float4 *__restric
           }
         }
       }
-      q.wcut = wmaxf(fmaxf(q.open[0] ? q.cut[0] : -3.0e38f, q.open[1] ? q.cut[1] : -3.0e38f));   // decided rays stop holding the warp
+      float c = -3.0e38f;
+#pragma unroll
+      for (int r = 0; r < NR; r++) c = fmaxf(c, q.open[r] ? q.cut[r] : -3.0e38f);   // decided rays stop holding the warp
+      q.wcut = wmaxf(c);
       if (q.wcut < -1.0e38f) return false;
     }
   }
   return true;
 }
 
-__device__ __forceinline__ void shadow_light(const Tab T, int npairs, int light, const float (&dx)[2], const float (&dy)[2],
-                                             const float (&dz)[2], const float (&so)[2], const bool (&want)[2],
-                                             const int (&self)[2], const float (&cosl)[2], const double *const (&p64)[2], float d64,
-                                             const double4 *sph64, bool (&occ)[2], int &n_fp64) {
-  ShadowQ q;
-  shadow_begin(q, T.inv, so, want, self, cosl);
-  shadow_range(q, T.pairs, T.gmin, T.perm, 0, npairs, light, dx, dy, dz, so, self, cosl, p64, d64, sph64, n_fp64);
-  occ[0] = q.occ[0]; occ[1] = q.occ[1];
+template <int NR>
+__device__ __forceinline__ void shadow_light(const Tab T, int npairs, int light, const float (&dx)[NR], const float (&dy)[NR],
+                                             const float (&dz)[NR], const float (&so)[NR], const bool (&want)[NR],
+                                             const int (&self)[NR], const float (&cosl)[NR], const double *const (&p64)[NR], float d64,
+                                             const double4 *sph64, bool (&occ)[NR], int &n_fp64) {
+  ShadowQ<NR> q;
+  shadow_begin<NR>(q, T.inv, so, want, self, cosl);
+  shadow_range<NR>(q, T.pairs, T.gmin, T.perm, 0, npairs, light, dx, dy, dz, so, self, cosl, p64, d64, sph64, n_fp64);
+#pragma unroll
+  for (int r = 0; r < NR; r++) occ[r] = q.occ[r];
+}
+
+// The same query with bundle culling (T staged in shared memory, wb = this warp's compacted table).
+template <int NR>
+__device__ __forceinline__ void shadow_light_culled(const Tab T, int npairs, const WarpBuf &wb, int light, const float (&dx)[NR],
+                                                    const float (&dy)[NR], const float (&dz)[NR], const float (&so)[NR],
+                                                    const bool (&want)[NR], const int (&self)[NR], const float (&cosl)[NR],
+                                                    const double *const (&p64)[NR], float d64, const double4 *sph64, bool (&occ)[NR],
+                                                    int &n_fp64, unsigned &c_cand, unsigned &c_walks) {
+  const Cone cone = warp_cone<NR>(dx, dy, dz, want);
+  if (!cone.ok) { shadow_light<NR>(T, npairs, light, dx, dy, dz, so, want, self, cosl, p64, d64, sph64, occ, n_fp64); return; }
+  c_walks++;
+  ShadowQ<NR> q;
+  shadow_begin<NR>(q, T.inv, so, want, self, cosl);
+#pragma unroll
+  for (int r = 0; r < NR; r++) q.sslot[r] = -1;
+  const int nslots = 2 * npairs;
+  int ncand = 0;
+  bool more = true;
+#pragma unroll 1
+  for (int base = 0; base < nslots && more; base += 32) {
+    const bool beyond = T.gmin[base >> 3] > q.wcut;  // the rest of the table is farther from the light than every open point
+    if (!beyond) {
+      const unsigned mk = cull_round(T, base, nslots, cone, q.wcut, wb, ncand);
+#pragma unroll
+      for (int r = 0; r < NR; r++) {                 // where did this ray's lit self sphere go?
+        const unsigned b = (unsigned)(q.tslot[r] - base);
+        if (b < 32u && ((mk >> b) & 1u)) q.sslot[r] = ncand + __popc(mk & ((1u << b) - 1u));
+      }
+      ncand += __popc(mk);
+    }
+    if (beyond || ncand > kCandMax - 32 || base + 32 >= nslots) {
+      if (ncand > 0) {
+        c_cand += (unsigned)ncand;
+        const int np = cull_finish(wb, ncand);
+        more = shadow_range<NR>(q, wb.pairs, wb.gmin, wb.perm, 0, np, light, dx, dy, dz, so, self, cosl, p64, d64, sph64, n_fp64);
+        __syncwarp();
+        ncand = 0;
+#pragma unroll
+        for (int r = 0; r < NR; r++) q.sslot[r] = -1;
+      }
+      if (beyond) break;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < NR; r++) occ[r] = q.occ[r];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -604,100 +821,6 @@ __device__ __forceinline__ void queue_push(bool want, const RayRec &rec, RayRec 
 struct Counters {
   unsigned long long closest, hits, shadow, occluded, fp64, violations;
 };
-
-// ---------------------------------------------------------------------------------------------
-// Shading of up to two hits per lane (shared by both kernels).
-//   in : hit[r], sphere index, exact FP64 ray (o, d) and t of the hit, carried acc/wt
-//   out: final[r] (pixel finished, colour in cr/cg/cb) or cont[r] + rec[r] (reflected ray).
-__device__ __forceinline__ void shade_hits(const FastArgs &a, const unsigned char *tabs_base, int first_light_table,
-                                           const bool (&hit)[2], const int (&idx)[2], const d3 (&o64)[2], const d3 (&d64v)[2],
-                                           const double (&t64)[2], const unsigned (&pix)[2], float (&wt)[2], float (&cr)[2],
-                                           float (&cg)[2], float (&cb)[2], bool (&final_)[2], bool (&cont)[2], RayRec (&rec)[2],
-                                           int level, Counters &cnt, int &n_fp64) {
-  d3 p[2], n[2];
-  float nx[2], ny[2], nz[2], vx[2], vy[2], vz[2];
-  float4 m[2]; float2 mx[2];
-  float sr[2], sg[2], sb[2];
-  unsigned smask[2] = {0u, 0u};
-#pragma unroll
-  for (int r = 0; r < 2; r++) {
-    p[r] = rtx::mk(0, 0, 0); n[r] = p[r];
-    m[r] = make_float4(0, 0, 0, 0); mx[r] = make_float2(0, 0);
-    nx[r] = ny[r] = nz[r] = vx[r] = vy[r] = vz[r] = 0.f; sr[r] = sg[r] = sb[r] = 0.f;
-    cont[r] = false;
-    if (hit[r]) {
-      const HitGeom hg = hit_geometry(a.r.sph64, idx[r], o64[r], d64v[r], t64[r]);   // src/main.cpp:32,35
-      p[r] = hg.p; n[r] = hg.n;
-      m[r] = __ldg(&a.r.mat[idx[r]]); mx[r] = __ldg(&a.r.matx[idx[r]]);
-      nx[r] = (float)n[r].x; ny[r] = (float)n[r].y; nz[r] = (float)n[r].z;
-      // view_dir = normalized(origin - hit) = -d up to rounding (src/main.cpp:38); colour only
-      vx[r] = -(float)d64v[r].x; vy[r] = -(float)d64v[r].y; vz[r] = -(float)d64v[r].z;
-      sr[r] = g_frame.ambient[0] * m[r].x; sg[r] = g_frame.ambient[1] * m[r].y; sb[r] = g_frame.ambient[2] * m[r].z;
-    }
-  }
-  const int L = a.L;
-  if (__any_sync(kFull, hit[0] || hit[1])) {
-    for (int l = 0; l < L; l++) {
-      float dx[2], dy[2], dz[2], so[2], cosl[2];
-      bool occ[2];
-      const d3 lp = ldc3(g_frame.light_pos[l]);
-#pragma unroll
-      for (int r = 0; r < 2; r++) {
-        dx[r] = dy[r] = dz[r] = 0.f; so[r] = 0.f; cosl[r] = 0.f;
-        if (hit[r]) {
-          // direction light -> point: FP64 difference, FP32 normalisation (error <= 12u, see filter_math.cuh)
-          const d3 w = rtx::sub(p[r], lp);
-          const float wx = (float)w.x, wy = (float)w.y, wz = (float)w.z;
-          const float l2 = fmaf(wz, wz, fmaf(wy, wy, wx * wx));
-          const float inv = rsqrtf(l2);
-          dx[r] = wx * inv; dy[r] = wy * inv; dz[r] = wz * inv;
-          so[r] = l2 * inv - kEps;
-          cosl[r] = -(nx[r] * dx[r] + ny[r] * dy[r] + nz[r] * dz[r]);         // n . light_dir
-        }
-      }
-      const double *const pp[2] = {&p[0].x, &p[1].x};
-      shadow_light(tab_at(tabs_base, a, first_light_table + l), a.npairs, l, dx, dy, dz, so, hit, idx, cosl, pp, a.d64,
-                   a.r.sph64, occ, n_fp64);
-#pragma unroll
-      for (int r = 0; r < 2; r++) {
-        if (!hit[r]) continue;
-        cnt.shadow++;
-        if (occ[r]) { cnt.occluded++; if (l < 32) smask[r] |= 1u << l; continue; }
-        // include/scene.h:104-117 in FP32; light_dir = -(dx,dy,dz)
-        const float ndl = fmaxf(0.0f, cosl[r]);
-        const float kd = (1.0f - m[r].w) * ndl;
-        const float dn = -cosl[r];                                                // dot(-light_dir, n)
-        const float rx = dx[r] - 2.0f * nx[r] * dn, ry = dy[r] - 2.0f * ny[r] * dn, rz = dz[r] - 2.0f * nz[r] * dn;
-        const float rdv = fmaxf(0.0f, rx * vx[r] + ry * vy[r] + rz * vz[r]);
-        const float spec = 0.5f * (mx[r].x == 0.0f ? 1.0f : __powf(rdv, mx[r].x));
-        sr[r] += g_frame.light_col[l][0] * spec + m[r].x * kd;
-        sg[r] += g_frame.light_col[l][1] * spec + m[r].y * kd;
-        sb[r] += g_frame.light_col[l][2] * spec + m[r].z * kd;
-      }
-    }
-  }
-  // continuation: src/main.cpp:43-55 unrolled front to back
-#pragma unroll
-  for (int r = 0; r < 2; r++) {
-    if (!hit[r]) continue;
-    if (a.r.shadow_mask) a.r.shadow_mask[(size_t)pix[r] * a.r.max_depth + level] = smask[r];
-    if (mx[r].y > 0.5f) {                         // reflectivity > 0, decided in double on the host
-      const float refl = m[r].w, k = wt[r] * (1.0f - refl);
-      cr[r] += k * sr[r]; cg[r] += k * sg[r]; cb[r] += k * sb[r];
-      wt[r] *= refl;
-      if (level + 1 < a.r.max_depth) {
-        reflected_ray(d64v[r], p[r], n[r], &rec[r]);
-        rec[r].pix = pix[r]; rec[r].wt = wt[r]; rec[r].ar = cr[r]; rec[r].ag = cg[r]; rec[r].ab = cb[r]; rec[r].pad = 0;
-        cont[r] = true;
-      } else {
-        final_[r] = true;                         // depth exhausted: the child contributes black
-      }
-    } else {
-      cr[r] += wt[r] * sr[r]; cg[r] += wt[r] * sg[r]; cb[r] += wt[r] * sb[r];
-      final_[r] = true;
-    }
-  }
-}
 
 __device__ __forceinline__ void flush_counters(const FastArgs &a, Counters &c, int &n_fp64, int level) {
   if (!a.r.counters) return;
@@ -719,224 +842,160 @@ __device__ __forceinline__ void flush_counters(const FastArgs &a, Counters &c, i
   n_fp64 = 0;
 }
 
-// Exact FP64 t of the winner (or the brute-force safety net if the filter contradicted itself).
-__device__ __forceinline__ void finish_closest(const FastArgs &a, const Best &b, const ExactRay &e, bool &hit, int &idx, double &t64,
-                                               Counters &cnt, int &n_fp64) {
-  double t = b.t;
-  bool ok = b.exact;
-  if (!ok) { n_fp64++; ok = exact_sphere(a.r.sph64, b.idx, e.o, e.d, e.a, t) && t < 1e20; }
-  int bi = b.idx;
-  if (!ok) { cnt.violations++; bi = exact_bruteforce(a.r.sph64, a.N, e.o, e.d, e.a, t); }
-  if (bi >= 0) { hit = true; idx = bi; t64 = t; cnt.hits++; }
-}
-
 // ---------------------------------------------------------------------------------------------
-// LEVEL 0: camera rays.  Each warp pulls 16x4-pixel tiles; lane = (lx, ly) = (lane & 15, lane >> 4)
-// owns the two vertically adjacent pixels (x, 2*ly) and (x, 2*ly + 1) of the tile.
+// THE TAIL (levels >= wave_levels): reflected rays from the queue, one per lane, 32 per warp fetch;
+// every lane follows its ray to termination, the queue record is updated in place.  Few rays are
+// left at these levels (a few percent of the frame), so the kernel is bound by the latency of one
+// warp's chain: closest hit -> exact t / geometry -> one shadow query per light -> Phong -> reflect.
+#ifndef RT_TAIL_THREADS
+#define RT_TAIL_THREADS 128
+#endif
+#ifndef RT_TAIL_CTAS
+#define RT_TAIL_CTAS 2
+#endif
+constexpr int kTailThreads = RT_TAIL_THREADS;
 template <bool kSmem>
-__global__ void __launch_bounds__(kThreads, 2) k_primary(const FastArgs a) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  const unsigned char *tabs = a.tabs;
-  if (kSmem) { stage_tables(smem, a.tabs, a.stage_bytes); tabs = smem + kSmemHeader; }
-  const Tab cam = tab_at(tabs, a, 0);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned char *s_rgb = smem + 64 + warp * (kWTileH * kWTileW * 3);
-  const int W = a.r.W, rows = a.r.bands.local_rows, depth = a.r.max_depth;
-  Counters cnt = {0, 0, 0, 0, 0, 0};
-  int n_fp64 = 0;
-  for (;;) {
-    const int tile = warp_fetch(a.tile_counter);
-    if (tile >= a.nwtiles) break;
-    const int tx0 = (tile % a.wtiles_x) * kWTileW, ty0 = (tile / a.wtiles_x) * kWTileH;
-    const int x = tx0 + (lane & 15);
-    int lr[2], j[2];
-    unsigned pix[2];
-    bool live[2];
-    float dx[2], dy[2], dz[2];
-#pragma unroll
-    for (int r = 0; r < 2; r++) {
-      lr[r] = ty0 + (lane >> 4) * 2 + r;
-      live[r] = x < W && lr[r] < rows && depth > 0;
-      j[r] = 0; pix[r] = 0; dx[r] = dy[r] = dz[r] = 0.f;
-      if (x < W && lr[r] < rows) {
-        j[r] = rt_local_to_global_row(a.r.bands, lr[r]);
-        pix[r] = (unsigned)lr[r] * (unsigned)W + (unsigned)x;
-      }
-      if (live[r]) {
-        // include/camera.h:21-22 in FP64 (un-normalised), then an FP32 unit vector for the filter
-        const d3 v = rtx::add(rtx::add(ldc3(g_frame.fwd), rtx::scale(ldc3(g_frame.right), a.r.su[x])),
-                              rtx::scale(ldc3(g_frame.up), a.r.sv[j[r]]));
-        const float fx = (float)v.x, fy = (float)v.y, fz = (float)v.z;
-        const float inv = rsqrtf(fmaf(fz, fz, fmaf(fy, fy, fx * fx)));
-        dx[r] = fx * inv; dy[r] = fy * inv; dz[r] = fz * inv;
-        if (a.r.hit_idx) for (int k = 0; k < depth; k++) a.r.hit_idx[(size_t)pix[r] * depth + k] = -2;
-        if (a.r.shadow_mask) for (int k = 0; k < depth; k++) a.r.shadow_mask[(size_t)pix[r] * depth + k] = 0u;
-      }
-    }
-    Best best[2];
-    best_init(best[0]); best_init(best[1]);
-    const RaySrc src[2] = {{a.r.su, a.r.sv, x, j[0], nullptr}, {a.r.su, a.r.sv, x, j[1], nullptr}};
-    closest_shared(cam, a.npairs, dx, dy, dz, live, a.d64, a.r.sph64, src, best);
-
-    bool hit[2], final_[2], cont[2];
-    int idx[2];
-    d3 o64[2], d64v[2];
-    double t64[2];
-    RayRec rec[2];
-    float wt[2] = {1.f, 1.f}, cr[2] = {0.f, 0.f}, cg[2] = {0.f, 0.f}, cb[2] = {0.f, 0.f};
-#pragma unroll
-    for (int r = 0; r < 2; r++) {
-      hit[r] = false; final_[r] = false; idx[r] = -1; t64[r] = 0;
-      o64[r] = rtx::mk(0, 0, 0); d64v[r] = o64[r];
-      if (!live[r]) continue;
-      cnt.closest++;
-      n_fp64 += best[r].nfp64;
-      if (best[r].idx >= 0) {
-        const ExactRay e = exact_ray(src[r]);
-        finish_closest(a, best[r], e, hit[r], idx[r], t64[r], cnt, n_fp64);
-        o64[r] = e.o; d64v[r] = e.d;
-      }
-      if (a.r.hit_idx) a.r.hit_idx[(size_t)pix[r] * depth] = idx[r];
-      if (!hit[r]) {                               // sky, src/main.cpp:26-30
-        const float ts = 0.5f * (dy[r] + 1.0f);
-        cr[r] = (1.0f - ts) + 0.5f * ts; cg[r] = (1.0f - ts) + 0.7f * ts; cb[r] = (1.0f - ts) + ts;
-        final_[r] = true;
-      }
-    }
-    shade_hits(a, tabs, 1, hit, idx, o64, d64v, t64, pix, wt, cr, cg, cb, final_, cont, rec, 0, cnt, n_fp64);
-#pragma unroll
-    for (int r = 0; r < 2; r++) queue_push(cont[r], rec[r], a.q_out, a.q_out_count);
-
-    // ---- 8-bit quantise (src/main.cpp:84-86) into the warp's staging buffer, then 128-bit row stores
-#pragma unroll
-    for (int r = 0; r < 2; r++) {
-      unsigned char *q = s_rgb + (((lane >> 4) * 2 + r) * kWTileW + (lane & 15)) * 3;
-      const bool fin = final_[r] || (x < W && lr[r] < rows && depth <= 0);
-      q[0] = (unsigned char)quant8(fin ? cr[r] : 0.f); q[1] = (unsigned char)quant8(fin ? cg[r] : 0.f);
-      q[2] = (unsigned char)quant8(fin ? cb[r] : 0.f);
-    }
-    __syncwarp();
-    if (tx0 + kWTileW <= W && (W & 15) == 0) {
-      // 3 x 16-byte stores per 48-byte row segment; pixels still in flight are overwritten by k_bounce
-      if (lane < kWTileH * 3) {
-        const int ty = lane / 3, seg = lane % 3;
-        if (ty0 + ty < rows)
-          *reinterpret_cast<uint4 *>(a.r.rgb + ((size_t)(ty0 + ty) * W + tx0) * 3 + seg * 16) =
-              *reinterpret_cast<const uint4 *>(s_rgb + ty * kWTileW * 3 + seg * 16);
-      }
-    } else {
-#pragma unroll
-      for (int r = 0; r < 2; r++) {
-        if (x < W && lr[r] < rows) {
-          const unsigned char *q = s_rgb + (((lane >> 4) * 2 + r) * kWTileW + (lane & 15)) * 3;
-          unsigned char *o = a.r.rgb + (size_t)pix[r] * 3;
-          o[0] = q[0]; o[1] = q[1]; o[2] = q[2];
-        }
-      }
-    }
-    __syncwarp();
-  }
-  flush_counters(a, cnt, n_fp64, 0);
-}
-
-// ---------------------------------------------------------------------------------------------
-// LEVEL >= 1: reflected rays from the queue, two per lane, 64 per warp fetch.
-// kTail = false: one level, survivors are compacted into q_out.
-// kTail = true : every lane follows its ray to termination; the record is updated in place.
-template <bool kSmem, bool kTail>
-__global__ void __launch_bounds__(kThreads, 2) k_bounce(const FastArgs a) {
+__global__ void __launch_bounds__(kTailThreads, RT_TAIL_CTAS) k_bounce(const FastArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const unsigned nq = *a.q_in_count;
   if (nq == 0u) return;                             // nothing survived to this level
   // staged: [L light tables][general table], contiguous in global memory in that order
   const unsigned char *tabs = a.tabs + a.tstride;
   if (kSmem) { stage_tables(smem, tabs, a.stage_bytes); tabs = smem + kSmemHeader; }
+  const WarpBuf wb = warp_buf(smem + kSmemHeader + ((a.stage_bytes + 127u) & ~127u));
   const float4 *gen = reinterpret_cast<const float4 *>(tabs + (size_t)a.L * a.tstride);
   const int lane = threadIdx.x & 31;
-  const int depth = a.r.max_depth;
+  const int depth = a.r.max_depth, L = a.L;
   Counters cnt = {0, 0, 0, 0, 0, 0};
   int n_fp64 = 0;
+  unsigned c_cand = 0, c_walks = 0;
   RayRec *qin = a.q_in;
   for (;;) {
-    // level 1: 64 rays per fetch (two per lane); tail: 32 (one per lane -- it is latency bound, the
-    // SMs are mostly empty there, so shorter per-warp chains beat packed arithmetic)
-    constexpr unsigned kRaysPerFetch = kTail ? 32u : 64u;
     const int chunk = warp_fetch(a.chunk_counter);
-    if ((unsigned)chunk * kRaysPerFetch >= nq) break;
-    bool live[2];
-    unsigned qi[2], pix[2];
-    float ox[2], oy[2], oz[2], dx[2], dy[2], dz[2];
-    float wt[2], cr[2], cg[2], cb[2];
-#pragma unroll
-    for (int r = 0; r < 2; r++) {
-      // the two rays of a lane are neighbours in the queue (coherent)
-      qi[r] = kTail ? (unsigned)chunk * 32u + lane : (unsigned)chunk * 64u + 2u * lane + r;
-      live[r] = qi[r] < nq && !(kTail && r == 1);
-      ox[r] = oy[r] = oz[r] = dx[r] = dy[r] = dz[r] = 0.f; wt[r] = cr[r] = cg[r] = cb[r] = 0.f; pix[r] = 0;
-      if (live[r]) {
-        const RayRec &q = qin[qi[r]];
-        // recentred FP32 origin and FP32 direction for the filter (exact values stay in the record)
-        ox[r] = (float)(q.ox - a.c0[0]); oy[r] = (float)(q.oy - a.c0[1]); oz[r] = (float)(q.oz - a.c0[2]);
-        dx[r] = (float)q.dx; dy[r] = (float)q.dy; dz[r] = (float)q.dz;
-        pix[r] = q.pix; wt[r] = q.wt; cr[r] = q.ar; cg[r] = q.ag; cb[r] = q.ab;
-      }
+    if ((unsigned)chunk * 32u >= nq) break;
+    const unsigned qi = (unsigned)chunk * 32u + lane;
+    bool live[1] = {qi < nq};
+    unsigned pix = 0;
+    float ox[1] = {0.f}, oy[1] = {0.f}, oz[1] = {0.f}, dx[1] = {0.f}, dy[1] = {0.f}, dz[1] = {0.f};
+    float wt = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
+    if (live[0]) {
+      const RayRec &q = qin[qi];
+      // recentred FP32 origin and FP32 direction for the filter (exact values stay in the record)
+      ox[0] = (float)(q.ox - a.c0[0]); oy[0] = (float)(q.oy - a.c0[1]); oz[0] = (float)(q.oz - a.c0[2]);
+      dx[0] = (float)q.dx; dy[0] = (float)q.dy; dz[0] = (float)q.dz;
+      pix = q.pix; wt = q.wt; cr = q.ar; cg = q.ag; cb = q.ab;
     }
-    const RaySrc src[2] = {{nullptr, nullptr, 0, 0, qin + qi[0]}, {nullptr, nullptr, 0, 0, qin + qi[1]}};
+    const RaySrc src[1] = {{nullptr, nullptr, 0, 0, qin + qi}};
     for (int level = a.level;; level++) {
-      Best best[2];
-      best_init(best[0]); best_init(best[1]);
-      closest_general(gen, a.npairs, a.N, ox, oy, oz, dx, dy, dz, live, a.d64, a.gS2, a.g_dtmax, a.r.sph64, src, best);
-      bool hit[2], final_[2], cont[2];
-      int idx[2];
-      d3 o64[2], d64v[2];
-      double t64[2];
-      RayRec rec[2];
-#pragma unroll
-      for (int r = 0; r < 2; r++) {
-        hit[r] = false; final_[r] = false; idx[r] = -1; t64[r] = 0;
-        o64[r] = rtx::mk(0, 0, 0); d64v[r] = o64[r];
-        if (!live[r]) continue;
+      Best best[1];
+      best_init(best[0]);
+      closest_general<1>(gen, a.npairs, a.N, ox, oy, oz, dx, dy, dz, live, a.d64, a.gS2, a.g_dtmax, a.r.sph64, src, best);
+      bool hit = false, final_ = false, cont = false;
+      int idx[1] = {-1};
+      double t64 = 0;
+      d3 o64 = rtx::mk(0, 0, 0), d64v = o64;
+      if (live[0]) {
         cnt.closest++;
-        n_fp64 += best[r].nfp64;
-        if (best[r].idx >= 0) {
-          const ExactRay e = exact_ray(src[r]);
-          finish_closest(a, best[r], e, hit[r], idx[r], t64[r], cnt, n_fp64);
-          o64[r] = e.o; d64v[r] = e.d;
+        n_fp64 += best[0].nfp64;
+        if (best[0].idx >= 0) {
+          const ExactRay e = exact_ray(src[0]);
+          // exact FP64 t of the winner (or the brute-force safety net if the filter contradicted itself)
+          double t = best[0].t;
+          bool ok = best[0].exact;
+          if (!ok) { n_fp64++; ok = exact_sphere(a.r.sph64, best[0].idx, e.o, e.d, e.a, t) && t < 1e20; }
+          int bi = best[0].idx;
+          if (!ok) { cnt.violations++; bi = exact_bruteforce(a.r.sph64, a.N, e.o, e.d, e.a, t); }
+          if (bi >= 0) { hit = true; idx[0] = bi; t64 = t; cnt.hits++; }
+          o64 = e.o; d64v = e.d;
         }
-        if (a.r.hit_idx) a.r.hit_idx[(size_t)pix[r] * depth + level] = idx[r];
-        if (!hit[r]) {
-          const float ts = 0.5f * (dy[r] + 1.0f);
-          cr[r] += wt[r] * ((1.0f - ts) + 0.5f * ts); cg[r] += wt[r] * ((1.0f - ts) + 0.7f * ts); cb[r] += wt[r] * ((1.0f - ts) + ts);
-          final_[r] = true;
-        }
-      }
-      shade_hits(a, tabs, 0, hit, idx, o64, d64v, t64, pix, wt, cr, cg, cb, final_, cont, rec, level, cnt, n_fp64);
-#pragma unroll
-      for (int r = 0; r < 2; r++) {
-        if (live[r] && final_[r]) {
-          unsigned char *o = a.r.rgb + (size_t)pix[r] * 3;
-          o[0] = (unsigned char)quant8(cr[r]); o[1] = (unsigned char)quant8(cg[r]); o[2] = (unsigned char)quant8(cb[r]);
+        if (a.r.hit_idx) a.r.hit_idx[(size_t)pix * depth + level] = idx[0];
+        if (!hit) {                                  // sky, src/main.cpp:26-30
+          const float ts = 0.5f * (dy[0] + 1.0f);
+          cr += wt * ((1.0f - ts) + 0.5f * ts); cg += wt * ((1.0f - ts) + 0.7f * ts); cb += wt * ((1.0f - ts) + ts);
+          final_ = true;
         }
       }
-      if (!kTail) {
-#pragma unroll
-        for (int r = 0; r < 2; r++) queue_push(cont[r], rec[r], a.q_out, a.q_out_count);
-        break;
+      // ---- shading of the hit (include/scene.h:89-121 in FP32, shadow booleans exact)
+      d3 p = rtx::mk(0, 0, 0), n = p;
+      float nx = 0.f, ny = 0.f, nz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f, sr = 0.f, sg = 0.f, sb = 0.f;
+      float4 m = make_float4(0, 0, 0, 0); float2 mx = make_float2(0, 0);
+      unsigned smask = 0u;
+      if (hit) {
+        const HitGeom hg = hit_geometry(a.r.sph64, idx[0], o64, d64v, t64);   // src/main.cpp:32,35
+        p = hg.p; n = hg.n;
+        m = __ldg(&a.r.mat[idx[0]]); mx = __ldg(&a.r.matx[idx[0]]);
+        nx = (float)n.x; ny = (float)n.y; nz = (float)n.z;
+        // view_dir = normalized(origin - hit) = -d up to rounding (src/main.cpp:38); colour only
+        vx = -(float)d64v.x; vy = -(float)d64v.y; vz = -(float)d64v.z;
+        sr = g_frame.ambient[0] * m.x; sg = g_frame.ambient[1] * m.y; sb = g_frame.ambient[2] * m.z;
       }
-      if (a.r.counters) flush_counters(a, cnt, n_fp64, level);
-#pragma unroll
-      for (int r = 0; r < 2; r++) {
-        live[r] = cont[r];
-        if (cont[r]) {
-          qin[qi[r]] = rec[r];                    // in place: the exact ray is re-read from here
-          ox[r] = (float)(rec[r].ox - a.c0[0]); oy[r] = (float)(rec[r].oy - a.c0[1]); oz[r] = (float)(rec[r].oz - a.c0[2]);
-          dx[r] = (float)rec[r].dx; dy[r] = (float)rec[r].dy; dz[r] = (float)rec[r].dz;
+      if (__any_sync(kFull, hit)) {
+        for (int l = 0; l < L; l++) {
+          float sdx[1] = {0.f}, sdy[1] = {0.f}, sdz[1] = {0.f}, so[1] = {0.f}, cosl[1] = {0.f};
+          bool occ[1] = {false};
+          const bool want[1] = {hit};
+          if (hit) {
+            // direction light -> point: FP64 difference, FP32 normalisation (error <= 12u, see filter_math.cuh)
+            const d3 w = rtx::sub(p, ldc3(g_frame.light_pos[l]));
+            const float wx = (float)w.x, wy = (float)w.y, wz = (float)w.z;
+            const float l2 = fmaf(wz, wz, fmaf(wy, wy, wx * wx));
+            const float inv = rsqrtf(l2);
+            sdx[0] = wx * inv; sdy[0] = wy * inv; sdz[0] = wz * inv;
+            so[0] = l2 * inv - kEps;
+            cosl[0] = -(nx * sdx[0] + ny * sdy[0] + nz * sdz[0]);             // n . light_dir
+          }
+          const double *const pp[1] = {&p.x};
+          if (kSmem) shadow_light_culled<1>(tab_at(tabs, a, l), a.npairs, wb, l, sdx, sdy, sdz, so, want, idx, cosl, pp, a.d64, a.r.sph64, occ, n_fp64, c_cand, c_walks);
+          else shadow_light<1>(tab_at(tabs, a, l), a.npairs, l, sdx, sdy, sdz, so, want, idx, cosl, pp, a.d64, a.r.sph64, occ, n_fp64);
+          if (!hit) continue;
+          cnt.shadow++;
+          if (occ[0]) { cnt.occluded++; if (l < 32) smask |= 1u << l; continue; }
+          // include/scene.h:104-117 in FP32; light_dir = -(dx,dy,dz)
+          const float ndl = fmaxf(0.0f, cosl[0]);
+          const float kd = (1.0f - m.w) * ndl;
+          const float dn = -cosl[0];                                              // dot(-light_dir, n)
+          const float rx = sdx[0] - 2.0f * nx * dn, ry = sdy[0] - 2.0f * ny * dn, rz = sdz[0] - 2.0f * nz * dn;
+          const float rdv = fmaxf(0.0f, rx * vx + ry * vy + rz * vz);
+          const float spec = 0.5f * (mx.x == 0.0f ? 1.0f : __powf(rdv, mx.x));
+          sr += g_frame.light_col[l][0] * spec + m.x * kd;
+          sg += g_frame.light_col[l][1] * spec + m.y * kd;
+          sb += g_frame.light_col[l][2] * spec + m.z * kd;
         }
       }
-      if (!__any_sync(kFull, live[0] || live[1])) break;
+      // continuation: src/main.cpp:43-55 unrolled front to back
+      if (hit) {
+        if (a.r.shadow_mask) a.r.shadow_mask[(size_t)pix * a.r.max_depth + level] = smask;
+        if (mx.y > 0.5f) {                          // reflectivity > 0, decided in double on the host
+          const float refl = m.w, k = wt * (1.0f - refl);
+          cr += k * sr; cg += k * sg; cb += k * sb;
+          wt *= refl;
+          if (level + 1 < a.r.max_depth) {
+            RayRec *rec = qin + qi;                 // in place: the exact ray of the next level is re-read from here
+            reflected_ray(d64v, p, n, rec);
+            ox[0] = (float)(rec->ox - a.c0[0]); oy[0] = (float)(rec->oy - a.c0[1]); oz[0] = (float)(rec->oz - a.c0[2]);
+            dx[0] = (float)rec->dx; dy[0] = (float)rec->dy; dz[0] = (float)rec->dz;
+            cont = true;
+          } else {
+            final_ = true;                          // depth exhausted: the child contributes black
+          }
+        } else {
+          cr += wt * sr; cg += wt * sg; cb += wt * sb;
+          final_ = true;
+        }
+      }
+      if (live[0] && final_) {
+        unsigned char *o = a.r.rgb + (size_t)pix * 3;
+        o[0] = (unsigned char)quant8(cr); o[1] = (unsigned char)quant8(cg); o[2] = (unsigned char)quant8(cb);
+      }
+      if (a.r.counters) {
+        flush_counters(a, cnt, n_fp64, level);
+        if (lane == 0 && c_walks) { atomicAdd(&a.r.counters[RT_CNT_CAND], (unsigned long long)c_cand); atomicAdd(&a.r.counters[RT_CNT_WALKS], (unsigned long long)c_walks); }
+        c_cand = c_walks = 0;
+      }
+      live[0] = cont;
+      if (!__any_sync(kFull, cont)) break;
     }
   }
-  if (!kTail) flush_counters(a, cnt, n_fp64, a.level);
 }
 
 }  // namespace rtf

@@ -14,14 +14,17 @@
 //   k_shade      HitRec      -> Phong (include/scene.h:89-121) -> final pixel, or the reflected
 //                               ray appended to the RayRec queue (warp-ballot compaction)
 // Levels >= 2 hold a few percent of the rays; they run in the fused tail kernel of
-// kernels_fast.cuh (k_bounce<.., true>), one launch for all remaining levels.
+// kernels_fast.cuh (k_bounce), one launch for all remaining levels.
 #ifndef RT_KERNELS_WAVE_CUH
 #define RT_KERNELS_WAVE_CUH
 
 #include "kernels_fast.cuh"
 
 #ifndef RT_SHADOW_CTAS
-#define RT_SHADOW_CTAS 3
+#define RT_SHADOW_CTAS 2
+#endif
+#ifndef RT_CLOSEST_CTAS
+#define RT_CLOSEST_CTAS 2
 #endif
 namespace rtf {
 
@@ -38,24 +41,34 @@ struct __align__(16) HitRec {      // 80 bytes
 
 struct WaveArgs {
   FastArgs f;
-  HitRec *hits; unsigned int *hit_count; unsigned hit_cap;
+  // Blocked hit queue: the hits of one warp work item (a 16x4 tile / 64 queued rays) occupy ONE 64-slot block,
+  // compacted to its front, so that the bundle of shadow rays a warp handles later stays spatially coherent.
+  HitRec *hits; unsigned int *hit_count;   // *hit_count = 64 x blocks in use
+  unsigned int *hit_n;             // hits per block
+  unsigned hit_cap;                // slots
   unsigned char *occ;              // [L][hit_cap] occlusion bytes
   unsigned int *work_counter;      // per-launch chunk counter
 };
 
-__device__ __forceinline__ void hit_push(bool want, const HitRec &rec, HitRec *q, unsigned int *count) {
-  const unsigned mk = __ballot_sync(kFull, want);
-  if (mk == 0) return;
-  const int lane = threadIdx.x & 31, leader = __ffs(mk) - 1;
+// Allocates the block of a work item with (m0, m1) = ballots of its candidate hits; slot[r] = where this
+// lane's hit r goes.  One atomic per work item.
+__device__ __forceinline__ void hit_block(const WaveArgs &w, unsigned m0, unsigned m1, unsigned (&slot)[2]) {
+  const int lane = threadIdx.x & 31;
+  const unsigned n = (unsigned)(__popc(m0) + __popc(m1));
   unsigned base = 0;
-  if (lane == leader) base = atomicAdd(count, (unsigned)__popc(mk));
-  base = __shfl_sync(kFull, base, leader);
-  if (want) q[base + __popc(mk & ((1u << lane) - 1u))] = rec;
+  if (n != 0u) {
+    if (lane == 0) { base = atomicAdd(w.hit_count, 64u); w.hit_n[base >> 6] = n; }
+    base = __shfl_sync(kFull, base, 0);
+  }
+  const unsigned lt = (1u << lane) - 1u;
+  slot[0] = base + (unsigned)__popc(m0 & lt);
+  slot[1] = base + (unsigned)__popc(m0) + (unsigned)__popc(m1 & lt);
 }
 
 // 32-bit per-thread counters, reduced once per warp at kernel end (cold path, out of line)
 __device__ __noinline__ void flush_counts(unsigned long long *counters, int level, unsigned closest, unsigned hits, unsigned shadow,
-                                          unsigned occluded, unsigned fp64, unsigned violations, unsigned long long n_spheres) {
+                                          unsigned occluded, unsigned fp64, unsigned violations, unsigned long long n_spheres,
+                                          unsigned cand = 0, unsigned walks = 0) {
   unsigned v[6] = {closest, hits, shadow, occluded, fp64, violations};
 #pragma unroll
   for (int k = 0; k < 6; k++) v[k] = __reduce_add_sync(kFull, v[k]);
@@ -67,6 +80,7 @@ __device__ __noinline__ void flush_counts(unsigned long long *counters, int leve
     if (v[4]) atomicAdd(&counters[RT_CNT_FP64], (unsigned long long)v[4]);
     if (v[5]) atomicAdd(&counters[RT_CNT_VIOLATIONS], (unsigned long long)v[5]);
     if (v[0] + v[2]) atomicAdd(&counters[RT_CNT_TESTS], (unsigned long long)(v[0] + v[2]) * n_spheres);
+    if (walks) { atomicAdd(&counters[RT_CNT_CAND], (unsigned long long)cand); atomicAdd(&counters[RT_CNT_WALKS], (unsigned long long)walks); }   // warp-uniform
   }
 }
 
@@ -141,7 +155,7 @@ __device__ __forceinline__ int cta_fetch(unsigned int *counter, unsigned char *s
 // ---------------------------------------------------------------------------------------------
 // LEVEL 0 closest hit: each warp pulls 16x4-pixel tiles, two vertically adjacent pixels per lane.
 template <int kMode>
-__global__ void __launch_bounds__(kThreads, 3) k_closest0(const WaveArgs w) {
+__global__ void __launch_bounds__(kThreads, RT_CLOSEST_CTAS) k_closest0(const WaveArgs w) {
   extern __shared__ __align__(128) unsigned char smem[];
   const FastArgs &a = w.f;
   const unsigned char *tabs = a.tabs;
@@ -149,11 +163,12 @@ __global__ void __launch_bounds__(kThreads, 3) k_closest0(const WaveArgs w) {
   if (kMode == kTabStream) ring_init(smem);
   const Tab camg = tab_at(a.tabs, a, 0);             // global view (gmin / perm of the streamed mode)
   const Tab cam = tab_at(tabs, a, 0);
+  const WarpBuf wb = warp_buf(smem + kSmemHeader + ((a.stage_bytes + 127u) & ~127u));   // kTabSmem only
   unsigned ring_phase = 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char *s_rgb = smem + 64 + warp * (kWTileH * kWTileW * 3);
   const int W = a.r.W, rows = a.r.bands.local_rows, depth = a.r.max_depth;
-  unsigned c_closest = 0, c_hits = 0, c_fp64 = 0, c_viol = 0;
+  unsigned c_closest = 0, c_hits = 0, c_fp64 = 0, c_viol = 0, c_cand = 0, c_walks = 0;
   for (;;) {
     int tile;
     if (kMode == kTabStream) {
@@ -194,11 +209,13 @@ __global__ void __launch_bounds__(kThreads, 3) k_closest0(const WaveArgs w) {
     Best best[2];
     best_init(best[0]); best_init(best[1]);
     const RaySrc src[2] = {{a.r.su, a.r.sv, x, j[0], nullptr}, {a.r.su, a.r.sv, x, j[1], nullptr}};
-    if (kMode != kTabStream) {
-      closest_shared(cam, a.npairs, dx, dy, dz, live, a.d64, a.r.sph64, src, best);
+    if (kMode == kTabSmem) {
+      closest_shared_culled<2>(cam, a.npairs, wb, dx, dy, dz, live, a.d64, a.r.sph64, src, best, c_cand, c_walks);
+    } else if (kMode == kTabGlobal) {
+      closest_shared<2>(cam, a.npairs, dx, dy, dz, live, a.d64, a.r.sph64, src, best);
     } else {
       // the eight warps of the CTA walk the sorted camera table together, tile by tile
-      ClosestQ q;
+      ClosestQ<2> q;
       closest_begin(q);
       bool need = true;
       const int ntiles = (a.npairs + kTilePairs - 1) / kTilePairs;
@@ -208,24 +225,28 @@ __global__ void __launch_bounds__(kThreads, 3) k_closest0(const WaveArgs w) {
         if (threadIdx.x == 0 && k + 1 < ntiles)
           ring_issue(smem, st ^ 1, camg.pairs + (size_t)(p0 + kTilePairs) * 2, min(kTilePairs, a.npairs - p0 - kTilePairs));
         ring_wait(smem, st, ring_phase);
-        if (need) need = closest_shared_range(q, ring_stage(smem, st) - (size_t)p0 * 2, camg.gmin, camg.perm, p0, p0 + np, dx, dy, dz,
+        if (need) need = closest_shared_range<2>(q, ring_stage(smem, st) - (size_t)p0 * 2, camg.gmin, camg.perm, p0, p0 + np, dx, dy, dz,
                                               live, a.d64, a.r.sph64, src);
         const int more = __syncthreads_or(need ? 1 : 0);        // also: stage st is free again
         if (!more || k + 1 == ntiles) { if (k + 1 < ntiles) ring_wait(smem, st ^ 1, ring_phase); break; }
       }
       best[0] = q.best[0]; best[1] = q.best[1];
     }
+    unsigned hslot[2];
+    hit_block(w, __ballot_sync(kFull, live[0] && best[0].idx >= 0), __ballot_sync(kFull, live[1] && best[1].idx >= 0), hslot);
 #pragma unroll
     for (int r = 0; r < 2; r++) {
       bool hit = false;
-      HitRec rec;
       if (live[r]) {
         c_closest++; c_fp64 += best[r].nfp64;
-        if (best[r].idx >= 0) hit = finish_hit(a, best[r], src[r], pix[r], 0u, 1.0f, 0.f, 0.f, 0.f, &rec, &c_viol, &c_fp64);
-        if (a.r.hit_idx) a.r.hit_idx[(size_t)pix[r] * depth] = hit ? rec.idx : -1;
+        if (best[r].idx >= 0) {
+          HitRec *rec = w.hits + hslot[r];
+          hit = finish_hit(a, best[r], src[r], pix[r], 0u, 1.0f, 0.f, 0.f, 0.f, rec, &c_viol, &c_fp64);
+          if (!hit) rec->idx = -1;                   // (filter violation resolved to a miss: dead slot)
+          if (a.r.hit_idx) a.r.hit_idx[(size_t)pix[r] * depth] = hit ? rec->idx : -1;
+        } else if (a.r.hit_idx) a.r.hit_idx[(size_t)pix[r] * depth] = -1;
       }
       c_hits += hit;
-      hit_push(hit, rec, w.hits, w.hit_count);
       // sky (src/main.cpp:26-30) is final now; hit pixels are written by k_shade / later levels
       const float ts = 0.5f * (dy[r] + 1.0f);
       const bool sky = live[r] && !hit;
@@ -256,13 +277,13 @@ __global__ void __launch_bounds__(kThreads, 3) k_closest0(const WaveArgs w) {
     }
     __syncwarp();
   }
-  if (a.r.counters) flush_counts(a.r.counters, 0, c_closest, c_hits, 0, 0, c_fp64, c_viol, (unsigned long long)a.N);
+  if (a.r.counters) flush_counts(a.r.counters, 0, c_closest, c_hits, 0, 0, c_fp64, c_viol, (unsigned long long)a.N, c_cand, c_walks);
 }
 
 // ---------------------------------------------------------------------------------------------
 // LEVEL >= 1 closest hit: reflected rays from the RayRec queue, 64 per warp fetch, two per lane.
 template <bool kSmem>
-__global__ void __launch_bounds__(kThreads, 3) k_closest1(const WaveArgs w) {
+__global__ void __launch_bounds__(kThreads, RT_CLOSEST_CTAS) k_closest1(const WaveArgs w) {
   extern __shared__ __align__(128) unsigned char smem[];
   const FastArgs &a = w.f;
   const unsigned nq = *a.q_in_count;
@@ -274,16 +295,19 @@ __global__ void __launch_bounds__(kThreads, 3) k_closest1(const WaveArgs w) {
   const int lane = threadIdx.x & 31, depth = a.r.max_depth, level = a.level;
   unsigned c_closest = 0, c_hits = 0, c_fp64 = 0, c_viol = 0;
   const RayRec *qin = a.q_in;
+  // few rays (deep levels): one ray per lane, so that twice as many warps share the work
+  const bool two = nq >= gridDim.x * (unsigned)kWarps * 64u;
+  const unsigned per = two ? 64u : 32u;
   for (;;) {
     const int chunk = warp_fetch(w.work_counter);
-    if ((unsigned)chunk * 64u >= nq) break;
+    if ((unsigned)chunk * per >= nq) break;
     bool live[2];
     unsigned qi[2], pix[2];
     float ox[2], oy[2], oz[2], dx[2], dy[2], dz[2], wt[2], cr[2], cg[2], cb[2];
 #pragma unroll
     for (int r = 0; r < 2; r++) {
-      qi[r] = (unsigned)chunk * 64u + 2u * lane + r;
-      live[r] = qi[r] < nq;
+      qi[r] = two ? (unsigned)chunk * 64u + 2u * lane + r : (unsigned)chunk * 32u + lane;
+      live[r] = qi[r] < nq && (two || r == 0);
       ox[r] = oy[r] = oz[r] = dx[r] = dy[r] = dz[r] = 0.f; wt[r] = cr[r] = cg[r] = cb[r] = 0.f; pix[r] = 0;
       if (live[r]) {
         const RayRec &q = qin[qi[r]];
@@ -295,15 +319,20 @@ __global__ void __launch_bounds__(kThreads, 3) k_closest1(const WaveArgs w) {
     Best best[2];
     best_init(best[0]); best_init(best[1]);
     const RaySrc src[2] = {{nullptr, nullptr, 0, 0, qin + qi[0]}, {nullptr, nullptr, 0, 0, qin + qi[1]}};
-    closest_general(gen, a.npairs, a.N, ox, oy, oz, dx, dy, dz, live, a.d64, a.gS2, a.g_dtmax, a.r.sph64, src, best);
+    closest_general<2>(gen, a.npairs, a.N, ox, oy, oz, dx, dy, dz, live, a.d64, a.gS2, a.g_dtmax, a.r.sph64, src, best);
+    unsigned hslot[2];
+    hit_block(w, __ballot_sync(kFull, live[0] && best[0].idx >= 0), __ballot_sync(kFull, live[1] && best[1].idx >= 0), hslot);
 #pragma unroll
     for (int r = 0; r < 2; r++) {
       bool hit = false;
-      HitRec rec;
       if (live[r]) {
         c_closest++; c_fp64 += best[r].nfp64;
-        if (best[r].idx >= 0) hit = finish_hit(a, best[r], src[r], pix[r], qi[r], wt[r], cr[r], cg[r], cb[r], &rec, &c_viol, &c_fp64);
-        if (a.r.hit_idx) a.r.hit_idx[(size_t)pix[r] * depth + level] = hit ? rec.idx : -1;
+        if (best[r].idx >= 0) {
+          HitRec *rec = w.hits + hslot[r];
+          hit = finish_hit(a, best[r], src[r], pix[r], qi[r], wt[r], cr[r], cg[r], cb[r], rec, &c_viol, &c_fp64);
+          if (!hit) rec->idx = -1;
+        }
+        if (a.r.hit_idx) a.r.hit_idx[(size_t)pix[r] * depth + level] = hit ? w.hits[hslot[r]].idx : -1;
         if (!hit) {                                // sky through the mirror(s): the pixel is final
           const float ts = 0.5f * (dy[r] + 1.0f);
           unsigned char *o = a.r.rgb + (size_t)pix[r] * 3;
@@ -313,7 +342,6 @@ __global__ void __launch_bounds__(kThreads, 3) k_closest1(const WaveArgs w) {
         }
       }
       c_hits += hit;
-      hit_push(hit, rec, w.hits, w.hit_count);
     }
   }
   if (a.r.counters) flush_counts(a.r.counters, level, c_closest, c_hits, 0, 0, c_fp64, c_viol, (unsigned long long)a.N);
@@ -339,10 +367,13 @@ __global__ void __launch_bounds__(kThreads, RT_SHADOW_CTAS) k_shadow(const WaveA
   const unsigned char *tabs = gtabs;
   if (kMode == kTabSmem) { stage_tables(smem, tabs, a.stage_bytes); tabs = smem + kSmemHeader; }
   if (kMode == kTabStream) ring_init(smem);
+  const WarpBuf wb = warp_buf(smem + kSmemHeader + ((a.stage_bytes + 127u) & ~127u));   // kTabSmem only
   unsigned ring_phase = 0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned nchunks = (nh + 63u) / 64u;
-  unsigned c_fp64 = 0;
+  // few hits (deep levels): one hit per lane, so that twice as many warps share the work
+  const bool two = kMode == kTabStream || nh >= gridDim.x * (unsigned)kWarps * 64u;
+  const unsigned nchunks = two ? nh / 64u : nh / 32u;            // nh = 64 x blocks
+  unsigned c_fp64 = 0, c_cand = 0, c_walks = 0;
   for (;;) {
     unsigned chunk;
     if (kMode == kTabStream) {
@@ -353,7 +384,8 @@ __global__ void __launch_bounds__(kThreads, RT_SHADOW_CTAS) k_shadow(const WaveA
       chunk = (unsigned)warp_fetch(w.work_counter);
       if (chunk >= nchunks) break;
     }
-    const unsigned h0 = chunk * 64u + 2u * lane;
+    const unsigned h0 = two ? chunk * 64u + 2u * lane : chunk * 32u + lane;
+    const unsigned hend = (h0 & ~63u) + (h0 < nh ? w.hit_n[h0 >> 6] : 0u);   // end of the block's live slots
     bool have[2];
     int self[2];
     float nx[2], ny[2], nz[2], backthr[2];
@@ -361,7 +393,7 @@ __global__ void __launch_bounds__(kThreads, RT_SHADOW_CTAS) k_shadow(const WaveA
     const double *pp[2];
 #pragma unroll
     for (int r = 0; r < 2; r++) {
-      have[r] = h0 + r < nh;
+      have[r] = h0 + r < hend && (two || r == 0) && w.hits[h0 + r].idx >= 0;
       self[r] = -1; nx[r] = ny[r] = nz[r] = 0.f; backthr[r] = 0.f; p[r] = rtx::mk(0, 0, 0); pp[r] = &w.hits[0].px;
       if (have[r]) {
         const HitRec &hr = w.hits[h0 + r];
@@ -396,14 +428,16 @@ __global__ void __launch_bounds__(kThreads, RT_SHADOW_CTAS) k_shadow(const WaveA
       }
       int n64 = 0;
       if (kMode != kTabStream) {
-        if (__any_sync(kFull, want[0] || want[1]))
-          shadow_light(T, a.npairs, l, dx, dy, dz, so, want, self, cosl, ppc, a.d64, a.r.sph64, occ, n64);
-        else occ[0] = occ[1] = false;
+        occ[0] = occ[1] = false;
+        if (__any_sync(kFull, want[0] || want[1])) {
+          if (kMode == kTabSmem) shadow_light_culled<2>(T, a.npairs, wb, l, dx, dy, dz, so, want, self, cosl, ppc, a.d64, a.r.sph64, occ, n64, c_cand, c_walks);
+          else shadow_light<2>(T, a.npairs, l, dx, dy, dz, so, want, self, cosl, ppc, a.d64, a.r.sph64, occ, n64);
+        }
       } else {
         // the eight warps of the CTA walk this light's sorted table together, tile by tile
         const Tab TG = tab_at(gtabs, a, l);
-        ShadowQ q;
-        shadow_begin(q, TG.inv, so, want, self, cosl);
+        ShadowQ<2> q;
+        shadow_begin<2>(q, TG.inv, so, want, self, cosl);
         bool need = q.wcut > -1.0e38f;
         if (__syncthreads_or(need ? 1 : 0)) {
           const int ntiles = (a.npairs + kTilePairs - 1) / kTilePairs;
@@ -413,7 +447,7 @@ __global__ void __launch_bounds__(kThreads, RT_SHADOW_CTAS) k_shadow(const WaveA
             if (threadIdx.x == 0 && k + 1 < ntiles)
               ring_issue(smem, st ^ 1, TG.pairs + (size_t)(p0 + kTilePairs) * 2, min(kTilePairs, a.npairs - p0 - kTilePairs));
             ring_wait(smem, st, ring_phase);
-            if (need) need = shadow_range(q, ring_stage(smem, st) - (size_t)p0 * 2, TG.gmin, TG.perm, p0, p0 + np, l, dx, dy, dz, so, self,
+            if (need) need = shadow_range<2>(q, ring_stage(smem, st) - (size_t)p0 * 2, TG.gmin, TG.perm, p0, p0 + np, l, dx, dy, dz, so, self,
                                           cosl, ppc, a.d64, a.r.sph64, n64);
             const int more = __syncthreads_or(need ? 1 : 0);      // also: stage st is free again
             if (!more || k + 1 == ntiles) { if (k + 1 < ntiles) ring_wait(smem, st ^ 1, ring_phase); break; }
@@ -429,7 +463,7 @@ __global__ void __launch_bounds__(kThreads, RT_SHADOW_CTAS) k_shadow(const WaveA
       else if (have[0]) o[0] = (unsigned char)o0;
     }
   }
-  if (a.r.counters) flush_counts(a.r.counters, 99, 0, 0, 0, 0, c_fp64, 0, 0);
+  if (a.r.counters) flush_counts(a.r.counters, 99, 0, 0, 0, 0, c_fp64, 0, 0, c_cand, c_walks);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -445,7 +479,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_shade(const WaveArgs w) {
     const unsigned chunk = (unsigned)warp_fetch(w.work_counter);
     if (chunk * 32u >= nh) break;
     const unsigned h = chunk * 32u + lane;
-    const bool live = h < nh;
+    const bool live = (h & 63u) < w.hit_n[h >> 6] && w.hits[h].idx >= 0;
     bool cont = false;
     RayRec rec;
     if (live) {

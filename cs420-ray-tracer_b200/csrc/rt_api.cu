@@ -142,6 +142,11 @@ extern "C" int rt_set_option(rt_ctx *c, const char *key, long long value) {
     return RT_OK;
   }
   if (!strcmp(key, "counters")) { c->counters_on = value != 0; return RT_OK; }
+  if (!strcmp(key, "wave_levels")) {
+    if (value < 1 || value > RT_MAX_LEVELS) return rt_fail(RT_ERR_ARG, "rt_set_option: wave_levels must be 1..32");
+    c->work.wave_levels = (int)value;
+    return RT_OK;
+  }
   return rt_fail(RT_ERR_ARG, std::string("rt_set_option: unknown key ") + key);
 }
 
@@ -265,6 +270,8 @@ static void fill_stats(rt_stats *st, const unsigned long long *cnt) {
   st->fp64_intersections = cnt[RT_CNT_FP64];
   st->sphere_tests = cnt[RT_CNT_TESTS];
   st->filter_violations = cnt[RT_CNT_VIOLATIONS];
+  st->bundle_walks = cnt[RT_CNT_WALKS];
+  st->bundle_candidates = cnt[RT_CNT_CAND];
   for (int k = 0; k < RT_MAX_LEVELS; k++) st->alive[k] = cnt[RT_CNT_ALIVE0 + k];
 }
 

@@ -46,7 +46,9 @@ enum {
   RT_CNT_TESTS = 5,
   RT_CNT_VIOLATIONS = 6,
   RT_CNT_ALIVE0 = 8,   // .. RT_CNT_ALIVE0 + 31
-  RT_CNT_TOTAL = 40
+  RT_CNT_CAND = 40,    // spheres left after bundle culling, summed over warp-level table walks
+  RT_CNT_WALKS = 41,   // warp-level table walks that were bundle-culled
+  RT_CNT_TOTAL = 48
 };
 
 struct RtRenderArgs {

@@ -29,8 +29,8 @@ int rtk_launch_exact(const RtRenderArgs &args, cudaStream_t stream) {
 // fast path, host side
 namespace {
 
-constexpr size_t kMaxSmemTables = 72 * 1024;    // stage a kernel's tables in shared memory up to this size (3 CTAs/SM stay resident)
-constexpr int kCtlWords = 128;                  // [0] tile counter, [1+k] chunk counter of level k, [64+k] rays entering level k
+constexpr size_t kMaxSmemTables = 96 * 1024;    // stage a kernel's tables in shared memory up to this size (2 CTAs/SM stay resident)
+constexpr int kCtlWords = 256;                  // device control words, layout: enum CTL_* below
 
 inline float float_up(double x) {               // smallest float >= x
   float f = (float)x;
@@ -49,7 +49,7 @@ inline float float_down(double x) {             // largest float <= x
 
 int rtk_fast_init(int) {
   const int big = 227 * 1024;
-  RTK_TRY(cudaFuncSetAttribute(rtf::k_bounce<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  RTK_TRY(cudaFuncSetAttribute(rtf::k_bounce<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   RTK_TRY(cudaFuncSetAttribute(rtf::k_closest0<rtf::kTabSmem>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   RTK_TRY(cudaFuncSetAttribute(rtf::k_closest0<rtf::kTabStream>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   RTK_TRY(cudaFuncSetAttribute(rtf::k_closest1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
@@ -105,8 +105,10 @@ int rtk_fast_build_scene(RtFastScene *fs, const double *sph, int N, const RtFram
   const unsigned gmin_bytes = ((unsigned)ngroups * 4u + 15u) & ~15u;
   const unsigned perm_bytes = (unsigned)nslots * 4u;
   const unsigned inv_bytes = (((unsigned)(N > 0 ? N : 1)) * 4u + 15u) & ~15u;
+  const unsigned cullA_bytes = (unsigned)nslots * 16u, cullB_bytes = (unsigned)nslots * 4u;
   fs->gmin_off = pairs_bytes; fs->perm_off = pairs_bytes + gmin_bytes; fs->inv_off = fs->perm_off + perm_bytes;
-  fs->tstride = pairs_bytes + gmin_bytes + perm_bytes + inv_bytes;
+  fs->cullA_off = fs->inv_off + inv_bytes; fs->cullB_off = fs->cullA_off + cullA_bytes;
+  fs->tstride = fs->cullB_off + cullB_bytes;
   fs->bytes_primary = (size_t)(L + 1) * fs->tstride;
   fs->bytes_bounce = (size_t)L * fs->tstride + pairs_bytes;
   const size_t total = (size_t)(L + 1) * fs->tstride + pairs_bytes;
@@ -123,6 +125,8 @@ int rtk_fast_build_scene(RtFastScene *fs, const double *sph, int N, const RtFram
     float *gmin = reinterpret_cast<float *>(base + fs->gmin_off);
     int *perm = reinterpret_cast<int *>(base + fs->perm_off);
     int *inv = reinterpret_cast<int *>(base + fs->inv_off);
+    float4 *cullA = reinterpret_cast<float4 *>(base + fs->cullA_off);
+    float *cullB = reinterpret_cast<float *>(base + fs->cullB_off);
     const double *O = t == 0 ? f->cam_pos : f->light_pos[t - 1];
     for (int i = 0; i < N; i++) {
       const double *s = sph + (size_t)i * 10;
@@ -132,7 +136,11 @@ int rtk_fast_build_scene(RtFastScene *fs, const double *sph, int N, const RtFram
     }
     std::stable_sort(order.begin(), order.begin() + N, [&](int p, int q) { return key[p] < key[q]; });
     for (int slot = 0; slot < nslots; slot++) {
-      if (slot >= N) { put(pairs, slot, 0.f, 0.f, 0.f, -1.0f); perm[slot] = -1; continue; }   // padding: never a candidate
+      if (slot >= N) {                                 // padding: never a candidate, always culled
+        put(pairs, slot, 0.f, 0.f, 0.f, -1.0f); perm[slot] = -1;
+        cullA[slot] = make_float4(0.f, 0.f, 0.f, 4.0f); cullB[slot] = 0.f;
+        continue;
+      }
       const int i = order[slot];
       const double *s = sph + (size_t)i * 10;
       const double x = s[0] - O[0], y = s[1] - O[1], z = s[2] - O[2];
@@ -140,6 +148,17 @@ int rtk_fast_build_scene(RtFastScene *fs, const double *sph, int N, const RtFram
       const double E = 2.01 * std::ldexp(1.0, -20) * oc2 * (1 + 1e-9) + delta64;
       put(pairs, slot, (float)x, (float)y, (float)z, float_up(E - (oc2 - s[3] * s[3])));
       perm[slot] = i;
+      // bundle culling (kernels_fast.cuh, cull_round): unit vector to the centre, cos / sin of the angular radius
+      {
+        const double n = std::sqrt(oc2), r = std::fabs(s[3]) * (1.0 + 1e-6) + 1e-12;
+        if (n > r * (1.0 + 1e-6)) {
+          const double sa = r / n, ca = std::sqrt((1.0 - sa) * (1.0 + sa));
+          cullA[slot] = make_float4((float)(x / n), (float)(y / n), (float)(z / n), float_down(ca));
+          cullB[slot] = float_up(sa);
+        } else {                                       // the origin is inside (or on) the sphere: never culled
+          cullA[slot] = make_float4(0.f, 0.f, 0.f, -4.0f); cullB[slot] = 0.f;
+        }
+      }
       // bit 30: the table origin (camera / light) is strictly outside sphere i, with a generous margin
       inv[i] = slot | ((oc2 - s[3] * s[3] > 1e-6 * (oc2 + s[3] * s[3]) + 4.0 * delta64) ? 0x40000000 : 0);
     }
@@ -172,34 +191,38 @@ void rtk_fast_free_scene(RtFastScene *fs) {
 }
 
 void rtk_fast_free_work(RtFastWork *w) {
-  cudaFree(w->queue[0]); cudaFree(w->queue[1]); cudaFree(w->ctl); cudaFree(w->hits); cudaFree(w->occ);
-  w->queue[0] = w->queue[1] = nullptr; w->ctl = nullptr; w->hits = nullptr; w->occ = nullptr;
+  cudaFree(w->queue[0]); cudaFree(w->queue[1]); cudaFree(w->ctl); cudaFree(w->hits); cudaFree(w->occ); cudaFree(w->hit_n);
+  w->queue[0] = w->queue[1] = nullptr; w->ctl = nullptr; w->hits = nullptr; w->occ = nullptr; w->hit_n = nullptr;
   w->queue_cap = w->hit_cap = w->occ_bytes = 0;
 }
 
 namespace {
 // persistent grid: as many CTAs as can be resident
 template <typename K>
-int resident_grid(K kernel, size_t smem, int num_sms) {
+int resident_grid(K kernel, size_t smem, int num_sms, int threads = rtf::kThreads) {
   int nb = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, rtf::kThreads, smem) != cudaSuccess || nb < 1) nb = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem) != cudaSuccess || nb < 1) nb = 1;
   return nb * num_sms;
 }
-// control words (u32): [0] tile counter; per level k: [1+k] tail chunk counter, [8+k] shadow, [16+k] shade,
-// [24+k] closest work counters, [32+k] hits of level k, [64+k] rays entering level k
-enum { CTL_TILE = 0, CTL_TAIL = 1, CTL_SHADOW = 8, CTL_SHADE = 16, CTL_CLOSEST = 24, CTL_HITS = 32, CTL_RAYS = 64 };
+// dynamic shared memory of a kernel that stages `bytes` of tables: header | tables | per-warp compacted tables
+inline size_t staged_smem(size_t bytes) { return rtf::kSmemHeader + ((bytes + 127) & ~(size_t)127) + rtf::kWarps * (size_t)rtf::kWarpBufBytes; }
+// control words (u32): [0] tile counter; per level k <= 33: tail chunk counter, shadow / shade / closest work
+// counters, hits of level k, rays entering level k
+enum { CTL_TILE = 0, CTL_TAIL = 8, CTL_SHADOW = 48, CTL_SHADE = 88, CTL_CLOSEST = 128, CTL_HITS = 168, CTL_RAYS = 208 };
 }  // namespace
 
 int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork *w, cudaStream_t stream,
                     const cudaEvent_t *marks) {
   const size_t npix = (size_t)args.W * args.bands.local_rows;
   if (!w->ctl) RTK_TRY(cudaMalloc(&w->ctl, kCtlWords * sizeof(unsigned int)));
-  const size_t hit_cap = (npix + 63) & ~(size_t)63;
+  // blocked hit queue: one 64-slot block per 16x4 tile (level 0) or per 64 queued rays (level >= 1)
+  const size_t hit_cap = ((size_t)((args.W + rtf::kWTileW - 1) / rtf::kWTileW) * ((args.bands.local_rows + rtf::kWTileH - 1) / rtf::kWTileH) + 2) * 64 + 2 * npix;
   if (w->hit_cap < hit_cap || w->occ_bytes < hit_cap * (size_t)(fs->L > 0 ? fs->L : 1) || (args.max_depth > 1 && w->queue_cap < npix)) {
     RTK_TRY(cudaStreamSynchronize(stream));
-    cudaFree(w->queue[0]); cudaFree(w->queue[1]); cudaFree(w->hits); cudaFree(w->occ);
-    w->queue[0] = w->queue[1] = nullptr; w->hits = nullptr; w->occ = nullptr; w->queue_cap = w->hit_cap = w->occ_bytes = 0;
+    cudaFree(w->queue[0]); cudaFree(w->queue[1]); cudaFree(w->hits); cudaFree(w->occ); cudaFree(w->hit_n);
+    w->queue[0] = w->queue[1] = nullptr; w->hits = nullptr; w->occ = nullptr; w->hit_n = nullptr; w->queue_cap = w->hit_cap = w->occ_bytes = 0;
     RTK_TRY(cudaMalloc(&w->hits, hit_cap * sizeof(rtf::HitRec)));
+    RTK_TRY(cudaMalloc(&w->hit_n, (hit_cap / 64) * sizeof(unsigned int)));
     w->occ_bytes = hit_cap * (size_t)(fs->L > 0 ? fs->L : 1);
     RTK_TRY(cudaMalloc(&w->occ, w->occ_bytes));
     w->hit_cap = hit_cap;
@@ -219,12 +242,13 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
   a.tabs = (const unsigned char *)fs->tabs;
   a.npairs = fs->npairs; a.ngroups = fs->ngroups; a.N = fs->N; a.L = fs->L;
   a.tstride = fs->tstride; a.gmin_off = fs->gmin_off; a.perm_off = fs->perm_off; a.inv_off = fs->inv_off;
+  a.cullA_off = fs->cullA_off; a.cullB_off = fs->cullB_off;
   a.d64 = fs->d64; a.gS2 = fs->gS2; a.g_dtmax = fs->g_dtmax;
   for (int k = 0; k < 3; k++) a.c0[k] = fs->c0[k];
   a.wtiles_x = (args.W + rtf::kWTileW - 1) / rtf::kWTileW;
   a.nwtiles = a.wtiles_x * ((args.bands.local_rows + rtf::kWTileH - 1) / rtf::kWTileH);
   a.tile_counter = w->ctl + CTL_TILE;
-  wa.hits = (rtf::HitRec *)w->hits; wa.hit_cap = (unsigned)w->hit_cap; wa.occ = w->occ;
+  wa.hits = (rtf::HitRec *)w->hits; wa.hit_cap = (unsigned)w->hit_cap; wa.occ = w->occ; wa.hit_n = w->hit_n;
   const size_t pairs_bytes = (size_t)fs->npairs * 32;
   const size_t light_bytes = (size_t)fs->L * fs->tstride;
   // per kernel: its tables are staged whole when they fit, else streamed (shared-origin tables) or read through L1/L2 (general table)
@@ -235,13 +259,16 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
   const size_t stream_smem = rtf::kSmemHeader + 2 * (size_t)rtf::kTileBytes;
   int launches = 0;
 
-  for (int level = 0; level < args.max_depth && level < 2; level++) {
+  // levels below wave_levels run as phase-separated wavefront kernels; the (few) rays left after that are
+  // followed to termination by one fused launch
+  const int wave_levels = w->wave_levels > 0 ? w->wave_levels : 2;
+  for (int level = 0; level < args.max_depth && level < wave_levels; level++) {
     a.level = level;
     wa.hit_count = w->ctl + CTL_HITS + level;
     // ---- closest hit
     if (level == 0) {
       a.stage_bytes = fs->tstride;
-      const size_t smem = cam_smem ? rtf::kSmemHeader + a.stage_bytes : stream_smem;
+      const size_t smem = cam_smem ? staged_smem(a.stage_bytes) : stream_smem;
       const int cta_tiles = (a.nwtiles + rtf::kWarps - 1) / rtf::kWarps;
       if (cam_smem) { int g = resident_grid(rtf::k_closest0<rtf::kTabSmem>, smem, w->num_sms); rtf::k_closest0<rtf::kTabSmem><<<g < cta_tiles ? g : cta_tiles, rtf::kThreads, smem, stream>>>(wa); }
       else { int g = resident_grid(rtf::k_closest0<rtf::kTabStream>, smem, w->num_sms); rtf::k_closest0<rtf::kTabStream><<<g < cta_tiles ? g : cta_tiles, rtf::kThreads, smem, stream>>>(wa); }
@@ -260,7 +287,7 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
     if (fs->L > 0) {
       wa.work_counter = w->ctl + CTL_SHADOW + level;
       a.stage_bytes = (unsigned)light_bytes;
-      const size_t smem = light_smem ? rtf::kSmemHeader + a.stage_bytes : stream_smem;
+      const size_t smem = light_smem ? staged_smem(a.stage_bytes) : stream_smem;
       if (light_smem) rtf::k_shadow<rtf::kTabSmem><<<resident_grid(rtf::k_shadow<rtf::kTabSmem>, smem, w->num_sms), rtf::kThreads, smem, stream>>>(wa);
       else rtf::k_shadow<rtf::kTabStream><<<resident_grid(rtf::k_shadow<rtf::kTabStream>, smem, w->num_sms), rtf::kThreads, smem, stream>>>(wa);
       launches++;
@@ -275,8 +302,8 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
     if (level == 0 && marks) RTK_TRY(cudaEventRecord(marks[2], stream));
   }
   // ---- levels >= 2: one fused launch that follows every remaining ray to termination
-  if (args.max_depth > 2) {
-    const int level = 2;
+  if (args.max_depth > wave_levels) {
+    const int level = wave_levels;
     a.level = level;
     a.q_in = (rtf::RayRec *)w->queue[(level - 1) & 1];
     a.q_in_count = w->ctl + CTL_RAYS + level;
@@ -284,9 +311,9 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
     a.q_out_count = w->ctl + CTL_RAYS + level + 1;
     a.chunk_counter = w->ctl + CTL_TAIL + level;
     a.stage_bytes = (unsigned)fs->bytes_bounce;
-    const size_t smem = rtf::kSmemHeader + (in_smem ? fs->bytes_bounce : 0);
-    if (in_smem) rtf::k_bounce<true, true><<<resident_grid(rtf::k_bounce<true, true>, smem, w->num_sms), rtf::kThreads, smem, stream>>>(a);
-    else rtf::k_bounce<false, true><<<resident_grid(rtf::k_bounce<false, true>, smem, w->num_sms), rtf::kThreads, smem, stream>>>(a);
+    const size_t smem = in_smem ? staged_smem(fs->bytes_bounce) : rtf::kSmemHeader;
+    if (in_smem) rtf::k_bounce<true><<<resident_grid(rtf::k_bounce<true>, smem, w->num_sms, rtf::kTailThreads), rtf::kTailThreads, smem, stream>>>(a);
+    else rtf::k_bounce<false><<<resident_grid(rtf::k_bounce<false>, smem, w->num_sms, rtf::kTailThreads), rtf::kTailThreads, smem, stream>>>(a);
     launches++;
   }
   cudaError_t e = cudaGetLastError();

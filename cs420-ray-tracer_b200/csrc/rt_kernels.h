@@ -17,7 +17,7 @@ struct RtFastScene {
   int N, L, npairs, ngroups;
   void *tabs;             // device: (1+L) shared-origin tables (pairs | gmin | perm), then the general table
   unsigned tstride;       // bytes per shared-origin table
-  unsigned gmin_off, perm_off, inv_off;
+  unsigned gmin_off, perm_off, inv_off, cullA_off, cullB_off;
   size_t bytes_primary;   // staged by k_primary: (1+L) * tstride
   size_t bytes_bounce;    // staged by k_bounce : L * tstride + npairs * 32
   float d64;              // absolute FP64/geometry slack (delta64)
@@ -27,10 +27,12 @@ struct RtFastScene {
 };
 struct RtFastWork {
   int num_sms;
+  int wave_levels;       // reflection levels run as wavefront kernels before the fused tail (0 = default)
   void *queue[2];        // reflected-ray records, ping-pong between levels
   size_t queue_cap;      // records per queue
   unsigned int *ctl;     // device control words: tile counter, per-level chunk counters, queue counts
-  void *hits;            // HitRec queue of the current level (kernels_wave.cuh)
+  void *hits;            // HitRec queue of the current level (kernels_wave.cuh), 64-slot blocks
+  unsigned int *hit_n;   // hits per block
   unsigned char *occ;    // [L][hit_cap] occlusion bytes of the current level
   size_t hit_cap, occ_bytes;
 };

@@ -73,6 +73,8 @@ typedef struct rt_stats {
   uint64_t filter_violations;   /* self-check of the FP32 filter; must be 0    */
   int32_t kernel_launches;      /* kernels launched by this call                               */
   int32_t rows_rendered;        /* image rows this call produced (all of H unless banded)      */
+  uint64_t bundle_walks;        /* warp-level table walks that used bundle culling  */
+  uint64_t bundle_candidates;   /* spheres left after culling, summed over those walks          */
 } rt_stats;
 
 /* ---- library ------------------------------------------------------------------------- */
