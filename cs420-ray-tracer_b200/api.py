@@ -177,11 +177,17 @@ class Renderer:
     """One rt_ctx.  ``render`` returns uint8 [H, W, 3] with row 0 = bottom of the image
     (the reference's framebuffer convention, src/main.cpp:153-154)."""
 
-    def __init__(self, device=0, mode="fast"):
+    def __init__(self, device=0, mode="fast", accel=None):
+        """mode: "fast" (FP32 filter / FP64 decide), "exact" (FP64 brute force, diagnostic) or "bvh"
+        (= fast with the LBVH forced for every scene size); accel overrides: 0 auto, 1 tables, 2 LBVH."""
         self._lib = load_library()
         self._h = C.c_void_p()
         _check(self._lib.rt_create(int(device), C.byref(self._h)), "rt_create")
+        if mode == "bvh":
+            mode, accel = "fast", 2
         self.set_mode(mode)
+        if accel is not None:
+            self.set_option("accel", accel)
         self._pinned = None
         self._pinned_bytes = 0
 

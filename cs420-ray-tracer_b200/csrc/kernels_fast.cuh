@@ -28,6 +28,7 @@
 #ifndef RT_KERNELS_FAST_CUH
 #define RT_KERNELS_FAST_CUH
 
+#include "bvh.cuh"
 #include "exact_fp64.cuh"
 #include "filter_math.cuh"
 #include "rt_device.h"
@@ -74,6 +75,7 @@ struct FastArgs {
   unsigned int *chunk_counter;
   int level;
   int tables_in_smem;
+  rtb::BvhView bvh;           // large scenes: candidates come from the LBVH instead of a table walk (bvh.cuh)
 };
 
 // One shared-origin table: sphere pairs in sorted order, per-group minimum distance, original indices
@@ -260,7 +262,7 @@ __device__ __noinline__ Best closest_consider_exact(Best b, int i, const double4
 }
 // the common outcomes are decided inline on the FP32 brackets
 __device__ __forceinline__ void closest_consider(Best &b, int i, int status, float lo, float hi, const double4 *sph64, RaySrc src) {
-  if (status == RT_MISS) return;
+  if (status == RT_MISS || i == b.idx) return;     // (BVH candidates can name a sphere twice)
   if (status == RT_HIT) {
     if (b.idx < 0) { b.lo = lo; b.hi = hi; b.idx = i; b.exact = false; return; }
     if (lo > b.hi) return;                        // strictly farther
@@ -807,6 +809,56 @@ __device__ __forceinline__ void shadow_light_culled(const Tab T, int npairs, con
 }
 
 // ---------------------------------------------------------------------------------------------
+// LBVH queries (large scenes).  Per lane: the traversal (bvh.cuh) names candidate spheres, each candidate
+// goes through the SAME slow paths as a flagged sphere of a table walk (the pair it sits in is evaluated
+// as a whole: its partner is a real sphere too, so considering it can only confirm the right answer).
+// Forward traversal only: the include/sphere.h:37 oddity (a ray whose LINE is exactly tangent to a sphere
+// BEHIND its origin counts as a hit with t < 0) is not reproduced in this mode, as in closest_general.
+__device__ __forceinline__ float3 recentred(const FastArgs &a, const double *p) {
+  return make_float3((float)(p[0] - a.c0[0]), (float)(p[1] - a.c0[1]), (float)(p[2] - a.c0[2]));
+}
+// closest hit of a ray from the shared origin O of table T (camera)
+__device__ __forceinline__ Best bvh_closest_shared(const FastArgs &a, const Tab T, float3 o, float dx, float dy, float dz, RaySrc src) {
+  Best b;
+  best_init(b);
+  const rtb::BvhRay r = rtb::bvh_ray(o.x, o.y, o.z, dx, dy, dz);
+  rtb::bvh_traverse(a.bvh, r, -1e-3f, 3.0e38f, [&](int i) {
+    const int slot = __ldg(&T.inv[i]) & 0x3fffffff;
+    b = slow_closest_shared(b, T.pairs, T.perm, slot >> 1, dx, dy, dz, a.d64, a.r.sph64, src);
+    return b.idx >= 0 ? __fmaf_ru(b.hi, 1e-6f, b.hi) + 1e-6f : 3.0e38f;
+  });
+  return b;
+}
+// closest hit of a general-origin ray (recentred FP32 origin o)
+__device__ __forceinline__ Best bvh_closest_general(const FastArgs &a, const float4 *gen, float ox, float oy, float oz, float dx, float dy,
+                                                    float dz, RaySrc src) {
+  Best b;
+  best_init(b);
+  const rtb::BvhRay r = rtb::bvh_ray(ox, oy, oz, dx, dy, dz);
+  rtb::bvh_traverse(a.bvh, r, -1e-3f, 3.0e38f, [&](int i) {
+    b = slow_closest_general(b, gen, i >> 1, a.N, ox, oy, oz, dx, dy, dz, a.d64, a.gS2, a.r.sph64, src);
+    return b.idx >= 0 ? __fmaf_ru(b.hi, 1e-6f, b.hi) + 1e-6f : 3.0e38f;
+  });
+  return b;
+}
+// any-hit shadow query, traversed FROM THE LIGHT (origin o = light, recentred) along dl up to the shaded point
+__device__ __forceinline__ bool bvh_shadow(const FastArgs &a, const Tab T, float3 o, int light, float dx, float dy, float dz, float so, int self,
+                                           float cosl, const double *p64, int &n_fp64) {
+  const float m = __fmaf_ru(1.9073486e-6f, so + kEps, 1e-7f);           // as in shadow_begin
+  bool occ = false;
+  const rtb::BvhRay r = rtb::bvh_ray(o.x, o.y, o.z, dx, dy, dz);
+  const float t1 = so + m;
+  rtb::bvh_traverse(a.bvh, r, -(kEps + m), t1, [&](int i) {
+    const int slot = __ldg(&T.inv[i]) & 0x3fffffff;
+    const int rc = slow_shadow(T.pairs, T.perm, slot >> 1, dx, dy, dz, so, m, self, cosl, p64, light, a.d64, a.r.sph64);
+    n_fp64 += rc >> 1;
+    if (rc & 1) occ = true;
+    return occ ? -3.0e38f : t1;
+  });
+  return occ;
+}
+
+// ---------------------------------------------------------------------------------------------
 // warp-ballot compaction: rays still alive are appended densely to the next level's queue
 __device__ __forceinline__ void queue_push(bool want, const RayRec &rec, RayRec *q, unsigned int *count) {
   const unsigned mk = __ballot_sync(kFull, want);
@@ -854,7 +906,7 @@ __device__ __forceinline__ void flush_counters(const FastArgs &a, Counters &c, i
 #define RT_TAIL_CTAS 2
 #endif
 constexpr int kTailThreads = RT_TAIL_THREADS;
-template <bool kSmem>
+template <bool kSmem, bool kBvh>
 __global__ void __launch_bounds__(kTailThreads, RT_TAIL_CTAS) k_bounce(const FastArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const unsigned nq = *a.q_in_count;
@@ -889,7 +941,8 @@ __global__ void __launch_bounds__(kTailThreads, RT_TAIL_CTAS) k_bounce(const Fas
     for (int level = a.level;; level++) {
       Best best[1];
       best_init(best[0]);
-      closest_general<1>(gen, a.npairs, a.N, ox, oy, oz, dx, dy, dz, live, a.d64, a.gS2, a.g_dtmax, a.r.sph64, src, best);
+      if (kBvh) { if (live[0]) best[0] = bvh_closest_general(a, gen, ox[0], oy[0], oz[0], dx[0], dy[0], dz[0], src[0]); }
+      else closest_general<1>(gen, a.npairs, a.N, ox, oy, oz, dx, dy, dz, live, a.d64, a.gS2, a.g_dtmax, a.r.sph64, src, best);
       bool hit = false, final_ = false, cont = false;
       int idx[1] = {-1};
       double t64 = 0;
@@ -929,7 +982,7 @@ __global__ void __launch_bounds__(kTailThreads, RT_TAIL_CTAS) k_bounce(const Fas
         vx = -(float)d64v.x; vy = -(float)d64v.y; vz = -(float)d64v.z;
         sr = g_frame.ambient[0] * m.x; sg = g_frame.ambient[1] * m.y; sb = g_frame.ambient[2] * m.z;
       }
-      if (__any_sync(kFull, hit)) {
+      if (kBvh || __any_sync(kFull, hit)) {
         for (int l = 0; l < L; l++) {
           float sdx[1] = {0.f}, sdy[1] = {0.f}, sdz[1] = {0.f}, so[1] = {0.f}, cosl[1] = {0.f};
           bool occ[1] = {false};
@@ -945,7 +998,8 @@ __global__ void __launch_bounds__(kTailThreads, RT_TAIL_CTAS) k_bounce(const Fas
             cosl[0] = -(nx * sdx[0] + ny * sdy[0] + nz * sdz[0]);             // n . light_dir
           }
           const double *const pp[1] = {&p.x};
-          if (kSmem) shadow_light_culled<1>(tab_at(tabs, a, l), a.npairs, wb, l, sdx, sdy, sdz, so, want, idx, cosl, pp, a.d64, a.r.sph64, occ, n_fp64, c_cand, c_walks);
+          if (kBvh) { if (hit) occ[0] = bvh_shadow(a, tab_at(tabs, a, l), recentred(a, g_frame.light_pos[l]), l, sdx[0], sdy[0], sdz[0], so[0], idx[0], cosl[0], &p.x, n_fp64); }
+          else if (kSmem) shadow_light_culled<1>(tab_at(tabs, a, l), a.npairs, wb, l, sdx, sdy, sdz, so, want, idx, cosl, pp, a.d64, a.r.sph64, occ, n_fp64, c_cand, c_walks);
           else shadow_light<1>(tab_at(tabs, a, l), a.npairs, l, sdx, sdy, sdz, so, want, idx, cosl, pp, a.d64, a.r.sph64, occ, n_fp64);
           if (!hit) continue;
           cnt.shadow++;

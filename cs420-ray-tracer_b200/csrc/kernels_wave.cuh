@@ -118,7 +118,7 @@ __device__ __noinline__ bool finish_hit(const FastArgs &a, Best b, RaySrc src, u
 //               two-stage ring of 32 KB tiles -- cp.async.bulk into stage k+1 while the eight warps
 //               test their rays against stage k (full barriers = mbarriers with expect_tx, the
 //               "stage is free again" edge = the CTA barrier that also votes on early termination).
-enum { kTabGlobal = 0, kTabSmem = 1, kTabStream = 2 };
+enum { kTabGlobal = 0, kTabSmem = 1, kTabStream = 2, kTabBvh = 3 };   // kTabBvh: candidates from the LBVH, tables in global memory
 constexpr int kTilePairs = 1024;                                   // sphere pairs per streamed tile
 constexpr unsigned kTileBytes = kTilePairs * 32u;                  // 32 KB per stage
 
@@ -213,6 +213,11 @@ __global__ void __launch_bounds__(kThreads, RT_CLOSEST_CTAS) k_closest0(const Wa
       closest_shared_culled<2>(cam, a.npairs, wb, dx, dy, dz, live, a.d64, a.r.sph64, src, best, c_cand, c_walks);
     } else if (kMode == kTabGlobal) {
       closest_shared<2>(cam, a.npairs, dx, dy, dz, live, a.d64, a.r.sph64, src, best);
+    } else if (kMode == kTabBvh) {
+      const float3 o = recentred(a, g_frame.cam_pos);
+#pragma unroll 1
+      for (int r = 0; r < 2; r++)
+        if (live[r]) best[r] = bvh_closest_shared(a, cam, o, dx[r], dy[r], dz[r], src[r]);
     } else {
       // the eight warps of the CTA walk the sorted camera table together, tile by tile
       ClosestQ<2> q;
@@ -282,7 +287,7 @@ __global__ void __launch_bounds__(kThreads, RT_CLOSEST_CTAS) k_closest0(const Wa
 
 // ---------------------------------------------------------------------------------------------
 // LEVEL >= 1 closest hit: reflected rays from the RayRec queue, 64 per warp fetch, two per lane.
-template <bool kSmem>
+template <bool kSmem, bool kBvh>
 __global__ void __launch_bounds__(kThreads, RT_CLOSEST_CTAS) k_closest1(const WaveArgs w) {
   extern __shared__ __align__(128) unsigned char smem[];
   const FastArgs &a = w.f;
@@ -319,7 +324,13 @@ __global__ void __launch_bounds__(kThreads, RT_CLOSEST_CTAS) k_closest1(const Wa
     Best best[2];
     best_init(best[0]); best_init(best[1]);
     const RaySrc src[2] = {{nullptr, nullptr, 0, 0, qin + qi[0]}, {nullptr, nullptr, 0, 0, qin + qi[1]}};
-    closest_general<2>(gen, a.npairs, a.N, ox, oy, oz, dx, dy, dz, live, a.d64, a.gS2, a.g_dtmax, a.r.sph64, src, best);
+    if (kBvh) {
+#pragma unroll 1
+      for (int r = 0; r < 2; r++)
+        if (live[r]) best[r] = bvh_closest_general(a, gen, ox[r], oy[r], oz[r], dx[r], dy[r], dz[r], src[r]);
+    } else {
+      closest_general<2>(gen, a.npairs, a.N, ox, oy, oz, dx, dy, dz, live, a.d64, a.gS2, a.g_dtmax, a.r.sph64, src, best);
+    }
     unsigned hslot[2];
     hit_block(w, __ballot_sync(kFull, live[0] && best[0].idx >= 0), __ballot_sync(kFull, live[1] && best[1].idx >= 0), hslot);
 #pragma unroll
@@ -427,7 +438,14 @@ __global__ void __launch_bounds__(kThreads, RT_SHADOW_CTAS) k_shadow(const WaveA
         want[r] = have[r] && !shortcut[r];
       }
       int n64 = 0;
-      if (kMode != kTabStream) {
+      if (kMode == kTabBvh) {
+        const float3 o = recentred(a, g_frame.light_pos[l]);
+#pragma unroll 1
+        for (int r = 0; r < 2; r++) {
+          occ[r] = false;
+          if (want[r]) occ[r] = bvh_shadow(a, T, o, l, dx[r], dy[r], dz[r], so[r], self[r], cosl[r], ppc[r], n64);
+        }
+      } else if (kMode != kTabStream) {
         occ[0] = occ[1] = false;
         if (__any_sync(kFull, want[0] || want[1])) {
           if (kMode == kTabSmem) shadow_light_culled<2>(T, a.npairs, wb, l, dx, dy, dz, so, want, self, cosl, ppc, a.d64, a.r.sph64, occ, n64, c_cand, c_walks);

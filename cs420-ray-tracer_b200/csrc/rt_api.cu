@@ -49,6 +49,7 @@ struct rt_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm[3] = {nullptr, nullptr, nullptr};
   int mode = 0;          // 0 fast, 1 exact
   int counters_on = 1;
+  int accel = 0;         // 0 auto, 1 table walks, 2 LBVH (takes effect at the next rt_upload_scene)
   // scene
   bool have_scene = false;
   int N = 0, L = 0;
@@ -142,6 +143,11 @@ extern "C" int rt_set_option(rt_ctx *c, const char *key, long long value) {
     return RT_OK;
   }
   if (!strcmp(key, "counters")) { c->counters_on = value != 0; return RT_OK; }
+  if (!strcmp(key, "accel")) {
+    if (value < 0 || value > 2) return rt_fail(RT_ERR_ARG, "rt_set_option: accel must be 0 (auto), 1 (tables) or 2 (LBVH)");
+    c->accel = (int)value;
+    return RT_OK;
+  }
   if (!strcmp(key, "wave_levels")) {
     if (value < 1 || value > RT_MAX_LEVELS) return rt_fail(RT_ERR_ARG, "rt_set_option: wave_levels must be 1..32");
     c->work.wave_levels = (int)value;
@@ -206,7 +212,7 @@ extern "C" int rt_upload_scene(rt_ctx *c, const double *spheres, int N, const do
   RT_CUDA(cudaMemcpyAsync(c->d_sph64, s64.data(), n1 * sizeof(double4), cudaMemcpyHostToDevice, c->stream));
   RT_CUDA(cudaMemcpyAsync(c->d_mat, mat.data(), n1 * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
   RT_CUDA(cudaMemcpyAsync(c->d_matx, matx.data(), n1 * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
-  int r = rtk_fast_build_scene(&c->fast, spheres, N, &f, c->stream);
+  int r = rtk_fast_build_scene(&c->fast, spheres, N, &f, c->accel, c->stream);
   if (r != 0) return rt_fail(RT_ERR_CUDA, std::string("rt_upload_scene: filter table build failed: ") + cudaGetErrorString((cudaError_t)-r));
   RT_CUDA(cudaStreamSynchronize(c->stream));
   c->scene_version++;

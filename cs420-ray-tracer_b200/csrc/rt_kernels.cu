@@ -49,10 +49,10 @@ inline float float_down(double x) {             // largest float <= x
 
 int rtk_fast_init(int) {
   const int big = 227 * 1024;
-  RTK_TRY(cudaFuncSetAttribute(rtf::k_bounce<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  RTK_TRY(cudaFuncSetAttribute(rtf::k_bounce<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   RTK_TRY(cudaFuncSetAttribute(rtf::k_closest0<rtf::kTabSmem>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   RTK_TRY(cudaFuncSetAttribute(rtf::k_closest0<rtf::kTabStream>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  RTK_TRY(cudaFuncSetAttribute(rtf::k_closest1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  RTK_TRY(cudaFuncSetAttribute(rtf::k_closest1<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   RTK_TRY(cudaFuncSetAttribute(rtf::k_shadow<rtf::kTabSmem>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   RTK_TRY(cudaFuncSetAttribute(rtf::k_shadow<rtf::kTabStream>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   return 0;
@@ -67,7 +67,67 @@ int rtk_fast_init(int) {
 //   general table (index order): c' = c_i - C0 (nearest float),
 //       rho' = round_up(r^2 (1+40u) + 12u S r + 64u^2 S^2 + delta64)
 // Sphere PAIRS are interleaved for the packed FP32x2 test: (x0,x1,y0,y1) (z0,z1,w0,w1).
-int rtk_fast_build_scene(RtFastScene *fs, const double *sph, int N, const RtFrameConst *f, cudaStream_t stream) {
+constexpr int RT_MAX_LEVELS_INTERNAL = 32;
+constexpr int kBvhAutoSpheres = 2048;   // automatic mode: scenes from this size on are traversed through the LBVH
+
+// Device build of the LBVH (bvh.cuh) over cen[i] = (c_i - C0, r_i) in FP32; eps inflates every box.
+static int bvh_build(RtFastScene *fs, const std::vector<float4> &cen, float eps, cudaStream_t stream) {
+  const int n = (int)cen.size(), nleaf = (n + rtb::kLeafSize - 1) / rtb::kLeafSize, nint = nleaf > 1 ? nleaf - 1 : 1;
+  float4 *d_cen = nullptr, *leaf_lo = nullptr, *leaf_hi = nullptr, *node_lo = nullptr, *node_hi = nullptr;
+  unsigned *keys[2] = {nullptr, nullptr}, *leaf_key = nullptr;
+  int *vals[2] = {nullptr, nullptr}, *bounds = nullptr, *left = nullptr, *right = nullptr, *par_i = nullptr, *par_l = nullptr, *flags = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int rc = 0;
+#define BV(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = -(int)e_; goto done; } } while (0)
+  BV(cudaEventCreate(&e0)); BV(cudaEventCreate(&e1));
+  BV(cudaMalloc(&d_cen, (size_t)n * 16));
+  for (int k = 0; k < 2; k++) { BV(cudaMalloc(&keys[k], (size_t)n * 4)); BV(cudaMalloc(&vals[k], (size_t)n * 4)); }
+  BV(cudaMalloc(&bounds, 6 * 4));
+  BV(cudaMalloc(&leaf_lo, (size_t)nleaf * 16)); BV(cudaMalloc(&leaf_hi, (size_t)nleaf * 16)); BV(cudaMalloc(&leaf_key, (size_t)nleaf * 4));
+  BV(cudaMalloc(&node_lo, (size_t)nint * 16)); BV(cudaMalloc(&node_hi, (size_t)nint * 16));
+  BV(cudaMalloc(&left, (size_t)nint * 4)); BV(cudaMalloc(&right, (size_t)nint * 4)); BV(cudaMalloc(&par_i, (size_t)nint * 4));
+  BV(cudaMalloc(&par_l, (size_t)nleaf * 4)); BV(cudaMalloc(&flags, (size_t)nint * 4));
+  BV(cudaMalloc(&fs->bvh_nodes, (size_t)nint * sizeof(rtb::BvhNode)));
+  BV(cudaMemcpyAsync(d_cen, cen.data(), (size_t)n * 16, cudaMemcpyHostToDevice, stream));
+  {
+    const int init[6] = {0x7f7fffff, 0x7f7fffff, 0x7f7fffff, (int)0x80800000, (int)0x80800000, (int)0x80800000};   // ord(+max) / ord(-max)
+    BV(cudaMemcpyAsync(bounds, init, sizeof(init), cudaMemcpyHostToDevice, stream));
+  }
+  BV(cudaMemsetAsync(flags, 0, (size_t)nint * 4, stream));
+  BV(cudaMemsetAsync(par_l, 0xff, (size_t)nleaf * 4, stream));
+  BV(cudaMemsetAsync(par_i, 0xff, (size_t)nint * 4, stream));
+  BV(cudaEventRecord(e0, stream));
+  {
+    const int tb = 256, gb = (n + tb - 1) / tb, gl = (nleaf + tb - 1) / tb;
+    rtb::k_bvh_bounds<<<gb < 592 ? gb : 592, tb, 0, stream>>>(d_cen, n, bounds);
+    rtb::k_bvh_morton<<<gb, tb, 0, stream>>>(d_cen, n, bounds, keys[0], vals[0]);
+    const size_t sort_smem = (16 * rtb::kSortThreads + 32) * sizeof(unsigned);
+    BV(cudaFuncSetAttribute(rtb::k_bvh_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
+    rtb::k_bvh_sort<<<1, rtb::kSortThreads, sort_smem, stream>>>(keys[0], vals[0], keys[1], vals[1], n, 8);   // 8 x 4 bits, result in [0]
+    rtb::k_bvh_leaves<<<gl, tb, 0, stream>>>(d_cen, keys[0], vals[0], n, nleaf, eps, leaf_lo, leaf_hi, leaf_key);
+    if (nleaf > 1) {
+      rtb::k_bvh_hier<<<(nleaf - 1 + tb - 1) / tb, tb, 0, stream>>>(leaf_key, nleaf, left, right, par_i, par_l);
+      rtb::k_bvh_refit<<<gl, tb, 0, stream>>>(nleaf, left, right, par_i, par_l, leaf_lo, leaf_hi, node_lo, node_hi, flags);
+    }
+    rtb::k_bvh_pack<<<(nint + tb - 1) / tb, tb, 0, stream>>>(nleaf, left, right, vals[0], leaf_lo, leaf_hi, node_lo, node_hi, (rtb::BvhNode *)fs->bvh_nodes);
+  }
+  BV(cudaGetLastError());
+  BV(cudaEventRecord(e1, stream));
+  BV(cudaStreamSynchronize(stream));
+  { float ms = 0; BV(cudaEventElapsedTime(&ms, e0, e1)); fs->bvh_build_ms = ms; }
+  fs->bvh_nleaf = nleaf;
+done:
+#undef BV
+  cudaFree(d_cen); cudaFree(keys[0]); cudaFree(keys[1]); cudaFree(vals[0]); cudaFree(vals[1]); cudaFree(bounds);
+  cudaFree(leaf_lo); cudaFree(leaf_hi); cudaFree(leaf_key); cudaFree(node_lo); cudaFree(node_hi);
+  cudaFree(left); cudaFree(right); cudaFree(par_i); cudaFree(par_l); cudaFree(flags);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  if (rc != 0) { cudaFree(fs->bvh_nodes); cudaFree(fs->bvh_leaves); fs->bvh_nodes = fs->bvh_leaves = nullptr; }
+  return rc;
+}
+
+int rtk_fast_build_scene(RtFastScene *fs, const double *sph, int N, const RtFrameConst *f, int accel, cudaStream_t stream) {
   const int L = f->nlights;
   int npairs = (N + 1) / 2;
   npairs = ((npairs + rtf::kGroupPairs - 1) / rtf::kGroupPairs) * rtf::kGroupPairs;
@@ -182,12 +242,25 @@ int rtk_fast_build_scene(RtFastScene *fs, const double *sph, int N, const RtFram
   RTK_TRY(cudaMalloc(&fs->tabs, total));
   RTK_TRY(cudaMemcpyAsync(fs->tabs, h.data(), total, cudaMemcpyHostToDevice, stream));
   RTK_TRY(cudaStreamSynchronize(stream));   // h goes out of scope
+  fs->bvh_nodes = fs->bvh_leaves = nullptr; fs->bvh_nleaf = 0; fs->bvh_build_ms = 0;
+  if (N > 0 && (accel == 2 || (accel == 0 && N >= kBvhAutoSpheres))) {
+    std::vector<float4> cen((size_t)N);
+    for (int i = 0; i < N; i++) {
+      const double *s = sph + (size_t)i * 10;
+      cen[i] = make_float4((float)(s[0] - fs->c0[0]), (float)(s[1] - fs->c0[1]), (float)(s[2] - fs->c0[2]), float_up(std::fabs(s[3])));
+    }
+    // box inflation: FP32 rounding of recentred centres / ray origins (<= u S each) and the 12u direction error over
+    // any distance <= 2S inside the scene ball, with a 2x reserve: 64u * 3S
+    const int r = bvh_build(fs, cen, float_up(64.0 * u * 3.0 * S), stream);
+    if (r != 0) return r;
+  }
   return 0;
 }
 
 void rtk_fast_free_scene(RtFastScene *fs) {
   if (fs->tabs) cudaFree(fs->tabs);
-  fs->tabs = nullptr;
+  cudaFree(fs->bvh_nodes); cudaFree(fs->bvh_leaves);
+  fs->tabs = nullptr; fs->bvh_nodes = fs->bvh_leaves = nullptr; fs->bvh_nleaf = 0;
 }
 
 void rtk_fast_free_work(RtFastWork *w) {
@@ -255,13 +328,16 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
   const bool cam_smem = fs->tstride <= kMaxSmemTables, light_smem = light_bytes <= kMaxSmemTables;
   const bool gen_smem = pairs_bytes <= kMaxSmemTables, in_smem = fs->bytes_bounce <= kMaxSmemTables;
   a.tables_in_smem = in_smem;
+  const bool bvh = fs->bvh_nodes != nullptr;
+  a.bvh.nodes = (const rtb::BvhNode *)fs->bvh_nodes;
   // larger tables are streamed through a two-stage ring of TMA tiles (kernels_wave.cuh, kTabStream)
   const size_t stream_smem = rtf::kSmemHeader + 2 * (size_t)rtf::kTileBytes;
   int launches = 0;
 
   // levels below wave_levels run as phase-separated wavefront kernels; the (few) rays left after that are
   // followed to termination by one fused launch
-  const int wave_levels = w->wave_levels > 0 ? w->wave_levels : 2;
+  // (large scenes: every level has enough rays to fill the machine, and the tail's one-warp chains would dominate)
+  const int wave_levels = w->wave_levels > 0 ? w->wave_levels : (fs->bvh_nodes ? RT_MAX_LEVELS_INTERNAL : 2);
   for (int level = 0; level < args.max_depth && level < wave_levels; level++) {
     a.level = level;
     wa.hit_count = w->ctl + CTL_HITS + level;
@@ -270,7 +346,8 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
       a.stage_bytes = fs->tstride;
       const size_t smem = cam_smem ? staged_smem(a.stage_bytes) : stream_smem;
       const int cta_tiles = (a.nwtiles + rtf::kWarps - 1) / rtf::kWarps;
-      if (cam_smem) { int g = resident_grid(rtf::k_closest0<rtf::kTabSmem>, smem, w->num_sms); rtf::k_closest0<rtf::kTabSmem><<<g < cta_tiles ? g : cta_tiles, rtf::kThreads, smem, stream>>>(wa); }
+      if (bvh) { int g = resident_grid(rtf::k_closest0<rtf::kTabBvh>, rtf::kSmemHeader, w->num_sms); rtf::k_closest0<rtf::kTabBvh><<<g < cta_tiles ? g : cta_tiles, rtf::kThreads, rtf::kSmemHeader, stream>>>(wa); }
+      else if (cam_smem) { int g = resident_grid(rtf::k_closest0<rtf::kTabSmem>, smem, w->num_sms); rtf::k_closest0<rtf::kTabSmem><<<g < cta_tiles ? g : cta_tiles, rtf::kThreads, smem, stream>>>(wa); }
       else { int g = resident_grid(rtf::k_closest0<rtf::kTabStream>, smem, w->num_sms); rtf::k_closest0<rtf::kTabStream><<<g < cta_tiles ? g : cta_tiles, rtf::kThreads, smem, stream>>>(wa); }
     } else {
       a.q_in = (rtf::RayRec *)w->queue[(level - 1) & 1];
@@ -278,8 +355,9 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
       wa.work_counter = w->ctl + CTL_CLOSEST + level;
       a.stage_bytes = (unsigned)pairs_bytes;
       const size_t smem = rtf::kSmemHeader + (gen_smem ? a.stage_bytes : 0);
-      if (gen_smem) rtf::k_closest1<true><<<resident_grid(rtf::k_closest1<true>, smem, w->num_sms), rtf::kThreads, smem, stream>>>(wa);
-      else rtf::k_closest1<false><<<resident_grid(rtf::k_closest1<false>, smem, w->num_sms), rtf::kThreads, smem, stream>>>(wa);
+      if (bvh) rtf::k_closest1<false, true><<<resident_grid(rtf::k_closest1<false, true>, rtf::kSmemHeader, w->num_sms), rtf::kThreads, rtf::kSmemHeader, stream>>>(wa);
+      else if (gen_smem) rtf::k_closest1<true, false><<<resident_grid(rtf::k_closest1<true, false>, smem, w->num_sms), rtf::kThreads, smem, stream>>>(wa);
+      else rtf::k_closest1<false, false><<<resident_grid(rtf::k_closest1<false, false>, smem, w->num_sms), rtf::kThreads, smem, stream>>>(wa);
     }
     launches++;
     if (level == 0 && marks) RTK_TRY(cudaEventRecord(marks[0], stream));
@@ -288,7 +366,8 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
       wa.work_counter = w->ctl + CTL_SHADOW + level;
       a.stage_bytes = (unsigned)light_bytes;
       const size_t smem = light_smem ? staged_smem(a.stage_bytes) : stream_smem;
-      if (light_smem) rtf::k_shadow<rtf::kTabSmem><<<resident_grid(rtf::k_shadow<rtf::kTabSmem>, smem, w->num_sms), rtf::kThreads, smem, stream>>>(wa);
+      if (bvh) rtf::k_shadow<rtf::kTabBvh><<<resident_grid(rtf::k_shadow<rtf::kTabBvh>, rtf::kSmemHeader, w->num_sms), rtf::kThreads, rtf::kSmemHeader, stream>>>(wa);
+      else if (light_smem) rtf::k_shadow<rtf::kTabSmem><<<resident_grid(rtf::k_shadow<rtf::kTabSmem>, smem, w->num_sms), rtf::kThreads, smem, stream>>>(wa);
       else rtf::k_shadow<rtf::kTabStream><<<resident_grid(rtf::k_shadow<rtf::kTabStream>, smem, w->num_sms), rtf::kThreads, smem, stream>>>(wa);
       launches++;
     }
@@ -312,8 +391,9 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
     a.chunk_counter = w->ctl + CTL_TAIL + level;
     a.stage_bytes = (unsigned)fs->bytes_bounce;
     const size_t smem = in_smem ? staged_smem(fs->bytes_bounce) : rtf::kSmemHeader;
-    if (in_smem) rtf::k_bounce<true><<<resident_grid(rtf::k_bounce<true>, smem, w->num_sms, rtf::kTailThreads), rtf::kTailThreads, smem, stream>>>(a);
-    else rtf::k_bounce<false><<<resident_grid(rtf::k_bounce<false>, smem, w->num_sms, rtf::kTailThreads), rtf::kTailThreads, smem, stream>>>(a);
+    if (bvh) rtf::k_bounce<false, true><<<resident_grid(rtf::k_bounce<false, true>, rtf::kSmemHeader, w->num_sms, rtf::kTailThreads), rtf::kTailThreads, rtf::kSmemHeader, stream>>>(a);
+    else if (in_smem) rtf::k_bounce<true, false><<<resident_grid(rtf::k_bounce<true, false>, smem, w->num_sms, rtf::kTailThreads), rtf::kTailThreads, smem, stream>>>(a);
+    else rtf::k_bounce<false, false><<<resident_grid(rtf::k_bounce<false, false>, smem, w->num_sms, rtf::kTailThreads), rtf::kTailThreads, smem, stream>>>(a);
     launches++;
   }
   cudaError_t e = cudaGetLastError();

@@ -24,6 +24,10 @@ struct RtFastScene {
   float gS2;              // squared radius bound of the recentred scene
   float g_dtmax;          // additive bound of the general filter's centre projection
   double c0[3];           // recentring offset of the general table
+  // device-built LBVH over the recentred spheres (bvh.cuh); built when the scene has >= bvh_min spheres
+  void *bvh_nodes, *bvh_leaves;
+  int bvh_nleaf;
+  double bvh_build_ms;    // device time of the build
 };
 struct RtFastWork {
   int num_sms;
@@ -37,7 +41,8 @@ struct RtFastWork {
   size_t hit_cap, occ_bytes;
 };
 int rtk_fast_init(int device);
-int rtk_fast_build_scene(RtFastScene *fs, const double *spheres, int N, const RtFrameConst *frame, cudaStream_t stream);
+// accel: 0 = automatic (LBVH from kBvhAutoSpheres spheres), 1 = table walks only, 2 = LBVH whenever N > 0
+int rtk_fast_build_scene(RtFastScene *fs, const double *spheres, int N, const RtFrameConst *frame, int accel, cudaStream_t stream);
 void rtk_fast_free_scene(RtFastScene *fs);
 void rtk_fast_free_work(RtFastWork *w);
 // marks (may be null): 3 events recorded after the level-0 closest-hit, shadow and shade kernels.

@@ -17,7 +17,7 @@ if name.startswith("synth"):
     sc = rtb200.Scene(*gen_scene.generate(int(p[1]), int(p[2]), *extra))
 else:
     sc = rtb200.load_scene(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "scenes", name + ".txt"))
-r = rtb200.Renderer(0)
+r = rtb200.Renderer(0, accel=int(os.environ["RT_ACCEL"]) if "RT_ACCEL" in os.environ else None)
 r.upload(sc)
 ms = []
 for _ in range(reps):

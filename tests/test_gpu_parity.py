@@ -13,7 +13,7 @@ import pytest
 from conftest import GOLDEN
 
 pytestmark = pytest.mark.gpu
-MODES = ["exact", "fast"]
+MODES = ["exact", "fast", "bvh"]     # "bvh" = fast path with the LBVH forced for every scene size
 
 
 @pytest.fixture(scope="module")
@@ -147,19 +147,26 @@ def test_row_bands_reassemble_to_the_full_frame(rt, renderers, scenes, band_h, n
     assert np.array_equal(out, full)
 
 
-def test_exact_and_fast_agree_on_large_synthetic(rt, renderers):
-    """BASELINE config 4 shape (10k spheres) at reduced resolution: the CPU oracle would need
-    minutes, so the FP64 brute-force kernel is the checker here (itself pinned to the oracle above)."""
+@pytest.mark.parametrize("n,seed,W,H,D,modes", [(10000, 420, 480, 270, 5, ("tables", "bvh")), (100000, 421, 384, 216, 8, ("bvh",))])
+def test_large_synthetic_against_fp64_brute_force(rt, renderers, n, seed, W, H, D, modes):
+    """BASELINE configs 4 (10k spheres, streamed tables and LBVH) and 5 (100k spheres, device-built LBVH)
+    at reduced resolution: the CPU oracle would need minutes to hours, so the FP64 brute-force kernel is
+    the checker here (itself pinned to the oracle by the tests above)."""
     import gen_scene
-    sc = rt.Scene(*gen_scene.generate(10000, 420))
-    out = {}
-    for m in MODES:
-        renderers[m].upload(sc)
-        out[m] = renderers[m].render_debug(480, 270, 5)
-    assert np.array_equal(out["exact"][1], out["fast"][1])
-    assert np.array_equal(out["exact"][2], out["fast"][2])
-    ok, pct, mx = rt.compare_rgb(out["exact"][0], out["fast"][0], 0.5)
-    assert ok and mx <= 2
+    sc = rt.Scene(*gen_scene.generate(n, seed))
+    renderers["exact"].upload(sc)
+    ref = renderers["exact"].render_debug(W, H, D)
+    for m in modes:
+        with rt.Renderer(0, mode="fast", accel={"tables": 1, "bvh": 2}[m]) as r:
+            r.upload(sc)
+            out = r.render_debug(W, H, D)
+        assert np.array_equal(ref[1], out[1]), m
+        assert np.array_equal(ref[2], out[2]), m
+        ok, pct, mx = rt.compare_rgb(ref[0], out[0], 0.5)
+        assert ok and mx <= 2, m
+        assert out[3].filter_violations == 0
+        for k in ("closest_queries", "hits", "shadow_queries", "occluded"):
+            assert getattr(out[3], k) == getattr(ref[3], k), (m, k)
 
 
 def test_errors(rt, renderers, scenes):
