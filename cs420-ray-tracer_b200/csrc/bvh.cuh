@@ -214,7 +214,7 @@ __global__ void k_bvh_refit(int nleaf, const int *left, const int *right, const 
 }
 
 // nint = max(nleaf - 1, 1) packed nodes.  A single-leaf tree gets one node whose second child is empty.
-__global__ void k_bvh_pack(int nleaf, const int *left, const int *right, const int *vals, const float4 *leaf_lo, const float4 *leaf_hi,
+__global__ void k_bvh_pack(int nleaf, const int *left, const int *right, const int *vals, const int *orig, const float4 *leaf_lo, const float4 *leaf_hi,
                            const float4 *node_lo, const float4 *node_hi, BvhNode *out) {
   static_assert(kLeafSize == 1, "leaf children are rewritten to sphere indices");
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -234,7 +234,7 @@ __global__ void k_bvh_pack(int nleaf, const int *left, const int *right, const i
   nd.a = make_float4(l0.x, l0.y, l0.z, h0.x);
   nd.b = make_float4(h0.y, h0.z, l1.x, l1.y);
   nd.c = make_float4(l1.z, h1.x, h1.y, h1.z);
-  nd.d = make_int4(c0 < 0 ? ~vals[~c0] : c0, c1 < 0 ? ~vals[~c1] : c1, 0, 0);
+  nd.d = make_int4(c0 < 0 ? ~orig[vals[~c0]] : c0, c1 < 0 ? ~orig[vals[~c1]] : c1, 0, 0);   // orig: build order -> sphere index
   out[i] = nd;
 }
 

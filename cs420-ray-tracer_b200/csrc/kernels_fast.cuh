@@ -76,6 +76,7 @@ struct FastArgs {
   int level;
   int tables_in_smem;
   rtb::BvhView bvh;           // large scenes: candidates come from the LBVH instead of a table walk (bvh.cuh)
+  int nbig, big[8];           // spheres too large for the LBVH (a ground sphere ...): tested for every ray instead
 };
 
 // One shared-origin table: sphere pairs in sorted order, per-group minimum distance, original indices
@@ -822,11 +823,15 @@ __device__ __forceinline__ Best bvh_closest_shared(const FastArgs &a, const Tab 
   Best b;
   best_init(b);
   const rtb::BvhRay r = rtb::bvh_ray(o.x, o.y, o.z, dx, dy, dz);
-  rtb::bvh_traverse(a.bvh, r, -1e-3f, 3.0e38f, [&](int i) {
+  auto leaf = [&](int i) {
     const int slot = __ldg(&T.inv[i]) & 0x3fffffff;
     b = slow_closest_shared(b, T.pairs, T.perm, slot >> 1, dx, dy, dz, a.d64, a.r.sph64, src);
     return b.idx >= 0 ? __fmaf_ru(b.hi, 1e-6f, b.hi) + 1e-6f : 3.0e38f;
-  });
+  };
+  float t1 = 3.0e38f;
+#pragma unroll 1
+  for (int k = 0; k < a.nbig; k++) t1 = leaf(a.big[k]);      // first: their hit distance prunes the traversal
+  rtb::bvh_traverse(a.bvh, r, -1e-3f, t1, leaf);
   return b;
 }
 // closest hit of a general-origin ray (recentred FP32 origin o)
@@ -835,10 +840,14 @@ __device__ __forceinline__ Best bvh_closest_general(const FastArgs &a, const flo
   Best b;
   best_init(b);
   const rtb::BvhRay r = rtb::bvh_ray(ox, oy, oz, dx, dy, dz);
-  rtb::bvh_traverse(a.bvh, r, -1e-3f, 3.0e38f, [&](int i) {
+  auto leaf = [&](int i) {
     b = slow_closest_general(b, gen, i >> 1, a.N, ox, oy, oz, dx, dy, dz, a.d64, a.gS2, a.r.sph64, src);
     return b.idx >= 0 ? __fmaf_ru(b.hi, 1e-6f, b.hi) + 1e-6f : 3.0e38f;
-  });
+  };
+  float t1 = 3.0e38f;
+#pragma unroll 1
+  for (int k = 0; k < a.nbig; k++) t1 = leaf(a.big[k]);
+  rtb::bvh_traverse(a.bvh, r, -1e-3f, t1, leaf);
   return b;
 }
 // any-hit shadow query, traversed FROM THE LIGHT (origin o = light, recentred) along dl up to the shaded point
@@ -848,13 +857,16 @@ __device__ __forceinline__ bool bvh_shadow(const FastArgs &a, const Tab T, float
   bool occ = false;
   const rtb::BvhRay r = rtb::bvh_ray(o.x, o.y, o.z, dx, dy, dz);
   const float t1 = so + m;
-  rtb::bvh_traverse(a.bvh, r, -(kEps + m), t1, [&](int i) {
+  auto leaf = [&](int i) {
     const int slot = __ldg(&T.inv[i]) & 0x3fffffff;
     const int rc = slow_shadow(T.pairs, T.perm, slot >> 1, dx, dy, dz, so, m, self, cosl, p64, light, a.d64, a.r.sph64);
     n_fp64 += rc >> 1;
     if (rc & 1) occ = true;
     return occ ? -3.0e38f : t1;
-  });
+  };
+#pragma unroll 1
+  for (int k = 0; k < a.nbig && !occ; k++) leaf(a.big[k]);
+  if (!occ) rtb::bvh_traverse(a.bvh, r, -(kEps + m), t1, leaf);
   return occ;
 }
 

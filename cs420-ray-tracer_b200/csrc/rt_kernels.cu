@@ -68,19 +68,20 @@ int rtk_fast_init(int) {
 //       rho' = round_up(r^2 (1+40u) + 12u S r + 64u^2 S^2 + delta64)
 // Sphere PAIRS are interleaved for the packed FP32x2 test: (x0,x1,y0,y1) (z0,z1,w0,w1).
 constexpr int RT_MAX_LEVELS_INTERNAL = 32;
-constexpr int kBvhAutoSpheres = 2048;   // automatic mode: scenes from this size on are traversed through the LBVH
+constexpr int kBvhAutoSpheres = 1024;   // automatic mode: scenes from this size on are traversed through the LBVH
 
 // Device build of the LBVH (bvh.cuh) over cen[i] = (c_i - C0, r_i) in FP32; eps inflates every box.
-static int bvh_build(RtFastScene *fs, const std::vector<float4> &cen, float eps, cudaStream_t stream) {
+static int bvh_build(RtFastScene *fs, const std::vector<float4> &cen, const std::vector<int> &orig, float eps, cudaStream_t stream) {
   const int n = (int)cen.size(), nleaf = (n + rtb::kLeafSize - 1) / rtb::kLeafSize, nint = nleaf > 1 ? nleaf - 1 : 1;
   float4 *d_cen = nullptr, *leaf_lo = nullptr, *leaf_hi = nullptr, *node_lo = nullptr, *node_hi = nullptr;
   unsigned *keys[2] = {nullptr, nullptr}, *leaf_key = nullptr;
-  int *vals[2] = {nullptr, nullptr}, *bounds = nullptr, *left = nullptr, *right = nullptr, *par_i = nullptr, *par_l = nullptr, *flags = nullptr;
+  int *vals[2] = {nullptr, nullptr}, *d_orig = nullptr, *bounds = nullptr, *left = nullptr, *right = nullptr, *par_i = nullptr, *par_l = nullptr, *flags = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   int rc = 0;
 #define BV(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = -(int)e_; goto done; } } while (0)
   BV(cudaEventCreate(&e0)); BV(cudaEventCreate(&e1));
   BV(cudaMalloc(&d_cen, (size_t)n * 16));
+  BV(cudaMalloc(&d_orig, (size_t)n * 4));
   for (int k = 0; k < 2; k++) { BV(cudaMalloc(&keys[k], (size_t)n * 4)); BV(cudaMalloc(&vals[k], (size_t)n * 4)); }
   BV(cudaMalloc(&bounds, 6 * 4));
   BV(cudaMalloc(&leaf_lo, (size_t)nleaf * 16)); BV(cudaMalloc(&leaf_hi, (size_t)nleaf * 16)); BV(cudaMalloc(&leaf_key, (size_t)nleaf * 4));
@@ -89,6 +90,7 @@ static int bvh_build(RtFastScene *fs, const std::vector<float4> &cen, float eps,
   BV(cudaMalloc(&par_l, (size_t)nleaf * 4)); BV(cudaMalloc(&flags, (size_t)nint * 4));
   BV(cudaMalloc(&fs->bvh_nodes, (size_t)nint * sizeof(rtb::BvhNode)));
   BV(cudaMemcpyAsync(d_cen, cen.data(), (size_t)n * 16, cudaMemcpyHostToDevice, stream));
+  BV(cudaMemcpyAsync(d_orig, orig.data(), (size_t)n * 4, cudaMemcpyHostToDevice, stream));
   {
     const int init[6] = {0x7f7fffff, 0x7f7fffff, 0x7f7fffff, (int)0x80800000, (int)0x80800000, (int)0x80800000};   // ord(+max) / ord(-max)
     BV(cudaMemcpyAsync(bounds, init, sizeof(init), cudaMemcpyHostToDevice, stream));
@@ -109,7 +111,7 @@ static int bvh_build(RtFastScene *fs, const std::vector<float4> &cen, float eps,
       rtb::k_bvh_hier<<<(nleaf - 1 + tb - 1) / tb, tb, 0, stream>>>(leaf_key, nleaf, left, right, par_i, par_l);
       rtb::k_bvh_refit<<<gl, tb, 0, stream>>>(nleaf, left, right, par_i, par_l, leaf_lo, leaf_hi, node_lo, node_hi, flags);
     }
-    rtb::k_bvh_pack<<<(nint + tb - 1) / tb, tb, 0, stream>>>(nleaf, left, right, vals[0], leaf_lo, leaf_hi, node_lo, node_hi, (rtb::BvhNode *)fs->bvh_nodes);
+    rtb::k_bvh_pack<<<(nint + tb - 1) / tb, tb, 0, stream>>>(nleaf, left, right, vals[0], d_orig, leaf_lo, leaf_hi, node_lo, node_hi, (rtb::BvhNode *)fs->bvh_nodes);
   }
   BV(cudaGetLastError());
   BV(cudaEventRecord(e1, stream));
@@ -118,7 +120,7 @@ static int bvh_build(RtFastScene *fs, const std::vector<float4> &cen, float eps,
   fs->bvh_nleaf = nleaf;
 done:
 #undef BV
-  cudaFree(d_cen); cudaFree(keys[0]); cudaFree(keys[1]); cudaFree(vals[0]); cudaFree(vals[1]); cudaFree(bounds);
+  cudaFree(d_cen); cudaFree(d_orig); cudaFree(keys[0]); cudaFree(keys[1]); cudaFree(vals[0]); cudaFree(vals[1]); cudaFree(bounds);
   cudaFree(leaf_lo); cudaFree(leaf_hi); cudaFree(leaf_key); cudaFree(node_lo); cudaFree(node_hi);
   cudaFree(left); cudaFree(right); cudaFree(par_i); cudaFree(par_l); cudaFree(flags);
   if (e0) cudaEventDestroy(e0);
@@ -242,16 +244,33 @@ int rtk_fast_build_scene(RtFastScene *fs, const double *sph, int N, const RtFram
   RTK_TRY(cudaMalloc(&fs->tabs, total));
   RTK_TRY(cudaMemcpyAsync(fs->tabs, h.data(), total, cudaMemcpyHostToDevice, stream));
   RTK_TRY(cudaStreamSynchronize(stream));   // h goes out of scope
-  fs->bvh_nodes = fs->bvh_leaves = nullptr; fs->bvh_nleaf = 0; fs->bvh_build_ms = 0;
+  fs->bvh_nodes = fs->bvh_leaves = nullptr; fs->bvh_nleaf = 0; fs->bvh_build_ms = 0; fs->nbig = 0;
   if (N > 0 && (accel == 2 || (accel == 0 && N >= kBvhAutoSpheres))) {
-    std::vector<float4> cen((size_t)N);
+    // Spheres far larger than the typical one (a ground sphere ...) stay out of the hierarchy: their boxes would make
+    // every ancestor cover the scene, so every ray would walk that whole root-to-leaf path.  They are tested per ray.
+    std::vector<double> rad((size_t)N);
+    for (int i = 0; i < N; i++) rad[i] = std::fabs(sph[(size_t)i * 10 + 3]);
+    std::vector<double> srt(rad);
+    std::nth_element(srt.begin(), srt.begin() + N / 2, srt.end());
+    const double big_r = 16.0 * srt[N / 2];
+    std::vector<int> bigs;
+    for (int i = 0; i < N; i++) if (rad[i] > big_r) bigs.push_back(i);
+    std::sort(bigs.begin(), bigs.end(), [&](int p, int q) { return rad[p] > rad[q]; });
+    if (bigs.size() > 8 || (int)bigs.size() == N) bigs.resize(bigs.size() > 8 ? 8 : 0);
+    fs->nbig = (int)bigs.size();
+    for (int k = 0; k < fs->nbig; k++) fs->big[k] = bigs[k];
+    std::vector<float4> cen;
+    std::vector<int> orig;
+    cen.reserve((size_t)N); orig.reserve((size_t)N);
     for (int i = 0; i < N; i++) {
+      if (std::find(bigs.begin(), bigs.end(), i) != bigs.end()) continue;
       const double *s = sph + (size_t)i * 10;
-      cen[i] = make_float4((float)(s[0] - fs->c0[0]), (float)(s[1] - fs->c0[1]), (float)(s[2] - fs->c0[2]), float_up(std::fabs(s[3])));
+      cen.push_back(make_float4((float)(s[0] - fs->c0[0]), (float)(s[1] - fs->c0[1]), (float)(s[2] - fs->c0[2]), float_up(rad[i])));
+      orig.push_back(i);
     }
     // box inflation: FP32 rounding of recentred centres / ray origins (<= u S each) and the 12u direction error over
     // any distance <= 2S inside the scene ball, with a 2x reserve: 64u * 3S
-    const int r = bvh_build(fs, cen, float_up(64.0 * u * 3.0 * S), stream);
+    const int r = bvh_build(fs, cen, orig, float_up(64.0 * u * 3.0 * S), stream);
     if (r != 0) return r;
   }
   return 0;
@@ -330,6 +349,8 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
   a.tables_in_smem = in_smem;
   const bool bvh = fs->bvh_nodes != nullptr;
   a.bvh.nodes = (const rtb::BvhNode *)fs->bvh_nodes;
+  a.nbig = fs->nbig;
+  for (int k = 0; k < 8; k++) a.big[k] = fs->big[k];
   // larger tables are streamed through a two-stage ring of TMA tiles (kernels_wave.cuh, kTabStream)
   const size_t stream_smem = rtf::kSmemHeader + 2 * (size_t)rtf::kTileBytes;
   int launches = 0;

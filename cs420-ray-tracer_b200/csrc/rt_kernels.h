@@ -27,6 +27,7 @@ struct RtFastScene {
   // device-built LBVH over the recentred spheres (bvh.cuh); built when the scene has >= bvh_min spheres
   void *bvh_nodes, *bvh_leaves;
   int bvh_nleaf;
+  int nbig, big[8];       // spheres kept out of the LBVH because their boxes would cover most of it
   double bvh_build_ms;    // device time of the build
 };
 struct RtFastWork {
