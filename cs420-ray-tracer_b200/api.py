@@ -17,7 +17,7 @@ RT_MAX_LEVELS = 32
 ABI_SYMBOLS = [
     "rt_abi_version", "rt_last_error", "rt_device_count",
     "rt_scene_load", "rt_scene_counts", "rt_scene_data", "rt_scene_free",
-    "rt_create", "rt_destroy", "rt_set_option", "rt_upload_scene",
+    "rt_create", "rt_destroy", "rt_set_option", "rt_upload_scene", "rt_render_tile",
     "rt_render", "rt_render_debug", "rt_render_bands", "rt_band_rows", "rt_band_row_list",
     "rt_host_alloc", "rt_host_free", "rt_write_ppm", "rt_measure_fp32_peak",
 ]
@@ -77,6 +77,7 @@ def load_library():
     lib.rt_destroy.argtypes = [vp]
     lib.rt_destroy.restype = None
     lib.rt_set_option.argtypes = [vp, C.c_char_p, C.c_longlong]
+    lib.rt_render_tile.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
     lib.rt_upload_scene.argtypes = [vp, vp, i, vp, i, vp, vp, vp, C.c_double]
     lib.rt_render.argtypes = [vp, i, i, i, vp, C.POINTER(RtStats)]
     lib.rt_render_debug.argtypes = [vp, i, i, i, vp, vp, vp, C.POINTER(RtStats)]
@@ -185,6 +186,7 @@ class Renderer:
         _check(self._lib.rt_create(int(device), C.byref(self._h)), "rt_create")
         if mode == "bvh":
             mode, accel = "fast", 2
+        self.antialias = False
         self.set_mode(mode)
         if accel is not None:
             self.set_option("accel", accel)
@@ -221,6 +223,14 @@ class Renderer:
 
     def set_option(self, key, value):
         _check(self._lib.rt_set_option(self._h, key.encode(), int(value)), "rt_set_option")
+        if key == "antialias":
+            self.antialias = bool(value)
+
+    def render_tile_device(self, W, H, depth, tile, dev_fb_ptr, stream_ptr=None):
+        """rt_render_tile: tile = (x, y, w, h); dev_fb_ptr = device pointer of a W*H*3 float32 framebuffer."""
+        x, y, w, h = tile
+        _check(self._lib.rt_render_tile(self._h, W, H, depth, x, y, w, h, C.c_void_p(dev_fb_ptr),
+                                        C.c_void_p(stream_ptr) if stream_ptr else None), "rt_render_tile")
 
     def upload(self, scene):
         self.scene = scene
@@ -255,8 +265,9 @@ class Renderer:
 
     def render_debug(self, W, H, depth):
         out = np.empty((H, W, 3), dtype=np.uint8)
-        hit = np.empty((H, W, max(depth, 1)), dtype=np.int32)
-        mask = np.empty((H, W, max(depth, 1)), dtype=np.uint32)
+        m = 2 if self.antialias else 1          # supersampling: debug buffers are per sample, [2H][2W][depth]
+        hit = np.empty((H * m, W * m, max(depth, 1)), dtype=np.int32)
+        mask = np.empty((H * m, W * m, max(depth, 1)), dtype=np.uint32)
         st = RtStats()
         _check(self._lib.rt_render_debug(self._h, W, H, depth, out.ctypes.data, hit.ctypes.data, mask.ctypes.data,
                                          C.byref(st)), "rt_render_debug")

@@ -111,6 +111,16 @@ __device__ __forceinline__ float wmaxf(float v) {
   return v;
 }
 __device__ __forceinline__ unsigned quant8(float c) { return (unsigned)(int)(255.99f * fminf(1.0f, c)); }
+// A finished pixel: 8-bit quantised (src/main.cpp:84-86) or, for tile renders / supersampling, FP32 colour.
+__device__ __forceinline__ void write_final(const RtRenderArgs &r, unsigned pix, float cr, float cg, float cb) {
+  size_t o = pix;
+  if (r.out_remap) {
+    const unsigned lr = pix / (unsigned)r.W, x = pix - lr * (unsigned)r.W;
+    o = (size_t)(lr + (unsigned)r.out_y0) * (size_t)r.out_pitch + x + (unsigned)r.out_x0;
+  }
+  if (r.fb) { float *f = r.fb + o * 3; f[0] = cr; f[1] = cg; f[2] = cb; }
+  else { unsigned char *q = r.rgb + o * 3; q[0] = (unsigned char)quant8(cr); q[1] = (unsigned char)quant8(cg); q[2] = (unsigned char)quant8(cb); }
+}
 __device__ __forceinline__ int warp_fetch(unsigned int *counter) {
   int v = 0;
   if ((threadIdx.x & 31) == 0) v = (int)atomicAdd(counter, 1u);
@@ -1049,10 +1059,7 @@ __global__ void __launch_bounds__(kTailThreads, RT_TAIL_CTAS) k_bounce(const Fas
           final_ = true;
         }
       }
-      if (live[0] && final_) {
-        unsigned char *o = a.r.rgb + (size_t)pix * 3;
-        o[0] = (unsigned char)quant8(cr); o[1] = (unsigned char)quant8(cg); o[2] = (unsigned char)quant8(cb);
-      }
+      if (live[0] && final_) write_final(a.r, pix, cr, cg, cb);
       if (a.r.counters) {
         flush_counters(a, cnt, n_fp64, level);
         if (lane == 0 && c_walks) { atomicAdd(&a.r.counters[RT_CNT_CAND], (unsigned long long)c_cand); atomicAdd(&a.r.counters[RT_CNT_WALKS], (unsigned long long)c_walks); }

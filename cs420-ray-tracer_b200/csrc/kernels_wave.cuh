@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(kThreads, RT_CLOSEST_CTAS) k_closest0(const Wa
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char *s_rgb = smem + 64 + warp * (kWTileH * kWTileW * 3);
   const int W = a.r.W, rows = a.r.bands.local_rows, depth = a.r.max_depth;
+  const bool kBytes = a.r.fb == nullptr && !a.r.out_remap;   // plain 8-bit frame: staged tile rows, 128-bit stores
   unsigned c_closest = 0, c_hits = 0, c_fp64 = 0, c_viol = 0, c_cand = 0, c_walks = 0;
   for (;;) {
     int tile;
@@ -255,11 +256,16 @@ __global__ void __launch_bounds__(kThreads, RT_CLOSEST_CTAS) k_closest0(const Wa
       // sky (src/main.cpp:26-30) is final now; hit pixels are written by k_shade / later levels
       const float ts = 0.5f * (dy[r] + 1.0f);
       const bool sky = live[r] && !hit;
-      unsigned char *q = s_rgb + (((lane >> 4) * 2 + r) * kWTileW + (lane & 15)) * 3;
-      q[0] = (unsigned char)quant8(sky ? (1.0f - ts) + 0.5f * ts : 0.f);
-      q[1] = (unsigned char)quant8(sky ? (1.0f - ts) + 0.7f * ts : 0.f);
-      q[2] = (unsigned char)quant8(sky ? (1.0f - ts) + ts : 0.f);
+      if (kBytes) {
+        unsigned char *q = s_rgb + (((lane >> 4) * 2 + r) * kWTileW + (lane & 15)) * 3;
+        q[0] = (unsigned char)quant8(sky ? (1.0f - ts) + 0.5f * ts : 0.f);
+        q[1] = (unsigned char)quant8(sky ? (1.0f - ts) + 0.7f * ts : 0.f);
+        q[2] = (unsigned char)quant8(sky ? (1.0f - ts) + ts : 0.f);
+      } else if (sky) {
+        write_final(a.r, pix[r], (1.0f - ts) + 0.5f * ts, (1.0f - ts) + 0.7f * ts, (1.0f - ts) + ts);
+      }
     }
+    if (!kBytes) continue;                           // float / remapped output: only finished pixels are written
     __syncwarp();
     if (!tile_ok) { __syncwarp(); continue; }
     if (tx0 + kWTileW <= W && (W & 15) == 0) {
@@ -346,10 +352,8 @@ __global__ void __launch_bounds__(kThreads, RT_CLOSEST_CTAS) k_closest1(const Wa
         if (a.r.hit_idx) a.r.hit_idx[(size_t)pix[r] * depth + level] = hit ? w.hits[hslot[r]].idx : -1;
         if (!hit) {                                // sky through the mirror(s): the pixel is final
           const float ts = 0.5f * (dy[r] + 1.0f);
-          unsigned char *o = a.r.rgb + (size_t)pix[r] * 3;
-          o[0] = (unsigned char)quant8(cr[r] + wt[r] * ((1.0f - ts) + 0.5f * ts));
-          o[1] = (unsigned char)quant8(cg[r] + wt[r] * ((1.0f - ts) + 0.7f * ts));
-          o[2] = (unsigned char)quant8(cb[r] + wt[r] * ((1.0f - ts) + ts));
+          write_final(a.r, pix[r], cr[r] + wt[r] * ((1.0f - ts) + 0.5f * ts), cg[r] + wt[r] * ((1.0f - ts) + 0.7f * ts),
+                      cb[r] + wt[r] * ((1.0f - ts) + ts));
         }
       }
       c_hits += hit;
@@ -551,10 +555,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_shade(const WaveArgs w) {
       } else {
         cr += wt * sr; cg += wt * sg; cb += wt * sb;
       }
-      if (final_) {
-        unsigned char *o = a.r.rgb + (size_t)hr.pix * 3;
-        o[0] = (unsigned char)quant8(cr); o[1] = (unsigned char)quant8(cg); o[2] = (unsigned char)quant8(cb);
-      }
+      if (final_) write_final(a.r, hr.pix, cr, cg, cb);
     }
     queue_push(cont, rec, a.q_out, a.q_out_count);
   }

@@ -50,6 +50,7 @@ struct rt_ctx {
   int mode = 0;          // 0 fast, 1 exact
   int counters_on = 1;
   int accel = 0;         // 0 auto, 1 table walks, 2 LBVH (takes effect at the next rt_upload_scene)
+  int antialias = 0;     // 2x2 supersampling (the reference's ray_cuda -a)
   // scene
   bool have_scene = false;
   int N = 0, L = 0;
@@ -61,9 +62,10 @@ struct rt_ctx {
   float2 *d_matx = nullptr;
   RtFastScene fast;      // FP32 filter tables (rt_kernels.h)
   // per-resolution tables
-  int tabW = 0, tabH = 0;
+  int tabW = 0, tabH = 0, tab_aa = 0;
   double tab_fov = 0;
   double *d_su = nullptr, *d_sv = nullptr;
+  float *d_fb = nullptr; size_t fb_cap = 0;   // float sample frame of a supersampled render
   // buffers
   uint8_t *d_rgb = nullptr; size_t rgb_cap = 0;
   int32_t *d_hit = nullptr; size_t hit_cap = 0;
@@ -129,7 +131,7 @@ extern "C" void rt_destroy(rt_ctx *c) {
   free_scene(c);
   rtk_fast_free_work(&c->work);
   cudaFree(c->d_su); cudaFree(c->d_sv);
-  cudaFree(c->d_rgb); cudaFree(c->d_hit); cudaFree(c->d_mask); cudaFree(c->d_counters);
+  cudaFree(c->d_rgb); cudaFree(c->d_hit); cudaFree(c->d_mask); cudaFree(c->d_counters); cudaFree(c->d_fb);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); for (int k = 0; k < 3; k++) cudaEventDestroy(c->evm[k]);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -143,6 +145,7 @@ extern "C" int rt_set_option(rt_ctx *c, const char *key, long long value) {
     return RT_OK;
   }
   if (!strcmp(key, "counters")) { c->counters_on = value != 0; return RT_OK; }
+  if (!strcmp(key, "antialias")) { c->antialias = value != 0; return RT_OK; }
   if (!strcmp(key, "accel")) {
     if (value < 0 || value > 2) return rt_fail(RT_ERR_ARG, "rt_set_option: accel must be 0 (auto), 1 (tables) or 2 (LBVH)");
     c->accel = (int)value;
@@ -222,20 +225,23 @@ extern "C" int rt_upload_scene(rt_ctx *c, const double *spheres, int N, const do
 
 // ------------------------------------------------------------------------------------------
 // render
-static int ensure_tables(rt_ctx *c, int W, int H) {
-  if (c->d_su && c->tabW == W && c->tabH == H && c->tab_fov == c->fov) return RT_OK;
+// Per-column / per-row camera-plane coordinates.  aa = 1: the 2W x 2H SAMPLE grid of the 2x2 supersampling
+// (sample (a, b) of pixel (i, j) sits at index (2i + a, 2j + b); u = (i + a/2)/(W-1), src/main_gpu.cu:253-256).
+static int ensure_tables(rt_ctx *c, int W, int H, int aa) {
+  if (c->d_su && c->tabW == W && c->tabH == H && c->tab_fov == c->fov && c->tab_aa == aa) return RT_OK;
   cudaFree(c->d_su); cudaFree(c->d_sv); c->d_su = c->d_sv = nullptr;
   // include/camera.h:18-22 and src/main.cpp:151-152, same operations in the same order
   const double aspect = 1.0;
   const double scale = std::tan(c->fov * 0.5 * M_PI / 180.0);
-  std::vector<double> su((size_t)W), sv((size_t)H);
-  for (int i = 0; i < W; i++) { double u = double(i) / (W - 1); su[i] = (u - 0.5) * scale * aspect; }
-  for (int j = 0; j < H; j++) { double v = double(j) / (H - 1); sv[j] = (v - 0.5) * scale; }
-  RT_CUDA(cudaMalloc(&c->d_su, (size_t)W * sizeof(double)));
-  RT_CUDA(cudaMalloc(&c->d_sv, (size_t)H * sizeof(double)));
-  RT_CUDA(cudaMemcpy(c->d_su, su.data(), (size_t)W * sizeof(double), cudaMemcpyHostToDevice));
-  RT_CUDA(cudaMemcpy(c->d_sv, sv.data(), (size_t)H * sizeof(double), cudaMemcpyHostToDevice));
-  c->tabW = W; c->tabH = H; c->tab_fov = c->fov;
+  const int m = aa ? 2 : 1;
+  std::vector<double> su((size_t)W * m), sv((size_t)H * m);
+  for (int i = 0; i < W * m; i++) { double u = (double(i / m) + 0.5 * (i % m)) / (W - 1); su[i] = (u - 0.5) * scale * aspect; }
+  for (int j = 0; j < H * m; j++) { double v = (double(j / m) + 0.5 * (j % m)) / (H - 1); sv[j] = (v - 0.5) * scale; }
+  RT_CUDA(cudaMalloc(&c->d_su, su.size() * sizeof(double)));
+  RT_CUDA(cudaMalloc(&c->d_sv, sv.size() * sizeof(double)));
+  RT_CUDA(cudaMemcpy(c->d_su, su.data(), su.size() * sizeof(double), cudaMemcpyHostToDevice));
+  RT_CUDA(cudaMemcpy(c->d_sv, sv.data(), sv.size() * sizeof(double), cudaMemcpyHostToDevice));
+  c->tabW = W; c->tabH = H; c->tab_fov = c->fov; c->tab_aa = aa;
   return RT_OK;
 }
 
@@ -282,16 +288,20 @@ static void fill_stats(rt_stats *st, const unsigned long long *cnt) {
 }
 
 // Launches the kernels of one (possibly banded) render on `stream`.  When `stats` is given the
-// call synchronises the stream and fills it.
+// call synchronises the stream and fills it.  With supersampling on, the kernels render the 2W x 2H sample
+// grid into a float frame and k_resolve_aa averages it into dev_rgb; debug buffers are per SAMPLE then.
+struct TileSpec { int x, y, w, h; float *fb; };   // rt_render_tile: float output into the caller's full-frame buffer
 static int render_common(rt_ctx *c, int W, int H, int depth, int band_h, int rank, int nranks, uint8_t *dev_rgb,
-                         int32_t *dev_hit, uint32_t *dev_mask, cudaStream_t stream, rt_stats *stats) {
+                         int32_t *dev_hit, uint32_t *dev_mask, cudaStream_t stream, rt_stats *stats, const TileSpec *tile = nullptr) {
   if (!c->have_scene) return rt_fail(RT_ERR_STATE, "render: no scene uploaded (call rt_upload_scene first)");
   if (W < 1 || H < 1 || depth < 0) return rt_fail(RT_ERR_ARG, "render: bad image size or depth");
   if (depth > RT_MAX_LEVELS) return rt_fail(RT_ERR_UNSUPPORTED, "render: max_depth above RT_MAX_LEVELS");
+  const int aa = (c->antialias && !tile) ? 1 : 0, m = aa ? 2 : 1;
+  if ((aa || tile) && c->mode == 1) return rt_fail(RT_ERR_UNSUPPORTED, "render: supersampling / tile renders need mode 0");
   int rows = rt_band_rows(H, band_h, rank, nranks);
   if (rows < 0) return rows;
   RT_CUDA(cudaSetDevice(c->device));
-  int rc = ensure_tables(c, W, H);
+  int rc = ensure_tables(c, W, H, aa);
   if (rc) return rc;
   {
     std::lock_guard<std::mutex> lk(g_const_mutex);
@@ -304,11 +314,26 @@ static int render_common(rt_ctx *c, int W, int H, int depth, int band_h, int ran
   const bool want_counters = c->counters_on && stats != nullptr;
   RtRenderArgs a;
   memset(&a, 0, sizeof(a));
-  a.W = W; a.H = H; a.max_depth = depth;
-  a.bands.band_h = band_h; a.bands.rank = rank; a.bands.nranks = nranks; a.bands.local_rows = rows;
+  a.W = W * m; a.H = H * m; a.max_depth = depth;
+  a.bands.band_h = band_h * m; a.bands.rank = rank; a.bands.nranks = nranks; a.bands.local_rows = rows * m;
   a.su = c->d_su; a.sv = c->d_sv;
   a.sph64 = c->d_sph64; a.mat = c->d_mat; a.matx = c->d_matx;
   a.rgb = dev_rgb; a.hit_idx = dev_hit; a.shadow_mask = dev_mask;
+  if (aa) {
+    if ((rc = ensure_cap(c->d_fb, c->fb_cap, (size_t)a.W * a.bands.local_rows * 3 + 4))) return rc;
+    a.fb = c->d_fb;
+    if (depth <= 0) RT_CUDA(cudaMemsetAsync(c->d_fb, 0, (size_t)a.W * a.bands.local_rows * 3 * sizeof(float), stream));
+  }
+  if (tile) {
+    // the tile is a W' x H' frame whose camera-plane coordinates start at (tile.x, tile.y) of the full image's tables
+    a.W = tile->w; a.H = tile->h;
+    a.bands.band_h = tile->h; a.bands.rank = 0; a.bands.nranks = 1; a.bands.local_rows = tile->h;
+    a.su = c->d_su + tile->x; a.sv = c->d_sv + tile->y;
+    a.fb = tile->fb; a.rgb = nullptr;
+    a.out_remap = 1; a.out_pitch = W; a.out_x0 = tile->x; a.out_y0 = tile->y;
+    rows = tile->h;
+    if (depth <= 0) RT_CUDA(cudaMemset2DAsync(tile->fb + ((size_t)tile->y * W + tile->x) * 3, (size_t)W * 12, 0, (size_t)tile->w * 12, tile->h, stream));
+  }
   a.counters = want_counters ? c->d_counters : nullptr;
   if (want_counters) RT_CUDA(cudaMemsetAsync(c->d_counters, 0, RT_CNT_TOTAL * sizeof(unsigned long long), stream));
   if (stats) RT_CUDA(cudaEventRecord(c->ev0, stream));
@@ -317,6 +342,11 @@ static int render_common(rt_ctx *c, int W, int H, int depth, int band_h, int ran
     if (c->mode == 1) launches = rtk_launch_exact(a, stream);
     else launches = rtk_launch_fast(a, &c->fast, &c->work, stream, (stats && depth > 0) ? c->evm : nullptr);
     if (launches < 0) return rt_fail(RT_ERR_CUDA, std::string("render: launch failed: ") + cudaGetErrorString((cudaError_t)-launches));
+    if (aa) {
+      const int r2 = rtk_resolve_aa(c->d_fb, W, rows, dev_rgb, stream);
+      if (r2 < 0) return rt_fail(RT_ERR_CUDA, std::string("render: resolve launch failed: ") + cudaGetErrorString((cudaError_t)-r2));
+      launches += r2;
+    }
   }
   if (stats) {
     RT_CUDA(cudaEventRecord(c->ev1, stream));
@@ -345,6 +375,18 @@ static int render_common(rt_ctx *c, int W, int H, int depth, int band_h, int ran
   return RT_OK;
 }
 
+// Renders the tile [tile_x, tile_x + tile_w) x [tile_y, tile_y + tile_h) of a width x height image into the
+// caller's device framebuffer as FP32 RGB: dev_fb[(j * width + i) * 3 + c], row j = 0 = bottom, asynchronously on
+// `stream` -- the calling convention of the reference's tile launcher (src/kernel.cu:185-200).
+extern "C" int rt_render_tile(rt_ctx *c, int W, int H, int depth, int tile_x, int tile_y, int tile_w, int tile_h,
+                              float *dev_fb, void *stream) {
+  if (!c || !dev_fb) return rt_fail(RT_ERR_ARG, "rt_render_tile: NULL argument");
+  if (tile_x < 0 || tile_y < 0 || tile_w < 1 || tile_h < 1 || tile_x + tile_w > W || tile_y + tile_h > H)
+    return rt_fail(RT_ERR_ARG, "rt_render_tile: tile outside the image");
+  const TileSpec t = {tile_x, tile_y, tile_w, tile_h, dev_fb};
+  return render_common(c, W, H, depth, H, 0, 1, nullptr, nullptr, nullptr, stream ? (cudaStream_t)stream : c->stream, nullptr, &t);
+}
+
 extern "C" int rt_render_bands(rt_ctx *c, int W, int H, int depth, int band_h, int rank, int nranks, void *dev_rgb,
                                void *stream, rt_stats *stats) {
   if (!c || !dev_rgb) return rt_fail(RT_ERR_ARG, "rt_render_bands: NULL argument");
@@ -365,7 +407,8 @@ extern "C" int rt_render_debug(rt_ctx *c, int W, int H, int depth, uint8_t *host
   const size_t npx = (size_t)W * H;
   int rc = ensure_cap(c->d_rgb, c->rgb_cap, npx * 3 + 16);
   if (rc) return rc;
-  const size_t nlev = npx * (size_t)(depth > 0 ? depth : 1);
+  // debug buffers are per SAMPLE when supersampling is on: [2H][2W][depth]
+  const size_t nlev = npx * (size_t)(c->antialias ? 4 : 1) * (size_t)(depth > 0 ? depth : 1);
   if (hit_idx && (rc = ensure_cap(c->d_hit, c->hit_cap, nlev))) return rc;
   if (shadow_mask && (rc = ensure_cap(c->d_mask, c->mask_cap, nlev))) return rc;
   rc = render_common(c, W, H, depth, H, 0, 1, c->d_rgb, hit_idx ? c->d_hit : nullptr,

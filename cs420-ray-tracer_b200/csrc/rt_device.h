@@ -59,7 +59,10 @@ struct RtRenderArgs {
   const double4 *sph64;
   const float4 *mat;
   const float2 *matx;
-  uint8_t *rgb;            // local_rows x W x 3
+  uint8_t *rgb;            // local_rows x W x 3 (8-bit output; unused when fb is set)
+  float *fb;               // optional FLOAT output, 3 floats per pixel (tile renders, supersampling): replaces rgb
+  int out_remap;           // 0: output pixel = local pixel lr*W + x; 1: (lr + out_y0) * out_pitch + x + out_x0
+  int out_pitch, out_x0, out_y0;
   int32_t *hit_idx;        // optional debug, local_rows*W*max_depth
   uint32_t *shadow_mask;   // optional debug
   unsigned long long *counters;  // optional

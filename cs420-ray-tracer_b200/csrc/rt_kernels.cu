@@ -325,7 +325,7 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
     }
   }
   RTK_TRY(cudaMemsetAsync(w->ctl, 0, kCtlWords * sizeof(unsigned int), stream));
-  if (args.max_depth <= 0) RTK_TRY(cudaMemsetAsync(args.rgb, 0, npix * 3, stream));   // src/main.cpp:17-18: black
+  if (args.max_depth <= 0 && !args.fb) RTK_TRY(cudaMemsetAsync(args.rgb, 0, npix * 3, stream));   // src/main.cpp:17-18: black (float output: the caller clears)
 
   rtf::WaveArgs wa;
   memset(&wa, 0, sizeof(wa));
@@ -419,6 +419,29 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
   }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? launches : -(int)e;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2x2 supersampling resolve (the reference's ray_cuda -a, src/main_gpu.cu:249-258,327-333): the four samples of
+// output pixel (i, j) are the pixels (2i + a, 2j + b) of the float sample frame; summed in the reference's order
+// s = 0..3 = (0,0) (1,0) (0,1) (1,1), scaled by 1/4, then quantised (src/main_gpu.cu:347-349).
+__global__ void k_resolve_aa(const float *__restrict__ fb, int W, int rows, uint8_t *__restrict__ rgb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+  if (i >= W || j >= rows) return;
+  const size_t W2 = 2 * (size_t)W;
+  const float *s0 = fb + ((size_t)(2 * j) * W2 + 2 * i) * 3, *s2 = s0 + W2 * 3;
+  uint8_t *o = rgb + ((size_t)j * W + i) * 3;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    const float v = (((s0[c] + s0[3 + c]) + s2[c]) + s2[3 + c]) * 0.25f;
+    o[c] = (uint8_t)(int)(255.99f * fminf(1.0f, v));
+  }
+}
+int rtk_resolve_aa(const float *fb, int W, int rows, uint8_t *rgb, cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  k_resolve_aa<<<dim3((W + 127) / 128, rows), 128, 0, stream>>>(fb, W, rows, rgb);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 1 : -(int)e;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -50,6 +50,9 @@ void rtk_fast_free_work(RtFastWork *w);
 int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork *w, cudaStream_t stream,
                     const cudaEvent_t *marks);
 
+// 2x2 supersampling resolve: float sample frame (2W x 2rows) -> 8-bit rows x W.
+int rtk_resolve_aa(const float *fb, int W, int rows, uint8_t *rgb, cudaStream_t stream);
+
 // FP32 FFMA issue peak of `device`, measured live (FLOP/s); used by bench.py as the roofline
 // denominator because MEASURED_PEAKS.json carries no FP32 entry.  Returns <0: -cudaError.
 double rtk_measure_fp32_peak(int device, double *sm_clock_mhz);

@@ -8,6 +8,7 @@
 //
 // Extra flags (none collide with the reference's): --width N --height N --depth N
 //   --output FILE --device N --exact (FP64 diagnostic kernels) --frames N (repeat, report best)
+// -a = 2x2 supersampling, as the reference's ray_cuda (src/main_gpu.cu:363-371).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -23,7 +24,7 @@ static int die(const char *what) {
 
 int main(int argc, char **argv) {
   int W = 1280, H = 720, depth = 10, device = 0, frames = 1;
-  bool exact = false;
+  bool exact = false, antialias = false;
   std::string scene_file = "scenes/simple.txt", output = "output_gpu.ppm";
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
@@ -35,7 +36,8 @@ int main(int argc, char **argv) {
     else if (a == "--frames") next(frames);
     else if (a == "--output" && i + 1 < argc) output = argv[++i];
     else if (a == "--exact") exact = true;
-    else if (a == "--openmp" || a == "-a") { /* accepted for command-line compatibility */ }
+    else if (a == "-a") { antialias = true; std::printf("Antialiasing Enabled.\n"); }   // src/main_gpu.cu:368-370
+    else if (a == "--openmp") { /* accepted for command-line compatibility */ }
     else scene_file = a;
   }
   std::printf("Testing scene loader with: %s\n\n", scene_file.c_str());
@@ -53,6 +55,7 @@ int main(int argc, char **argv) {
   rt_ctx *ctx = nullptr;
   if (rt_create(device, &ctx) != RT_OK) return die("rt_create");
   if (exact && rt_set_option(ctx, "mode", 1) != RT_OK) return die("rt_set_option");
+  if (antialias && rt_set_option(ctx, "antialias", 1) != RT_OK) return die("rt_set_option");
   if (rt_upload_scene(ctx, sph, N, lig, L, amb, cam, cam + 3, cam[6]) != RT_OK) return die("rt_upload_scene");
   std::vector<uint8_t> rgb((size_t)W * H * 3);
   std::printf("Rendering (GPU, B200 sm_100a)...\n");

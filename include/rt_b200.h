@@ -16,6 +16,8 @@
  *   rt_render / rt_render_bands    src/main.cpp:146-157,185-199    the pixel loop + trace_ray
  *                                  src/kernel.cu:185-200           launch_gpu_kernel (tile launch)
  *                                  src/main.cpp:84-86              the 8-bit quantiser of write_ppm
+ *   rt_render_tile                 src/kernel.cu:185-200           launch_gpu_kernel (tile + stream + float3 fb)
+ *   rt_set_option("antialias")     src/main_gpu.cu:249-258,327-333 ray_cuda -a (2x2 supersampling)
  *   rt_write_ppm                   src/main.cpp:69-91              write_ppm (P3 text)
  *
  * Semantics are those of the reference's SERIAL renderer (FP64; src/main.cpp + include/ *.h),
@@ -102,7 +104,13 @@ void rt_scene_free(rt_scene *s);
 int rt_create(int device, rt_ctx **out);
 void rt_destroy(rt_ctx *ctx);
 /* Integer options: "mode" 0 = fast FP32-filter kernels (default), 1 = exact FP64 brute force
- * (diagnostic; same results, slower); "counters" 0/1 = collect ray counters (default 1).   */
+ * (diagnostic; same results, slower); "counters" 0/1 = collect ray counters (default 1);
+ * "accel" 0 = automatic (LBVH from 1024 spheres), 1 = table walks only, 2 = LBVH always (read at the
+ * next rt_upload_scene); "wave_levels" 1..32 = reflection levels run as wavefront kernels before
+ * the fused tail; "antialias" 0/1 = 2x2 supersampling as the reference's `ray_cuda -a`
+ * (src/main_gpu.cu:249-258,327-333: samples at pixel offsets (0,0) (.5,0) (0,.5) (.5,.5),
+ * averaged before the 8-bit quantiser); with it on, the debug buffers of rt_render_debug are
+ * per sample: [2H][2W][max_depth], sample (a,b) of pixel (i,j) at (2j+b, 2i+a).            */
 int rt_set_option(rt_ctx *ctx, const char *key, long long value);
 
 /* Copies the scene to the device (host -> device inside the call) and precomputes the
@@ -131,6 +139,15 @@ int rt_render_debug(rt_ctx *ctx, int width, int height, int max_depth, uint8_t *
  * filled after a stream synchronise only when counters are enabled.                        */
 int rt_render_bands(rt_ctx *ctx, int width, int height, int max_depth, int band_h, int rank,
                     int nranks, void *dev_rgb, void *stream, rt_stats *stats);
+/* Tile render with the calling convention of the reference's launch_gpu_kernel
+ * (src/kernel.cu:185-200; caller src/main_hybrid.cpp:461-466): renders pixels
+ * [tile_x, tile_x+tile_w) x [tile_y, tile_y+tile_h) of a width x height image into the CALLER's
+ * device framebuffer as FP32 RGB, dev_fb[(j*width + i)*3 + c] (= the reference's float3
+ * d_framebuffer[pixel_idx]), row j = 0 = bottom, asynchronously on `stream` (NULL = ctx
+ * stream).  The scene is the ctx's (rt_upload_scene replaces GPUResources::upload_scene +
+ * upload_lights_and_ambience).  Pixels outside the tile are not touched.                   */
+int rt_render_tile(rt_ctx *ctx, int width, int height, int max_depth, int tile_x, int tile_y,
+                   int tile_w, int tile_h, float *dev_fb, void *stream);
 /* Rows owned by `rank` under the band rule above. */
 int rt_band_rows(int height, int band_h, int rank, int nranks);
 /* Writes the owned row indices (ascending) into rows[rt_band_rows()]. */

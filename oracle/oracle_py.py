@@ -38,6 +38,7 @@ def lib():
         _lib.rto_intersect.argtypes = [vp, vp, vp, C.c_double, C.POINTER(C.c_double)]
         _lib.rto_write_ppm.argtypes = [C.c_char_p, vp, i, i]
         _lib.rto_num_threads.restype = i
+        _lib.rto_set_sample_offset.argtypes = [C.c_double, C.c_double]
     return _lib
 
 
@@ -45,7 +46,18 @@ def num_threads():
     return lib().rto_num_threads()
 
 
-def render(scene, W, H, depth, want_fb=False, want_idx=False, pix_step=1, nthreads=0):
+def render_supersampled(scene, W, H, depth):
+    """The reference's `ray_cuda -a` rule (src/main_gpu.cu:249-258,327-333) in the serial renderer's FP64: four
+    samples per pixel at offsets (0,0) (.5,0) (0,.5) (.5,.5), summed in that order, x 1/4, then quantised.
+    Returns dict(rgb [H,W,3], samples = the four per-sample render() dicts in that order)."""
+    passes = [render(scene, W, H, depth, want_fb=True, want_idx=True, sample_offset=o)
+              for o in ((0.0, 0.0), (0.5, 0.0), (0.0, 0.5), (0.5, 0.5))]
+    acc = ((passes[0]["fb"] + passes[1]["fb"]) + passes[2]["fb"]) + passes[3]["fb"]
+    rgb = (255.99 * np.minimum(1.0, acc * 0.25)).astype(np.int32).astype(np.uint8)
+    return {"rgb": rgb, "samples": passes}
+
+
+def render(scene, W, H, depth, want_fb=False, want_idx=False, pix_step=1, nthreads=0, sample_offset=(0.0, 0.0)):
     """scene: any object with .spheres [N,10], .lights [L,7], .ambient [3], .camera [7] (float64).
     Returns dict(rgb [H,W,3] uint8 bottom-row-first, fb, hit_idx [H,W,depth], shadow_mask, counters)."""
     sph = np.ascontiguousarray(scene.spheres, dtype=np.float64).reshape(-1, 10)
@@ -59,11 +71,13 @@ def render(scene, W, H, depth, want_fb=False, want_idx=False, pix_step=1, nthrea
     hit = np.full((H, W, d), -2, dtype=np.int32) if want_idx else None
     mask = np.zeros((H, W, d), dtype=np.uint32) if want_idx else None
     cnt = Counters()
+    lib().rto_set_sample_offset(float(sample_offset[0]), float(sample_offset[1]))
     rc = lib().rto_render(sph.ctypes.data, sph.shape[0], lig.ctypes.data, lig.shape[0], amb.ctypes.data,
                           pos.ctypes.data, look.ctypes.data, float(cam[6]), W, H, depth,
                           fb.ctypes.data if want_fb else None, rgb.ctypes.data,
                           hit.ctypes.data if want_idx else None, mask.ctypes.data if want_idx else None,
                           C.byref(cnt), pix_step, nthreads)
+    lib().rto_set_sample_offset(0.0, 0.0)
     if rc != 0:
         raise RuntimeError("rto_render failed: %d" % rc)
     return {"rgb": rgb, "fb": fb, "hit_idx": hit, "shadow_mask": mask, "counters": cnt.as_dict()}

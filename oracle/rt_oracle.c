@@ -210,6 +210,12 @@ static inline uint8_t quantise(double c) { return (uint8_t)(int)(255.99 * std_mi
  * nthreads <= 0 -> all OpenMP threads; 1 -> serial (src/main.cpp:146-157), else the
  * schedule(dynamic) collapse(2) loop of src/main.cpp:185-199.
  */
+/* Sample position inside the pixel, in pixels (default 0,0 = the reference's serial renderer).  The 2x2
+ * supersampling of the reference's ray_cuda -a (src/main_gpu.cu:253-256) renders the offsets (0,0) (.5,0)
+ * (0,.5) (.5,.5): u = (i + off_x)/(W-1), v = (j + off_y)/(H-1).  Set before rto_render, reset after. */
+static double g_off_x = 0.0, g_off_y = 0.0;
+void rto_set_sample_offset(double off_x, double off_y) { g_off_x = off_x; g_off_y = off_y; }
+
 int rto_render(const double *spheres, int N, const double *lights, int L, const double *ambient,
                const double *cam_pos, const double *cam_look, double fov_deg,
                int W, int H, int max_depth,
@@ -249,8 +255,8 @@ int rto_render(const double *spheres, int N, const double *lights, int L, const 
             for (int i = 0; i < W; i++) {
                 size_t p = (size_t)j * W + i;
                 if (p % (size_t)pix_step) continue;
-                double u = (double)i / (W - 1);
-                double v = (double)j / (H - 1);
+                double u = ((double)i + g_off_x) / (W - 1);
+                double v = ((double)j + g_off_y) / (H - 1);
                 ray_t ray = camera_get_ray(&cam, u, v);
                 int32_t *hi = hit_idx ? hit_idx + p * (size_t)md : NULL;
                 uint32_t *sm = shadow_mask ? shadow_mask + p * (size_t)md : NULL;

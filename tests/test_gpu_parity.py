@@ -169,6 +169,64 @@ def test_large_synthetic_against_fp64_brute_force(rt, renderers, n, seed, W, H, 
             assert getattr(out[3], k) == getattr(ref[3], k), (m, k)
 
 
+@pytest.mark.parametrize("mode", ["fast", "bvh"])
+@pytest.mark.parametrize("name,W,H,D", [("simple", 160, 90, 5), ("complex", 192, 108, 5), ("medium", 97, 61, 3)])
+def test_supersampling_matches_the_four_sample_oracle(rt, oracle, scenes, name, W, H, D, mode):
+    """rt_set_option antialias = the reference's ray_cuda -a (src/main_gpu.cu:249-258,327-333): per-sample hit
+    indices / shadow masks bit-exact against four offset renders of the oracle, averaged RGB within 1 LSB."""
+    o = oracle.render_supersampled(scenes[name], W, H, D)
+    with rt.Renderer(0, mode=mode) as r:
+        r.set_option("antialias", 1)
+        r.upload(scenes[name])
+        rgb, hit, mask, st = r.render_debug(W, H, D)
+        plain, _ = r.render(W, H, D)
+        r.set_option("antialias", 0)
+        off, _ = r.render(W, H, D)
+    assert hit.shape == (2 * H, 2 * W, D)
+    for s, (a, b) in enumerate(((0, 0), (1, 0), (0, 1), (1, 1))):
+        assert np.array_equal(hit[b::2, a::2], o["samples"][s]["hit_idx"]), s
+        assert np.array_equal(mask[b::2, a::2], o["samples"][s]["shadow_mask"]), s
+    ok, pct, mx = rt.compare_rgb(o["rgb"], rgb, 0.5)
+    assert ok and mx <= 2, (pct, mx)
+    assert np.array_equal(rgb, plain) and not np.array_equal(rgb, off)
+    assert st.closest_queries == sum(p["counters"]["closest_queries"] for p in o["samples"])
+    assert st.filter_violations == 0
+
+
+@pytest.mark.parametrize("mode", ["fast", "bvh"])
+def test_tile_renders_assemble_to_the_frame(rt, oracle, scenes, mode):
+    """rt_render_tile (the reference's launch_gpu_kernel convention: tile offsets, caller-owned float3 framebuffer,
+    stream): ragged tiles assemble to exactly the whole-frame tile render; quantised, that is rt_render's frame."""
+    import torch
+    W, H, D = 200, 120, 5
+    with rt.Renderer(0, mode=mode) as r:
+        r.upload(scenes["complex"])
+        whole = torch.full((H, W, 3), -1.0, dtype=torch.float32, device="cuda:0")
+        torch.cuda.synchronize()
+        r.render_tile_device(W, H, D, (0, 0, W, H), whole.data_ptr())
+        tiled = torch.full((H, W, 3), -1.0, dtype=torch.float32, device="cuda:0")
+        stream = torch.cuda.Stream()
+        torch.cuda.synchronize()                     # the fills above ran on torch's default stream
+        for (x, y, w, h) in [(0, 0, 64, 64), (64, 0, 136, 64), (0, 64, 33, 56), (33, 64, 167, 17), (33, 81, 167, 39)]:
+            r.render_tile_device(W, H, D, (x, y, w, h), tiled.data_ptr(), stream.cuda_stream)
+        stream.synchronize()
+        torch.cuda.synchronize()
+        assert torch.equal(whole, tiled)
+        partial = torch.full((H, W, 3), -1.0, dtype=torch.float32, device="cuda:0")
+        torch.cuda.synchronize()
+        r.render_tile_device(W, H, D, (10, 20, 50, 30), partial.data_ptr())
+        torch.cuda.synchronize()
+        inside = torch.zeros((H, W), dtype=torch.bool, device="cuda:0"); inside[20:50, 10:60] = True
+        assert torch.equal(partial[inside], whole[inside]) and bool((partial[~inside] == -1.0).all())
+        frame, _ = r.render(W, H, D)
+        q = (255.99 * torch.clamp(whole, max=1.0)).to(torch.int32).to(torch.uint8).cpu().numpy()
+        assert np.array_equal(q, frame)
+        with pytest.raises(rt.RtError):
+            r.render_tile_device(W, H, D, (150, 0, 64, 64), whole.data_ptr())
+    o = oracle.render(scenes["complex"], W, H, D, want_fb=True)
+    assert np.abs(whole.cpu().numpy() - o["fb"]).max() < 2e-3
+
+
 def test_errors(rt, renderers, scenes):
     r = rt.Renderer(0)
     with pytest.raises(rt.RtError, match="no scene uploaded"):
