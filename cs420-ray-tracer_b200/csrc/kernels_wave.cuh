@@ -388,6 +388,10 @@ __global__ void __launch_bounds__(kThreads, RT_SHADOW_CTAS) k_shadow(const WaveA
   // few hits (deep levels): one hit per lane, so that twice as many warps share the work
   const bool two = kMode == kTabStream || nh >= gridDim.x * (unsigned)kWarps * 64u;
   const unsigned nchunks = two ? nh / 64u : nh / 32u;            // nh = 64 x blocks
+  // few chunks (reflection levels >= 1): one (chunk, light) item per fetch instead of (chunk, all lights) -- L times
+  // as many, L times shorter items, so the warps of the machine share them evenly
+  const bool lightpar = kMode != kTabStream && nchunks < 4u * gridDim.x * (unsigned)kWarps;
+  const unsigned nitems = lightpar ? nchunks * (unsigned)a.L : nchunks;
   unsigned c_fp64 = 0, c_cand = 0, c_walks = 0;
   for (;;) {
     unsigned chunk;
@@ -397,8 +401,10 @@ __global__ void __launch_bounds__(kThreads, RT_SHADOW_CTAS) k_shadow(const WaveA
       chunk = cc * kWarps + warp;
     } else {
       chunk = (unsigned)warp_fetch(w.work_counter);
-      if (chunk >= nchunks) break;
+      if (chunk >= nitems) break;
     }
+    int l_beg = 0, l_end = a.L;
+    if (lightpar) { l_beg = (int)(chunk % (unsigned)a.L); l_end = l_beg + 1; chunk /= (unsigned)a.L; }
     const unsigned h0 = two ? chunk * 64u + 2u * lane : chunk * 32u + lane;
     const unsigned hend = (h0 & ~63u) + (h0 < nh ? w.hit_n[h0 >> 6] : 0u);   // end of the block's live slots
     bool have[2];
@@ -420,7 +426,7 @@ __global__ void __launch_bounds__(kThreads, RT_SHADOW_CTAS) k_shadow(const WaveA
       }
     }
     const double *const ppc[2] = {pp[0], pp[1]};
-    for (int l = 0; l < a.L; l++) {
+    for (int l = l_beg; l < l_end; l++) {
       const Tab T = tab_at(kMode == kTabStream ? gtabs : tabs, a, l);
       const d3 lp = ldc3(g_frame.light_pos[l]);
       bool want[2], occ[2], shortcut[2];
