@@ -9,8 +9,10 @@ One "step" = one full frame of the hot path (camera rays -> closest hit -> Phong
 depth) -- R_c + R_s in the oracle's definition -- so Mrays/s = rays / time.
 
   value     frame already scheduled from device-resident scene tables, output into HBM; at N > 1
-            each rank renders its interleaved 16-row bands and the bands are gathered to rank 0
-            over NCCL inside the timed step.  CUDA events per step, L2 flushed between steps.
+            each rank renders its interleaved 16-row bands and its kernels store them straight
+            into rank 0's frame over NVLink (peer memory, rt_render_bands_frame; completion flags
+            inside the timed step; --gather nccl = the NCCL gather instead).  CUDA events per
+            step, L2 flushed between steps.
   e2e       the same through the public C ABI with HOST buffers every step: rt_upload_scene
             (host -> device) + render + frame copy into pinned host memory (device -> host).
   roofline  FP32 FMA bound: algorithmic flops = 16 x N_spheres x rays.
@@ -27,6 +29,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# NCCL prints its version banner to STDOUT at NCCL_DEBUG=VERSION; stdout carries exactly one JSON line here
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 SCENE = os.path.join(ROOT, "tests", "golden", "scenes", "complex.txt")
 W, H, DEPTH, BAND_H = 1920, 1080, 5, 16
@@ -205,13 +210,23 @@ def main_b200(args, rank, local_rank, world):
     # CUDA events below are recorded on that same stream
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
-    bands = rtb200.BandGather(W, H, BAND_H, rank, n, dev, dist)
-    part, full = bands.part, bands.full
+    peer = n > 1 and args.gather == "peer"
+    if peer:
+        # rank 0 owns the assembled frame; everybody's kernels write their rows into it (CUDA IPC + NVLink)
+        pf = rtb200.PeerFrame(r, W, H, BAND_H, rank, n, dist)
+        full = pf.frame() if rank == 0 else None
 
-    def step_device():
-        r.render_bands_device(W, H, DEPTH, BAND_H, rank, n, part.data_ptr(), stream.cuda_stream)
-        if n > 1:
-            bands.gather()                          # NCCL gather of the 8-bit bands to rank 0 + row scatter
+        def step_device():
+            pf.render(DEPTH, stream.cuda_stream)
+            pf.release(stream.cuda_stream)          # `value`: the frame stays in rank 0's HBM, nothing consumes it
+    else:
+        bands = rtb200.BandGather(W, H, BAND_H, rank, n, dev, dist)
+        part, full = bands.part, bands.full
+
+        def step_device():
+            r.render_bands_device(W, H, DEPTH, BAND_H, rank, n, part.data_ptr(), stream.cuda_stream)
+            if n > 1:
+                bands.gather()                      # NCCL gather of the 8-bit bands to rank 0 + row scatter
 
     # ray counts of the frame (one counted render on rank 0's full frame, outside the timed region)
     _, st = r.render(W, H, DEPTH)
@@ -254,9 +269,15 @@ def main_b200(args, rank, local_rank, world):
 
         def step_e2e():
             r.upload(scene)
-            step_device()
-            if rank == 0:
-                host_frame.copy_(full, non_blocking=True)
+            if peer:
+                pf.render(DEPTH, stream.cuda_stream)
+                if rank == 0:
+                    host_frame.copy_(full, non_blocking=True)
+                pf.release(stream.cuda_stream)      # after the copy: the next frame may overwrite rank 0's buffer
+            else:
+                step_device()
+                if rank == 0:
+                    host_frame.copy_(full, non_blocking=True)
             torch.cuda.synchronize()
         d2h = W * H * 3
     h2d = r.scene_bytes()
@@ -303,12 +324,14 @@ def main_b200(args, rank, local_rank, world):
             "data": ("reference scene file %s.txt (tests/golden fixture, identical doubles); no dataset involved" % args.workload)
                     if not WORKLOADS[args.workload][0].startswith("synth") else "synthetic scene, scripts/gen_scene.py (SURVEY 8d spec)",
             "config": {"workload": WORKLOAD, "rays_per_frame": rays, "parallelism": "interleaved %d-row bands x %d GPU%s"
-                       % (BAND_H, n, "" if n == 1 else "s, NCCL gather to rank 0"), "band_h": BAND_H,
+                       % (BAND_H, n, "" if n == 1 else ("s, rows stored into rank 0's frame over NVLink peer memory + completion flags"
+                                                         if peer else "s, NCCL gather to rank 0")), "band_h": BAND_H,
                        "l2": "flushed between timed steps (256 MiB write, untimed)"},
             "e2e": {"value": round(rays / e2e_s * 1e-6, 1), "unit": "Mrays/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_s * 1e3, 4), "steps": Ke,
                     "path": "rt_upload_scene + rt_render into pinned host memory" if n == 1 else
-                            "rt_upload_scene + rt_render_bands + NCCL gather + copy to pinned host on rank 0"},
+                            ("rt_upload_scene + rt_render_bands_frame (peer stores) + copy to pinned host on rank 0" if peer else
+                             "rt_upload_scene + rt_render_bands + NCCL gather + copy to pinned host on rank 0")},
             "gpu_launches": launches_per_step * K,
             "clocks": sampler.summary(),
         }
@@ -341,6 +364,13 @@ def main_b200(args, rank, local_rank, world):
                 line["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "reference",
                                         "sample": "failed: %r" % (e,)}
         print(json.dumps(line), flush=True)
+    if peer:
+        torch.cuda.synchronize()
+        err = pf.error()
+        dist.barrier()
+        pf.close()
+        if err:
+            raise RuntimeError("peer frame: a completion wait timed out (flag %d)" % (err - 1))
     r.close()
     if n > 1:
         dist.destroy_process_group()
@@ -356,6 +386,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="complex", choices=sorted(WORKLOADS))
     ap.add_argument("--accel", type=int, default=None, help="0 auto, 1 table walks, 2 LBVH (rt_set_option accel)")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="N > 1: how the bands reach rank 0")
     args = ap.parse_args()
     global SCENE, W, H, DEPTH, WORKLOAD
     _, W, H, DEPTH, WORKLOAD = WORKLOADS[args.workload]
@@ -373,6 +404,7 @@ def main():
                "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup), "--workload", args.workload]
         if args.accel is not None:
             cmd += ["--accel", str(args.accel)]
+        cmd += ["--gather", args.gather]
         return subprocess.call(cmd)
     return main_b200(args, rank, local_rank, world)
 

@@ -16,4 +16,4 @@ from .api import (  # noqa: F401
 )
 from .ppmtools import read_ppm, compare_rgb, ppm_text  # noqa: F401
 from .build import build_all, build_library  # noqa: F401
-from .bands import BandGather  # noqa: F401
+from .bands import BandGather, PeerFrame  # noqa: F401

@@ -17,7 +17,8 @@ RT_MAX_LEVELS = 32
 ABI_SYMBOLS = [
     "rt_abi_version", "rt_last_error", "rt_device_count",
     "rt_scene_load", "rt_scene_counts", "rt_scene_data", "rt_scene_free",
-    "rt_create", "rt_destroy", "rt_set_option", "rt_upload_scene", "rt_render_tile",
+    "rt_create", "rt_destroy", "rt_set_option", "rt_upload_scene", "rt_render_tile", "rt_render_bands_frame",
+    "rt_dev_alloc", "rt_dev_free", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_peer_signal", "rt_peer_wait",
     "rt_render", "rt_render_debug", "rt_render_bands", "rt_band_rows", "rt_band_row_list",
     "rt_host_alloc", "rt_host_free", "rt_write_ppm", "rt_measure_fp32_peak",
 ]
@@ -78,6 +79,14 @@ def load_library():
     lib.rt_destroy.restype = None
     lib.rt_set_option.argtypes = [vp, C.c_char_p, C.c_longlong]
     lib.rt_render_tile.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
+    lib.rt_render_bands_frame.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.POINTER(RtStats)]
+    lib.rt_dev_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    lib.rt_dev_free.argtypes = [vp, vp]
+    lib.rt_ipc_export.argtypes = [vp, vp, C.c_char_p]
+    lib.rt_ipc_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+    lib.rt_ipc_close.argtypes = [vp, vp]
+    lib.rt_peer_signal.argtypes = [vp, vp, C.c_uint32, vp]
+    lib.rt_peer_wait.argtypes = [vp, vp, C.c_int, C.c_uint32, vp, vp]
     lib.rt_upload_scene.argtypes = [vp, vp, i, vp, i, vp, vp, vp, C.c_double]
     lib.rt_render.argtypes = [vp, i, i, i, vp, C.POINTER(RtStats)]
     lib.rt_render_debug.argtypes = [vp, i, i, i, vp, vp, vp, C.POINTER(RtStats)]
@@ -225,6 +234,44 @@ class Renderer:
         _check(self._lib.rt_set_option(self._h, key.encode(), int(value)), "rt_set_option")
         if key == "antialias":
             self.antialias = bool(value)
+
+    def render_bands_frame(self, W, H, depth, band_h, rank, nranks, dev_frame_ptr, stream_ptr=None, want_stats=False):
+        """rt_render_bands_frame: this rank's rows at their image positions of an assembled frame (local or peer memory)."""
+        st = RtStats()
+        _check(self._lib.rt_render_bands_frame(self._h, W, H, depth, band_h, rank, nranks, C.c_void_p(dev_frame_ptr),
+                                               C.c_void_p(stream_ptr) if stream_ptr else None,
+                                               C.byref(st) if want_stats else None), "rt_render_bands_frame")
+        return st
+
+    # ---- device memory shared between the processes of one box, completion flags (rt_b200.h) ----
+    def dev_alloc(self, nbytes):
+        p = C.c_void_p()
+        _check(self._lib.rt_dev_alloc(self._h, nbytes, C.byref(p)), "rt_dev_alloc")
+        return p.value
+
+    def dev_free(self, ptr):
+        _check(self._lib.rt_dev_free(self._h, C.c_void_p(ptr)), "rt_dev_free")
+
+    def ipc_export(self, ptr):
+        buf = C.create_string_buffer(64)
+        _check(self._lib.rt_ipc_export(self._h, C.c_void_p(ptr), buf), "rt_ipc_export")
+        return buf.raw
+
+    def ipc_open(self, handle):
+        p = C.c_void_p()
+        _check(self._lib.rt_ipc_open(self._h, handle, C.byref(p)), "rt_ipc_open")
+        return p.value
+
+    def ipc_close(self, ptr):
+        _check(self._lib.rt_ipc_close(self._h, C.c_void_p(ptr)), "rt_ipc_close")
+
+    def peer_signal(self, flag_ptr, value, stream_ptr=None):
+        _check(self._lib.rt_peer_signal(self._h, C.c_void_p(flag_ptr), value & 0xffffffff,
+                                        C.c_void_p(stream_ptr) if stream_ptr else None), "rt_peer_signal")
+
+    def peer_wait(self, flags_ptr, n, value, err_ptr, stream_ptr=None):
+        _check(self._lib.rt_peer_wait(self._h, C.c_void_p(flags_ptr), n, value & 0xffffffff, C.c_void_p(err_ptr),
+                                      C.c_void_p(stream_ptr) if stream_ptr else None), "rt_peer_wait")
 
     def render_tile_device(self, W, H, depth, tile, dev_fb_ptr, stream_ptr=None):
         """rt_render_tile: tile = (x, y, w, h); dev_fb_ptr = device pointer of a W*H*3 float32 framebuffer."""

@@ -5,6 +5,11 @@ balances sky rows against sphere-dense rows) and renders them compactly with
 ``rt_render_bands``.  The only exchange step of the path is the gather of the 8-bit bands to
 rank 0, done with ``torch.distributed`` (NCCL over NVLink on GPUs, gloo in the CPU tests);
 rank 0 then scatters the rows of every rank back to their image positions.
+
+PeerFrame is the B200-native form of that step: rank 0 owns the assembled frame, every other rank maps it
+through CUDA IPC and its render kernels store their finished rows straight into it over NVLink
+(rt_render_bands_frame) -- the transfer overlaps the compute pixel by pixel, and what is left of the gather is
+one completion flag per rank (rt_peer_signal / rt_peer_wait) plus an acknowledge word for back-pressure.
 """
 import numpy as np
 
@@ -47,3 +52,78 @@ class BandGather:
             idx = self.row_idx[k]
             self.full[idx] = parts[k][: idx.numel() * self.W * 3].view(idx.numel(), self.W, 3)
         return self.full
+
+
+class _DevArray:
+    """Exposes a raw device allocation to torch (zero-copy) through __cuda_array_interface__."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class PeerFrame:
+    """One assembled [H, W, 3] frame in rank 0's HBM that all ranks of the box render into.
+
+    Per frame:  rank r > 0: wait(ack >= seq-1) -> render rows into rank 0's frame -> signal(flag[r] = seq)
+                rank 0    : render its own rows -> wait(flag[1..n) >= seq) -> (consumer) -> release(): ack = seq
+    Handles travel once through `dist` (any backend; object broadcast).  All waits / signals are stream ordered."""
+
+    def __init__(self, renderer, W, H, band_h, rank, nranks, dist=None):
+        self.r, self.W, self.H, self.band_h, self.rank, self.n, self.dist = renderer, W, H, band_h, rank, nranks, dist
+        self.seq = 0
+        self.nbytes = H * W * 3 + 16
+        self._owned = []
+        if rank == 0:
+            self.frame_ptr = renderer.dev_alloc(self.nbytes)
+            self.ctl_ptr = renderer.dev_alloc(4 * 128)          # [0..64) flags, [64] ack, [65] error word
+            self._owned = [self.frame_ptr, self.ctl_ptr]
+            handles = [renderer.ipc_export(self.frame_ptr), renderer.ipc_export(self.ctl_ptr)] if nranks > 1 else None
+        else:
+            handles = None
+        if nranks > 1:
+            box = [handles]
+            dist.broadcast_object_list(box, src=0)
+            if rank != 0:
+                self.frame_ptr = renderer.ipc_open(box[0][0])
+                self.ctl_ptr = renderer.ipc_open(box[0][1])
+                self.err_ptr = renderer.dev_alloc(4)            # local error word of this rank's waits
+                self._owned = [self.err_ptr]
+        if rank == 0:
+            self.err_ptr = self.ctl_ptr + 4 * 65
+
+    def render(self, depth, stream_ptr=None, want_stats=False):
+        """Enqueues this rank's share of the next frame (and, on rank 0, the wait for everybody else's)."""
+        self.seq += 1
+        r = self.r
+        if self.rank != 0:
+            r.peer_wait(self.ctl_ptr + 4 * 64, 1, self.seq - 1, self.err_ptr, stream_ptr)     # frame seq-1 consumed?
+        st = r.render_bands_frame(self.W, self.H, depth, self.band_h, self.rank, self.n, self.frame_ptr, stream_ptr, want_stats)
+        if self.n > 1:
+            if self.rank != 0:
+                r.peer_signal(self.ctl_ptr + 4 * self.rank, self.seq, stream_ptr)
+            else:
+                r.peer_wait(self.ctl_ptr + 4, self.n - 1, self.seq, self.err_ptr, stream_ptr)
+        return st
+
+    def release(self, stream_ptr=None):
+        """Rank 0, after whatever consumes the frame has been enqueued: lets the other ranks start the next frame."""
+        if self.rank == 0 and self.n > 1:
+            self.r.peer_signal(self.ctl_ptr + 4 * 64, self.seq, stream_ptr)
+
+    def frame(self):
+        """Rank 0: the assembled frame as a torch uint8 [H, W, 3] view of the device memory."""
+        import torch
+        assert self.rank == 0
+        return torch.as_tensor(_DevArray(self.frame_ptr, (self.H, self.W, 3), "|u1"), device="cuda")
+
+    def error(self):
+        """After a synchronise: 0, or 1 + index of the flag a wait timed out on."""
+        import torch
+        return int(torch.as_tensor(_DevArray(self.err_ptr, (1,), "<u4"), device="cuda").item())
+
+    def close(self):
+        if self.rank != 0 and self.n > 1:
+            self.r.ipc_close(self.frame_ptr); self.r.ipc_close(self.ctl_ptr)
+        for p in self._owned:
+            self.r.dev_free(p)
+        self._owned = []

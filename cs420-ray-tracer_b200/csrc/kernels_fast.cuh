@@ -116,7 +116,8 @@ __device__ __forceinline__ void write_final(const RtRenderArgs &r, unsigned pix,
   size_t o = pix;
   if (r.out_remap) {
     const unsigned lr = pix / (unsigned)r.W, x = pix - lr * (unsigned)r.W;
-    o = (size_t)(lr + (unsigned)r.out_y0) * (size_t)r.out_pitch + x + (unsigned)r.out_x0;
+    if (r.out_remap == 2) o = (size_t)rt_local_to_global_row(r.bands, (int)lr) * (size_t)r.W + x;
+    else o = (size_t)(lr + (unsigned)r.out_y0) * (size_t)r.out_pitch + x + (unsigned)r.out_x0;
   }
   if (r.fb) { float *f = r.fb + o * 3; f[0] = cr; f[1] = cg; f[2] = cb; }
   else { unsigned char *q = r.rgb + o * 3; q[0] = (unsigned char)quant8(cr); q[1] = (unsigned char)quant8(cg); q[2] = (unsigned char)quant8(cb); }

@@ -168,7 +168,8 @@ __global__ void __launch_bounds__(kThreads, RT_CLOSEST_CTAS) k_closest0(const Wa
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char *s_rgb = smem + 64 + warp * (kWTileH * kWTileW * 3);
   const int W = a.r.W, rows = a.r.bands.local_rows, depth = a.r.max_depth;
-  const bool kBytes = a.r.fb == nullptr && !a.r.out_remap;   // plain 8-bit frame: staged tile rows, 128-bit stores
+  const bool kBytes = a.r.fb == nullptr && a.r.out_remap != 1;   // 8-bit frame (compact or assembled): staged tile rows, 128-bit stores
+  const bool kFrame = a.r.out_remap == 2;                        // rows go to their image positions (maybe in a peer GPU's memory)
   unsigned c_closest = 0, c_hits = 0, c_fp64 = 0, c_viol = 0, c_cand = 0, c_walks = 0;
   for (;;) {
     int tile;
@@ -272,16 +273,18 @@ __global__ void __launch_bounds__(kThreads, RT_CLOSEST_CTAS) k_closest0(const Wa
       // 3 x 16-byte stores per 48-byte row segment (src/main.cpp:84-86 quantiser applied above)
       if (lane < kWTileH * 3) {
         const int ty = lane / 3, seg = lane % 3;
-        if (ty0 + ty < rows)
-          *reinterpret_cast<uint4 *>(a.r.rgb + ((size_t)(ty0 + ty) * W + tx0) * 3 + seg * 16) =
+        if (ty0 + ty < rows) {
+          const size_t orow = kFrame ? (size_t)rt_local_to_global_row(a.r.bands, ty0 + ty) : (size_t)(ty0 + ty);
+          *reinterpret_cast<uint4 *>(a.r.rgb + (orow * W + tx0) * 3 + seg * 16) =
               *reinterpret_cast<const uint4 *>(s_rgb + ty * kWTileW * 3 + seg * 16);
+        }
       }
     } else {
 #pragma unroll
       for (int r = 0; r < 2; r++) {
         if (x < W && lr[r] < rows) {
           const unsigned char *q = s_rgb + (((lane >> 4) * 2 + r) * kWTileW + (lane & 15)) * 3;
-          unsigned char *o = a.r.rgb + (size_t)pix[r] * 3;
+          unsigned char *o = a.r.rgb + (kFrame ? ((size_t)j[r] * W + x) : (size_t)pix[r]) * 3;
           o[0] = q[0]; o[1] = q[1]; o[2] = q[2];
         }
       }

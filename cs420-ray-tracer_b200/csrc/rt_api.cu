@@ -290,14 +290,18 @@ static void fill_stats(rt_stats *st, const unsigned long long *cnt) {
 // Launches the kernels of one (possibly banded) render on `stream`.  When `stats` is given the
 // call synchronises the stream and fills it.  With supersampling on, the kernels render the 2W x 2H sample
 // grid into a float frame and k_resolve_aa averages it into dev_rgb; debug buffers are per SAMPLE then.
-struct TileSpec { int x, y, w, h; float *fb; };   // rt_render_tile: float output into the caller's full-frame buffer
+struct TileSpec { int x, y, w, h; float *fb; int frame; };   // rt_render_tile: float output into the caller's full-frame buffer;
+                                                            // frame = 1 (rt_render_bands_frame): 8-bit rows at their image positions
 static int render_common(rt_ctx *c, int W, int H, int depth, int band_h, int rank, int nranks, uint8_t *dev_rgb,
                          int32_t *dev_hit, uint32_t *dev_mask, cudaStream_t stream, rt_stats *stats, const TileSpec *tile = nullptr) {
   if (!c->have_scene) return rt_fail(RT_ERR_STATE, "render: no scene uploaded (call rt_upload_scene first)");
   if (W < 1 || H < 1 || depth < 0) return rt_fail(RT_ERR_ARG, "render: bad image size or depth");
   if (depth > RT_MAX_LEVELS) return rt_fail(RT_ERR_UNSUPPORTED, "render: max_depth above RT_MAX_LEVELS");
+  const bool frame_mode = tile && tile->frame;
+  if (frame_mode) tile = nullptr;
+  if (frame_mode && c->antialias) return rt_fail(RT_ERR_UNSUPPORTED, "rt_render_bands_frame: not with supersampling");
   const int aa = (c->antialias && !tile) ? 1 : 0, m = aa ? 2 : 1;
-  if ((aa || tile) && c->mode == 1) return rt_fail(RT_ERR_UNSUPPORTED, "render: supersampling / tile renders need mode 0");
+  if ((aa || tile || frame_mode) && c->mode == 1) return rt_fail(RT_ERR_UNSUPPORTED, "render: supersampling / tile renders need mode 0");
   int rows = rt_band_rows(H, band_h, rank, nranks);
   if (rows < 0) return rows;
   RT_CUDA(cudaSetDevice(c->device));
@@ -333,6 +337,14 @@ static int render_common(rt_ctx *c, int W, int H, int depth, int band_h, int ran
     a.out_remap = 1; a.out_pitch = W; a.out_x0 = tile->x; a.out_y0 = tile->y;
     rows = tile->h;
     if (depth <= 0) RT_CUDA(cudaMemset2DAsync(tile->fb + ((size_t)tile->y * W + tile->x) * 3, (size_t)W * 12, 0, (size_t)tile->w * 12, tile->h, stream));
+  }
+  if (frame_mode) {
+    a.out_remap = 2;
+    if (depth <= 0)                                  // src/main.cpp:17-18: black; this rank's bands only
+      for (int b = rank; b * band_h < H; b += nranks) {
+        const int j0 = b * band_h, j1 = j0 + band_h < H ? j0 + band_h : H;
+        RT_CUDA(cudaMemsetAsync(dev_rgb + (size_t)j0 * W * 3, 0, (size_t)(j1 - j0) * W * 3, stream));
+      }
   }
   a.counters = want_counters ? c->d_counters : nullptr;
   if (want_counters) RT_CUDA(cudaMemsetAsync(c->d_counters, 0, RT_CNT_TOTAL * sizeof(unsigned long long), stream));
@@ -383,7 +395,7 @@ extern "C" int rt_render_tile(rt_ctx *c, int W, int H, int depth, int tile_x, in
   if (!c || !dev_fb) return rt_fail(RT_ERR_ARG, "rt_render_tile: NULL argument");
   if (tile_x < 0 || tile_y < 0 || tile_w < 1 || tile_h < 1 || tile_x + tile_w > W || tile_y + tile_h > H)
     return rt_fail(RT_ERR_ARG, "rt_render_tile: tile outside the image");
-  const TileSpec t = {tile_x, tile_y, tile_w, tile_h, dev_fb};
+  const TileSpec t = {tile_x, tile_y, tile_w, tile_h, dev_fb, 0};
   return render_common(c, W, H, depth, H, 0, 1, nullptr, nullptr, nullptr, stream ? (cudaStream_t)stream : c->stream, nullptr, &t);
 }
 
@@ -396,6 +408,67 @@ extern "C" int rt_render_bands(rt_ctx *c, int W, int H, int depth, int band_h, i
   if (rc == RT_OK && stats)
     stats->ms_host = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return rc;
+}
+
+// As rt_render_bands, but the rows this rank owns are stored at their IMAGE positions of an assembled H x W x 3 frame:
+// dev_frame may be memory of this GPU or peer-mapped memory of another GPU of the box (rt_ipc_open), so that the ranks'
+// kernels write rank 0's frame directly over NVLink and no gather / de-interleave step is left.
+extern "C" int rt_render_bands_frame(rt_ctx *c, int W, int H, int depth, int band_h, int rank, int nranks, void *dev_frame,
+                                     void *stream, rt_stats *stats) {
+  if (!c || !dev_frame) return rt_fail(RT_ERR_ARG, "rt_render_bands_frame: NULL argument");
+  const TileSpec t = {0, 0, 0, 0, nullptr, 1};
+  return render_common(c, W, H, depth, band_h, rank, nranks, (uint8_t *)dev_frame, nullptr, nullptr,
+                       stream ? (cudaStream_t)stream : c->stream, stats, &t);
+}
+
+// ---- device memory that can be shared between the processes of one box (one process per GPU) ----------------------
+extern "C" int rt_dev_alloc(rt_ctx *c, size_t bytes, void **out) {
+  if (!c || !out || bytes == 0) return rt_fail(RT_ERR_ARG, "rt_dev_alloc: bad argument");
+  RT_CUDA(cudaSetDevice(c->device));
+  RT_CUDA(cudaMalloc(out, bytes));
+  RT_CUDA(cudaMemset(*out, 0, bytes));
+  return RT_OK;
+}
+extern "C" int rt_dev_free(rt_ctx *c, void *p) {
+  if (!c) return rt_fail(RT_ERR_ARG, "rt_dev_free: NULL ctx");
+  RT_CUDA(cudaSetDevice(c->device));
+  RT_CUDA(cudaFree(p));
+  return RT_OK;
+}
+extern "C" int rt_ipc_export(rt_ctx *c, void *dev_ptr, unsigned char handle[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  if (!c || !dev_ptr || !handle) return rt_fail(RT_ERR_ARG, "rt_ipc_export: NULL argument");
+  RT_CUDA(cudaSetDevice(c->device));
+  cudaIpcMemHandle_t h;
+  RT_CUDA(cudaIpcGetMemHandle(&h, dev_ptr));
+  memcpy(handle, &h, 64);
+  return RT_OK;
+}
+extern "C" int rt_ipc_open(rt_ctx *c, const unsigned char handle[64], void **out) {
+  if (!c || !handle || !out) return rt_fail(RT_ERR_ARG, "rt_ipc_open: NULL argument");
+  RT_CUDA(cudaSetDevice(c->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  RT_CUDA(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+  return RT_OK;
+}
+extern "C" int rt_ipc_close(rt_ctx *c, void *p) {
+  if (!c) return rt_fail(RT_ERR_ARG, "rt_ipc_close: NULL ctx");
+  RT_CUDA(cudaSetDevice(c->device));
+  RT_CUDA(cudaIpcCloseMemHandle(p));
+  return RT_OK;
+}
+extern "C" int rt_peer_signal(rt_ctx *c, uint32_t *flag, uint32_t value, void *stream) {
+  if (!c || !flag) return rt_fail(RT_ERR_ARG, "rt_peer_signal: NULL argument");
+  RT_CUDA(cudaSetDevice(c->device));
+  const int r = rtk_peer_signal(flag, value, stream ? (cudaStream_t)stream : c->stream);
+  return r < 0 ? rt_fail(RT_ERR_CUDA, std::string("rt_peer_signal: ") + cudaGetErrorString((cudaError_t)-r)) : RT_OK;
+}
+extern "C" int rt_peer_wait(rt_ctx *c, uint32_t *flags, int n, uint32_t value, uint32_t *dev_err, void *stream) {
+  if (!c || !flags || !dev_err || n < 1 || n > 64) return rt_fail(RT_ERR_ARG, "rt_peer_wait: bad argument");
+  RT_CUDA(cudaSetDevice(c->device));
+  const int r = rtk_peer_wait(flags, n, value, dev_err, stream ? (cudaStream_t)stream : c->stream);
+  return r < 0 ? rt_fail(RT_ERR_CUDA, std::string("rt_peer_wait: ") + cudaGetErrorString((cudaError_t)-r)) : RT_OK;
 }
 
 extern "C" int rt_render_debug(rt_ctx *c, int W, int H, int depth, uint8_t *host_rgb, int32_t *hit_idx,

@@ -61,7 +61,8 @@ struct RtRenderArgs {
   const float2 *matx;
   uint8_t *rgb;            // local_rows x W x 3 (8-bit output; unused when fb is set)
   float *fb;               // optional FLOAT output, 3 floats per pixel (tile renders, supersampling): replaces rgb
-  int out_remap;           // 0: output pixel = local pixel lr*W + x; 1: (lr + out_y0) * out_pitch + x + out_x0
+  int out_remap;           // 0: output pixel = local pixel lr*W + x; 1: (lr + out_y0) * out_pitch + x + out_x0;
+                           // 2: global_row(lr) * W + x -- rows land at their image positions of an assembled frame
   int out_pitch, out_x0, out_y0;
   int32_t *hit_idx;        // optional debug, local_rows*W*max_depth
   uint32_t *shadow_mask;   // optional debug

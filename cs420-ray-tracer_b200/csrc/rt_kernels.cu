@@ -325,7 +325,7 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
     }
   }
   RTK_TRY(cudaMemsetAsync(w->ctl, 0, kCtlWords * sizeof(unsigned int), stream));
-  if (args.max_depth <= 0 && !args.fb) RTK_TRY(cudaMemsetAsync(args.rgb, 0, npix * 3, stream));   // src/main.cpp:17-18: black (float output: the caller clears)
+  if (args.max_depth <= 0 && !args.fb && !args.out_remap) RTK_TRY(cudaMemsetAsync(args.rgb, 0, npix * 3, stream));   // src/main.cpp:17-18: black (other output modes: the caller clears)
 
   rtf::WaveArgs wa;
   memset(&wa, 0, sizeof(wa));
@@ -358,7 +358,8 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
   // levels below wave_levels run as phase-separated wavefront kernels; the (few) rays left after that are
   // followed to termination by one fused launch
   // (large scenes: every level has enough rays to fill the machine, and the tail's one-warp chains would dominate)
-  const int wave_levels = w->wave_levels > 0 ? w->wave_levels : (fs->bvh_nodes ? RT_MAX_LEVELS_INTERNAL : 2);
+  // small shares of a frame (one rank's bands of many): level 1 has too few rays to pay for three more launches
+  const int wave_levels = w->wave_levels > 0 ? w->wave_levels : (fs->bvh_nodes ? RT_MAX_LEVELS_INTERNAL : (npix >= 750000 ? 2 : 1));
   for (int level = 0; level < args.max_depth && level < wave_levels; level++) {
     a.level = level;
     wa.hit_count = w->ctl + CTL_HITS + level;
@@ -419,6 +420,38 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
   }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? launches : -(int)e;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Frame assembly over peer memory (rt_render_bands_frame): every rank's kernels store their finished rows straight
+// into rank 0's frame over NVLink; what is left of the "gather" is this completion signal.
+//   k_peer_signal  (every rank, after its render, same stream): system-scope fence, then flag[rank] = value in rank 0's
+//                  memory -- ordered after all pixel stores of the rank.
+//   k_peer_wait    (rank 0): spins until every flag has reached `value`; gives up after ~2 s and reports through err.
+__global__ void k_peer_signal(volatile unsigned int *flag, unsigned int value) {
+  __threadfence_system();
+  *flag = value;
+  __threadfence_system();
+}
+__global__ void k_peer_wait(volatile unsigned int *flags, int n, unsigned int value, unsigned int *err) {
+  const int k = threadIdx.x;
+  if (k >= n) return;
+  const long long t0 = clock64();
+  while ((int)(flags[k] - value) < 0) {
+    if (clock64() - t0 > 4000000000LL) { atomicExch(err, 1u + (unsigned)k); break; }
+    __nanosleep(200);
+  }
+  __threadfence_system();
+}
+int rtk_peer_signal(unsigned int *flag, unsigned int value, cudaStream_t stream) {
+  k_peer_signal<<<1, 1, 0, stream>>>(flag, value);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 1 : -(int)e;
+}
+int rtk_peer_wait(unsigned int *flags, int n, unsigned int value, unsigned int *err, cudaStream_t stream) {
+  k_peer_wait<<<1, 64, 0, stream>>>(flags, n, value, err);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 1 : -(int)e;
 }
 
 // ---------------------------------------------------------------------------------------------

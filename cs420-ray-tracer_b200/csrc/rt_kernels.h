@@ -50,6 +50,10 @@ void rtk_fast_free_work(RtFastWork *w);
 int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork *w, cudaStream_t stream,
                     const cudaEvent_t *marks);
 
+// Completion signalling of the peer-memory frame assembly (flags live in rank 0's memory, n <= 64).
+int rtk_peer_signal(unsigned int *flag, unsigned int value, cudaStream_t stream);
+int rtk_peer_wait(unsigned int *flags, int n, unsigned int value, unsigned int *err, cudaStream_t stream);
+
 // 2x2 supersampling resolve: float sample frame (2W x 2rows) -> 8-bit rows x W.
 int rtk_resolve_aa(const float *fb, int W, int rows, uint8_t *rgb, cudaStream_t stream);
 

@@ -139,6 +139,30 @@ int rt_render_debug(rt_ctx *ctx, int width, int height, int max_depth, uint8_t *
  * filled after a stream synchronise only when counters are enabled.                        */
 int rt_render_bands(rt_ctx *ctx, int width, int height, int max_depth, int band_h, int rank,
                     int nranks, void *dev_rgb, void *stream, rt_stats *stats);
+/* As rt_render_bands, but the rows this rank owns are stored at their IMAGE positions of an assembled
+ * H*W*3-byte frame (row j at dev_frame + j*W*3).  dev_frame may be memory of this GPU or peer-mapped
+ * memory of another GPU of the box (rt_ipc_open): the ranks' kernels then write rank 0's frame directly
+ * over NVLink while they compute, and the "gather" of SURVEY 8e shrinks to a completion signal
+ * (rt_peer_signal / rt_peer_wait).  Not available with supersampling.                         */
+int rt_render_bands_frame(rt_ctx *ctx, int width, int height, int max_depth, int band_h, int rank,
+                          int nranks, void *dev_frame, void *stream, rt_stats *stats);
+/* Device memory that processes of one box can share (one process per GPU, as under torchrun):
+ * rt_dev_alloc = zeroed cudaMalloc on the ctx's device; rt_ipc_export writes the 64-byte CUDA IPC
+ * handle of such an allocation; rt_ipc_open maps an exported allocation of another process (peer
+ * access is enabled on demand) and returns a device pointer valid in the calling process.     */
+int rt_dev_alloc(rt_ctx *ctx, size_t bytes, void **dev_ptr);
+int rt_dev_free(rt_ctx *ctx, void *dev_ptr);
+int rt_ipc_export(rt_ctx *ctx, void *dev_ptr, unsigned char handle[64]);
+int rt_ipc_open(rt_ctx *ctx, const unsigned char handle[64], void **dev_ptr);
+int rt_ipc_close(rt_ctx *ctx, void *dev_ptr);
+/* Completion signalling on `stream` (NULL = ctx stream).  rt_peer_signal: after everything already
+ * enqueued on the stream, store `value` to *flag (typically flag = rank 0's flags + rank, peer
+ * mapped) with system-scope release ordering.  rt_peer_wait: enqueue a wait until flags[0..n) have
+ * all reached `value` (n <= 64); on a ~2 s timeout it writes 1 + the missing index to *dev_err
+ * (a device uint32 the caller zeroed) and returns to the stream.                               */
+int rt_peer_signal(rt_ctx *ctx, uint32_t *flag, uint32_t value, void *stream);
+int rt_peer_wait(rt_ctx *ctx, uint32_t *flags, int n, uint32_t value, uint32_t *dev_err, void *stream);
+
 /* Tile render with the calling convention of the reference's launch_gpu_kernel
  * (src/kernel.cu:185-200; caller src/main_hybrid.cpp:461-466): renders pixels
  * [tile_x, tile_x+tile_w) x [tile_y, tile_y+tile_h) of a width x height image into the CALLER's
