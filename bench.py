@@ -130,30 +130,42 @@ def physical_gpu_index(local_rank):
 
 # -------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the reference's own CPU renderer on this box's host cores
-def run_reference_frames(steps, warmup, budget_s=150.0):
+def run_reference_frames(steps, warmup, budget_s=150.0, workload="complex"):
     """Times `steps` renders with oracle/_ref/ref_harness (the unmodified reference sources, OpenMP
     loop of src/main.cpp:185 on all host threads).  Each step is a bounded sample of the frame
     (every `pix_step`-th pixel) sized so the run fits the budget.  Falls back to the C port."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py
-    import rtb200
-    scene = rtb200.load_scene(SCENE)
+    scene = load_workload(workload)
+    scene_file = SCENE
+    if WORKLOADS[workload][0].startswith("synth:"):
+        # the reference reads scene FILES: write the synthetic scene in its text grammar (%.6f = the same doubles)
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import gen_scene
+        import tempfile
+        _, nn, seed = WORKLOADS[workload][0].split(":")
+        scene_file = os.path.join(tempfile.gettempdir(), "rtb200_%s.txt" % workload)
+        with open(scene_file, "w") as f:
+            f.write(gen_scene.to_text(*gen_scene.generate(int(nn), int(seed))))
+    elif workload != "complex":
+        scene_file = os.path.join(ROOT, "tests", "golden", "scenes", WORKLOADS[workload][0] + ".txt")
     cores = os.cpu_count() or 1
     kind = "reference" if oracle_py.ref_available() else "port"
 
     def one(pix_step):
         if kind == "reference":
-            out = oracle_py.ref_harness("render", SCENE, W, H, DEPTH, "-", "omp", pix_step,
+            out = oracle_py.ref_harness("render", scene_file, W, H, DEPTH, "-", "omp", pix_step,
                                         env={"OMP_NUM_THREADS": str(cores)})
             return float([l for l in out.splitlines() if "time:" in l][0].split()[2])
         t0 = time.perf_counter()
         oracle_py.render(scene, W, H, DEPTH, pix_step=pix_step, nthreads=0)
         return time.perf_counter() - t0
 
-    t_probe = one(16) * 16                       # estimate of a full frame
+    probe_step = 16 if workload in ("complex", "medium", "simple") else 4096
+    t_probe = one(probe_step) * probe_step       # estimate of a full frame
     total = max(1, steps + warmup)
     pix_step = 1
-    while t_probe / pix_step * total > budget_s and pix_step < 4096:
+    while t_probe / pix_step * total > budget_s and pix_step < 65536:
         pix_step *= 2
     rays = oracle_py.render(scene, W, H, DEPTH, pix_step=pix_step, nthreads=0)["counters"]["rays"]
     for _ in range(warmup):
@@ -357,7 +369,7 @@ def main_b200(args, rank, local_rank, world):
         line["roofline"] = roof
         if n == 1 and not args.no_cpu_baseline:
             try:
-                cb = run_reference_frames(3, 1, budget_s=30.0)
+                cb = run_reference_frames(3, 1, budget_s=30.0, workload=args.workload)
                 line["cpu_baseline"] = {"value": round(cb["mrays_s"], 3), "unit": "Mrays/s", "cores": cb["cores"],
                                         "kind": cb["kind"], "sample": cb["sample"]}
             except Exception as e:  # noqa: BLE001
@@ -390,8 +402,7 @@ def main():
     args = ap.parse_args()
     global SCENE, W, H, DEPTH, WORKLOAD
     _, W, H, DEPTH, WORKLOAD = WORKLOADS[args.workload]
-    if args.workload != "complex":
-        args.no_cpu_baseline = True          # the CPU arm is the headline workload only
+
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -60,6 +60,7 @@ struct rt_ctx {
   double4 *d_sph64 = nullptr;
   float4 *d_mat = nullptr;
   float2 *d_matx = nullptr;
+  size_t scene_cap = 0;  // spheres the three arrays above can hold (kept across uploads: cudaMalloc/cudaFree are slow and synchronise)
   RtFastScene fast;      // FP32 filter tables (rt_kernels.h)
   // per-resolution tables
   int tabW = 0, tabH = 0, tab_aa = 0;
@@ -116,7 +117,8 @@ static void free_scene(rt_ctx *c) {
   cudaFree(c->d_sph64); c->d_sph64 = nullptr;
   cudaFree(c->d_mat); c->d_mat = nullptr;
   cudaFree(c->d_matx); c->d_matx = nullptr;
-  rtk_fast_free_scene(&c->fast);
+  c->scene_cap = 0;
+  rtk_fast_free_scene(&c->fast, 1);
   c->have_scene = false;
 }
 
@@ -178,7 +180,8 @@ extern "C" int rt_upload_scene(rt_ctx *c, const double *spheres, int N, const do
     return rt_fail(RT_ERR_UNSUPPORTED, "rt_upload_scene: more than " + std::to_string(RT_MAX_LIGHTS) + " lights");
   RT_CUDA(cudaSetDevice(c->device));
   RT_CUDA(cudaStreamSynchronize(c->stream));
-  free_scene(c);
+  c->have_scene = false;
+  rtk_fast_free_scene(&c->fast, 0);              // keeps the table allocation for reuse
   c->N = N; c->L = L; c->fov = fov_deg;
 
   // include/camera.h:10-15, in double on the host
@@ -209,9 +212,14 @@ extern "C" int rt_upload_scene(rt_ctx *c, const double *spheres, int N, const do
     matx[i] = make_float2((float)r[9], r[7] > 0 ? 1.0f : 0.0f);   // recurse flag decided in double
   }
   size_t n1 = (size_t)(N > 0 ? N : 1);
-  RT_CUDA(cudaMalloc(&c->d_sph64, n1 * sizeof(double4)));
-  RT_CUDA(cudaMalloc(&c->d_mat, n1 * sizeof(float4)));
-  RT_CUDA(cudaMalloc(&c->d_matx, n1 * sizeof(float2)));
+  if (c->scene_cap < n1) {
+    cudaFree(c->d_sph64); cudaFree(c->d_mat); cudaFree(c->d_matx);
+    c->d_sph64 = nullptr; c->d_mat = nullptr; c->d_matx = nullptr; c->scene_cap = 0;
+    RT_CUDA(cudaMalloc(&c->d_sph64, n1 * sizeof(double4)));
+    RT_CUDA(cudaMalloc(&c->d_mat, n1 * sizeof(float4)));
+    RT_CUDA(cudaMalloc(&c->d_matx, n1 * sizeof(float2)));
+    c->scene_cap = n1;
+  }
   RT_CUDA(cudaMemcpyAsync(c->d_sph64, s64.data(), n1 * sizeof(double4), cudaMemcpyHostToDevice, c->stream));
   RT_CUDA(cudaMemcpyAsync(c->d_mat, mat.data(), n1 * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
   RT_CUDA(cudaMemcpyAsync(c->d_matx, matx.data(), n1 * sizeof(float2), cudaMemcpyHostToDevice, c->stream));

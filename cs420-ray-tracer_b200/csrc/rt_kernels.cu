@@ -241,7 +241,11 @@ int rtk_fast_build_scene(RtFastScene *fs, const double *sph, int N, const RtFram
       put(pairs, i, (float)(s[0] - fs->c0[0]), (float)(s[1] - fs->c0[1]), (float)(s[2] - fs->c0[2]), float_up(rho));
     }
   }
-  RTK_TRY(cudaMalloc(&fs->tabs, total));
+  if (fs->tabs_cap < total) {
+    cudaFree(fs->tabs); fs->tabs = nullptr; fs->tabs_cap = 0;
+    RTK_TRY(cudaMalloc(&fs->tabs, total));
+    fs->tabs_cap = total;
+  }
   RTK_TRY(cudaMemcpyAsync(fs->tabs, h.data(), total, cudaMemcpyHostToDevice, stream));
   RTK_TRY(cudaStreamSynchronize(stream));   // h goes out of scope
   fs->bvh_nodes = fs->bvh_leaves = nullptr; fs->bvh_nleaf = 0; fs->bvh_build_ms = 0; fs->nbig = 0;
@@ -276,10 +280,10 @@ int rtk_fast_build_scene(RtFastScene *fs, const double *sph, int N, const RtFram
   return 0;
 }
 
-void rtk_fast_free_scene(RtFastScene *fs) {
-  if (fs->tabs) cudaFree(fs->tabs);
+void rtk_fast_free_scene(RtFastScene *fs, int release_tables) {
+  if (release_tables) { cudaFree(fs->tabs); fs->tabs = nullptr; fs->tabs_cap = 0; }
   cudaFree(fs->bvh_nodes); cudaFree(fs->bvh_leaves);
-  fs->tabs = nullptr; fs->bvh_nodes = fs->bvh_leaves = nullptr; fs->bvh_nleaf = 0;
+  fs->bvh_nodes = fs->bvh_leaves = nullptr; fs->bvh_nleaf = 0;
 }
 
 void rtk_fast_free_work(RtFastWork *w) {

@@ -16,6 +16,7 @@ int rtk_launch_exact(const RtRenderArgs &args, cudaStream_t stream);
 struct RtFastScene {
   int N, L, npairs, ngroups;
   void *tabs;             // device: (1+L) shared-origin tables (pairs | gmin | perm), then the general table
+  size_t tabs_cap;        // bytes allocated behind tabs (reused by the next upload when large enough)
   unsigned tstride;       // bytes per shared-origin table
   unsigned gmin_off, perm_off, inv_off, cullA_off, cullB_off;
   size_t bytes_primary;   // staged by k_primary: (1+L) * tstride
@@ -44,7 +45,7 @@ struct RtFastWork {
 int rtk_fast_init(int device);
 // accel: 0 = automatic (LBVH from kBvhAutoSpheres spheres), 1 = table walks only, 2 = LBVH whenever N > 0
 int rtk_fast_build_scene(RtFastScene *fs, const double *spheres, int N, const RtFrameConst *frame, int accel, cudaStream_t stream);
-void rtk_fast_free_scene(RtFastScene *fs);
+void rtk_fast_free_scene(RtFastScene *fs, int release_tables);   // release_tables = 0: keep the table allocation
 void rtk_fast_free_work(RtFastWork *w);
 // marks (may be null): 3 events recorded after the level-0 closest-hit, shadow and shade kernels.
 int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork *w, cudaStream_t stream,

@@ -169,6 +169,27 @@ def test_large_synthetic_against_fp64_brute_force(rt, renderers, n, seed, W, H, 
             assert getattr(out[3], k) == getattr(ref[3], k), (m, k)
 
 
+@pytest.mark.parametrize("n,seed,W,H,D", [(10000, 420, 3840, 2160, 5), (100000, 421, 7680, 4320, 8)])
+def test_full_size_large_configs_two_algorithms_agree(rt, n, seed, W, H, D):
+    """BASELINE configs 4 and 5 at FULL size: far too large for the CPU oracle, so the check is that two independent
+    candidate-selection algorithms -- streamed brute-force table walks and the device-built LBVH -- produce the
+    bit-identical frame and identical ray counters (every level's alive count, hits, occluded shadow rays), with
+    no filter violation.  Both decide through the same exact FP64 routines pinned by the tests above."""
+    import gen_scene
+    sc = rt.Scene(*gen_scene.generate(n, seed))
+    out = {}
+    for m, acc in (("tables", 1), ("bvh", 2)):
+        with rt.Renderer(0, mode="fast", accel=acc) as r:
+            r.upload(sc)
+            out[m] = r.render(W, H, D)
+    (fa, sa), (fb, sb) = out["tables"], out["bvh"]
+    assert np.array_equal(fa, fb)
+    for k in ("closest_queries", "hits", "shadow_queries", "occluded", "filter_violations"):
+        assert getattr(sa, k) == getattr(sb, k), k
+    assert [int(x) for x in sa.alive] == [int(x) for x in sb.alive] and sa.filter_violations == 0
+    assert sa.alive[0] == W * H and sa.shadow_queries == sa.hits * sc.nlights
+
+
 @pytest.mark.parametrize("mode", ["fast", "bvh"])
 @pytest.mark.parametrize("name,W,H,D", [("simple", 160, 90, 5), ("complex", 192, 108, 5), ("medium", 97, 61, 3)])
 def test_supersampling_matches_the_four_sample_oracle(rt, oracle, scenes, name, W, H, D, mode):
