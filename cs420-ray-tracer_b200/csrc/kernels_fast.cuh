@@ -128,6 +128,12 @@ __device__ __forceinline__ int warp_fetch(unsigned int *counter) {
   return __shfl_sync(kFull, v, 0);
 }
 
+// Programmatic dependent launch: everything a kernel does BEFORE this point (table staging) may overlap the tail of the
+// previous kernel of the stream; after it, that kernel has completed and its writes are visible.  The early
+// launch_dependents lets the NEXT kernel's CTAs take SM slots as soon as ours exit (they wait at their own RT_PDL_SYNC).
+// Both are no-ops for a launch without the PDL attribute.
+#define RT_PDL_SYNC() do { asm volatile("griddepcontrol.wait;" ::: "memory"); asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); } while (0)
+
 // mbarrier + TMA bulk copy (global -> shared), one phase, used once per CTA
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
   unsigned a = (unsigned)__cvta_generic_to_shared(bar);
@@ -932,11 +938,12 @@ constexpr int kTailThreads = RT_TAIL_THREADS;
 template <bool kSmem, bool kBvh>
 __global__ void __launch_bounds__(kTailThreads, RT_TAIL_CTAS) k_bounce(const FastArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const unsigned nq = *a.q_in_count;
-  if (nq == 0u) return;                             // nothing survived to this level
   // staged: [L light tables][general table], contiguous in global memory in that order
   const unsigned char *tabs = a.tabs + a.tstride;
   if (kSmem) { stage_tables(smem, tabs, a.stage_bytes); tabs = smem + kSmemHeader; }
+  RT_PDL_SYNC();
+  const unsigned nq = *a.q_in_count;
+  if (nq == 0u) return;                             // nothing survived to this level
   const WarpBuf wb = warp_buf(smem + kSmemHeader + ((a.stage_bytes + 127u) & ~127u));
   const float4 *gen = reinterpret_cast<const float4 *>(tabs + (size_t)a.L * a.tstride);
   const int lane = threadIdx.x & 31;

@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(kThreads, RT_CLOSEST_CTAS) k_closest0(const Wa
   const unsigned char *tabs = a.tabs;
   if (kMode == kTabSmem) { stage_tables(smem, a.tabs, a.stage_bytes); tabs = smem + kSmemHeader; }
   if (kMode == kTabStream) ring_init(smem);
+  RT_PDL_SYNC();
   const Tab camg = tab_at(a.tabs, a, 0);             // global view (gmin / perm of the streamed mode)
   const Tab cam = tab_at(tabs, a, 0);
   const WarpBuf wb = warp_buf(smem + kSmemHeader + ((a.stage_bytes + 127u) & ~127u));   // kTabSmem only
@@ -300,11 +301,12 @@ template <bool kSmem, bool kBvh>
 __global__ void __launch_bounds__(kThreads, RT_CLOSEST_CTAS) k_closest1(const WaveArgs w) {
   extern __shared__ __align__(128) unsigned char smem[];
   const FastArgs &a = w.f;
-  const unsigned nq = *a.q_in_count;
-  if (nq == 0u) return;
   // staged: the general table only (it follows the (1+L) shared-origin tables)
   const unsigned char *tabs = a.tabs + (size_t)(a.L + 1) * a.tstride;
   if (kSmem) { stage_tables(smem, tabs, a.stage_bytes); tabs = smem + kSmemHeader; }
+  RT_PDL_SYNC();
+  const unsigned nq = *a.q_in_count;
+  if (nq == 0u) return;
   const float4 *gen = reinterpret_cast<const float4 *>(tabs);
   const int lane = threadIdx.x & 31, depth = a.r.max_depth, level = a.level;
   unsigned c_closest = 0, c_hits = 0, c_fp64 = 0, c_viol = 0;
@@ -378,13 +380,14 @@ template <int kMode>
 __global__ void __launch_bounds__(kThreads, RT_SHADOW_CTAS) k_shadow(const WaveArgs w) {
   extern __shared__ __align__(128) unsigned char smem[];
   const FastArgs &a = w.f;
-  const unsigned nh = *w.hit_count;
-  if (nh == 0u || a.L == 0) return;
   // staged: the L light tables
   const unsigned char *gtabs = a.tabs + a.tstride;
   const unsigned char *tabs = gtabs;
-  if (kMode == kTabSmem) { stage_tables(smem, tabs, a.stage_bytes); tabs = smem + kSmemHeader; }
+  if (kMode == kTabSmem && a.L > 0) { stage_tables(smem, tabs, a.stage_bytes); tabs = smem + kSmemHeader; }
   if (kMode == kTabStream) ring_init(smem);
+  RT_PDL_SYNC();
+  const unsigned nh = *w.hit_count;
+  if (nh == 0u || a.L == 0) return;
   const WarpBuf wb = warp_buf(smem + kSmemHeader + ((a.stage_bytes + 127u) & ~127u));   // kTabSmem only
   unsigned ring_phase = 0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -502,6 +505,7 @@ __global__ void __launch_bounds__(kThreads, RT_SHADOW_CTAS) k_shadow(const WaveA
 // src/main.cpp:43-55: final pixel, or the reflected ray (exact FP64) appended to the RayRec queue.
 __global__ void __launch_bounds__(kThreads, 4) k_shade(const WaveArgs w) {
   const FastArgs &a = w.f;
+  RT_PDL_SYNC();
   const unsigned nh = *w.hit_count;
   if (nh == 0u) return;
   const int lane = threadIdx.x & 31, level = a.level, L = a.L, W = a.r.W;

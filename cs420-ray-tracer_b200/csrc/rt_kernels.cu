@@ -3,7 +3,11 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <tuple>
 #include <vector>
 
 // Camera basis, lights and ambient: one copy per device, refreshed by rt_upload_scene.
@@ -296,9 +300,32 @@ namespace {
 // persistent grid: as many CTAs as can be resident
 template <typename K>
 int resident_grid(K kernel, size_t smem, int num_sms, int threads = rtf::kThreads) {
-  int nb = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem) != cudaSuccess || nb < 1) nb = 1;
-  return nb * num_sms;
+  // cached: the occupancy query costs microseconds of host time per launch
+  static std::mutex mu;
+  static std::map<std::tuple<const void *, size_t, int>, int> cache;
+  const auto key = std::make_tuple((const void *)kernel, smem, threads);
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem) != cudaSuccess || nb < 1) nb = 1;
+    it = cache.emplace(key, nb).first;
+  }
+  return it->second * num_sms;
+}
+// Launch with programmatic dependent launch (PDL): the grid may start while the previous kernel of the stream is
+// still draining, run its prologue (table staging) and then block in griddepcontrol.wait (RT_PDL_SYNC in the kernels)
+// until that kernel has completed and flushed.  Hides launch latency + prologue behind the predecessor's tail.
+template <typename K, typename A>
+void launch(K kernel, int grid, int block, size_t smem, cudaStream_t stream, bool pdl, const A &arg) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1u : 0u;
+  cudaLaunchKernelEx(&cfg, kernel, arg);
 }
 // dynamic shared memory of a kernel that stages `bytes` of tables: header | tables | per-warp compacted tables
 inline size_t staged_smem(size_t bytes) { return rtf::kSmemHeader + ((bytes + 127) & ~(size_t)127) + rtf::kWarps * (size_t)rtf::kWarpBufBytes; }
@@ -358,6 +385,9 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
   // larger tables are streamed through a two-stage ring of TMA tiles (kernels_wave.cuh, kTabStream)
   const size_t stream_smem = rtf::kSmemHeader + 2 * (size_t)rtf::kTileBytes;
   int launches = 0;
+  // event records between the kernels (stats) break the launch adjacency PDL needs; RT_NO_PDL=1 turns it off (A/B)
+  static const bool pdl_env = !(getenv("RT_NO_PDL") && getenv("RT_NO_PDL")[0] == '1');
+  const bool pdl = pdl_env && marks == nullptr;
 
   // levels below wave_levels run as phase-separated wavefront kernels; the (few) rays left after that are
   // followed to termination by one fused launch
@@ -372,18 +402,18 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
       a.stage_bytes = fs->tstride;
       const size_t smem = cam_smem ? staged_smem(a.stage_bytes) : stream_smem;
       const int cta_tiles = (a.nwtiles + rtf::kWarps - 1) / rtf::kWarps;
-      if (bvh) { int g = resident_grid(rtf::k_closest0<rtf::kTabBvh>, rtf::kSmemHeader, w->num_sms); rtf::k_closest0<rtf::kTabBvh><<<g < cta_tiles ? g : cta_tiles, rtf::kThreads, rtf::kSmemHeader, stream>>>(wa); }
-      else if (cam_smem) { int g = resident_grid(rtf::k_closest0<rtf::kTabSmem>, smem, w->num_sms); rtf::k_closest0<rtf::kTabSmem><<<g < cta_tiles ? g : cta_tiles, rtf::kThreads, smem, stream>>>(wa); }
-      else { int g = resident_grid(rtf::k_closest0<rtf::kTabStream>, smem, w->num_sms); rtf::k_closest0<rtf::kTabStream><<<g < cta_tiles ? g : cta_tiles, rtf::kThreads, smem, stream>>>(wa); }
+      if (bvh) { int g = resident_grid(rtf::k_closest0<rtf::kTabBvh>, rtf::kSmemHeader, w->num_sms); launch(rtf::k_closest0<rtf::kTabBvh>, g < cta_tiles ? g : cta_tiles, rtf::kThreads, rtf::kSmemHeader, stream, false, wa); }
+      else if (cam_smem) { int g = resident_grid(rtf::k_closest0<rtf::kTabSmem>, smem, w->num_sms); launch(rtf::k_closest0<rtf::kTabSmem>, g < cta_tiles ? g : cta_tiles, rtf::kThreads, smem, stream, false, wa); }
+      else { int g = resident_grid(rtf::k_closest0<rtf::kTabStream>, smem, w->num_sms); launch(rtf::k_closest0<rtf::kTabStream>, g < cta_tiles ? g : cta_tiles, rtf::kThreads, smem, stream, false, wa); }
     } else {
       a.q_in = (rtf::RayRec *)w->queue[(level - 1) & 1];
       a.q_in_count = w->ctl + CTL_RAYS + level;
       wa.work_counter = w->ctl + CTL_CLOSEST + level;
       a.stage_bytes = (unsigned)pairs_bytes;
       const size_t smem = rtf::kSmemHeader + (gen_smem ? a.stage_bytes : 0);
-      if (bvh) rtf::k_closest1<false, true><<<resident_grid(rtf::k_closest1<false, true>, rtf::kSmemHeader, w->num_sms), rtf::kThreads, rtf::kSmemHeader, stream>>>(wa);
-      else if (gen_smem) rtf::k_closest1<true, false><<<resident_grid(rtf::k_closest1<true, false>, smem, w->num_sms), rtf::kThreads, smem, stream>>>(wa);
-      else rtf::k_closest1<false, false><<<resident_grid(rtf::k_closest1<false, false>, smem, w->num_sms), rtf::kThreads, smem, stream>>>(wa);
+      if (bvh) launch(rtf::k_closest1<false, true>, resident_grid(rtf::k_closest1<false, true>, rtf::kSmemHeader, w->num_sms), rtf::kThreads, rtf::kSmemHeader, stream, pdl, wa);
+      else if (gen_smem) launch(rtf::k_closest1<true, false>, resident_grid(rtf::k_closest1<true, false>, smem, w->num_sms), rtf::kThreads, smem, stream, pdl, wa);
+      else launch(rtf::k_closest1<false, false>, resident_grid(rtf::k_closest1<false, false>, smem, w->num_sms), rtf::kThreads, smem, stream, pdl, wa);
     }
     launches++;
     if (level == 0 && marks) RTK_TRY(cudaEventRecord(marks[0], stream));
@@ -392,9 +422,9 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
       wa.work_counter = w->ctl + CTL_SHADOW + level;
       a.stage_bytes = (unsigned)light_bytes;
       const size_t smem = light_smem ? staged_smem(a.stage_bytes) : stream_smem;
-      if (bvh) rtf::k_shadow<rtf::kTabBvh><<<resident_grid(rtf::k_shadow<rtf::kTabBvh>, rtf::kSmemHeader, w->num_sms), rtf::kThreads, rtf::kSmemHeader, stream>>>(wa);
-      else if (light_smem) rtf::k_shadow<rtf::kTabSmem><<<resident_grid(rtf::k_shadow<rtf::kTabSmem>, smem, w->num_sms), rtf::kThreads, smem, stream>>>(wa);
-      else rtf::k_shadow<rtf::kTabStream><<<resident_grid(rtf::k_shadow<rtf::kTabStream>, smem, w->num_sms), rtf::kThreads, smem, stream>>>(wa);
+      if (bvh) launch(rtf::k_shadow<rtf::kTabBvh>, resident_grid(rtf::k_shadow<rtf::kTabBvh>, rtf::kSmemHeader, w->num_sms), rtf::kThreads, rtf::kSmemHeader, stream, pdl, wa);
+      else if (light_smem) launch(rtf::k_shadow<rtf::kTabSmem>, resident_grid(rtf::k_shadow<rtf::kTabSmem>, smem, w->num_sms), rtf::kThreads, smem, stream, pdl, wa);
+      else launch(rtf::k_shadow<rtf::kTabStream>, resident_grid(rtf::k_shadow<rtf::kTabStream>, smem, w->num_sms), rtf::kThreads, smem, stream, pdl, wa);
       launches++;
     }
     if (level == 0 && marks) RTK_TRY(cudaEventRecord(marks[1], stream));
@@ -402,7 +432,7 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
     wa.work_counter = w->ctl + CTL_SHADE + level;
     a.q_out = (rtf::RayRec *)w->queue[level & 1];
     a.q_out_count = w->ctl + CTL_RAYS + level + 1;
-    rtf::k_shade<<<resident_grid(rtf::k_shade, 0, w->num_sms), rtf::kThreads, 0, stream>>>(wa);
+    launch(rtf::k_shade, resident_grid(rtf::k_shade, 0, w->num_sms), rtf::kThreads, 0, stream, pdl, wa);
     launches++;
     if (level == 0 && marks) RTK_TRY(cudaEventRecord(marks[2], stream));
   }
@@ -417,9 +447,9 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
     a.chunk_counter = w->ctl + CTL_TAIL + level;
     a.stage_bytes = (unsigned)fs->bytes_bounce;
     const size_t smem = in_smem ? staged_smem(fs->bytes_bounce) : rtf::kSmemHeader;
-    if (bvh) rtf::k_bounce<false, true><<<resident_grid(rtf::k_bounce<false, true>, rtf::kSmemHeader, w->num_sms, rtf::kTailThreads), rtf::kTailThreads, rtf::kSmemHeader, stream>>>(a);
-    else if (in_smem) rtf::k_bounce<true, false><<<resident_grid(rtf::k_bounce<true, false>, smem, w->num_sms, rtf::kTailThreads), rtf::kTailThreads, smem, stream>>>(a);
-    else rtf::k_bounce<false, false><<<resident_grid(rtf::k_bounce<false, false>, smem, w->num_sms, rtf::kTailThreads), rtf::kTailThreads, smem, stream>>>(a);
+    if (bvh) launch(rtf::k_bounce<false, true>, resident_grid(rtf::k_bounce<false, true>, rtf::kSmemHeader, w->num_sms, rtf::kTailThreads), rtf::kTailThreads, rtf::kSmemHeader, stream, pdl, a);
+    else if (in_smem) launch(rtf::k_bounce<true, false>, resident_grid(rtf::k_bounce<true, false>, smem, w->num_sms, rtf::kTailThreads), rtf::kTailThreads, smem, stream, pdl, a);
+    else launch(rtf::k_bounce<false, false>, resident_grid(rtf::k_bounce<false, false>, smem, w->num_sms, rtf::kTailThreads), rtf::kTailThreads, smem, stream, pdl, a);
     launches++;
   }
   cudaError_t e = cudaGetLastError();

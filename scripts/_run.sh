@@ -1,11 +1,6 @@
 cd $GRAFT_REPO_ROOT
-timeout 1800 python -m pytest tests -m gpu -x -q -k "full_size" 2>&1 | tail -3
-python bench.py --steps 20 --warmup 3 --workload synth10k > gpurun_out/r01_bench_synth10k_bvh.json 2>/dev/null; python -c "
-import json; d=json.load(open('gpurun_out/r01_bench_synth10k_bvh.json')); print(d['ms_per_step'], d['value'], d['cpu_baseline'])"
-python bench.py --steps 5 --warmup 3 --workload synth100k > gpurun_out/r01_bench_synth100k.json 2>/dev/null; python -c "
-import json; d=json.load(open('gpurun_out/r01_bench_synth100k.json')); print(d['ms_per_step'], d['value'], d['cpu_baseline'])"
-python bench.py --steps 50 --warmup 3 --workload medium > gpurun_out/r01_bench_medium.json 2>/dev/null
-python bench.py --steps 50 --warmup 3 --workload simple > gpurun_out/r01_bench_simple.json 2>/dev/null; python -c "
-import json
-for w in ('medium','simple'):
-    d=json.load(open('gpurun_out/r01_bench_%s.json'%w)); print(w, d['ms_per_step'], d['value'], d['cpu_baseline']['value'])"
+timeout 1800 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+for e in 0 1; do RT_NO_PDL=$e python bench.py --no-cpu-baseline --steps 300 > gpurun_out/bench_pdl$e.json 2>gpurun_out/bench_pdl$e.err; python -c "
+import json; d=json.load(open('gpurun_out/bench_pdl$e.json')); print('RT_NO_PDL=$e', d['ms_per_step'], d['value'], 'e2e', d['e2e']['ms_per_step'])"; done
+RT_NO_PDL=0 timeout 300 python scripts/probe_rank.py | grep "n=8"
+RT_NO_PDL=1 timeout 300 python scripts/probe_rank.py | grep "n=8"
