@@ -118,6 +118,31 @@ def ncu_traffic():
         return None
 
 
+def ncu_executed():
+    """FP32-pipe and issue-slot utilisation of the dominant kernel from the committed ncu capture (profiles/): the
+    EXECUTED counterpart of the algorithmic roofline fraction."""
+    try:
+        out, take = {}, False
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_full_summary.txt")) as f:
+            for line in f:
+                if line.startswith("==="):
+                    if take:
+                        break
+                    take = "k_shadow" in line
+                elif take:
+                    p = line.split()
+                    for key, name in (("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "fma_pipe_active_pct"),
+                                      ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_slots_active_pct"),
+                                      ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved_occupancy_pct"),
+                                      ("launch__registers_per_thread", "registers_per_thread")):
+                        if p and p[0] == key:
+                            out[name] = round(float(p[1]), 2)
+        out["source"] = "profiles/r01_ncu_full_summary.txt (ncu --set full of this bench command; first k_shadow launch)"
+        return out
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def physical_gpu_index(local_rank):
     vis = os.environ.get("CUDA_VISIBLE_DEVICES")
     if vis:
@@ -356,7 +381,7 @@ def main_b200(args, rank, local_rank, world):
                         "is in profiles/ (ncu sm__pipe_fma_cycles_active)",
                 "peak_source": "measured live: FFMA issue peak of this GPU (rt_measure_fp32_peak, SM clock %.0f MHz); "
                                "MEASURED_PEAKS.json has no FP32 entry" % peak_mhz,
-                "flop_per_test": FLOP_PER_TEST, "traffic": ncu_traffic(),
+                "flop_per_test": FLOP_PER_TEST, "traffic": ncu_traffic(), "executed": ncu_executed(),
                 "frame": {"achieved": round(ach, 2), "frac": round(ach / (peak * 1e-12), 4), "flops": frame_flops}}
         if k_ms:
             a0 = FLOP_PER_TEST * nsph * k_rays / (k_ms * 1e-3) * 1e-12

@@ -295,5 +295,46 @@ __device__ __forceinline__ void bvh_traverse(const BvhView v, const BvhRay &r, f
   }
 }
 
+// Resumable form of the same traversal, for kernels that keep every lane busy by handing it a new ray as soon as its
+// old one is finished (persistent threads with dynamic ray fetch): bvh_next() advances to the next candidate sphere.
+struct BvhIter {
+  int stack[kStack];
+  int sp, node;
+  float t0, t1;
+  BvhRay r;
+};
+constexpr int kBvhDone = 0x7fffffff;
+__device__ __forceinline__ void bvh_begin(BvhIter &it, const BvhRay &r, float t0, float t1) {
+  it.sp = 0; it.node = 0; it.t0 = t0; it.t1 = t1; it.r = r;
+}
+// Visits at most `budget` internal nodes.  Returns the next candidate sphere (>= 0), -1 when the traversal is complete,
+// -2 when the budget ran out first (call again).
+__device__ __forceinline__ int bvh_next(const BvhView v, BvhIter &it, int budget) {
+  int node = it.node, sp = it.sp;
+  while (node >= 0 && node != kBvhDone && budget-- > 0) {
+    const BvhNode *nd = v.nodes + node;
+    const float4 a = __ldg(&nd->a), b = __ldg(&nd->b), c = __ldg(&nd->c);
+    const int4 d = __ldg(&nd->d);
+    const float e0 = bvh_slab(it.r, a.x, a.y, a.z, a.w, b.x, b.y, it.t0, it.t1);
+    const float e1 = bvh_slab(it.r, b.z, b.w, c.x, c.y, c.z, c.w, it.t0, it.t1);
+    const bool h0 = e0 < 3.0e38f, h1 = e1 < 3.0e38f;
+    if (h0 && h1) {
+      const bool swap = e1 < e0;
+      it.stack[sp++] = swap ? d.x : d.y;
+      node = swap ? d.y : d.x;
+    } else if (h0 || h1) {
+      node = h0 ? d.x : d.y;
+    } else {
+      node = sp > 0 ? it.stack[--sp] : kBvhDone;
+    }
+  }
+  int ret;
+  if (node == kBvhDone) ret = -1;
+  else if (node >= 0) ret = -2;
+  else { ret = ~node; node = sp > 0 ? it.stack[--sp] : kBvhDone; }
+  it.node = node; it.sp = sp;
+  return ret;
+}
+
 }  // namespace rtb
 #endif

@@ -501,6 +501,88 @@ __global__ void __launch_bounds__(kThreads, RT_SHADOW_CTAS) k_shadow(const WaveA
 }
 
 // ---------------------------------------------------------------------------------------------
+// SHADOW through the LBVH with DYNAMIC RAY FETCH (large scenes).  Work item = one (light, hit slot) shadow ray.  The
+// traversal lengths of neighbouring rays differ by an order of magnitude once rays are incoherent (k_shadow<kTabBvh> ran
+// at 5-6 active lanes of 32 from reflection level 1 on), so here a lane does not wait for its warp: whenever enough
+// lanes are idle they fetch the next items together (one atomic per refill) and everybody goes on traversing
+// (persistent threads, Aila & Laine 2009).  Same queries, same slow paths, same occlusion bytes as k_shadow.
+__global__ void __launch_bounds__(kThreads, RT_SHADOW_CTAS) k_shadow_dyn(const WaveArgs w) {
+  const FastArgs &a = w.f;
+  RT_PDL_SYNC();
+  const unsigned nh = *w.hit_count;
+  if (nh == 0u || a.L == 0) return;
+  const unsigned total = nh * (unsigned)a.L;         // item = light * nh + slot: neighbouring lanes start on neighbouring hits
+  const unsigned char *gtabs = a.tabs + a.tstride;
+  const int lane = threadIdx.x & 31;
+  rtb::BvhIter it;
+  bool active = false, more = true;                  // more: the item counter has not run out yet
+  unsigned slot = 0;
+  int light = 0, self = -1, big_k = 0;
+  float dx = 0.f, dy = 0.f, dz = 0.f, so = 0.f, m = 0.f, cosl = 0.f;
+  unsigned c_fp64 = 0;
+  for (;;) {
+    // ---- refill: idle lanes take the next items (skipped while few lanes are idle, to amortise the atomic)
+    const unsigned idle = __ballot_sync(kFull, !active);
+    if (more && (__popc(idle) >= 8 || idle == kFull)) {
+      unsigned base = 0;
+      if (lane == __ffs(idle) - 1) base = atomicAdd(w.work_counter, (unsigned)__popc(idle));
+      base = __shfl_sync(kFull, base, __ffs(idle) - 1);
+      if (base + (unsigned)__popc(idle) >= total) more = false;
+      if (!active) {
+        const unsigned item = base + (unsigned)__popc(idle & ((1u << lane) - 1u));
+        if (item < total) {
+          light = (int)(item / nh); slot = item - (unsigned)light * nh;
+          const HitRec &hr = w.hits[slot];
+          if ((slot & 63u) < w.hit_n[slot >> 6] && hr.idx >= 0) {
+            self = hr.idx;
+            // direction light -> point: FP64 difference, FP32 normalisation (error <= 12u, see filter_math.cuh)
+            const d3 wv = rtx::sub(rtx::mk(hr.px, hr.py, hr.pz), ldc3(g_frame.light_pos[light]));
+            const float wx = (float)wv.x, wy = (float)wv.y, wz = (float)wv.z;
+            const float l2 = fmaf(wz, wz, fmaf(wy, wy, wx * wx));
+            const float inv = rsqrtf(l2);
+            dx = wx * inv; dy = wy * inv; dz = wz * inv;
+            so = l2 * inv - kEps;
+            cosl = -(hr.nx * dx + hr.ny * dy + hr.nz * dz);                       // n . light_dir
+            const Tab T = tab_at(gtabs, a, light);
+            const float backthr = -fmaxf(4.0f * kEps * rsqrtf((float)a.r.sph64[self].w), 1e-4f);   // -4 EPS / r
+            if (cosl < backthr && (T.inv[self] & 0x40000000) != 0) {
+              w.occ[(size_t)light * w.hit_cap + slot] = 1;                        // self-shadow shortcut (see k_shadow)
+            } else {
+              m = __fmaf_ru(1.9073486e-6f, so + kEps, 1e-7f);                     // as in shadow_begin
+              const float3 o = recentred(a, g_frame.light_pos[light]);
+              rtb::bvh_begin(it, rtb::bvh_ray(o.x, o.y, o.z, dx, dy, dz), -(kEps + m), so + m);
+              big_k = 0;
+              active = true;
+            }
+          }
+        }
+      }
+    }
+    if (!__any_sync(kFull, active)) { if (!more) break; else continue; }
+    // ---- a few traversal steps for every active lane, then look at the warp again
+#pragma unroll 1
+    for (int step = 0; step < 6; step++) {
+      if (active) {
+        int cand;
+        if (big_k < a.nbig) cand = a.big[big_k++];                                // the spheres kept out of the tree first
+        else cand = rtb::bvh_next(a.bvh, it, 6);
+        if (cand >= 0) {
+          const Tab T = tab_at(gtabs, a, light);
+          const int sl = __ldg(&T.inv[cand]) & 0x3fffffff;
+          const int rc = slow_shadow(T.pairs, T.perm, sl >> 1, dx, dy, dz, so, m, self, cosl, &w.hits[slot].px, light, a.d64, a.r.sph64);
+          c_fp64 += (unsigned)(rc >> 1);
+          if (rc & 1) { w.occ[(size_t)light * w.hit_cap + slot] = 1; active = false; }
+        } else if (cand == -1) {
+          w.occ[(size_t)light * w.hit_cap + slot] = 0;
+          active = false;
+        }
+      }
+    }
+  }
+  if (a.r.counters) flush_counts(a.r.counters, 99, 0, 0, 0, 0, c_fp64, 0, 0);
+}
+
+// ---------------------------------------------------------------------------------------------
 // SHADE: one hit per lane.  include/scene.h:89-121 in FP32 with the occlusion bytes of k_shadow, then
 // src/main.cpp:43-55: final pixel, or the reflected ray (exact FP64) appended to the RayRec queue.
 __global__ void __launch_bounds__(kThreads, 4) k_shade(const WaveArgs w) {

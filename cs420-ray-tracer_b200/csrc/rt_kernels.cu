@@ -388,6 +388,7 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
   // event records between the kernels (stats) break the launch adjacency PDL needs; RT_NO_PDL=1 turns it off (A/B)
   static const bool pdl_env = !(getenv("RT_NO_PDL") && getenv("RT_NO_PDL")[0] == '1');
   const bool pdl = pdl_env && marks == nullptr;
+  static const bool bvh_dyn = !(getenv("RT_BVH_DYN") && getenv("RT_BVH_DYN")[0] == '0');   // A/B: 0 = warp-synchronous LBVH shadow kernel
 
   // levels below wave_levels run as phase-separated wavefront kernels; the (few) rays left after that are
   // followed to termination by one fused launch
@@ -422,7 +423,10 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
       wa.work_counter = w->ctl + CTL_SHADOW + level;
       a.stage_bytes = (unsigned)light_bytes;
       const size_t smem = light_smem ? staged_smem(a.stage_bytes) : stream_smem;
-      if (bvh) launch(rtf::k_shadow<rtf::kTabBvh>, resident_grid(rtf::k_shadow<rtf::kTabBvh>, rtf::kSmemHeader, w->num_sms), rtf::kThreads, rtf::kSmemHeader, stream, pdl, wa);
+      // camera-ray hits are coherent: the warp-synchronous kernel wins at level 0 (4.3 vs 5.9 ms on config 4); from level 1 on
+      // the rays are not, and the dynamic-fetch kernel does (levels >= 1 of config 5: 57.6 -> 38 ms)
+      if (bvh && bvh_dyn && level > 0) launch(rtf::k_shadow_dyn, resident_grid(rtf::k_shadow_dyn, 0, w->num_sms), rtf::kThreads, 0, stream, pdl, wa);
+      else if (bvh) launch(rtf::k_shadow<rtf::kTabBvh>, resident_grid(rtf::k_shadow<rtf::kTabBvh>, rtf::kSmemHeader, w->num_sms), rtf::kThreads, rtf::kSmemHeader, stream, pdl, wa);
       else if (light_smem) launch(rtf::k_shadow<rtf::kTabSmem>, resident_grid(rtf::k_shadow<rtf::kTabSmem>, smem, w->num_sms), rtf::kThreads, smem, stream, pdl, wa);
       else launch(rtf::k_shadow<rtf::kTabStream>, resident_grid(rtf::k_shadow<rtf::kTabStream>, smem, w->num_sms), rtf::kThreads, smem, stream, pdl, wa);
       launches++;
