@@ -48,6 +48,8 @@ struct WaveArgs {
   unsigned hit_cap;                // slots
   unsigned char *occ;              // [L][hit_cap] occlusion bytes
   unsigned int *work_counter;      // per-launch chunk counter
+  Best *cand;                      // LBVH scenes, level >= 1: per queued ray, the closest-hit candidate k_closest1_dyn found
+  unsigned int *work_counter2;     // ... and that kernel's item counter
 };
 
 // Allocates the block of a work item with (m0, m1) = ballots of its candidate hits; slot[r] = where this
@@ -335,7 +337,11 @@ __global__ void __launch_bounds__(kThreads, RT_CLOSEST_CTAS) k_closest1(const Wa
     Best best[2];
     best_init(best[0]); best_init(best[1]);
     const RaySrc src[2] = {{nullptr, nullptr, 0, 0, qin + qi[0]}, {nullptr, nullptr, 0, 0, qin + qi[1]}};
-    if (kBvh) {
+    if (kBvh && w.cand) {                            // the traversal already ran (k_closest1_dyn): pick up its result
+#pragma unroll
+      for (int r = 0; r < 2; r++)
+        if (live[r]) best[r] = w.cand[qi[r]];
+    } else if (kBvh) {
 #pragma unroll 1
       for (int r = 0; r < 2; r++)
         if (live[r]) best[r] = bvh_closest_general(a, gen, ox[r], oy[r], oz[r], dx[r], dy[r], dz[r], src[r]);
@@ -498,6 +504,65 @@ __global__ void __launch_bounds__(kThreads, RT_SHADOW_CTAS) k_shadow(const WaveA
     }
   }
   if (a.r.counters) flush_counts(a.r.counters, 99, 0, 0, 0, 0, c_fp64, 0, 0, c_cand, c_walks);
+}
+
+// ---------------------------------------------------------------------------------------------
+// CLOSEST HIT through the LBVH with DYNAMIC RAY FETCH (large scenes, reflection levels >= 1; see k_shadow_dyn for the
+// scheme).  Only the traversal runs here: a lane's result is the candidate bracket (Best) of its ray, stored per queued
+// ray; k_closest1 then does the exact finish for 64 neighbouring rays at a time, as before.
+__global__ void __launch_bounds__(kThreads, RT_CLOSEST_CTAS) k_closest1_dyn(const WaveArgs w) {
+  const FastArgs &a = w.f;
+  RT_PDL_SYNC();
+  const unsigned nq = *a.q_in_count;
+  if (nq == 0u) return;
+  const float4 *gen = reinterpret_cast<const float4 *>(a.tabs + (size_t)(a.L + 1) * a.tstride);
+  const RayRec *qin = a.q_in;
+  const int lane = threadIdx.x & 31;
+  rtb::BvhIter it;
+  Best b;
+  best_init(b);
+  bool active = false, more = true;
+  unsigned qi = 0;
+  int big_k = 0;
+  float ox = 0.f, oy = 0.f, oz = 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
+  for (;;) {
+    const unsigned idle = __ballot_sync(kFull, !active);
+    if (more && (__popc(idle) >= 8 || idle == kFull)) {
+      unsigned base = 0;
+      if (lane == __ffs(idle) - 1) base = atomicAdd(w.work_counter2, (unsigned)__popc(idle));
+      base = __shfl_sync(kFull, base, __ffs(idle) - 1);
+      if (base + (unsigned)__popc(idle) >= nq) more = false;
+      if (!active) {
+        qi = base + (unsigned)__popc(idle & ((1u << lane) - 1u));
+        if (qi < nq) {
+          const RayRec &q = qin[qi];
+          ox = (float)(q.ox - a.c0[0]); oy = (float)(q.oy - a.c0[1]); oz = (float)(q.oz - a.c0[2]);
+          dx = (float)q.dx; dy = (float)q.dy; dz = (float)q.dz;
+          best_init(b);
+          rtb::bvh_begin(it, rtb::bvh_ray(ox, oy, oz, dx, dy, dz), -1e-3f, 3.0e38f);
+          big_k = 0;
+          active = true;
+        }
+      }
+    }
+    if (!__any_sync(kFull, active)) { if (!more) break; else continue; }
+#pragma unroll 1
+    for (int step = 0; step < 6; step++) {
+      if (active) {
+        int cnd;
+        if (big_k < a.nbig) cnd = a.big[big_k++];
+        else cnd = rtb::bvh_next(a.bvh, it, 6);
+        if (cnd >= 0) {
+          const RaySrc src = {nullptr, nullptr, 0, 0, qin + qi};
+          b = slow_closest_general(b, gen, cnd >> 1, a.N, ox, oy, oz, dx, dy, dz, a.d64, a.gS2, a.r.sph64, src);
+          if (b.idx >= 0) it.t1 = fminf(it.t1, __fmaf_ru(b.hi, 1e-6f, b.hi) + 1e-6f);     // prune by the best bracket so far
+        } else if (cnd == -1) {
+          w.cand[qi] = b;
+          active = false;
+        }
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

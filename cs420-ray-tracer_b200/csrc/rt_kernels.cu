@@ -291,7 +291,8 @@ void rtk_fast_free_scene(RtFastScene *fs, int release_tables) {
 }
 
 void rtk_fast_free_work(RtFastWork *w) {
-  cudaFree(w->queue[0]); cudaFree(w->queue[1]); cudaFree(w->ctl); cudaFree(w->hits); cudaFree(w->occ); cudaFree(w->hit_n);
+  cudaFree(w->queue[0]); cudaFree(w->queue[1]); cudaFree(w->ctl); cudaFree(w->hits); cudaFree(w->occ); cudaFree(w->hit_n); cudaFree(w->cand);
+  w->cand = nullptr; w->cand_cap = 0;
   w->queue[0] = w->queue[1] = nullptr; w->ctl = nullptr; w->hits = nullptr; w->occ = nullptr; w->hit_n = nullptr;
   w->queue_cap = w->hit_cap = w->occ_bytes = 0;
 }
@@ -354,6 +355,13 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
       RTK_TRY(cudaMalloc(&w->queue[1], npix * sizeof(rtf::RayRec)));
       w->queue_cap = npix;
     }
+
+  }
+  if (fs->bvh_nodes && args.max_depth > 1 && w->cand_cap < npix) {
+    RTK_TRY(cudaStreamSynchronize(stream));
+    cudaFree(w->cand); w->cand = nullptr; w->cand_cap = 0;
+    RTK_TRY(cudaMalloc(&w->cand, npix * sizeof(rtf::Best)));
+    w->cand_cap = npix;
   }
   RTK_TRY(cudaMemsetAsync(w->ctl, 0, kCtlWords * sizeof(unsigned int), stream));
   if (args.max_depth <= 0 && !args.fb && !args.out_remap) RTK_TRY(cudaMemsetAsync(args.rgb, 0, npix * 3, stream));   // src/main.cpp:17-18: black (other output modes: the caller clears)
@@ -412,7 +420,16 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
       wa.work_counter = w->ctl + CTL_CLOSEST + level;
       a.stage_bytes = (unsigned)pairs_bytes;
       const size_t smem = rtf::kSmemHeader + (gen_smem ? a.stage_bytes : 0);
-      if (bvh) launch(rtf::k_closest1<false, true>, resident_grid(rtf::k_closest1<false, true>, rtf::kSmemHeader, w->num_sms), rtf::kThreads, rtf::kSmemHeader, stream, pdl, wa);
+      if (bvh) {
+        wa.cand = nullptr;
+        if (bvh_dyn && w->cand && w->cand_cap >= npix) {                    // incoherent rays: traversal with dynamic ray fetch, then the coherent finish
+          wa.cand = (rtf::Best *)w->cand;
+          wa.work_counter2 = w->ctl + CTL_TAIL + level;     // (the tail's counters are unused in LBVH scenes)
+          launch(rtf::k_closest1_dyn, resident_grid(rtf::k_closest1_dyn, 0, w->num_sms), rtf::kThreads, 0, stream, pdl, wa);
+          launches++;
+        }
+        launch(rtf::k_closest1<false, true>, resident_grid(rtf::k_closest1<false, true>, rtf::kSmemHeader, w->num_sms), rtf::kThreads, rtf::kSmemHeader, stream, pdl, wa);
+      }
       else if (gen_smem) launch(rtf::k_closest1<true, false>, resident_grid(rtf::k_closest1<true, false>, smem, w->num_sms), rtf::kThreads, smem, stream, pdl, wa);
       else launch(rtf::k_closest1<false, false>, resident_grid(rtf::k_closest1<false, false>, smem, w->num_sms), rtf::kThreads, smem, stream, pdl, wa);
     }

@@ -39,6 +39,8 @@ struct RtFastWork {
   unsigned int *ctl;     // device control words: tile counter, per-level chunk counters, queue counts
   void *hits;            // HitRec queue of the current level (kernels_wave.cuh), 64-slot blocks
   unsigned int *hit_n;   // hits per block
+  void *cand;            // LBVH scenes: closest-hit candidate per queued ray (k_closest1_dyn -> k_closest1)
+  size_t cand_cap;
   unsigned char *occ;    // [L][hit_cap] occlusion bytes of the current level
   size_t hit_cap, occ_bytes;
 };
