@@ -888,6 +888,166 @@ __device__ __forceinline__ bool bvh_shadow(const FastArgs &a, const Tab T, float
 }
 
 // ---------------------------------------------------------------------------------------------
+// BUNDLE TRAVERSAL of the LBVH: bundle culling (see cull_round) for scenes too large for a table scan.  The warp's
+// ray bundle descends the hierarchy BREADTH FIRST with the lanes working on 32 frontier nodes at a time: a child
+// survives when the interval-arithmetic slab test (bundle_slab) cannot exclude that some ray of the bundle touches its
+// (inflated) box within the distance cutoff.  Surviving leaves name candidate spheres; these are gathered into the warp's compacted table
+// (any order: its group minima are -inf, so nothing relies on sortedness) and the unchanged chunk test + slow paths
+// run over it.  O(candidates x depth / 32) warp steps instead of one traversal per ray.  Coherent bundles only
+// (camera tiles, the shadow rays of one hit block): incoherent ones use the per-lane traversals above.
+constexpr int kFront = 192;                          // frontier capacity (nodes per BVH level that touch the cone)
+constexpr int kCandList = 128;                       // candidate list capacity; processed (and emptied) in fills of kCandMax
+constexpr unsigned kBundleBufBytes = (2 * kFront + kCandList) * 4;
+struct BundleBuf { int *cur, *nxt, *cand; };
+__device__ __forceinline__ BundleBuf bundle_buf(unsigned char *base) {
+  int *p = reinterpret_cast<int *>(base + (threadIdx.x >> 5) * kBundleBufBytes);
+  BundleBuf b;
+  b.cur = p; b.nxt = p + kFront; b.cand = p + 2 * kFront;
+  return b;
+}
+// The bundle as a "direction box": per axis the interval [1/d] of the reciprocal direction components of its rays
+// (+-inf when the components change sign: no constraint from that axis).  bundle_slab is the slab test in interval
+// arithmetic: a lower bound of every ray's entry distance and an upper bound of every exit distance; the box can be
+// touched by SOME ray of the bundle only if these overlap -- conservative, and tight for coherent rays even for the
+// elongated boxes of the upper levels (a bounding-sphere test lets most of them through).
+struct BundleBox { float ox, oy, oz, ilo[3], ihi[3]; };
+__device__ __forceinline__ float wredf(float v, bool want_max) {
+  int i = __float_as_int(v);
+  i = i >= 0 ? i : i ^ 0x7fffffff;                   // order-preserving map float -> int
+  i = want_max ? __reduce_max_sync(kFull, i) : __reduce_min_sync(kFull, i);
+  return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff);
+}
+template <int NR>
+__device__ __forceinline__ BundleBox bundle_box(float3 o, const float (&dx)[NR], const float (&dy)[NR], const float (&dz)[NR], const bool (&act)[NR]) {
+  float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+#pragma unroll
+  for (int r = 0; r < NR; r++)
+    if (act[r]) {
+      lo[0] = fminf(lo[0], dx[r]); hi[0] = fmaxf(hi[0], dx[r]);
+      lo[1] = fminf(lo[1], dy[r]); hi[1] = fmaxf(hi[1], dy[r]);
+      lo[2] = fminf(lo[2], dz[r]); hi[2] = fmaxf(hi[2], dz[r]);
+    }
+  BundleBox b;
+  b.ox = o.x; b.oy = o.y; b.oz = o.z;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const float dl = wredf(lo[k], false) - 2e-6f, dh = wredf(hi[k], true) + 2e-6f;   // 12u direction error and more
+    if (dl <= 0.f && dh >= 0.f) { b.ilo[k] = -INFINITY; b.ihi[k] = INFINITY; }
+    else {
+      const float i0 = __frcp_rn(dl), i1 = __frcp_rn(dh);
+      const float mn = fminf(i0, i1), mx = fmaxf(i0, i1);
+      b.ilo[k] = mn - fabsf(mn) * 1e-6f; b.ihi[k] = mx + fabsf(mx) * 1e-6f;
+    }
+  }
+  return b;
+}
+// lower bound of the entry distance of any ray of the bundle into the box, or 3e38 when no ray with t in [t0, t1] can touch it
+__device__ __forceinline__ float bundle_slab(const BundleBox &b, float lx, float ly, float lz, float hx, float hy, float hz, float t0, float t1) {
+  float tn = -3.0e38f, tf = 3.0e38f;
+  const float lo[3] = {lx - b.ox, ly - b.oy, lz - b.oz}, hi[3] = {hx - b.ox, hy - b.oy, hz - b.oz};
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const float a0 = lo[k] * b.ilo[k], a1 = lo[k] * b.ihi[k], a2 = hi[k] * b.ilo[k], a3 = hi[k] * b.ihi[k];
+    tn = fmaxf(tn, fminf(fminf(a0, a1), fminf(a2, a3)));      // (fminf / fmaxf drop the NaN of 0 * inf)
+    tf = fminf(tf, fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)));
+  }
+  tn = tn - fabsf(tn) * 1e-6f;
+  tf = tf + fabsf(tf) * 1e-6f;
+  return (tn <= tf && tn <= t1 && tf >= t0) ? tn : 3.0e38f;
+}
+
+// Gathers candidates [0, n) (n <= kCandMax) from table T (global memory) into the warp's compacted table; returns its pair count.
+__device__ __forceinline__ int bundle_fill(const Tab &T, const int *cand, int n, const WarpBuf &wb) {
+  const int lane = threadIdx.x & 31;
+  for (int k = lane; k < n; k += 32) {
+    const int id = cand[k], slot = __ldg(&T.inv[id]) & 0x3fffffff;
+    const float *src = reinterpret_cast<const float *>(T.pairs) + (slot >> 1) * 8 + (slot & 1);
+    float *dst = reinterpret_cast<float *>(wb.pairs) + (k >> 1) * 8 + (k & 1);
+    dst[0] = __ldg(src); dst[2] = __ldg(src + 2); dst[4] = __ldg(src + 4); dst[6] = __ldg(src + 6);
+    wb.perm[k] = id;
+  }
+  if (lane < kCandMax / 8) wb.gmin[lane] = -3.0e38f;
+  return cull_finish(wb, n);
+}
+
+// Walks the hierarchy; calls process(n) -- warp-uniform, consumes bb.cand[0, n), returns the new distance cutoff (a
+// negative value: the query is finished) -- whenever kCandMax candidates are collected and at the end.  Returns false
+// when a frontier overflowed (the caller falls back to per-ray traversal; nothing has been processed then... the
+// candidates processed so far are harmless: the queries are resumable and idempotent per sphere).
+template <typename F>
+__device__ __forceinline__ bool bundle_traverse(const FastArgs &a, const BundleBox &bx, float t0, float wcut, const BundleBuf &bb, F &&process) {
+  const int lane = threadIdx.x & 31;
+  int ncur = 1, ncand = 0;
+  if (lane == 0) bb.cur[0] = 0;
+  // the spheres kept out of the tree are candidates of every bundle; tested first: a hit on them (the ground) bounds
+  // the depth the bundle has to search
+  if (a.nbig > 0) {
+    if (lane < a.nbig) bb.cand[lane] = a.big[lane];
+    __syncwarp();
+    wcut = process(a.nbig);
+    if (wcut < 0.f) return true;
+  }
+  __syncwarp();
+  int *cur = bb.cur, *nxt = bb.nxt;
+  while (ncur > 0) {
+    int nnxt = 0;
+    for (int base = 0; base < ncur; base += 32) {
+      bool p0 = false, p1 = false;
+      int c0 = 0, c1 = 0;
+      if (base + lane < ncur) {
+        const rtb::BvhNode *nd = a.bvh.nodes + cur[base + lane];
+        const float4 A = __ldg(&nd->a), B = __ldg(&nd->b), C = __ldg(&nd->c);
+        const int4 D = __ldg(&nd->d);
+        c0 = D.x; c1 = D.y;
+        p0 = bundle_slab(bx, A.x, A.y, A.z, A.w, B.x, B.y, t0, wcut) < 3.0e38f;
+        p1 = bundle_slab(bx, B.z, B.w, C.x, C.y, C.z, C.w, t0, wcut) < 3.0e38f;
+      }
+      // leaves -> candidate list, internal nodes -> next frontier (ballot compaction, child 0 then child 1)
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        const bool p = k ? p1 : p0;
+        const int ch = k ? c1 : c0;
+        const unsigned ml = __ballot_sync(kFull, p && ch < 0), mi = __ballot_sync(kFull, p && ch >= 0);
+        const unsigned lt = (1u << lane) - 1u;
+        if (nnxt + __popc(mi) > kFront) return false;
+        if (p && ch >= 0) nxt[nnxt + __popc(mi & lt)] = ch;
+        nnxt += __popc(mi);
+        if (p && ch < 0) bb.cand[ncand + __popc(ml & lt)] = ~ch;
+        ncand += __popc(ml);
+        __syncwarp();
+        if (ncand > kCandList - 32) {                  // room for one more ballot's worth is gone: consume one fill now
+          wcut = process(kCandMax);
+          if (wcut < 0.f) return true;
+          const int rem = ncand - kCandMax;            // <= kCandList - kCandMax = 64: two values per lane
+          const int v0 = lane < rem ? bb.cand[kCandMax + lane] : 0, v1 = lane + 32 < rem ? bb.cand[kCandMax + lane + 32] : 0;
+          __syncwarp();
+          if (lane < rem) bb.cand[lane] = v0;
+          if (lane + 32 < rem) bb.cand[lane + 32] = v1;
+          ncand = rem;
+          __syncwarp();
+        }
+      }
+    }
+    int *t = cur; cur = nxt; nxt = t;
+    ncur = nnxt;
+    __syncwarp();
+  }
+  while (ncand > 0) {
+    const int n = min(ncand, kCandMax);
+    wcut = process(n);
+    if (wcut < 0.f) return true;
+    const int rem = ncand - n;
+    const int v0 = lane < rem ? bb.cand[n + lane] : 0, v1 = lane + 32 < rem ? bb.cand[n + lane + 32] : 0;
+    __syncwarp();
+    if (lane < rem) bb.cand[lane] = v0;
+    if (lane + 32 < rem) bb.cand[lane + 32] = v1;
+    ncand = rem;
+    __syncwarp();
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
 // warp-ballot compaction: rays still alive are appended densely to the next level's queue
 __device__ __forceinline__ void queue_push(bool want, const RayRec &rec, RayRec *q, unsigned int *count) {
   const unsigned mk = __ballot_sync(kFull, want);

@@ -166,7 +166,8 @@ __global__ void __launch_bounds__(kThreads, RT_CLOSEST_CTAS) k_closest0(const Wa
   RT_PDL_SYNC();
   const Tab camg = tab_at(a.tabs, a, 0);             // global view (gmin / perm of the streamed mode)
   const Tab cam = tab_at(tabs, a, 0);
-  const WarpBuf wb = warp_buf(smem + kSmemHeader + ((a.stage_bytes + 127u) & ~127u));   // kTabSmem only
+  const WarpBuf wb = warp_buf(smem + kSmemHeader + (kMode == kTabBvh ? 0u : ((a.stage_bytes + 127u) & ~127u)));   // kTabSmem / kTabBvh
+  const BundleBuf bb = bundle_buf(smem + kSmemHeader + kWarps * kWarpBufBytes);                                      // kTabBvh only
   unsigned ring_phase = 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char *s_rgb = smem + 64 + warp * (kWTileH * kWTileW * 3);
@@ -220,9 +221,28 @@ __global__ void __launch_bounds__(kThreads, RT_CLOSEST_CTAS) k_closest0(const Wa
       closest_shared<2>(cam, a.npairs, dx, dy, dz, live, a.d64, a.r.sph64, src, best);
     } else if (kMode == kTabBvh) {
       const float3 o = recentred(a, g_frame.cam_pos);
+      // the tile's rays descend the hierarchy as ONE bundle; a per-ray traversal only if the bundle is too wide
+      const Cone cone = warp_cone<2>(dx, dy, dz, live);
+      bool done = false;
+      if (cone.ok) {
+        ClosestQ<2> q;
+        closest_begin(q);
+        c_walks++;
+        const BundleBox bx = bundle_box<2>(o, dx, dy, dz, live);
+        done = bundle_traverse(a, bx, -1e-3f, 3.0e38f, bb, [&](int n) {
+          c_cand += (unsigned)n;
+          const int np = bundle_fill(cam, bb.cand, n, wb);
+          closest_shared_range<2>(q, wb.pairs, wb.gmin, wb.perm, 0, np, dx, dy, dz, live, a.d64, a.r.sph64, src);
+          __syncwarp();
+          return q.wcut;
+        });
+        if (done) { best[0] = q.best[0]; best[1] = q.best[1]; }
+      }
+      if (!done) {
 #pragma unroll 1
-      for (int r = 0; r < 2; r++)
-        if (live[r]) best[r] = bvh_closest_shared(a, cam, o, dx[r], dy[r], dz[r], src[r]);
+        for (int r = 0; r < 2; r++)
+          if (live[r]) best[r] = bvh_closest_shared(a, cam, o, dx[r], dy[r], dz[r], src[r]);
+      }
     } else {
       // the eight warps of the CTA walk the sorted camera table together, tile by tile
       ClosestQ<2> q;
@@ -394,7 +414,8 @@ __global__ void __launch_bounds__(kThreads, RT_SHADOW_CTAS) k_shadow(const WaveA
   RT_PDL_SYNC();
   const unsigned nh = *w.hit_count;
   if (nh == 0u || a.L == 0) return;
-  const WarpBuf wb = warp_buf(smem + kSmemHeader + ((a.stage_bytes + 127u) & ~127u));   // kTabSmem only
+  const WarpBuf wb = warp_buf(smem + kSmemHeader + (kMode == kTabBvh ? 0u : ((a.stage_bytes + 127u) & ~127u)));   // kTabSmem / kTabBvh
+  const BundleBuf bb = bundle_buf(smem + kSmemHeader + kWarps * kWarpBufBytes);                                      // kTabBvh only
   unsigned ring_phase = 0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // few hits (deep levels): one hit per lane, so that twice as many warps share the work
@@ -462,10 +483,28 @@ __global__ void __launch_bounds__(kThreads, RT_SHADOW_CTAS) k_shadow(const WaveA
       int n64 = 0;
       if (kMode == kTabBvh) {
         const float3 o = recentred(a, g_frame.light_pos[l]);
+        occ[0] = occ[1] = false;
+        if (__any_sync(kFull, want[0] || want[1])) {
+          // the block's shadow rays towards this light descend the hierarchy as one bundle (from the light)
+          const Cone cone = warp_cone<2>(dx, dy, dz, want);
+          ShadowQ<2> q;
+          shadow_begin<2>(q, T.inv, so, want, self, cosl);
+          q.sslot[0] = q.sslot[1] = -1;              // (no pre-clearing of the lit self sphere here: slow_shadow skips it)
+          bool done = false;
+          if (cone.ok) c_walks++;
+          if (cone.ok)
+            done = bundle_traverse(a, bundle_box<2>(o, dx, dy, dz, want), -(kEps + fmaxf(q.m[0], q.m[1])), q.wcut, bb, [&](int n) {
+              c_cand += (unsigned)n;
+              const int np = bundle_fill(T, bb.cand, n, wb);
+              shadow_range<2>(q, wb.pairs, wb.gmin, wb.perm, 0, np, l, dx, dy, dz, so, self, cosl, ppc, a.d64, a.r.sph64, n64);
+              __syncwarp();
+              return q.wcut < -1.0e38f ? -1.0f : q.wcut;
+            });
 #pragma unroll 1
-        for (int r = 0; r < 2; r++) {
-          occ[r] = false;
-          if (want[r]) occ[r] = bvh_shadow(a, T, o, l, dx[r], dy[r], dz[r], so[r], self[r], cosl[r], ppc[r], n64);
+          for (int r = 0; r < 2; r++) {
+            occ[r] = q.occ[r];
+            if (!done && q.open[r]) occ[r] = bvh_shadow(a, T, o, l, dx[r], dy[r], dz[r], so[r], self[r], cosl[r], ppc[r], n64);
+          }
         }
       } else if (kMode != kTabStream) {
         occ[0] = occ[1] = false;

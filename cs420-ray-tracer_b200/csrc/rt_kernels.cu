@@ -329,6 +329,8 @@ void launch(K kernel, int grid, int block, size_t smem, cudaStream_t stream, boo
   cudaLaunchKernelEx(&cfg, kernel, arg);
 }
 // dynamic shared memory of a kernel that stages `bytes` of tables: header | tables | per-warp compacted tables
+// ... of the LBVH level-0 kernels: header | per-warp compacted tables | per-warp bundle-traversal frontiers
+inline size_t bvh_smem() { return rtf::kSmemHeader + rtf::kWarps * (size_t)(rtf::kWarpBufBytes + rtf::kBundleBufBytes); }
 inline size_t staged_smem(size_t bytes) { return rtf::kSmemHeader + ((bytes + 127) & ~(size_t)127) + rtf::kWarps * (size_t)rtf::kWarpBufBytes; }
 // control words (u32): [0] tile counter; per level k <= 33: tail chunk counter, shadow / shade / closest work
 // counters, hits of level k, rays entering level k
@@ -411,7 +413,7 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
       a.stage_bytes = fs->tstride;
       const size_t smem = cam_smem ? staged_smem(a.stage_bytes) : stream_smem;
       const int cta_tiles = (a.nwtiles + rtf::kWarps - 1) / rtf::kWarps;
-      if (bvh) { int g = resident_grid(rtf::k_closest0<rtf::kTabBvh>, rtf::kSmemHeader, w->num_sms); launch(rtf::k_closest0<rtf::kTabBvh>, g < cta_tiles ? g : cta_tiles, rtf::kThreads, rtf::kSmemHeader, stream, false, wa); }
+      if (bvh) { int g = resident_grid(rtf::k_closest0<rtf::kTabBvh>, bvh_smem(), w->num_sms); launch(rtf::k_closest0<rtf::kTabBvh>, g < cta_tiles ? g : cta_tiles, rtf::kThreads, bvh_smem(), stream, false, wa); }
       else if (cam_smem) { int g = resident_grid(rtf::k_closest0<rtf::kTabSmem>, smem, w->num_sms); launch(rtf::k_closest0<rtf::kTabSmem>, g < cta_tiles ? g : cta_tiles, rtf::kThreads, smem, stream, false, wa); }
       else { int g = resident_grid(rtf::k_closest0<rtf::kTabStream>, smem, w->num_sms); launch(rtf::k_closest0<rtf::kTabStream>, g < cta_tiles ? g : cta_tiles, rtf::kThreads, smem, stream, false, wa); }
     } else {
@@ -443,7 +445,7 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
       // camera-ray hits are coherent: the warp-synchronous kernel wins at level 0 (4.3 vs 5.9 ms on config 4); from level 1 on
       // the rays are not, and the dynamic-fetch kernel does (levels >= 1 of config 5: 57.6 -> 38 ms)
       if (bvh && bvh_dyn && level > 0) launch(rtf::k_shadow_dyn, resident_grid(rtf::k_shadow_dyn, 0, w->num_sms), rtf::kThreads, 0, stream, pdl, wa);
-      else if (bvh) launch(rtf::k_shadow<rtf::kTabBvh>, resident_grid(rtf::k_shadow<rtf::kTabBvh>, rtf::kSmemHeader, w->num_sms), rtf::kThreads, rtf::kSmemHeader, stream, pdl, wa);
+      else if (bvh) launch(rtf::k_shadow<rtf::kTabBvh>, resident_grid(rtf::k_shadow<rtf::kTabBvh>, bvh_smem(), w->num_sms), rtf::kThreads, bvh_smem(), stream, pdl, wa);
       else if (light_smem) launch(rtf::k_shadow<rtf::kTabSmem>, resident_grid(rtf::k_shadow<rtf::kTabSmem>, smem, w->num_sms), rtf::kThreads, smem, stream, pdl, wa);
       else launch(rtf::k_shadow<rtf::kTabStream>, resident_grid(rtf::k_shadow<rtf::kTabStream>, smem, w->num_sms), rtf::kThreads, smem, stream, pdl, wa);
       launches++;
