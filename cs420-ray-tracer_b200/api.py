@@ -37,7 +37,7 @@ class RtStats(C.Structure):
         ("fp64_intersections", C.c_uint64), ("sphere_tests", C.c_uint64),
         ("filter_violations", C.c_uint64),
         ("kernel_launches", C.c_int32), ("rows_rendered", C.c_int32),
-        ("bundle_walks", C.c_uint64), ("bundle_candidates", C.c_uint64),
+        ("bundle_walks", C.c_uint64), ("bundle_candidates", C.c_uint64), ("bundle_fallbacks", C.c_uint64),
     ]
 
     def as_dict(self):

@@ -897,6 +897,7 @@ __device__ __forceinline__ bool bvh_shadow(const FastArgs &a, const Tab T, float
 // (camera tiles, the shadow rays of one hit block): incoherent ones use the per-lane traversals above.
 constexpr int kFront = 192;                          // frontier capacity (nodes per BVH level that touch the cone)
 constexpr int kCandList = 128;                       // candidate list capacity; processed (and emptied) in fills of kCandMax
+constexpr int kBundleMaxCand = 1 << 20;              // candidate budget of one bundle (measured: giving up early at 96 did not pay; the frontier bound decides)
 constexpr unsigned kBundleBufBytes = (2 * kFront + kCandList) * 4;
 struct BundleBuf { int *cur, *nxt, *cand; };
 __device__ __forceinline__ BundleBuf bundle_buf(unsigned char *base) {
@@ -977,7 +978,7 @@ __device__ __forceinline__ int bundle_fill(const Tab &T, const int *cand, int n,
 template <typename F>
 __device__ __forceinline__ bool bundle_traverse(const FastArgs &a, const BundleBox &bx, float t0, float wcut, const BundleBuf &bb, F &&process) {
   const int lane = threadIdx.x & 31;
-  int ncur = 1, ncand = 0;
+  int ncur = 1, ncand = 0, ntotal = 0;
   if (lane == 0) bb.cur[0] = 0;
   // the spheres kept out of the tree are candidates of every bundle; tested first: a hit on them (the ground) bounds
   // the depth the bundle has to search
@@ -1014,6 +1015,8 @@ __device__ __forceinline__ bool bundle_traverse(const FastArgs &a, const BundleB
         nnxt += __popc(mi);
         if (p && ch < 0) bb.cand[ncand + __popc(ml & lt)] = ~ch;
         ncand += __popc(ml);
+        ntotal += __popc(ml);
+        if (ntotal > kBundleMaxCand) return false;     // a wide bundle: per-ray traversals are cheaper from here on
         __syncwarp();
         if (ncand > kCandList - 32) {                  // room for one more ballot's worth is gone: consume one fill now
           wcut = process(kCandMax);

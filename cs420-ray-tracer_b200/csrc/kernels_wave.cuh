@@ -70,7 +70,7 @@ __device__ __forceinline__ void hit_block(const WaveArgs &w, unsigned m0, unsign
 // 32-bit per-thread counters, reduced once per warp at kernel end (cold path, out of line)
 __device__ __noinline__ void flush_counts(unsigned long long *counters, int level, unsigned closest, unsigned hits, unsigned shadow,
                                           unsigned occluded, unsigned fp64, unsigned violations, unsigned long long n_spheres,
-                                          unsigned cand = 0, unsigned walks = 0) {
+                                          unsigned cand = 0, unsigned walks = 0, unsigned fallbacks = 0) {
   unsigned v[6] = {closest, hits, shadow, occluded, fp64, violations};
 #pragma unroll
   for (int k = 0; k < 6; k++) v[k] = __reduce_add_sync(kFull, v[k]);
@@ -83,6 +83,7 @@ __device__ __noinline__ void flush_counts(unsigned long long *counters, int leve
     if (v[5]) atomicAdd(&counters[RT_CNT_VIOLATIONS], (unsigned long long)v[5]);
     if (v[0] + v[2]) atomicAdd(&counters[RT_CNT_TESTS], (unsigned long long)(v[0] + v[2]) * n_spheres);
     if (walks) { atomicAdd(&counters[RT_CNT_CAND], (unsigned long long)cand); atomicAdd(&counters[RT_CNT_WALKS], (unsigned long long)walks); }   // warp-uniform
+    if (fallbacks) atomicAdd(&counters[RT_CNT_FALLBACKS], (unsigned long long)fallbacks);
   }
 }
 
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(kThreads, RT_CLOSEST_CTAS) k_closest0(const Wa
   const int W = a.r.W, rows = a.r.bands.local_rows, depth = a.r.max_depth;
   const bool kBytes = a.r.fb == nullptr && a.r.out_remap != 1;   // 8-bit frame (compact or assembled): staged tile rows, 128-bit stores
   const bool kFrame = a.r.out_remap == 2;                        // rows go to their image positions (maybe in a peer GPU's memory)
-  unsigned c_closest = 0, c_hits = 0, c_fp64 = 0, c_viol = 0, c_cand = 0, c_walks = 0;
+  unsigned c_closest = 0, c_hits = 0, c_fp64 = 0, c_viol = 0, c_cand = 0, c_walks = 0, c_fall = 0;
   for (;;) {
     int tile;
     if (kMode == kTabStream) {
@@ -239,6 +240,7 @@ __global__ void __launch_bounds__(kThreads, RT_CLOSEST_CTAS) k_closest0(const Wa
         if (done) { best[0] = q.best[0]; best[1] = q.best[1]; }
       }
       if (!done) {
+        c_fall++;
 #pragma unroll 1
         for (int r = 0; r < 2; r++)
           if (live[r]) best[r] = bvh_closest_shared(a, cam, o, dx[r], dy[r], dz[r], src[r]);
@@ -314,7 +316,7 @@ __global__ void __launch_bounds__(kThreads, RT_CLOSEST_CTAS) k_closest0(const Wa
     }
     __syncwarp();
   }
-  if (a.r.counters) flush_counts(a.r.counters, 0, c_closest, c_hits, 0, 0, c_fp64, c_viol, (unsigned long long)a.N, c_cand, c_walks);
+  if (a.r.counters) flush_counts(a.r.counters, 0, c_closest, c_hits, 0, 0, c_fp64, c_viol, (unsigned long long)a.N, c_cand, c_walks, c_fall);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -425,7 +427,7 @@ __global__ void __launch_bounds__(kThreads, RT_SHADOW_CTAS) k_shadow(const WaveA
   // as many, L times shorter items, so the warps of the machine share them evenly
   const bool lightpar = kMode != kTabStream && nchunks < 4u * gridDim.x * (unsigned)kWarps;
   const unsigned nitems = lightpar ? nchunks * (unsigned)a.L : nchunks;
-  unsigned c_fp64 = 0, c_cand = 0, c_walks = 0;
+  unsigned c_fp64 = 0, c_cand = 0, c_walks = 0, c_fall = 0;
   for (;;) {
     unsigned chunk;
     if (kMode == kTabStream) {
@@ -500,6 +502,7 @@ __global__ void __launch_bounds__(kThreads, RT_SHADOW_CTAS) k_shadow(const WaveA
               __syncwarp();
               return q.wcut < -1.0e38f ? -1.0f : q.wcut;
             });
+          if (!done) c_fall++;
 #pragma unroll 1
           for (int r = 0; r < 2; r++) {
             occ[r] = q.occ[r];
@@ -542,7 +545,7 @@ __global__ void __launch_bounds__(kThreads, RT_SHADOW_CTAS) k_shadow(const WaveA
       else if (have[0]) o[0] = (unsigned char)o0;
     }
   }
-  if (a.r.counters) flush_counts(a.r.counters, 99, 0, 0, 0, 0, c_fp64, 0, 0, c_cand, c_walks);
+  if (a.r.counters) flush_counts(a.r.counters, 99, 0, 0, 0, 0, c_fp64, 0, 0, c_cand, c_walks, c_fall);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -292,6 +292,7 @@ static void fill_stats(rt_stats *st, const unsigned long long *cnt) {
   st->filter_violations = cnt[RT_CNT_VIOLATIONS];
   st->bundle_walks = cnt[RT_CNT_WALKS];
   st->bundle_candidates = cnt[RT_CNT_CAND];
+  st->bundle_fallbacks = cnt[RT_CNT_FALLBACKS];
   for (int k = 0; k < RT_MAX_LEVELS; k++) st->alive[k] = cnt[RT_CNT_ALIVE0 + k];
 }
 

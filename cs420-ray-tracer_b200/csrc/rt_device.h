@@ -48,6 +48,7 @@ enum {
   RT_CNT_ALIVE0 = 8,   // .. RT_CNT_ALIVE0 + 31
   RT_CNT_CAND = 40,    // spheres left after bundle culling, summed over warp-level table walks
   RT_CNT_WALKS = 41,   // warp-level table walks that were bundle-culled
+  RT_CNT_FALLBACKS = 42,  // LBVH bundles that fell back to one traversal per ray (too wide / frontier overflow)
   RT_CNT_TOTAL = 48
 };
 

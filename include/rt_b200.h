@@ -77,6 +77,7 @@ typedef struct rt_stats {
   int32_t rows_rendered;        /* image rows this call produced (all of H unless banded)      */
   uint64_t bundle_walks;        /* warp-level table walks that used bundle culling  */
   uint64_t bundle_candidates;   /* spheres left after culling, summed over those walks          */
+  uint64_t bundle_fallbacks;    /* LBVH bundles that fell back to one traversal per ray          */
 } rt_stats;
 
 /* ---- library ------------------------------------------------------------------------- */

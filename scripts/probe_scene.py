@@ -25,9 +25,9 @@ for _ in range(reps):
     ms.append((st.ms_device, st.ms_closest0, st.ms_shadow0, st.ms_level0))
 ms = sorted(ms)[len(ms) // 2]
 rays = st.closest_queries + st.shadow_queries
-print("%s %dx%d d%d: frame %.3f ms (closest0 %.3f shadow0 %.3f level0 %.3f)  rays %d  %.1f Mrays/s  fp64 %d viol %d launches %d alive %s cand/walk %.1f (%d walks)" % (
+print("%s %dx%d d%d: frame %.3f ms (closest0 %.3f shadow0 %.3f level0 %.3f)  rays %d  %.1f Mrays/s  fp64 %d viol %d launches %d alive %s cand/walk %.1f (%d walks, %d fallbacks)" % (
     name, W, H, D, ms[0], ms[1], ms[2], ms[3], rays, rays / ms[0] / 1e3, st.fp64_intersections, st.filter_violations, st.kernel_launches,
-    [int(x) for x in st.alive[:D]], st.bundle_candidates / max(1, st.bundle_walks), st.bundle_walks))
+    [int(x) for x in st.alive[:D]], st.bundle_candidates / max(1, st.bundle_walks), st.bundle_walks, st.bundle_fallbacks))
 if check:
     rgb, hit, mask, st = r.render_debug(W, H, D)
     with rtb200.Renderer(0, mode="exact") as e:
