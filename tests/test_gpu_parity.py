@@ -147,6 +147,24 @@ def test_row_bands_reassemble_to_the_full_frame(rt, renderers, scenes, band_h, n
     assert np.array_equal(out, full)
 
 
+def test_row_bands_with_supersampling(rt, scenes):
+    """rt_render_bands with antialias on: the bands of the 2x2-supersampled frame reassemble to rt_render's."""
+    import torch
+    W, H, D, band_h, n = 200, 114, 4, 16, 3
+    with rt.Renderer(0) as r:
+        r.set_option("antialias", 1)
+        r.upload(scenes["complex"])
+        full, _ = r.render(W, H, D)
+        out = np.zeros_like(full)
+        for rank in range(n):
+            rows = rt.band_row_list(H, band_h, rank, n)
+            buf = torch.zeros(len(rows) * W * 3 + 16, dtype=torch.uint8, device="cuda:0")
+            torch.cuda.synchronize()
+            r.render_bands_device(W, H, D, band_h, rank, n, buf.data_ptr(), None, want_stats=True)
+            out[rows] = buf[:len(rows) * W * 3].cpu().numpy().reshape(len(rows), W, 3)
+    assert np.array_equal(out, full)
+
+
 @pytest.mark.parametrize("n,seed,W,H,D,modes", [(10000, 420, 480, 270, 5, ("tables", "bvh")), (100000, 421, 384, 216, 8, ("bvh",))])
 def test_large_synthetic_against_fp64_brute_force(rt, renderers, n, seed, W, H, D, modes):
     """BASELINE configs 4 (10k spheres, streamed tables and LBVH) and 5 (100k spheres, device-built LBVH)
