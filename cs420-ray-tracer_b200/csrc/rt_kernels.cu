@@ -7,6 +7,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -79,22 +80,37 @@ constexpr int kBvhAutoSpheres = 1024;   // automatic mode: scenes from this size
 // Device build of the LBVH (bvh.cuh) over cen[i] = (c_i - C0, r_i) in FP32; eps inflates every box.
 static int bvh_build(RtFastScene *fs, const std::vector<float4> &cen, const std::vector<int> &orig, float eps, cudaStream_t stream) {
   const int n = (int)cen.size(), nleaf = (n + rtb::kLeafSize - 1) / rtb::kLeafSize, nint = nleaf > 1 ? nleaf - 1 : 1;
-  float4 *d_cen = nullptr, *leaf_lo = nullptr, *leaf_hi = nullptr, *node_lo = nullptr, *node_hi = nullptr;
-  unsigned *keys[2] = {nullptr, nullptr}, *leaf_key = nullptr;
-  int *vals[2] = {nullptr, nullptr}, *d_orig = nullptr, *bounds = nullptr, *left = nullptr, *right = nullptr, *par_i = nullptr, *par_l = nullptr, *flags = nullptr;
+  // one scratch arena and the node array, both kept (grow-only) across uploads: cudaMalloc / cudaFree cost milliseconds
+  // each once gigabytes of frame buffers are allocated, and a build needs seventeen arrays
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   int rc = 0;
 #define BV(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = -(int)e_; goto done; } } while (0)
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_cen = carve((size_t)n * 16), o_orig = carve((size_t)n * 4), o_k0 = carve((size_t)n * 4), o_k1 = carve((size_t)n * 4),
+               o_v0 = carve((size_t)n * 4), o_v1 = carve((size_t)n * 4), o_bounds = carve(6 * 4), o_llo = carve((size_t)nleaf * 16),
+               o_lhi = carve((size_t)nleaf * 16), o_lkey = carve((size_t)nleaf * 4), o_nlo = carve((size_t)nint * 16),
+               o_nhi = carve((size_t)nint * 16), o_left = carve((size_t)nint * 4), o_right = carve((size_t)nint * 4),
+               o_pi = carve((size_t)nint * 4), o_pl = carve((size_t)nleaf * 4), o_flags = carve((size_t)nint * 4);
+  if (fs->bvh_scratch_cap < off) {
+    cudaFree(fs->bvh_scratch); fs->bvh_scratch = nullptr; fs->bvh_scratch_cap = 0;
+    if (cudaMalloc(&fs->bvh_scratch, off) != cudaSuccess) return -(int)cudaErrorMemoryAllocation;
+    fs->bvh_scratch_cap = off;
+  }
+  if (fs->bvh_nodes_cap < (size_t)nint * sizeof(rtb::BvhNode)) {
+    cudaFree(fs->bvh_nodes_buf); fs->bvh_nodes_buf = nullptr; fs->bvh_nodes_cap = 0;
+    if (cudaMalloc(&fs->bvh_nodes_buf, (size_t)nint * sizeof(rtb::BvhNode)) != cudaSuccess) return -(int)cudaErrorMemoryAllocation;
+    fs->bvh_nodes_cap = (size_t)nint * sizeof(rtb::BvhNode);
+  }
+  unsigned char *sc = (unsigned char *)fs->bvh_scratch;
+  float4 *d_cen = (float4 *)(sc + o_cen), *leaf_lo = (float4 *)(sc + o_llo), *leaf_hi = (float4 *)(sc + o_lhi),
+         *node_lo = (float4 *)(sc + o_nlo), *node_hi = (float4 *)(sc + o_nhi);
+  unsigned *keys[2] = {(unsigned *)(sc + o_k0), (unsigned *)(sc + o_k1)}, *leaf_key = (unsigned *)(sc + o_lkey);
+  int *vals[2] = {(int *)(sc + o_v0), (int *)(sc + o_v1)}, *d_orig = (int *)(sc + o_orig), *bounds = (int *)(sc + o_bounds),
+      *left = (int *)(sc + o_left), *right = (int *)(sc + o_right), *par_i = (int *)(sc + o_pi), *par_l = (int *)(sc + o_pl),
+      *flags = (int *)(sc + o_flags);
+  fs->bvh_nodes = fs->bvh_nodes_buf;
   BV(cudaEventCreate(&e0)); BV(cudaEventCreate(&e1));
-  BV(cudaMalloc(&d_cen, (size_t)n * 16));
-  BV(cudaMalloc(&d_orig, (size_t)n * 4));
-  for (int k = 0; k < 2; k++) { BV(cudaMalloc(&keys[k], (size_t)n * 4)); BV(cudaMalloc(&vals[k], (size_t)n * 4)); }
-  BV(cudaMalloc(&bounds, 6 * 4));
-  BV(cudaMalloc(&leaf_lo, (size_t)nleaf * 16)); BV(cudaMalloc(&leaf_hi, (size_t)nleaf * 16)); BV(cudaMalloc(&leaf_key, (size_t)nleaf * 4));
-  BV(cudaMalloc(&node_lo, (size_t)nint * 16)); BV(cudaMalloc(&node_hi, (size_t)nint * 16));
-  BV(cudaMalloc(&left, (size_t)nint * 4)); BV(cudaMalloc(&right, (size_t)nint * 4)); BV(cudaMalloc(&par_i, (size_t)nint * 4));
-  BV(cudaMalloc(&par_l, (size_t)nleaf * 4)); BV(cudaMalloc(&flags, (size_t)nint * 4));
-  BV(cudaMalloc(&fs->bvh_nodes, (size_t)nint * sizeof(rtb::BvhNode)));
   BV(cudaMemcpyAsync(d_cen, cen.data(), (size_t)n * 16, cudaMemcpyHostToDevice, stream));
   BV(cudaMemcpyAsync(d_orig, orig.data(), (size_t)n * 4, cudaMemcpyHostToDevice, stream));
   {
@@ -126,12 +142,9 @@ static int bvh_build(RtFastScene *fs, const std::vector<float4> &cen, const std:
   fs->bvh_nleaf = nleaf;
 done:
 #undef BV
-  cudaFree(d_cen); cudaFree(d_orig); cudaFree(keys[0]); cudaFree(keys[1]); cudaFree(vals[0]); cudaFree(vals[1]); cudaFree(bounds);
-  cudaFree(leaf_lo); cudaFree(leaf_hi); cudaFree(leaf_key); cudaFree(node_lo); cudaFree(node_hi);
-  cudaFree(left); cudaFree(right); cudaFree(par_i); cudaFree(par_l); cudaFree(flags);
   if (e0) cudaEventDestroy(e0);
   if (e1) cudaEventDestroy(e1);
-  if (rc != 0) { cudaFree(fs->bvh_nodes); cudaFree(fs->bvh_leaves); fs->bvh_nodes = fs->bvh_leaves = nullptr; }
+  if (rc != 0) fs->bvh_nodes = nullptr;
   return rc;
 }
 
@@ -187,7 +200,7 @@ int rtk_fast_build_scene(RtFastScene *fs, const double *sph, int N, const RtFram
   };
   std::vector<int> order((size_t)(N > 0 ? N : 1));
   std::vector<double> key((size_t)(N > 0 ? N : 1));
-  for (int t = 0; t <= L; t++) {
+  auto build_table = [&](int t, std::vector<int> &order, std::vector<double> &key) {
     unsigned char *base = h.data() + (size_t)t * fs->tstride;
     float4 *pairs = reinterpret_cast<float4 *>(base);
     float *gmin = reinterpret_cast<float *>(base + fs->gmin_off);
@@ -236,6 +249,15 @@ int rtk_fast_build_scene(RtFastScene *fs, const double *sph, int N, const RtFram
       const double k = key[order[slot]];
       gmin[g] = float_down(k - std::fabs(k) * 1e-6 - 1e-6 - delta64);
     }
+  };
+  // the (1+L) tables are independent: large scenes build them on separate host threads
+  if (N >= 4096 && L >= 1) {
+    std::vector<std::thread> th;
+    for (int t = 0; t <= L; t++)
+      th.emplace_back([&, t]() { std::vector<int> o2((size_t)N); std::vector<double> k2((size_t)N); build_table(t, o2, k2); });
+    for (auto &x : th) x.join();
+  } else {
+    for (int t = 0; t <= L; t++) build_table(t, order, key);
   }
   {
     float4 *pairs = reinterpret_cast<float4 *>(h.data() + (size_t)(L + 1) * fs->tstride);
@@ -287,8 +309,11 @@ int rtk_fast_build_scene(RtFastScene *fs, const double *sph, int N, const RtFram
 }
 
 void rtk_fast_free_scene(RtFastScene *fs, int release_tables) {
-  if (release_tables) { cudaFree(fs->tabs); fs->tabs = nullptr; fs->tabs_cap = 0; }
-  cudaFree(fs->bvh_nodes); cudaFree(fs->bvh_leaves);
+  if (release_tables) {
+    cudaFree(fs->tabs); fs->tabs = nullptr; fs->tabs_cap = 0;
+    cudaFree(fs->bvh_nodes_buf); cudaFree(fs->bvh_scratch);
+    fs->bvh_nodes_buf = fs->bvh_scratch = nullptr; fs->bvh_nodes_cap = fs->bvh_scratch_cap = 0;
+  }
   fs->bvh_nodes = fs->bvh_leaves = nullptr; fs->bvh_nleaf = 0;
 }
 

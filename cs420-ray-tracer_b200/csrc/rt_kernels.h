@@ -26,7 +26,9 @@ struct RtFastScene {
   float g_dtmax;          // additive bound of the general filter's centre projection
   double c0[3];           // recentring offset of the general table
   // device-built LBVH over the recentred spheres (bvh.cuh); built when the scene has >= bvh_min spheres
-  void *bvh_nodes, *bvh_leaves;
+  void *bvh_nodes, *bvh_leaves;   // bvh_nodes = bvh_nodes_buf when the current scene has a hierarchy, else NULL
+  void *bvh_nodes_buf, *bvh_scratch;   // grow-only allocations kept across uploads
+  size_t bvh_nodes_cap, bvh_scratch_cap;
   int bvh_nleaf;
   int nbig, big[8];       // spheres kept out of the LBVH because their boxes would cover most of it
   double bvh_build_ms;    // device time of the build
