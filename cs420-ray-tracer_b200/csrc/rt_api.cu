@@ -114,10 +114,7 @@ extern "C" int rt_create(int device, rt_ctx **out) {
 }
 
 static void free_scene(rt_ctx *c) {
-  cudaFree(c->d_sph64); c->d_sph64 = nullptr;
-  cudaFree(c->d_mat); c->d_mat = nullptr;
-  cudaFree(c->d_matx); c->d_matx = nullptr;
-  c->scene_cap = 0;
+  c->d_sph64 = nullptr; c->d_mat = nullptr; c->d_matx = nullptr;   // (they point into the table arena)
   rtk_fast_free_scene(&c->fast, 1);
   c->have_scene = false;
 }
@@ -202,30 +199,10 @@ extern "C" int rt_upload_scene(rt_ctx *c, const double *spheres, int N, const do
   for (int k = 0; k < 3; k++) f.ambient[k] = (float)ambient[k];
   f.nlights = L; f.nspheres = N;
 
-  std::vector<double4> s64((size_t)(N > 0 ? N : 1));
-  std::vector<float4> mat((size_t)(N > 0 ? N : 1));
-  std::vector<float2> matx((size_t)(N > 0 ? N : 1));
-  for (int i = 0; i < N; i++) {
-    const double *r = spheres + (size_t)i * RT_SPHERE_STRIDE;
-    s64[i] = make_double4(r[0], r[1], r[2], r[3] * r[3]);
-    mat[i] = make_float4((float)r[4], (float)r[5], (float)r[6], (float)r[7]);
-    matx[i] = make_float2((float)r[9], r[7] > 0 ? 1.0f : 0.0f);   // recurse flag decided in double
-  }
-  size_t n1 = (size_t)(N > 0 ? N : 1);
-  if (c->scene_cap < n1) {
-    cudaFree(c->d_sph64); cudaFree(c->d_mat); cudaFree(c->d_matx);
-    c->d_sph64 = nullptr; c->d_mat = nullptr; c->d_matx = nullptr; c->scene_cap = 0;
-    RT_CUDA(cudaMalloc(&c->d_sph64, n1 * sizeof(double4)));
-    RT_CUDA(cudaMalloc(&c->d_mat, n1 * sizeof(float4)));
-    RT_CUDA(cudaMalloc(&c->d_matx, n1 * sizeof(float2)));
-    c->scene_cap = n1;
-  }
-  RT_CUDA(cudaMemcpyAsync(c->d_sph64, s64.data(), n1 * sizeof(double4), cudaMemcpyHostToDevice, c->stream));
-  RT_CUDA(cudaMemcpyAsync(c->d_mat, mat.data(), n1 * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
-  RT_CUDA(cudaMemcpyAsync(c->d_matx, matx.data(), n1 * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+  // exact geometry, materials and the FP32 filter tables: one staged arena, one host->device copy (rt_kernels.cu)
   int r = rtk_fast_build_scene(&c->fast, spheres, N, &f, c->accel, c->stream);
   if (r != 0) return rt_fail(RT_ERR_CUDA, std::string("rt_upload_scene: filter table build failed: ") + cudaGetErrorString((cudaError_t)-r));
-  RT_CUDA(cudaStreamSynchronize(c->stream));
+  c->d_sph64 = (double4 *)c->fast.sph64; c->d_mat = (float4 *)c->fast.mat; c->d_matx = (float2 *)c->fast.matx;
   c->scene_version++;
   c->have_scene = true;
   return RT_OK;

@@ -193,7 +193,30 @@ int rtk_fast_build_scene(RtFastScene *fs, const double *sph, int N, const RtFram
   fs->bytes_primary = (size_t)(L + 1) * fs->tstride;
   fs->bytes_bounce = (size_t)L * fs->tstride + pairs_bytes;
   const size_t total = (size_t)(L + 1) * fs->tstride + pairs_bytes;
-  std::vector<unsigned char> h(total, 0);
+  // arena = tables | sph64 | mat | matx, staged in one pinned buffer (grow-only)
+  const size_t n1 = (size_t)(N > 0 ? N : 1);
+  const size_t o_s64 = (total + 255) & ~(size_t)255, o_mat = o_s64 + n1 * sizeof(double4), o_matx = o_mat + n1 * sizeof(float4);
+  const size_t arena = ((o_matx + n1 * sizeof(float2)) + 255) & ~(size_t)255;
+  if (fs->h_stage_cap < arena) {
+    if (fs->h_stage) cudaFreeHost(fs->h_stage);
+    fs->h_stage = nullptr; fs->h_stage_cap = 0;
+    RTK_TRY(cudaHostAlloc(&fs->h_stage, arena, cudaHostAllocDefault));
+    fs->h_stage_cap = arena;
+  }
+  struct { unsigned char *p; unsigned char *data() const { return p; } } h = {(unsigned char *)fs->h_stage};
+  memset(h.p, 0, total);
+  {
+    double4 *s64 = reinterpret_cast<double4 *>(h.p + o_s64);
+    float4 *mat = reinterpret_cast<float4 *>(h.p + o_mat);
+    float2 *matx = reinterpret_cast<float2 *>(h.p + o_matx);
+    for (int i = 0; i < N; i++) {
+      const double *r = sph + (size_t)i * 10;
+      s64[i] = make_double4(r[0], r[1], r[2], r[3] * r[3]);
+      mat[i] = make_float4((float)r[4], (float)r[5], (float)r[6], (float)r[7]);
+      matx[i] = make_float2((float)r[9], r[7] > 0 ? 1.0f : 0.0f);   // recurse flag decided in double
+    }
+    if (N == 0) { s64[0] = make_double4(0, 0, 0, 0); mat[0] = make_float4(0, 0, 0, 0); matx[0] = make_float2(0, 0); }
+  }
   auto put = [&](float4 *pairs, int slot, float x, float y, float z, float w) {
     float4 *A = pairs + (size_t)(slot >> 1) * 2, *B = A + 1;
     if (slot & 1) { A->y = x; A->w = y; B->y = z; B->w = w; } else { A->x = x; A->z = y; B->x = z; B->z = w; }
@@ -269,12 +292,13 @@ int rtk_fast_build_scene(RtFastScene *fs, const double *sph, int N, const RtFram
       put(pairs, i, (float)(s[0] - fs->c0[0]), (float)(s[1] - fs->c0[1]), (float)(s[2] - fs->c0[2]), float_up(rho));
     }
   }
-  if (fs->tabs_cap < total) {
+  if (fs->tabs_cap < arena) {
     cudaFree(fs->tabs); fs->tabs = nullptr; fs->tabs_cap = 0;
-    RTK_TRY(cudaMalloc(&fs->tabs, total));
-    fs->tabs_cap = total;
+    RTK_TRY(cudaMalloc(&fs->tabs, arena));
+    fs->tabs_cap = arena;
   }
-  RTK_TRY(cudaMemcpyAsync(fs->tabs, h.data(), total, cudaMemcpyHostToDevice, stream));
+  fs->sph64 = (unsigned char *)fs->tabs + o_s64; fs->mat = (unsigned char *)fs->tabs + o_mat; fs->matx = (unsigned char *)fs->tabs + o_matx;
+  RTK_TRY(cudaMemcpyAsync(fs->tabs, h.data(), arena, cudaMemcpyHostToDevice, stream));
   RTK_TRY(cudaStreamSynchronize(stream));   // h goes out of scope
   fs->bvh_nodes = fs->bvh_leaves = nullptr; fs->bvh_nleaf = 0; fs->bvh_build_ms = 0; fs->nbig = 0;
   if (N > 0 && (accel == 2 || (accel == 0 && N >= kBvhAutoSpheres))) {
@@ -311,6 +335,9 @@ int rtk_fast_build_scene(RtFastScene *fs, const double *sph, int N, const RtFram
 void rtk_fast_free_scene(RtFastScene *fs, int release_tables) {
   if (release_tables) {
     cudaFree(fs->tabs); fs->tabs = nullptr; fs->tabs_cap = 0;
+    if (fs->h_stage) cudaFreeHost(fs->h_stage);
+    fs->h_stage = nullptr; fs->h_stage_cap = 0;
+    fs->sph64 = fs->mat = fs->matx = nullptr;
     cudaFree(fs->bvh_nodes_buf); cudaFree(fs->bvh_scratch);
     fs->bvh_nodes_buf = fs->bvh_scratch = nullptr; fs->bvh_nodes_cap = fs->bvh_scratch_cap = 0;
   }

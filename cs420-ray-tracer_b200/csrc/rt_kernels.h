@@ -17,6 +17,10 @@ struct RtFastScene {
   int N, L, npairs, ngroups;
   void *tabs;             // device: (1+L) shared-origin tables (pairs | gmin | perm), then the general table
   size_t tabs_cap;        // bytes allocated behind tabs (reused by the next upload when large enough)
+  // the exact geometry / materials live in the same device arena, behind the tables: ONE pinned staging buffer and ONE
+  // host->device copy per upload
+  void *sph64, *mat, *matx;   // device: N x double4, N x float4, N x float2
+  void *h_stage; size_t h_stage_cap;   // pinned host staging of the whole arena
   unsigned tstride;       // bytes per shared-origin table
   unsigned gmin_off, perm_off, inv_off, cullA_off, cullB_off;
   size_t bytes_primary;   // staged by k_primary: (1+L) * tstride
