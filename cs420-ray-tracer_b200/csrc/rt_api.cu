@@ -60,7 +60,6 @@ struct rt_ctx {
   double4 *d_sph64 = nullptr;
   float4 *d_mat = nullptr;
   float2 *d_matx = nullptr;
-  size_t scene_cap = 0;  // spheres the three arrays above can hold (kept across uploads: cudaMalloc/cudaFree are slow and synchronise)
   RtFastScene fast;      // FP32 filter tables (rt_kernels.h)
   // per-resolution tables
   int tabW = 0, tabH = 0, tab_aa = 0;
