@@ -25,8 +25,12 @@
  * sphere index, 8-bit RGB within 1 LSB.
  *
  * Threading: one host thread per rt_ctx at a time.  A ctx owns one CUDA device, one stream
- * and all device memory it allocates.  There is no CPU fallback: every render entry point
- * fails with RT_ERR_CUDA when no sm_100 device is usable.
+ * and all device memory it allocates.  Camera, lights and ambient live in one __constant__
+ * bank per DEVICE (as in the reference, src/kernel.cu:7-9): contexts that share a device may
+ * alternate (the bank is refreshed on demand) but must not have renders of DIFFERENT scenes
+ * in flight at the same time.  rt_upload_scene must not be called while a render of this ctx
+ * that was enqueued on a caller's stream is still running.  There is no CPU fallback: every
+ * render entry point fails with RT_ERR_CUDA when no sm_100 device is usable.
  */
 #ifndef RT_B200_H
 #define RT_B200_H
