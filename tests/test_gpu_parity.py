@@ -266,6 +266,41 @@ def test_tile_renders_assemble_to_the_frame(rt, oracle, scenes, mode):
     assert np.abs(whole.cpu().numpy() - o["fb"]).max() < 2e-3
 
 
+def _random_scene(rt, seed):
+    """Adversarial little scenes: overlapping / nested / coincident spheres of very different sizes, lights and camera
+    anywhere (inside spheres too), odd fields of view, shininess 0, zero and negative reflectivity."""
+    g = np.random.default_rng(1000 + seed)
+    n = int(g.integers(1, 60))
+    c = g.uniform(-6, 6, (n, 3)); c[:, 2] -= 8
+    r = np.exp(g.uniform(np.log(0.05), np.log(4.0), n))
+    if n > 3:
+        c[1] = c[0]                                       # concentric
+        c[2] = c[0] + np.array([r[0] + r[2], 0, 0])        # externally tangent
+    if n > 6 and seed % 3 == 0:
+        c[5], r[5] = c[4], r[4]                            # coincident twins (lowest index wins, SURVEY F8)
+    col = g.uniform(0, 1, (n, 3))
+    refl = np.where(g.random(n) < 0.4, 0.0, g.uniform(-0.2, 1.0, n))
+    shin = np.where(g.random(n) < 0.15, 0.0, g.integers(1, 200, n).astype(np.float64))
+    sph = np.column_stack([c, r, col, refl, 1 - refl, shin])
+    if seed % 4 == 1:
+        sph = np.vstack([sph, [0, -1003, -8, 1000, 0.4, 0.4, 0.4, 0.3, 1, 10]])   # a huge ground sphere
+    L = int(g.integers(0, 6))
+    lights = np.column_stack([g.uniform(-8, 8, (L, 3)) - np.array([0, -4, 6]), g.uniform(0.2, 1, (L, 3)), np.ones(L)]) if L else np.zeros((0, 7))
+    cam_pos = g.uniform(-3, 3, 3) + np.array([0, 0, 4.0])
+    if seed % 5 == 2:
+        cam_pos = sph[0, :3] + 0.3 * sph[0, 3]             # camera inside a sphere
+    cam = np.concatenate([cam_pos, sph[int(g.integers(0, n)), :3] + g.uniform(-0.5, 0.5, 3), [float(g.uniform(20, 110))]])
+    sph = np.array([[float("%.6f" % v) for v in row] for row in sph.tolist()])
+    return rt.Scene(sph, np.asarray(lights, dtype=np.float64), g.uniform(0, 0.3, 3), cam)
+
+
+@pytest.mark.parametrize("mode", ["fast", "bvh"])
+@pytest.mark.parametrize("seed", range(24))
+def test_fuzz_random_scenes(rt, oracle, renderers, seed, mode):
+    W, H, D = [(96, 54, 4), (61, 47, 6), (130, 40, 3)][seed % 3]
+    check(rt, oracle, renderers[mode], _random_scene(rt, seed), W, H, D)
+
+
 def test_errors(rt, renderers, scenes):
     r = rt.Renderer(0)
     with pytest.raises(rt.RtError, match="no scene uploaded"):
