@@ -8,7 +8,7 @@ import numpy as np
 import rtb200, oracle_py
 from test_gpu_parity import _random_scene
 first, count = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (100, 200)
-rs = {"fast": rtb200.Renderer(0), "bvh": rtb200.Renderer(0, mode="bvh"), "stream": rtb200.Renderer(0, accel=1)}
+rs = {"fast": rtb200.Renderer(0), "bvh": rtb200.Renderer(0, mode="bvh")}
 bad = 0
 for seed in range(first, first + count):
     sc = _random_scene(rtb200, seed)
