@@ -692,7 +692,10 @@ __global__ void __launch_bounds__(kThreads, RT_SHADOW_CTAS) k_shadow_dyn(const W
 // ---------------------------------------------------------------------------------------------
 // SHADE: one hit per lane.  include/scene.h:89-121 in FP32 with the occlusion bytes of k_shadow, then
 // src/main.cpp:43-55: final pixel, or the reflected ray (exact FP64) appended to the RayRec queue.
-__global__ void __launch_bounds__(kThreads, 4) k_shade(const WaveArgs w) {
+#ifndef RT_SHADE_CTAS
+#define RT_SHADE_CTAS 4
+#endif
+__global__ void __launch_bounds__(kThreads, RT_SHADE_CTAS) k_shade(const WaveArgs w) {
   const FastArgs &a = w.f;
   RT_PDL_SYNC();
   const unsigned nh = *w.hit_count;

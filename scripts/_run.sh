@@ -1,2 +1,2 @@
 cd $GRAFT_REPO_ROOT
-timeout 1500 python scripts/fuzz_parity.py 1000 6000 2>&1 | tail -12
+for v in "" sh3 sh5 sh6; do echo "== $v"; RTB200_LIB=${v:+$PWD/build_tools/librt_$v.so} timeout 300 python scripts/probe_wave2.py complex 1920 1080 5 1 2>/dev/null | sed -n 2p; done
