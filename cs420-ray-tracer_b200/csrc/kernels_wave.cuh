@@ -225,7 +225,9 @@ __global__ void __launch_bounds__(kThreads, RT_CLOSEST_CTAS) k_closest0(const Wa
       // the tile's rays descend the hierarchy as ONE bundle; a per-ray traversal only if the bundle is too wide
       const Cone cone = warp_cone<2>(dx, dy, dz, live);
       bool done = false;
-      if (cone.ok) {
+      // (camera tiles: the bundle walk costs about the same per tile whatever the scene size, a per-ray traversal grows
+      // with it -- measured crossover between 10 k and 100 k spheres; the shadow bundles win at both sizes)
+      if (cone.ok && a.N >= 32768) {
         ClosestQ<2> q;
         closest_begin(q);
         c_walks++;

@@ -1,2 +1,3 @@
 cd $GRAFT_REPO_ROOT
-for v in "" sh3 sh5 sh6; do echo "== $v"; RTB200_LIB=${v:+$PWD/build_tools/librt_$v.so} timeout 300 python scripts/probe_wave2.py complex 1920 1080 5 1 2>/dev/null | sed -n 2p; done
+timeout 1800 python -m pytest tests -m gpu -x -q -k "bvh or large or full_size" 2>&1 | tail -2
+RT_ACCEL=2 timeout 300 python scripts/probe_scene.py synth:10000:420 3840 2160 5 4 | cut -c1-150;  timeout 300 python scripts/probe_scene.py synth:100000:421 7680 4320 8 4 | cut -c1-150
