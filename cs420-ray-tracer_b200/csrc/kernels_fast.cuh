@@ -7,7 +7,8 @@
 //               general-origin closest hit, Phong + one any-hit shadow query per light; each lane
 //               follows its ray to termination, the queue record is updated in place.
 // Sphere tables are staged once per CTA into shared memory with ONE TMA bulk copy
-// (cp.async.bulk + mbarrier) when they fit, otherwise they are read through L1/L2.
+// (cp.async.bulk + mbarrier) when they fit; larger ones are streamed tile by tile (kernels_wave.cuh) or, from
+// 1024 spheres on, replaced as the source of candidates by the device-built LBVH (bvh.cuh).
 //
 // Shared-origin tables (camera, each light) are SORTED by the distance of the sphere's nearest
 // point from that origin; a query stops at the first 8-sphere group that lies entirely beyond

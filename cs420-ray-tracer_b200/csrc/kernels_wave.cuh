@@ -1,20 +1,22 @@
-// kernels_wave.cuh -- the phase-separated wavefront used for reflection levels 0 and 1.
+// kernels_wave.cuh -- the phase-separated wavefront used for reflection levels 0 and 1 (every level in LBVH scenes).
 //
-// Profiling the fused per-warp pipeline (kernels_fast.cuh) showed that the packed FP32 sphere
+// Profiling a fused per-warp pipeline (one kernel per level) showed that the packed FP32 sphere
 // loops were only ~30 % of its time: the rest was FP64 geometry, shading and slow-path code that
 // is latency bound at 16 warps/SM and too large for the instruction cache.  Here every phase is its
-// own lean kernel, so the loops run at high occupancy with a few-hundred-instruction footprint and
-// every warp is full because each phase consumes a COMPACTED queue:
+// own kernel and every warp is full because each phase consumes a COMPACTED queue:
 //
-//   k_closest0   pixels      -> camera-table loop -> exact t -> hit point / normal -> HitRec queue
+//   k_closest0   pixels      -> camera-table walk -> exact t -> hit point / normal -> HitRec block
 //                               (sky pixels are final: staged per warp, 128-bit stores)
 //   k_closest1   RayRec queue-> general-origin loop -> same, for reflected rays (misses are final)
-//   k_shadow     HitRec x light items (light-major, two hits per lane) -> light-table loop ->
-//                               one occlusion byte per (light, hit)
+//   k_shadow     HitRec blocks (two hits per lane) x lights -> light-table walk -> one occlusion byte per (light, hit)
 //   k_shade      HitRec      -> Phong (include/scene.h:89-121) -> final pixel, or the reflected
 //                               ray appended to the RayRec queue (warp-ballot compaction)
-// Levels >= 2 hold a few percent of the rays; they run in the fused tail kernel of
-// kernels_fast.cuh (k_bounce), one launch for all remaining levels.
+// Where the candidate spheres of a query come from is the template mode of k_closest0 / k_shadow (kTab*): a bundle-culled
+// table staged in shared memory, a table streamed through a ring of TMA tiles, or the LBVH (bundle traversal at level 0;
+// k_closest1_dyn / k_shadow_dyn -- per-ray traversal with dynamic ray fetch -- from level 1 on).
+// Levels >= 2 of small scenes hold a few percent of the rays; they run in the fused tail kernel of
+// kernels_fast.cuh (k_bounce), one launch for all remaining levels.  Every kernel but the first of a frame is launched with
+// programmatic dependent launch (RT_PDL_SYNC).
 #ifndef RT_KERNELS_WAVE_CUH
 #define RT_KERNELS_WAVE_CUH
 
