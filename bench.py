@@ -268,7 +268,6 @@ def main_b200(args, rank, local_rank, world):
     # ray counts of the frame (one counted render on rank 0's full frame, outside the timed region)
     _, st = r.render(W, H, DEPTH)
     rays = int(st.closest_queries + st.shadow_queries)
-    launches_per_step = int(st.kernel_launches)
     assert st.filter_violations == 0
 
     for _ in range(max(3, args.warmup)):
@@ -284,6 +283,19 @@ def main_b200(args, rank, local_rank, world):
         ev[k][0].record(stream)
         step_device()
         ev[k][1].record(stream)
+    torch.cuda.synchronize()
+    if n > 1:
+        dist.barrier()
+    # kernels per frame, counted in the steady state the timed loop ran in (the library picks the number of wavefront
+    # levels from the previous frame's ray counts, so the very first frame of a scene may launch more)
+    if n == 1:
+        _, st_l = r.render(W, H, DEPTH)
+    elif peer:
+        st_l = pf.render(DEPTH, stream.cuda_stream, want_stats=True)
+        pf.release(stream.cuda_stream)
+    else:
+        st_l = r.render_bands_device(W, H, DEPTH, BAND_H, rank, n, part.data_ptr(), stream.cuda_stream, want_stats=True)
+    launches_per_step = int(st_l.kernel_launches)
     torch.cuda.synchronize()
     if n > 1:
         dist.barrier()

@@ -155,6 +155,19 @@ int rtk_fast_build_scene(RtFastScene *fs, const double *sph, int N, const RtFram
   if (npairs == 0) npairs = rtf::kGroupPairs;
   const int ngroups = npairs / rtf::kGroupPairs, nslots = 2 * npairs;
   fs->N = N; fs->L = L; fs->npairs = npairs; fs->ngroups = ngroups;
+  // identity of the scene for the wave-level feedback: re-uploading the SAME scene (an end-to-end loop does, every frame)
+  // keeps the ray statistics valid.  a 64-bit multiplicative hash over the input doubles; large scenes (LBVH: no feedback) just get a new id.
+  if (N < 4096) {
+    unsigned long long hsh = 1469598103934665603ull;
+    auto mix = [&](const void *p, size_t n) {       // 8 bytes per step (n is a multiple of 8 for both inputs)
+      const unsigned char *b = (const unsigned char *)p;
+      for (size_t i = 0; i + 8 <= n; i += 8) { unsigned long long w; memcpy(&w, b + i, 8); hsh = (hsh ^ w) * 0x9E3779B97F4A7C15ull; hsh ^= hsh >> 29; }
+    };
+    mix(sph, (size_t)N * 10 * sizeof(double)); mix(f, sizeof(*f));
+    fs->generation = hsh;
+  } else {
+    fs->generation++;
+  }
   const double u = std::ldexp(1.0, -24);
 
   // absolute magnitude bound of every coordinate the reference touches -> delta64
@@ -347,6 +360,8 @@ void rtk_fast_free_scene(RtFastScene *fs, int release_tables) {
 void rtk_fast_free_work(RtFastWork *w) {
   cudaFree(w->queue[0]); cudaFree(w->queue[1]); cudaFree(w->ctl); cudaFree(w->hits); cudaFree(w->occ); cudaFree(w->hit_n); cudaFree(w->cand);
   w->cand = nullptr; w->cand_cap = 0;
+  if (w->h_fb) { cudaFreeHost(w->h_fb); cudaEventDestroy(w->fb_event); }
+  w->h_fb = nullptr; w->fb_pending = 0; w->fb_levels = 0;
   w->queue[0] = w->queue[1] = nullptr; w->ctl = nullptr; w->hits = nullptr; w->occ = nullptr; w->hit_n = nullptr;
   w->queue_cap = w->hit_cap = w->occ_bytes = 0;
 }
@@ -458,7 +473,24 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
   // followed to termination by one fused launch
   // (large scenes: every level has enough rays to fill the machine, and the tail's one-warp chains would dominate)
   // small shares of a frame (one rank's bands of many): level 1 has too few rays to pay for three more launches
-  const int wave_levels = w->wave_levels > 0 ? w->wave_levels : (fs->bvh_nodes ? RT_MAX_LEVELS_INTERNAL : (npix >= 750000 ? 2 : 1));
+  int wave_levels = w->wave_levels > 0 ? w->wave_levels : (fs->bvh_nodes ? RT_MAX_LEVELS_INTERNAL : (npix >= 750000 ? 2 : 1));
+  // ... better: the ray counts of the previous frame of this very (scene, size, depth).  A level runs as a wavefront when
+  // at least kWaveMinRays rays enter it (measured break-even between 89 k and 161 k), the rest goes to the tail.
+  const unsigned long long fb_key = fs->generation * 1000003ull + (unsigned long long)npix * 131ull + (unsigned long long)args.max_depth;
+  const bool fb_auto = w->wave_levels <= 0 && !fs->bvh_nodes && args.max_depth > 1;
+  if (fb_auto) {
+    if (!w->h_fb) {
+      RTK_TRY(cudaHostAlloc(&w->h_fb, 34 * sizeof(unsigned int), cudaHostAllocDefault));
+      RTK_TRY(cudaEventCreateWithFlags(&w->fb_event, cudaEventDisableTiming));
+    }
+    if (w->fb_pending && cudaEventQuery(w->fb_event) == cudaSuccess) {
+      constexpr unsigned kWaveMinRays = 120000u;
+      int lv = 1;
+      while (lv < 33 && w->h_fb[lv] >= kWaveMinRays) lv++;
+      w->fb_levels = lv; w->fb_key = w->fb_pending_key; w->fb_pending = 0;
+    }
+    if (w->fb_levels > 0 && w->fb_key == fb_key) wave_levels = w->fb_levels;
+  }
   for (int level = 0; level < args.max_depth && level < wave_levels; level++) {
     a.level = level;
     wa.hit_count = w->ctl + CTL_HITS + level;
@@ -528,6 +560,11 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
     else if (in_smem) launch(rtf::k_bounce<true, false>, resident_grid(rtf::k_bounce<true, false>, smem, w->num_sms, rtf::kTailThreads), rtf::kTailThreads, smem, stream, pdl, a);
     else launch(rtf::k_bounce<false, false>, resident_grid(rtf::k_bounce<false, false>, smem, w->num_sms, rtf::kTailThreads), rtf::kTailThreads, smem, stream, pdl, a);
     launches++;
+  }
+  if (fb_auto && !w->fb_pending) {
+    RTK_TRY(cudaMemcpyAsync(w->h_fb, w->ctl + CTL_RAYS, 34 * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+    RTK_TRY(cudaEventRecord(w->fb_event, stream));
+    w->fb_pending = 1; w->fb_pending_key = fb_key;
   }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? launches : -(int)e;

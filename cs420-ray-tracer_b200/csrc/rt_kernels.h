@@ -28,6 +28,7 @@ struct RtFastScene {
   float d64;              // absolute FP64/geometry slack (delta64)
   float gS2;              // squared radius bound of the recentred scene
   float g_dtmax;          // additive bound of the general filter's centre projection
+  unsigned long long generation;   // bumped by every rtk_fast_build_scene
   double c0[3];           // recentring offset of the general table
   // device-built LBVH over the recentred spheres (bvh.cuh); built when the scene has >= bvh_min spheres
   void *bvh_nodes, *bvh_leaves;   // bvh_nodes = bvh_nodes_buf when the current scene has a hierarchy, else NULL
@@ -39,7 +40,13 @@ struct RtFastScene {
 };
 struct RtFastWork {
   int num_sms;
-  int wave_levels;       // reflection levels run as wavefront kernels before the fused tail (0 = default)
+  int wave_levels;       // reflection levels run as wavefront kernels before the fused tail (0 = automatic)
+  // automatic choice: the per-level ray counts of the previous frame of the same (scene, size, depth) are read back
+  // asynchronously (136 bytes) and decide where the next frame switches from wavefront levels to the tail
+  unsigned int *h_fb;    // pinned: rays entering level k of the frame the read-back was taken from
+  cudaEvent_t fb_event;
+  int fb_pending, fb_levels;
+  unsigned long long fb_key, fb_pending_key;
   void *queue[2];        // reflected-ray records, ping-pong between levels
   size_t queue_cap;      // records per queue
   unsigned int *ctl;     // device control words: tile counter, per-level chunk counters, queue counts
