@@ -483,7 +483,9 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
       RTK_TRY(cudaHostAlloc(&w->h_fb, 34 * sizeof(unsigned int), cudaHostAllocDefault));
       RTK_TRY(cudaEventCreateWithFlags(&w->fb_event, cudaEventDisableTiming));
     }
-    if (w->fb_pending && cudaEventQuery(w->fb_event) == cudaSuccess) {
+    const cudaError_t fbq = w->fb_pending ? cudaEventQuery(w->fb_event) : cudaErrorNotReady;
+    if (fbq != cudaSuccess) cudaGetLastError();      // (cudaErrorNotReady must not surface as this call's launch error)
+    if (w->fb_pending && fbq == cudaSuccess) {
       constexpr unsigned kWaveMinRays = 120000u;
       int lv = 1;
       while (lv < 33 && w->h_fb[lv] >= kWaveMinRays) lv++;
