@@ -450,7 +450,10 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
   a.wtiles_x = (args.W + rtf::kWTileW - 1) / rtf::kWTileW;
   a.nwtiles = a.wtiles_x * ((args.bands.local_rows + rtf::kWTileH - 1) / rtf::kWTileH);
   a.tile_counter = w->ctl + CTL_TILE;
-  wa.hits = (rtf::HitRec *)w->hits; wa.hit_cap = (unsigned)w->hit_cap; wa.occ = w->occ; wa.hit_n = w->hit_n;
+  wa.hits = (rtf::HitRec *)w->hits; wa.hit_cap = (unsigned)hit_cap;   // THIS frame's slot count = the stride of the per-light occlusion rows (the allocation may be
+                                                          // larger; with its size as stride a scene with more lights than the one the buffers were sized
+                                                          // for would index past occ_bytes)
+  wa.occ = w->occ; wa.hit_n = w->hit_n;
   const size_t pairs_bytes = (size_t)fs->npairs * 32;
   const size_t light_bytes = (size_t)fs->L * fs->tstride;
   // per kernel: its tables are staged whole when they fit, else streamed (shared-origin tables) or read through L1/L2 (general table)

@@ -24,5 +24,37 @@ for seed in range(first, first + count):
             bad += 1
             print("MISMATCH seed %d mode %s: hit %s mask %s rgb %s (%.4f%%, max %d) viol %d" % (
                 seed, m, np.array_equal(hit, o["hit_idx"]), np.array_equal(mask, o["shadow_mask"]), ok_rgb, pct, mx, st.filter_violations))
+            badh = np.argwhere(hit != o["hit_idx"]); badm = np.argwhere(mask != o["shadow_mask"])
+            print("   N %d L %d %dx%d d%d; hit mismatches by level %s, mask by level %s, counters gpu (%d %d %d %d) oracle %s" % (
+                sc.nspheres, sc.nlights, W, H, D, np.bincount(badh[:, 2], minlength=D).tolist() if len(badh) else [],
+                np.bincount(badm[:, 2], minlength=D).tolist() if len(badm) else [], st.closest_queries, st.hits, st.shadow_queries, st.occluded,
+                {k: o["counters"][k] for k in ("closest_queries", "hits", "shadow_queries", "occluded")}))
+            if len(badh):
+                j, i, k = badh[0]
+                print("   first hit mismatch (row %d col %d level %d): got %d want %d; rows %s" % (j, i, k, hit[j, i, k], o["hit_idx"][j, i, k], sorted(set(badh[:, 0].tolist()))[:16]))
+            # is it the scene on the device or the render?  upload again and re-render
+            r.upload(sc)
+            _, hit2, mask2, _ = r.render_debug(W, H, D)
+            print("   after a second upload of the same scene: hit %s mask %s" % (np.array_equal(hit2, o["hit_idx"]), np.array_equal(mask2, o["shadow_mask"])))
+    if seed % 10 == 0:                                   # supersampling and the assembled-frame output mode on the same scene
+        import torch
+        r = rs["fast"] if (seed // 10) % 2 == 0 else rs["bvh"]
+        r.upload(sc)
+        plain, _ = r.render(W, H, D)
+        fr = torch.zeros((H, W, 3), dtype=torch.uint8, device="cuda:0")
+        torch.cuda.synchronize()
+        for rank in range(3):
+            r.render_bands_frame(W, H, D, 8, rank, 3, fr.data_ptr())
+        torch.cuda.synchronize()
+        if not np.array_equal(fr.cpu().numpy(), plain):
+            bad += 1; print("MISMATCH seed %d: assembled frame != rt_render" % seed)
+        osamp = oracle_py.render_supersampled(sc, W, H, D)
+        r.set_option("antialias", 1)
+        rgb, hit, mask, st = r.render_debug(W, H, D)
+        r.set_option("antialias", 0)
+        okk = all(np.array_equal(hit[b::2, a::2], osamp["samples"][k]["hit_idx"]) for k, (a, b) in enumerate(((0, 0), (1, 0), (0, 1), (1, 1))))
+        ok_rgb, pct, mx = rtb200.compare_rgb(osamp["rgb"], rgb, 0.5)
+        if not (okk and ok_rgb and mx <= 2):
+            bad += 1; print("MISMATCH seed %d: supersampling hit %s rgb %s max %d" % (seed, okk, ok_rgb, mx))
 print("fuzz: %d scenes x %d modes, %d mismatches" % (count, len(rs), bad))
 sys.exit(1 if bad else 0)

@@ -301,6 +301,20 @@ def test_fuzz_random_scenes(rt, oracle, renderers, seed, mode):
     check(rt, oracle, renderers[mode], _random_scene(rt, seed), W, H, D)
 
 
+@pytest.mark.parametrize("mode", ["fast", "bvh"])
+def test_buffers_sized_by_an_earlier_frame(rt, oracle, scenes, mode):
+    """Regression: work buffers only grow.  A context that rendered a large frame of a one-light scene and then renders a
+    small frame of a five-light scene must stride its per-light occlusion rows by THIS frame's slot count (found by
+    scripts/fuzz_parity.py: the allocated capacity as stride indexed past the buffer)."""
+    one = scenes["complex"]
+    one_light = rt.Scene(one.spheres, one.lights[:1], one.ambient, one.camera)
+    with rt.Renderer(0, mode=mode) as r:
+        r.upload(one_light)
+        r.render(640, 360, 3)
+        for name, W, H, D in (("complex", 96, 54, 4), ("medium", 61, 47, 6)):
+            check(rt, oracle, r, scenes[name], W, H, D)
+
+
 def test_errors(rt, renderers, scenes):
     r = rt.Renderer(0)
     with pytest.raises(rt.RtError, match="no scene uploaded"):
