@@ -8,15 +8,36 @@ import numpy as np
 import rtb200, oracle_py
 from test_gpu_parity import _random_scene
 first, count = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (100, 200)
-rs = {"fast": rtb200.Renderer(0), "bvh": rtb200.Renderer(0, mode="bvh")}
+BIG = len(sys.argv) > 3 and sys.argv[3] == "big"          # 300..4000 spheres: streamed tables (accel=1) and the LBVH
+if BIG:
+    import gen_scene
+rs = {"fast": rtb200.Renderer(0, accel=1 if BIG else None), "bvh": rtb200.Renderer(0, mode="bvh")}
 bad = 0
 for seed in range(first, first + count):
-    sc = _random_scene(rtb200, seed)
-    W, H, D = [(96, 54, 4), (61, 47, 6), (130, 40, 3), (40, 90, 8)][seed % 4]
+    g = np.random.default_rng(seed)
+    if BIG:
+        sc = rtb200.Scene(*gen_scene.generate(int(g.integers(300, 4000)), seed, 0.05, float(g.uniform(0.3, 1.5))))
+    else:
+        sc = _random_scene(rtb200, seed)
+    if BIG:
+        W, H, D = int(g.integers(16, 120)), int(g.integers(16, 70)), int(g.integers(1, 7))
+    elif seed % 2:
+        W, H, D = [(96, 54, 4), (61, 47, 6), (130, 40, 3), (40, 90, 8)][seed % 4]
+    else:                                                  # any size (buffers grow and are reused), any depth
+        W, H, D = int(g.integers(2, 260)), int(g.integers(2, 200)), int(g.integers(0, 9))
+    if seed % 37 == 0:
+        sc = rtb200.Scene(sc.spheres, sc.lights[:0], sc.ambient, sc.camera)      # no lights
+    if seed % 41 == 0:
+        sc = rtb200.Scene(sc.spheres[:0], sc.lights, sc.ambient, sc.camera)      # no spheres
     o = oracle_py.render(sc, W, H, D, want_idx=True)
     for m, r in rs.items():
         r.upload(sc)
+        first = r.render(W, H, D)[0]                       # (the next frame may pick another wavefront / tail split)
         rgb, hit, mask, st = r.render_debug(W, H, D)
+        if not np.array_equal(first, rgb):
+            bad += 1; print("MISMATCH seed %d mode %s: two renders of one scene differ" % (seed, m))
+        if D == 0:
+            hit, mask = o["hit_idx"], o["shadow_mask"]     # (no levels: nothing to compare)
         ok_rgb, pct, mx = rtb200.compare_rgb(o["rgb"], rgb, 0.5)
         good = np.array_equal(hit, o["hit_idx"]) and np.array_equal(mask, o["shadow_mask"]) and ok_rgb and mx <= 2 and st.filter_violations == 0 \
             and st.closest_queries == o["counters"]["closest_queries"] and st.occluded == o["counters"]["occluded"]
@@ -48,11 +69,23 @@ for seed in range(first, first + count):
         torch.cuda.synchronize()
         if not np.array_equal(fr.cpu().numpy(), plain):
             bad += 1; print("MISMATCH seed %d: assembled frame != rt_render" % seed)
+        if W > 8 and H > 8:                              # a random tile against the whole-frame tile render
+            whole = torch.full((H, W, 3), -1.0, dtype=torch.float32, device="cuda:0")
+            part = torch.full((H, W, 3), -1.0, dtype=torch.float32, device="cuda:0")
+            torch.cuda.synchronize()
+            tx, ty = int(g.integers(0, W - 4)), int(g.integers(0, H - 4))
+            tw, th = int(g.integers(1, W - tx + 1)), int(g.integers(1, H - ty + 1))
+            r.render_tile_device(W, H, D, (0, 0, W, H), whole.data_ptr())
+            r.render_tile_device(W, H, D, (tx, ty, tw, th), part.data_ptr())
+            torch.cuda.synchronize()
+            inside = torch.zeros((H, W), dtype=torch.bool, device="cuda:0"); inside[ty:ty + th, tx:tx + tw] = True
+            if not torch.equal(part[inside], whole[inside]) or not bool((part[~inside] == -1.0).all()) or bool((whole == -1.0).any()):
+                bad += 1; print("MISMATCH seed %d: tile render (%d,%d,%d,%d) of %dx%d d%d" % (seed, tx, ty, tw, th, W, H, D))
         osamp = oracle_py.render_supersampled(sc, W, H, D)
         r.set_option("antialias", 1)
         rgb, hit, mask, st = r.render_debug(W, H, D)
         r.set_option("antialias", 0)
-        okk = all(np.array_equal(hit[b::2, a::2], osamp["samples"][k]["hit_idx"]) for k, (a, b) in enumerate(((0, 0), (1, 0), (0, 1), (1, 1))))
+        okk = D == 0 or all(np.array_equal(hit[b::2, a::2], osamp["samples"][k]["hit_idx"]) for k, (a, b) in enumerate(((0, 0), (1, 0), (0, 1), (1, 1))))
         ok_rgb, pct, mx = rtb200.compare_rgb(osamp["rgb"], rgb, 0.5)
         if not (okk and ok_rgb and mx <= 2):
             bad += 1; print("MISMATCH seed %d: supersampling hit %s rgb %s max %d" % (seed, okk, ok_rgb, mx))
