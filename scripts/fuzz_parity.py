@@ -25,6 +25,12 @@ for seed in range(first, first + count):
         W, H, D = [(96, 54, 4), (61, 47, 6), (130, 40, 3), (40, 90, 8)][seed % 4]
     else:                                                  # any size (buffers grow and are reused), any depth
         W, H, D = int(g.integers(2, 260)), int(g.integers(2, 200)), int(g.integers(0, 9))
+    if not BIG and seed % 3 == 0:                          # similarity transform: scale 1e-2 .. 1e3, offset up to 1e4 scene units
+        k = float(10.0 ** g.uniform(-2, 3)); off = g.uniform(-1, 1, 3) * float(10.0 ** g.uniform(0, 4)) * k
+        sp = sc.spheres.copy(); sp[:, :3] = sp[:, :3] * k + off; sp[:, 3] *= k
+        li = sc.lights.copy(); li[:, :3] = li[:, :3] * k + off
+        cm = sc.camera.copy(); cm[:3] = cm[:3] * k + off; cm[3:6] = cm[3:6] * k + off
+        sc = rtb200.Scene(sp, li, sc.ambient, cm)
     if seed % 37 == 0:
         sc = rtb200.Scene(sc.spheres, sc.lights[:0], sc.ambient, sc.camera)      # no lights
     if seed % 41 == 0:
