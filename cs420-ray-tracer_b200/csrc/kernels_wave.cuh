@@ -556,7 +556,10 @@ __global__ void __launch_bounds__(kThreads, RT_SHADOW_CTAS) k_shadow(const WaveA
 // CLOSEST HIT through the LBVH with DYNAMIC RAY FETCH (large scenes, reflection levels >= 1; see k_shadow_dyn for the
 // scheme).  Only the traversal runs here: a lane's result is the candidate bracket (Best) of its ray, stored per queued
 // ray; k_closest1 then does the exact finish for 64 neighbouring rays at a time, as before.
-__global__ void __launch_bounds__(kThreads, RT_CLOSEST_CTAS) k_closest1_dyn(const WaveArgs w) {
+#ifndef RT_DYN_CTAS
+#define RT_DYN_CTAS 4     // the traversal kernels are memory-latency bound: 64 registers / 32 warps per SM beat 97 / 16 (measured)
+#endif
+__global__ void __launch_bounds__(kThreads, RT_DYN_CTAS) k_closest1_dyn(const WaveArgs w) {
   const FastArgs &a = w.f;
   RT_PDL_SYNC();
   const unsigned nq = *a.q_in_count;
@@ -617,7 +620,7 @@ __global__ void __launch_bounds__(kThreads, RT_CLOSEST_CTAS) k_closest1_dyn(cons
 // at 5-6 active lanes of 32 from reflection level 1 on), so here a lane does not wait for its warp: whenever enough
 // lanes are idle they fetch the next items together (one atomic per refill) and everybody goes on traversing
 // (persistent threads, Aila & Laine 2009).  Same queries, same slow paths, same occlusion bytes as k_shadow.
-__global__ void __launch_bounds__(kThreads, RT_SHADOW_CTAS) k_shadow_dyn(const WaveArgs w) {
+__global__ void __launch_bounds__(kThreads, RT_DYN_CTAS) k_shadow_dyn(const WaveArgs w) {
   const FastArgs &a = w.f;
   RT_PDL_SYNC();
   const unsigned nh = *w.hit_count;
