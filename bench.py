@@ -299,6 +299,22 @@ def main_b200(args, rank, local_rank, world):
     torch.cuda.synchronize()
     if n > 1:
         dist.barrier()
+    # ---- N > 1: the assembled frame of one more sharded step must be rank 0's own full-frame render, byte for byte
+    frame_check = None
+    if n > 1:
+        if rank == 0:
+            full.zero_()                                # (stale pixels of the timed frames must not pass the check)
+        torch.cuda.synchronize()
+        dist.barrier()
+        step_device()
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:
+            own, _ = r.render(W, H, DEPTH)
+            import numpy as np
+            frame_check = "identical" if np.array_equal(own, full.cpu().numpy()) else "DIFFERENT"
+        torch.cuda.synchronize()
+        dist.barrier()
     ms_total = sum(a.elapsed_time(b) for a, b in ev)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if n > 1:
@@ -351,11 +367,13 @@ def main_b200(args, rank, local_rank, world):
     k_ms, lvl0_ms, frame_ms, k_rays = None, None, None, None
     if rank == 0 and n == 1:
         msk, ms0, msf = [], [], []
+        r.set_option("level_timing", 1)                     # events between the level-0 kernels (PDL off for these renders)
         for _ in range(30):
             flush.fill_(1)
             _, s2 = r.render(W, H, DEPTH)
             msk.append(s2.ms_shadow0); ms0.append(s2.ms_level0); msf.append(s2.ms_device)
         k_ms, lvl0_ms, frame_ms = sum(msk) / len(msk), sum(ms0) / len(ms0), sum(msf) / len(msf)
+        r.set_option("level_timing", 0)
         _, s1 = r.render(W, H, 1)                           # level 0 only: pixels + L x primary hits
         k_rays = int(s1.shadow_queries)                     # the shadow queries k_shadow(level 0) answers
 
@@ -412,7 +430,11 @@ def main_b200(args, rank, local_rank, world):
             except Exception as e:  # noqa: BLE001
                 line["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "reference",
                                         "sample": "failed: %r" % (e,)}
+        if frame_check is not None:
+            line["frame_check"] = frame_check
         print(json.dumps(line), flush=True)
+        if frame_check == "DIFFERENT":
+            raise RuntimeError("the frame assembled from %d ranks differs from rank 0's own full-frame render" % n)
     if peer:
         torch.cuda.synchronize()
         err = pf.error()

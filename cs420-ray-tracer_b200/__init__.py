@@ -11,7 +11,7 @@ The directory name contains a hyphen, so import it through ``rtb200.py`` at the 
 (``import rtb200``) or ``importlib`` (see ``__graft_entry__.py``).
 """
 from .api import (  # noqa: F401
-    RtError, RtStats, Scene, Renderer, load_library, library_path, load_scene, write_ppm,
+    RtError, RtStats, Scene, Renderer, MultiRenderer, load_library, library_path, load_scene, write_ppm,
     band_rows, band_row_list, measure_fp32_peak, ABI_SYMBOLS,
 )
 from .ppmtools import read_ppm, compare_rgb, ppm_text  # noqa: F401

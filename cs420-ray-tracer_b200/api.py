@@ -21,6 +21,8 @@ ABI_SYMBOLS = [
     "rt_dev_alloc", "rt_dev_free", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_peer_signal", "rt_peer_wait",
     "rt_render", "rt_render_debug", "rt_render_bands", "rt_band_rows", "rt_band_row_list",
     "rt_host_alloc", "rt_host_free", "rt_write_ppm", "rt_measure_fp32_peak",
+    "rt_create_multi", "rt_multi_destroy", "rt_multi_ranks", "rt_multi_ctx", "rt_multi_set_option", "rt_multi_upload_scene",
+    "rt_multi_render",
 ]
 
 
@@ -98,6 +100,15 @@ def load_library():
     lib.rt_host_free.restype = None
     lib.rt_write_ppm.argtypes = [C.c_char_p, vp, i, i]
     lib.rt_measure_fp32_peak.argtypes = [i, dp, dp]
+    lib.rt_create_multi.argtypes = [i, C.POINTER(vp)]
+    lib.rt_multi_destroy.argtypes = [vp]
+    lib.rt_multi_destroy.restype = None
+    lib.rt_multi_ranks.argtypes = [vp]
+    lib.rt_multi_ctx.argtypes = [vp, i]
+    lib.rt_multi_ctx.restype = vp
+    lib.rt_multi_set_option.argtypes = [vp, C.c_char_p, C.c_longlong]
+    lib.rt_multi_upload_scene.argtypes = [vp, vp, i, vp, i, vp, vp, vp, C.c_double]
+    lib.rt_multi_render.argtypes = [vp, i, i, i, i, vp, C.POINTER(RtStats)]
     for name in ABI_SYMBOLS:
         getattr(lib, name)
     _lib = lib
@@ -310,14 +321,14 @@ class Renderer:
         _check(self._lib.rt_render(self._h, W, H, depth, out.ctypes.data, C.byref(st) if want_stats else None), "rt_render")
         return out, st
 
-    def render_debug(self, W, H, depth):
+    def render_debug(self, W, H, depth, want_stats=True):
         out = np.empty((H, W, 3), dtype=np.uint8)
         m = 2 if self.antialias else 1          # supersampling: debug buffers are per sample, [2H][2W][depth]
         hit = np.empty((H * m, W * m, max(depth, 1)), dtype=np.int32)
         mask = np.empty((H * m, W * m, max(depth, 1)), dtype=np.uint32)
         st = RtStats()
         _check(self._lib.rt_render_debug(self._h, W, H, depth, out.ctypes.data, hit.ctypes.data, mask.ctypes.data,
-                                         C.byref(st)), "rt_render_debug")
+                                         C.byref(st) if want_stats else None), "rt_render_debug")
         return out, hit, mask, st
 
     def render_bands_device(self, W, H, depth, band_h, rank, nranks, dev_ptr, stream_ptr=None, want_stats=False):
@@ -327,3 +338,55 @@ class Renderer:
                                          C.c_void_p(stream_ptr) if stream_ptr else None,
                                          C.byref(st) if want_stats else None), "rt_render_bands")
         return st
+
+
+class MultiRenderer:
+    """rt_create_multi: one frame sharded by interleaved row bands over `ngpus` ranks inside this process; every rank
+    copies its bands to the host frame over its own link."""
+
+    def __init__(self, ngpus, mode="fast", accel=None):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        _check(self._lib.rt_create_multi(int(ngpus), C.byref(self._h)), "rt_create_multi")
+        self.n = int(ngpus)
+        if mode == "bvh":
+            mode, accel = "fast", 2
+        self.set_option("mode", {"fast": 0, "exact": 1}[mode])
+        if accel is not None:
+            self.set_option("accel", accel)
+
+    def set_option(self, key, value):
+        _check(self._lib.rt_multi_set_option(self._h, key.encode(), int(value)), "rt_multi_set_option")
+
+    def upload(self, scene):
+        self.scene = scene
+        cam = scene.camera
+        pos = np.ascontiguousarray(cam[0:3]); look = np.ascontiguousarray(cam[3:6])
+        _check(self._lib.rt_multi_upload_scene(
+            self._h, scene.spheres.ctypes.data, scene.nspheres, scene.lights.ctypes.data, scene.nlights,
+            scene.ambient.ctypes.data, pos.ctypes.data, look.ctypes.data, float(cam[6])), "rt_multi_upload_scene")
+
+    def render(self, W, H, depth, band_h=16, out=None, want_stats=True):
+        if out is None:
+            out = np.empty((H, W, 3), dtype=np.uint8)
+        st = RtStats()
+        _check(self._lib.rt_multi_render(self._h, W, H, depth, band_h, out.ctypes.data, C.byref(st) if want_stats else None),
+               "rt_multi_render")
+        return out, st
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.rt_multi_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

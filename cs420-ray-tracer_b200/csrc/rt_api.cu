@@ -11,6 +11,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "rt_device.h"
@@ -47,6 +48,14 @@ struct rt_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm[3] = {nullptr, nullptr, nullptr};
+  // Every render of a ctx shares one set of work buffers (queues, counters, hit blocks) and the device's __constant__
+  // bank, so renders of one ctx are SERIALISED on the device whatever streams the caller hands in: ev_last is recorded
+  // behind the last kernel of each render and the next render's stream waits for it when it is a different stream.
+  cudaEvent_t ev_last = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool last_valid = false;
+  int pend_launches = 0, pend_rows = 0; bool pend_counters = false, pend_marks = false; cudaStream_t pend_stream = nullptr;   // collect_stats
+  int level_timing = 0;  // 1: event records between the level-0 kernels (rt_stats.ms_closest0 / ms_shadow0); turns PDL off
   int mode = 0;          // 0 fast, 1 exact
   int counters_on = 1;
   int accel = 0;         // 0 auto, 1 table walks, 2 LBVH (takes effect at the next rt_upload_scene)
@@ -79,6 +88,7 @@ static std::mutex g_const_mutex;
 static const rt_ctx *g_const_owner[64] = {nullptr};
 static unsigned long long g_const_version[64] = {0};
 
+extern "C" void rt_destroy(rt_ctx *c);
 extern "C" int rt_create(int device, rt_ctx **out) {
   if (!out) return rt_fail(RT_ERR_ARG, "rt_create: NULL out");
   int n = 0;
@@ -101,13 +111,22 @@ extern "C" int rt_create(int device, rt_ctx **out) {
   memset(&c->fast, 0, sizeof(c->fast));
   memset(&c->work, 0, sizeof(c->work));
   c->work.num_sms = prop.multiProcessorCount;
-  RT_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  RT_CUDA(cudaEventCreate(&c->ev0));
-  RT_CUDA(cudaEventCreate(&c->ev1));
-  for (int k = 0; k < 3; k++) RT_CUDA(cudaEventCreate(&c->evm[k]));
-  RT_CUDA(cudaMalloc(&c->d_counters, RT_CNT_TOTAL * sizeof(unsigned long long)));
+  // (a failure below must not leak the half-built context: rt_destroy copes with null members)
+  cudaError_t ce = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (ce == cudaSuccess) ce = cudaEventCreate(&c->ev0);
+  if (ce == cudaSuccess) ce = cudaEventCreate(&c->ev1);
+  for (int k = 0; k < 3 && ce == cudaSuccess; k++) ce = cudaEventCreate(&c->evm[k]);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->ev_last, cudaEventDisableTiming);
+  if (ce == cudaSuccess) ce = cudaMalloc(&c->d_counters, RT_CNT_TOTAL * sizeof(unsigned long long));
+  if (ce != cudaSuccess) {
+    rt_destroy(c);
+    return rt_fail(RT_ERR_CUDA, std::string("rt_create: ") + cudaGetErrorString(ce));
+  }
   int r = rtk_fast_init(c->device);
-  if (r != 0) return rt_fail(RT_ERR_CUDA, std::string("rt_create: kernel attribute setup failed: ") + cudaGetErrorString((cudaError_t)-r));
+  if (r != 0) {
+    rt_destroy(c);
+    return rt_fail(RT_ERR_CUDA, std::string("rt_create: kernel attribute setup failed: ") + cudaGetErrorString((cudaError_t)-r));
+  }
   *out = c;
   return RT_OK;
 }
@@ -121,7 +140,8 @@ static void free_scene(rt_ctx *c) {
 extern "C" void rt_destroy(rt_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->last_valid) cudaEventSynchronize(c->ev_last);       // renders enqueued on caller streams
   {
     std::lock_guard<std::mutex> lk(g_const_mutex);
     if (g_const_owner[c->device] == c) g_const_owner[c->device] = nullptr;
@@ -130,8 +150,12 @@ extern "C" void rt_destroy(rt_ctx *c) {
   rtk_fast_free_work(&c->work);
   cudaFree(c->d_su); cudaFree(c->d_sv);
   cudaFree(c->d_rgb); cudaFree(c->d_hit); cudaFree(c->d_mask); cudaFree(c->d_counters); cudaFree(c->d_fb);
-  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); for (int k = 0; k < 3; k++) cudaEventDestroy(c->evm[k]);
-  cudaStreamDestroy(c->stream);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  for (int k = 0; k < 3; k++) if (c->evm[k]) cudaEventDestroy(c->evm[k]);
+  if (c->ev_last) cudaEventDestroy(c->ev_last);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  cudaGetLastError();
   delete c;
 }
 
@@ -144,6 +168,7 @@ extern "C" int rt_set_option(rt_ctx *c, const char *key, long long value) {
   }
   if (!strcmp(key, "counters")) { c->counters_on = value != 0; return RT_OK; }
   if (!strcmp(key, "antialias")) { c->antialias = value != 0; return RT_OK; }
+  if (!strcmp(key, "level_timing")) { c->level_timing = value != 0; return RT_OK; }
   if (!strcmp(key, "accel")) {
     if (value < 0 || value > 2) return rt_fail(RT_ERR_ARG, "rt_set_option: accel must be 0 (auto), 1 (tables) or 2 (LBVH)");
     c->accel = (int)value;
@@ -176,6 +201,8 @@ extern "C" int rt_upload_scene(rt_ctx *c, const double *spheres, int N, const do
     return rt_fail(RT_ERR_UNSUPPORTED, "rt_upload_scene: more than " + std::to_string(RT_MAX_LIGHTS) + " lights");
   RT_CUDA(cudaSetDevice(c->device));
   RT_CUDA(cudaStreamSynchronize(c->stream));
+  // the tables are rebuilt in place: renders of this ctx still running on a CALLER's stream must finish first
+  if (c->last_valid) RT_CUDA(cudaEventSynchronize(c->ev_last));
   c->have_scene = false;
   rtk_fast_free_scene(&c->fast, 0);              // keeps the table allocation for reuse
   c->N = N; c->L = L; c->fov = fov_deg;
@@ -275,10 +302,39 @@ static void fill_stats(rt_stats *st, const unsigned long long *cnt) {
 // Launches the kernels of one (possibly banded) render on `stream`.  When `stats` is given the
 // call synchronises the stream and fills it.  With supersampling on, the kernels render the 2W x 2H sample
 // grid into a float frame and k_resolve_aa averages it into dev_rgb; debug buffers are per SAMPLE then.
+// Second half of a render that asked for stats: waits for the stream and fills *stats.  Split from the launch half so
+// that a multi-GPU frame (rt_multi_render) can enqueue every rank's share before it waits for any of them.
+static int collect_stats(rt_ctx *c, rt_stats *stats) {
+  RT_CUDA(cudaSetDevice(c->device));
+  RT_CUDA(cudaStreamSynchronize(c->pend_stream));
+  float ms = 0;
+  RT_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  memset(stats, 0, sizeof(*stats));
+  stats->ms_device = ms;
+  stats->ms_level0 = ms;
+  stats->ms_closest0 = ms; stats->ms_shadow0 = 0;
+  if (c->pend_marks) {
+    float m0 = 0, m1 = 0, m2 = 0;
+    RT_CUDA(cudaEventElapsedTime(&m0, c->ev0, c->evm[0]));
+    RT_CUDA(cudaEventElapsedTime(&m1, c->evm[0], c->evm[1]));
+    RT_CUDA(cudaEventElapsedTime(&m2, c->ev0, c->evm[2]));
+    stats->ms_closest0 = m0; stats->ms_shadow0 = m1; stats->ms_level0 = m2;
+  }
+  stats->kernel_launches = c->pend_launches;
+  stats->rows_rendered = c->pend_rows;
+  if (c->pend_counters) {
+    unsigned long long cnt[RT_CNT_TOTAL];
+    RT_CUDA(cudaMemcpy(cnt, c->d_counters, sizeof(cnt), cudaMemcpyDeviceToHost));
+    fill_stats(stats, cnt);
+  }
+  return RT_OK;
+}
+
 struct TileSpec { int x, y, w, h; float *fb; int frame; };   // rt_render_tile: float output into the caller's full-frame buffer;
                                                             // frame = 1 (rt_render_bands_frame): 8-bit rows at their image positions
 static int render_common(rt_ctx *c, int W, int H, int depth, int band_h, int rank, int nranks, uint8_t *dev_rgb,
-                         int32_t *dev_hit, uint32_t *dev_mask, cudaStream_t stream, rt_stats *stats, const TileSpec *tile = nullptr) {
+                         int32_t *dev_hit, uint32_t *dev_mask, cudaStream_t stream, rt_stats *stats, const TileSpec *tile = nullptr,
+                         bool defer_collect = false) {
   if (!c->have_scene) return rt_fail(RT_ERR_STATE, "render: no scene uploaded (call rt_upload_scene first)");
   if (W < 1 || H < 1 || depth < 0) return rt_fail(RT_ERR_ARG, "render: bad image size or depth");
   if (depth > RT_MAX_LEVELS) return rt_fail(RT_ERR_UNSUPPORTED, "render: max_depth above RT_MAX_LEVELS");
@@ -292,9 +348,17 @@ static int render_common(rt_ctx *c, int W, int H, int depth, int band_h, int ran
   RT_CUDA(cudaSetDevice(c->device));
   int rc = ensure_tables(c, W, H, aa);
   if (rc) return rc;
+  // renders of one ctx are serialised on the device (shared work buffers): a render on another stream than the
+  // previous one first waits for that one's last kernel
+  if (c->last_valid && c->last_stream != stream) RT_CUDA(cudaStreamWaitEvent(stream, c->ev_last, 0));
   {
+    // The camera / lights / ambient bank is one __constant__ symbol per device.  It is rewritten only when its
+    // content changes hands, and only after the previous owner's last render has finished (its ev_last); the copy is
+    // stream ordered before this render's kernels, and later renders of this ctx are ordered behind it by ev_last.
     std::lock_guard<std::mutex> lk(g_const_mutex);
     if (g_const_owner[c->device] != c || g_const_version[c->device] != c->scene_version) {
+      const rt_ctx *prev = g_const_owner[c->device];
+      if (prev && prev != c && prev->last_valid) RT_CUDA(cudaStreamWaitEvent(stream, prev->ev_last, 0));
       RT_CUDA(rtk_set_frame_const(&c->frame, stream));
       g_const_owner[c->device] = c;
       g_const_version[c->device] = c->scene_version;
@@ -337,7 +401,7 @@ static int render_common(rt_ctx *c, int W, int H, int depth, int band_h, int ran
   int launches = 0;
   if (rows > 0) {
     if (c->mode == 1) launches = rtk_launch_exact(a, stream);
-    else launches = rtk_launch_fast(a, &c->fast, &c->work, stream, (stats && depth > 0) ? c->evm : nullptr);
+    else launches = rtk_launch_fast(a, &c->fast, &c->work, stream, (stats && depth > 0 && c->level_timing) ? c->evm : nullptr);
     if (launches < 0) return rt_fail(RT_ERR_CUDA, std::string("render: launch failed: ") + cudaGetErrorString((cudaError_t)-launches));
     if (aa) {
       const int r2 = rtk_resolve_aa(c->d_fb, W, rows, dev_rgb, stream);
@@ -345,29 +409,17 @@ static int render_common(rt_ctx *c, int W, int H, int depth, int band_h, int ran
       launches += r2;
     }
   }
+  {
+    std::lock_guard<std::mutex> lk(g_const_mutex);   // (another ctx's render may look at ev_last when the constant bank changes hands)
+    RT_CUDA(cudaEventRecord(c->ev_last, stream));
+    c->last_stream = stream; c->last_valid = true;
+  }
   if (stats) {
     RT_CUDA(cudaEventRecord(c->ev1, stream));
-    RT_CUDA(cudaStreamSynchronize(stream));
-    float ms = 0;
-    RT_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-    memset(stats, 0, sizeof(*stats));
-    stats->ms_device = ms;
-    stats->ms_level0 = ms;
-    stats->ms_closest0 = ms; stats->ms_shadow0 = 0;
-    if (rows > 0 && c->mode == 0 && depth > 0) {
-      float m0 = 0, m1 = 0, m2 = 0;
-      RT_CUDA(cudaEventElapsedTime(&m0, c->ev0, c->evm[0]));
-      RT_CUDA(cudaEventElapsedTime(&m1, c->evm[0], c->evm[1]));
-      RT_CUDA(cudaEventElapsedTime(&m2, c->ev0, c->evm[2]));
-      stats->ms_closest0 = m0; stats->ms_shadow0 = m1; stats->ms_level0 = m2;
-    }
-    stats->kernel_launches = launches;
-    stats->rows_rendered = rows;
-    if (want_counters) {
-      unsigned long long cnt[RT_CNT_TOTAL];
-      RT_CUDA(cudaMemcpy(cnt, c->d_counters, sizeof(cnt), cudaMemcpyDeviceToHost));
-      fill_stats(stats, cnt);
-    }
+    c->pend_launches = launches; c->pend_rows = rows; c->pend_counters = want_counters;
+    c->pend_marks = rows > 0 && c->mode == 0 && depth > 0 && c->level_timing;
+    c->pend_stream = stream;
+    if (!defer_collect) return collect_stats(c, stats);
   }
   return RT_OK;
 }
@@ -499,5 +551,145 @@ extern "C" int rt_measure_fp32_peak(int device, double *flops_per_s, double *sm_
   double v = rtk_measure_fp32_peak(device, sm_clock_mhz);
   if (v < 0) return rt_fail(RT_ERR_CUDA, "rt_measure_fp32_peak: probe kernel failed");
   *flops_per_s = v;
+  return RT_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Multi-GPU frame in ONE process ("rt_create(int ngpus, ...): the ctx owns devices, streams and comms").
+// rank r of n renders the interleaved row bands b with b % n == r on its own device and stream, compactly,
+// and copies them -- every rank over ITS OWN host link, all ranks concurrently -- to their image positions of the
+// caller's host frame: a band is band_h consecutive rows = one contiguous run both in the rank's compact buffer and in
+// the frame, so the whole share of a rank is ONE strided copy (cudaMemcpy2DAsync; + one for a ragged last band).
+// Nothing crosses between the GPUs: for a frame that ends in host memory the gather of 8e is the host frame itself.
+struct rt_multi {
+  int n = 0;
+  std::vector<rt_ctx *> ctx;
+  std::vector<uint8_t *> part;       // per rank: compact band buffer on its device
+  std::vector<size_t> part_cap;
+  void *registered = nullptr; size_t registered_bytes = 0;   // host frame pinned by us (cudaHostRegister) for async copies
+};
+
+extern "C" void rt_multi_destroy(rt_multi *m) {
+  if (!m) return;
+  for (int r = 0; r < (int)m->ctx.size(); r++) {
+    if (!m->ctx[r]) continue;
+    cudaSetDevice(m->ctx[r]->device);
+    cudaStreamSynchronize(m->ctx[r]->stream);
+    if (r < (int)m->part.size()) cudaFree(m->part[r]);
+    rt_destroy(m->ctx[r]);
+  }
+  if (m->registered) cudaHostUnregister(m->registered);
+  cudaGetLastError();
+  delete m;
+}
+
+extern "C" int rt_create_multi(int ngpus, rt_multi **out) {
+  if (!out || ngpus < 1 || ngpus > 64) return rt_fail(RT_ERR_ARG, "rt_create_multi: bad argument (1 <= ngpus <= 64)");
+  const int ndev = rt_device_count();
+  if (ndev == 0) return rt_fail(RT_ERR_CUDA, "rt_create_multi: no CUDA device (this library has no CPU fallback)");
+  rt_multi *m = new (std::nothrow) rt_multi();
+  if (!m) return rt_fail(RT_ERR_NOMEM, "rt_create_multi: out of memory");
+  m->n = ngpus;
+  m->ctx.assign((size_t)ngpus, nullptr); m->part.assign((size_t)ngpus, nullptr); m->part_cap.assign((size_t)ngpus, 0);
+  for (int r = 0; r < ngpus; r++) {
+    // more ranks than devices: ranks share devices round robin (same frame, no speed-up) -- lets a 1-GPU box run the
+    // N-rank code path
+    const int rc = rt_create(r % ndev, &m->ctx[r]);
+    if (rc != RT_OK) { const std::string msg = g_last_error; rt_multi_destroy(m); return rt_fail(rc, msg); }
+  }
+  *out = m;
+  return RT_OK;
+}
+
+extern "C" int rt_multi_ranks(const rt_multi *m) { return m ? m->n : 0; }
+extern "C" rt_ctx *rt_multi_ctx(rt_multi *m, int rank) { return (m && rank >= 0 && rank < m->n) ? m->ctx[rank] : nullptr; }
+
+extern "C" int rt_multi_set_option(rt_multi *m, const char *key, long long value) {
+  if (!m) return rt_fail(RT_ERR_ARG, "rt_multi_set_option: NULL argument");
+  for (int r = 0; r < m->n; r++) { const int rc = rt_set_option(m->ctx[r], key, value); if (rc != RT_OK) return rc; }
+  return RT_OK;
+}
+
+extern "C" int rt_multi_upload_scene(rt_multi *m, const double *spheres, int N, const double *lights, int L,
+                                     const double ambient[3], const double cam_pos[3], const double cam_look[3], double fov_deg) {
+  if (!m) return rt_fail(RT_ERR_ARG, "rt_multi_upload_scene: NULL argument");
+  // every rank holds a full scene replica; the per-rank table builds are independent: one host thread each
+  std::vector<int> rc((size_t)m->n, RT_OK);
+  std::vector<std::string> msg((size_t)m->n);
+  auto one = [&](int r) {
+    rc[r] = rt_upload_scene(m->ctx[r], spheres, N, lights, L, ambient, cam_pos, cam_look, fov_deg);
+    if (rc[r] != RT_OK) msg[r] = g_last_error;          // (thread local: copy it out of the worker thread)
+  };
+  if (m->n == 1) one(0);
+  else {
+    std::vector<std::thread> th;
+    for (int r = 0; r < m->n; r++) th.emplace_back(one, r);
+    for (auto &t : th) t.join();
+  }
+  for (int r = 0; r < m->n; r++) if (rc[r] != RT_OK) return rt_fail(rc[r], msg[r]);
+  return RT_OK;
+}
+
+extern "C" int rt_multi_render(rt_multi *m, int W, int H, int depth, int band_h, uint8_t *host_rgb, rt_stats *stats) {
+  if (!m || !host_rgb) return rt_fail(RT_ERR_ARG, "rt_multi_render: NULL argument");
+  if (W < 1 || H < 1 || depth < 0 || band_h < 1) return rt_fail(RT_ERR_ARG, "rt_multi_render: bad image size, depth or band height");
+  auto t0 = std::chrono::steady_clock::now();
+  const int n = m->n;
+  const size_t row_bytes = (size_t)W * 3, band_bytes = row_bytes * (size_t)band_h;
+  // asynchronous device -> host copies need page-locked memory: pin the caller's frame once (kept while it stays the same
+  // buffer); a frame that is already pinned (rt_host_alloc) reports cudaErrorHostMemoryAlreadyRegistered -- fine
+  if (n > 1 && (m->registered != host_rgb || m->registered_bytes != row_bytes * H)) {
+    if (m->registered) { cudaHostUnregister(m->registered); m->registered = nullptr; }
+    const cudaError_t e = cudaHostRegister(host_rgb, row_bytes * H, cudaHostRegisterPortable);
+    if (e == cudaSuccess) { m->registered = host_rgb; m->registered_bytes = row_bytes * H; }
+    else cudaGetLastError();                           // already pinned, or not pinnable: the copies still work (staged)
+  }
+  for (int r = 0; r < n; r++) {
+    rt_ctx *c = m->ctx[r];
+    const int rows = rt_band_rows(H, band_h, r, n);
+    if (rows < 0) return rows;
+    RT_CUDA(cudaSetDevice(c->device));
+    int rc = ensure_cap(m->part[r], m->part_cap[r], (size_t)(rows > 0 ? rows : 1) * row_bytes + 16);
+    if (rc) return rc;
+    rc = render_common(c, W, H, depth, band_h, r, n, m->part[r], nullptr, nullptr, c->stream, stats, nullptr, true);
+    if (rc) return rc;
+    if (rows == 0) continue;
+    // bands r, r + n, r + 2n, ...: full bands as one strided copy, a ragged last band (H % band_h rows) separately
+    const int nb_all = (H + band_h - 1) / band_h;
+    int nb = 0, nfull = 0;
+    for (int b = r; b < nb_all; b += n) { nb++; if ((b + 1) * band_h <= H) nfull++; }
+    uint8_t *dst0 = host_rgb + (size_t)r * band_bytes;
+    if (nfull > 0)
+      RT_CUDA(cudaMemcpy2DAsync(dst0, (size_t)n * band_bytes, m->part[r], band_bytes, band_bytes, (size_t)nfull, cudaMemcpyDeviceToHost, c->stream));
+    if (nb > nfull) {
+      const int b = r + nfull * n, tail_rows = H - b * band_h;
+      RT_CUDA(cudaMemcpyAsync(host_rgb + (size_t)b * band_bytes, m->part[r] + (size_t)nfull * band_bytes, (size_t)tail_rows * row_bytes,
+                              cudaMemcpyDeviceToHost, c->stream));
+    }
+  }
+  rt_stats acc;
+  memset(&acc, 0, sizeof(acc));
+  for (int r = 0; r < n; r++) {
+    rt_ctx *c = m->ctx[r];
+    RT_CUDA(cudaSetDevice(c->device));
+    if (stats) {
+      rt_stats s;
+      const int rc = collect_stats(c, &s);
+      if (rc) return rc;
+      // time-like fields: the slowest rank; counters: summed (every ray of the frame is traced by exactly one rank)
+      acc.ms_device = std::fmax(acc.ms_device, s.ms_device); acc.ms_level0 = std::fmax(acc.ms_level0, s.ms_level0);
+      acc.ms_closest0 = std::fmax(acc.ms_closest0, s.ms_closest0); acc.ms_shadow0 = std::fmax(acc.ms_shadow0, s.ms_shadow0);
+      acc.closest_queries += s.closest_queries; acc.hits += s.hits; acc.shadow_queries += s.shadow_queries; acc.occluded += s.occluded;
+      for (int k = 0; k < RT_MAX_LEVELS; k++) acc.alive[k] += s.alive[k];
+      acc.fp64_intersections += s.fp64_intersections; acc.sphere_tests += s.sphere_tests; acc.filter_violations += s.filter_violations;
+      acc.kernel_launches += s.kernel_launches; acc.rows_rendered += s.rows_rendered;
+      acc.bundle_walks += s.bundle_walks; acc.bundle_candidates += s.bundle_candidates; acc.bundle_fallbacks += s.bundle_fallbacks;
+    }
+    RT_CUDA(cudaStreamSynchronize(c->stream));         // also: this rank's device -> host copies have landed
+  }
+  if (stats) {
+    *stats = acc;
+    stats->ms_host = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  }
   return RT_OK;
 }

@@ -386,6 +386,8 @@ int resident_grid(K kernel, size_t smem, int num_sms, int threads = rtf::kThread
 // Launch with programmatic dependent launch (PDL): the grid may start while the previous kernel of the stream is
 // still draining, run its prologue (table staging) and then block in griddepcontrol.wait (RT_PDL_SYNC in the kernels)
 // until that kernel has completed and flushed.  Hides launch latency + prologue behind the predecessor's tail.
+// The first failing launch of a frame is remembered (g_launch_err, thread local) and reported by rtk_launch_fast.
+thread_local cudaError_t g_launch_err = cudaSuccess;
 template <typename K, typename A>
 void launch(K kernel, int grid, int block, size_t smem, cudaStream_t stream, bool pdl, const A &arg) {
   cudaLaunchConfig_t cfg;
@@ -395,7 +397,8 @@ void launch(K kernel, int grid, int block, size_t smem, cudaStream_t stream, boo
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = pdl ? 1u : 0u;
-  cudaLaunchKernelEx(&cfg, kernel, arg);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, arg);
+  if (e != cudaSuccess && g_launch_err == cudaSuccess) g_launch_err = e;
 }
 // dynamic shared memory of a kernel that stages `bytes` of tables: header | tables | per-warp compacted tables
 // ... of the LBVH level-0 kernels: header | per-warp compacted tables | per-warp bundle-traversal frontiers
@@ -440,6 +443,7 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
   RTK_TRY(cudaMemsetAsync(w->ctl, 0, kCtlWords * sizeof(unsigned int), stream));
   if (args.max_depth <= 0 && !args.fb && !args.out_remap) RTK_TRY(cudaMemsetAsync(args.rgb, 0, npix * 3, stream));   // src/main.cpp:17-18: black (other output modes: the caller clears)
 
+  g_launch_err = cudaSuccess;
   rtf::WaveArgs wa;
   memset(&wa, 0, sizeof(wa));
   rtf::FastArgs &a = wa.f;
@@ -575,6 +579,7 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
     w->fb_pending = 1; w->fb_pending_key = fb_key;
   }
   cudaError_t e = cudaGetLastError();
+  if (g_launch_err != cudaSuccess) e = g_launch_err;
   return e == cudaSuccess ? launches : -(int)e;
 }
 
@@ -592,9 +597,11 @@ __global__ void k_peer_signal(volatile unsigned int *flag, unsigned int value) {
 __global__ void k_peer_wait(volatile unsigned int *flags, int n, unsigned int value, unsigned int *err) {
   const int k = threadIdx.x;
   if (k >= n) return;
-  const long long t0 = clock64();
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
   while ((int)(flags[k] - value) < 0) {
-    if (clock64() - t0 > 4000000000LL) { atomicExch(err, 1u + (unsigned)k); break; }
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 2000000000ULL) { atomicExch(err, 1u + (unsigned)k); break; }    // 2 s of wall clock (ns timer), whatever the SM clock
     __nanosleep(200);
   }
   __threadfence_system();

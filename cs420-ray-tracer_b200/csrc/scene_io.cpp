@@ -4,6 +4,7 @@
 // north star keeps: include/scene_loader.h:27-135 (scene grammar, warn-and-skip behaviour,
 // "Loaded scene:" line) and src/main.cpp:69-91 (P3 writer).  No GPU is needed for these.
 #include <cerrno>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -51,6 +52,9 @@ bool extract_double(const char *&p, double &out) {
   char *end = nullptr;
   out = std::strtod(tok.c_str(), &end);
   if (end == tok.c_str()) return false;
+  // libstdc++'s num_get (`iss >> double`, include/scene_loader.h:63-101) sets failbit when strtod overflows to
+  // +-HUGE_VAL, so the reference warns and skips such a line; underflow is accepted there and here
+  if (out == HUGE_VAL || out == -HUGE_VAL) return false;
   p = q;
   return true;
 }

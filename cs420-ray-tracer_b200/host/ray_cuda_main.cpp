@@ -8,6 +8,7 @@
 //
 // Extra flags (none collide with the reference's): --width N --height N --depth N
 //   --output FILE --device N --exact (FP64 diagnostic kernels) --frames N (repeat, report best)
+//   --gpus N --band H : the frame sharded by interleaved H-row bands over N GPUs of the box (rt_create_multi)
 // -a = 2x2 supersampling, as the reference's ray_cuda (src/main_gpu.cu:363-371).
 #include <cstdio>
 #include <cstdlib>
@@ -23,7 +24,7 @@ static int die(const char *what) {
 }
 
 int main(int argc, char **argv) {
-  int W = 1280, H = 720, depth = 10, device = 0, frames = 1;
+  int W = 1280, H = 720, depth = 10, device = 0, frames = 1, gpus = 1, band = 16;
   bool exact = false, antialias = false;
   std::string scene_file = "scenes/simple.txt", output = "output_gpu.ppm";
   for (int i = 1; i < argc; i++) {
@@ -34,6 +35,8 @@ int main(int argc, char **argv) {
     else if (a == "--depth") next(depth);
     else if (a == "--device") next(device);
     else if (a == "--frames") next(frames);
+    else if (a == "--gpus") next(gpus);
+    else if (a == "--band") next(band);
     else if (a == "--output" && i + 1 < argc) output = argv[++i];
     else if (a == "--exact") exact = true;
     else if (a == "-a") { antialias = true; std::printf("Antialiasing Enabled.\n"); }   // src/main_gpu.cu:368-370
@@ -53,16 +56,26 @@ int main(int argc, char **argv) {
   rt_scene_data(sc, &sph, &lig, &amb, &cam);
 
   rt_ctx *ctx = nullptr;
-  if (rt_create(device, &ctx) != RT_OK) return die("rt_create");
-  if (exact && rt_set_option(ctx, "mode", 1) != RT_OK) return die("rt_set_option");
-  if (antialias && rt_set_option(ctx, "antialias", 1) != RT_OK) return die("rt_set_option");
-  if (rt_upload_scene(ctx, sph, N, lig, L, amb, cam, cam + 3, cam[6]) != RT_OK) return die("rt_upload_scene");
+  rt_multi *multi = nullptr;
+  if (gpus > 1) {
+    if (rt_create_multi(gpus, &multi) != RT_OK) return die("rt_create_multi");
+    if (exact && rt_multi_set_option(multi, "mode", 1) != RT_OK) return die("rt_multi_set_option");
+    if (antialias && rt_multi_set_option(multi, "antialias", 1) != RT_OK) return die("rt_multi_set_option");
+    if (rt_multi_upload_scene(multi, sph, N, lig, L, amb, cam, cam + 3, cam[6]) != RT_OK) return die("rt_multi_upload_scene");
+  } else {
+    if (rt_create(device, &ctx) != RT_OK) return die("rt_create");
+    if (exact && rt_set_option(ctx, "mode", 1) != RT_OK) return die("rt_set_option");
+    if (antialias && rt_set_option(ctx, "antialias", 1) != RT_OK) return die("rt_set_option");
+    if (rt_upload_scene(ctx, sph, N, lig, L, amb, cam, cam + 3, cam[6]) != RT_OK) return die("rt_upload_scene");
+  }
   std::vector<uint8_t> rgb((size_t)W * H * 3);
-  std::printf("Rendering (GPU, B200 sm_100a)...\n");
+  if (gpus > 1) std::printf("Rendering (GPU, B200 sm_100a, %d-row bands over %d GPUs)...\n", band, gpus);
+  else std::printf("Rendering (GPU, B200 sm_100a)...\n");
   rt_stats st;
   double best = 1e30;
   for (int f = 0; f < (frames > 0 ? frames : 1); f++) {
-    if (rt_render(ctx, W, H, depth, rgb.data(), &st) != RT_OK) return die("rt_render");
+    if (multi) { if (rt_multi_render(multi, W, H, depth, band, rgb.data(), &st) != RT_OK) return die("rt_multi_render"); }
+    else if (rt_render(ctx, W, H, depth, rgb.data(), &st) != RT_OK) return die("rt_render");
     if (st.ms_device < best) best = st.ms_device;
   }
   std::printf("GPU rendering time: %g seconds\n", best * 1e-3);
@@ -71,6 +84,7 @@ int main(int argc, char **argv) {
               (unsigned long long)st.closest_queries, (unsigned long long)st.shadow_queries, rays,
               rays / (best * 1e-3) * 1e-6, st.kernel_launches);
   if (rt_write_ppm(output.c_str(), rgb.data(), W, H) != RT_OK) return die("rt_write_ppm");
+  if (multi) rt_multi_destroy(multi);
   rt_destroy(ctx);
   rt_scene_free(sc);
   return 0;

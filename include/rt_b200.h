@@ -17,6 +17,7 @@
  *                                  src/kernel.cu:185-200           launch_gpu_kernel (tile launch)
  *                                  src/main.cpp:84-86              the 8-bit quantiser of write_ppm
  *   rt_render_tile                 src/kernel.cu:185-200           launch_gpu_kernel (tile + stream + float3 fb)
+ *   rt_create_multi / rt_multi_*   src/main.cpp:185-199            the OpenMP pixel loop, sharded by row bands over GPUs
  *   rt_set_option("antialias")     src/main_gpu.cu:249-258,327-333 ray_cuda -a (2x2 supersampling)
  *   rt_write_ppm                   src/main.cpp:69-91              write_ppm (P3 text)
  *
@@ -25,12 +26,16 @@
  * sphere index, 8-bit RGB within 1 LSB.
  *
  * Threading: one host thread per rt_ctx at a time.  A ctx owns one CUDA device, one stream
- * and all device memory it allocates.  Camera, lights and ambient live in one __constant__
- * bank per DEVICE (as in the reference, src/kernel.cu:7-9): contexts that share a device may
- * alternate (the bank is refreshed on demand) but must not have renders of DIFFERENT scenes
- * in flight at the same time.  rt_upload_scene must not be called while a render of this ctx
- * that was enqueued on a caller's stream is still running.  There is no CPU fallback: every
- * render entry point fails with RT_ERR_CUDA when no sm_100 device is usable.
+ * and all device memory it allocates.  Renders of ONE ctx are serialised on the device, whatever
+ * streams the caller passes (they share the ctx's ray queues and counters): a render enqueued on
+ * stream B waits -- on the device, not on the host -- for the ctx's previous render on stream A, so
+ * the reference's "tiles round-robin over three streams" loop (src/main_hybrid.cpp:611-622) is safe,
+ * it just does not overlap tiles of the same ctx.  Camera, lights and ambient live in one
+ * __constant__ bank per DEVICE (as in the reference, src/kernel.cu:7-9): contexts that share a
+ * device may interleave renders freely; the bank is rewritten when it changes hands, stream-ordered
+ * behind the previous owner's last render.  rt_upload_scene waits (on the host) for every render of
+ * the ctx that is still in flight, also those enqueued on caller streams.  There is no CPU
+ * fallback: every render entry point fails with RT_ERR_CUDA when no sm_100 device is usable.
  */
 #ifndef RT_B200_H
 #define RT_B200_H
@@ -115,7 +120,11 @@ void rt_destroy(rt_ctx *ctx);
  * the fused tail; "antialias" 0/1 = 2x2 supersampling as the reference's `ray_cuda -a`
  * (src/main_gpu.cu:249-258,327-333: samples at pixel offsets (0,0) (.5,0) (0,.5) (.5,.5),
  * averaged before the 8-bit quantiser); with it on, the debug buffers of rt_render_debug are
- * per sample: [2H][2W][max_depth], sample (a,b) of pixel (i,j) at (2j+b, 2i+a).            */
+ * per sample: [2H][2W][max_depth], sample (a,b) of pixel (i,j) at (2j+b, 2i+a);
+ * "level_timing" 0/1 = record CUDA events between the level-0 kernels so that rt_stats carries
+ * ms_closest0 / ms_shadow0 / ms_level0 (default 0: the events break the back-to-back programmatic
+ * dependent launches of the production path, so timing renders run a slightly different launch
+ * sequence; without it those three fields equal ms_device / 0 / ms_device).                   */
 int rt_set_option(rt_ctx *ctx, const char *key, long long value);
 
 /* Copies the scene to the device (host -> device inside the call) and precomputes the
@@ -181,6 +190,27 @@ int rt_render_tile(rt_ctx *ctx, int width, int height, int max_depth, int tile_x
 int rt_band_rows(int height, int band_h, int rank, int nranks);
 /* Writes the owned row indices (ascending) into rows[rt_band_rows()]. */
 int rt_band_row_list(int height, int band_h, int rank, int nranks, int32_t *rows);
+
+/* ---- one frame on several GPUs of the box, in ONE process ---------------------------------
+ * rt_create_multi(ngpus): ranks 0..ngpus-1, rank r on device r (r modulo the device count when the
+ * box has fewer GPUs: same frame, no speed-up), each with its own rt_ctx (device, stream, scene
+ * replica, buffers).  rt_multi_render: rank r renders the interleaved bands b with b % ngpus == r
+ * (band = band_h rows; the rule of rt_render_bands) and copies them over ITS OWN host link to their
+ * image positions in host_rgb (W*H*3, row 0 = bottom); the call returns when the frame is complete.
+ * host_rgb is page-locked for the duration if it is not already (rt_host_alloc avoids that).
+ * stats (may be NULL): counters summed over the ranks, times = the slowest rank.  rt_multi_ctx gives
+ * the per-rank context for the calls that have no multi form (valid until rt_multi_destroy).     */
+typedef struct rt_multi rt_multi;
+int rt_create_multi(int ngpus, rt_multi **out);
+void rt_multi_destroy(rt_multi *m);
+int rt_multi_ranks(const rt_multi *m);
+rt_ctx *rt_multi_ctx(rt_multi *m, int rank);
+int rt_multi_set_option(rt_multi *m, const char *key, long long value);
+int rt_multi_upload_scene(rt_multi *m, const double *spheres, int nspheres, const double *lights,
+                          int nlights, const double ambient[3], const double cam_pos[3],
+                          const double cam_look[3], double fov_deg);
+int rt_multi_render(rt_multi *m, int width, int height, int max_depth, int band_h, uint8_t *host_rgb,
+                    rt_stats *stats);
 
 /* ---- pinned host memory -----------------------------------------------------------------
  * Page-locked buffers so that the frame copy of rt_render runs at full host-link rate.

@@ -1,0 +1,80 @@
+"""The process-level drop-in contract (SURVEY 8b level 1): the `ray_cuda` binary run the way the reference's own
+smoke test runs its binaries (scripts/test.sh:22-70, 205-256) -- from a directory holding scenes/, default scene
+scenes/simple.txt, exit code 0, output_gpu.ppm larger than 1000 bytes, a line matching `time:|seconds`, and the image
+compared with ray_serial's output_serial.ppm by the rule of scripts/compare_ppm.py at tolerance 0.5 (1 LSB).
+oracle/_ref/ray_serial is the UNMODIFIED reference binary (oracle/Makefile).  Needs a B200: run with -m gpu."""
+import os
+import re
+import shutil
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+pytestmark = pytest.mark.gpu
+PKG = os.path.join(ROOT, "cs420-ray-tracer_b200")
+REF = os.path.join(ROOT, "oracle", "_ref")
+REF_COMPARE = "/root/reference/scripts/compare_ppm.py"      # only in the build container; the rule is pinned by tests/test_host.py
+
+
+@pytest.fixture(scope="module")
+def workdir(tmp_path_factory):
+    d = tmp_path_factory.mktemp("dropin")
+    os.makedirs(d / "scenes")
+    for n in ("simple", "medium", "complex"):
+        shutil.copy(os.path.join(GOLDEN, "scenes", n + ".txt"), d / "scenes" / (n + ".txt"))
+    return d
+
+
+def run(cmd, cwd):
+    p = subprocess.run(cmd, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    return p.returncode, p.stdout
+
+
+def compare(rt, a, b, tol=0.5):
+    if os.path.exists(REF_COMPARE):                     # the reference's own script when it is there
+        p = subprocess.run([sys.executable, REF_COMPARE, str(a), str(b), str(tol)], stdout=subprocess.PIPE, text=True)
+        assert p.returncode == 0, p.stdout
+    Wa, Ha, _, ia = rt.read_ppm(str(a))
+    Wb, Hb, _, ib = rt.read_ppm(str(b))
+    assert (Wa, Ha) == (Wb, Hb)
+    ok, pct, mx = rt.compare_rgb(ia, ib, tol)
+    assert ok and mx <= 2, (pct, mx)
+
+
+@pytest.mark.parametrize("args", [[], ["scenes/medium.txt"], ["scenes/complex.txt"]])
+def test_ray_cuda_is_a_drop_in_for_ray_serial(rt, workdir, args):
+    if not os.path.exists(os.path.join(REF, "ray_serial")):
+        pytest.skip("oracle/_ref/ray_serial was not built (needs /root/reference at build time)")
+    for f in ("output_gpu.ppm", "output_serial.ppm"):
+        if os.path.exists(workdir / f):
+            os.remove(workdir / f)
+    rc, out = run([os.path.join(PKG, "ray_cuda")] + args, workdir)
+    assert rc == 0, out
+    rc2, out2 = run([os.path.join(REF, "ray_serial")] + args, workdir)
+    assert rc2 == 0, out2
+    # scripts/test.sh:49-62: output exists, > 1000 bytes, a timing line
+    assert os.path.getsize(workdir / "output_gpu.ppm") > 1000
+    timing = [l for l in out.splitlines() if re.search(r"(time:|seconds)", l)]
+    assert timing and re.search(r"time: [0-9.eE+-]+ seconds", timing[0]), out
+    # both announce the scene the same way (include/scene_loader.h:131-132)
+    loaded = [l for l in out.splitlines() if l.startswith("Loaded scene:")]
+    assert loaded and loaded == [l for l in out2.splitlines() if l.startswith("Loaded scene:")]
+    compare(rt, workdir / "output_serial.ppm", workdir / "output_gpu.ppm", 0.5)
+
+
+def test_ray_cuda_flags_and_multi_gpu_bands(rt, workdir):
+    """--width/--height/--depth/--output, -a, and --gpus N --band H (all ranks in ONE process through rt_create_multi;
+    with fewer physical GPUs the ranks share devices, the frame is the same)."""
+    rc, out = run([os.path.join(PKG, "ray_cuda"), "--width", "320", "--height", "180", "--depth", "5", "--output", "one.ppm",
+                   "scenes/complex.txt"], workdir)
+    assert rc == 0, out
+    rc, out = run([os.path.join(PKG, "ray_cuda"), "--width", "320", "--height", "180", "--depth", "5", "--output", "four.ppm",
+                   "--gpus", "4", "--band", "8", "scenes/complex.txt"], workdir)
+    assert rc == 0, out
+    assert (workdir / "one.ppm").read_bytes() == (workdir / "four.ppm").read_bytes()
+    rc, out = run([os.path.join(PKG, "ray_cuda"), "scenes/missing.txt"], workdir)
+    assert rc != 0 and "Could not open scene file" in out

@@ -148,3 +148,41 @@ def test_row_bands_partition_the_image(rt, H, band_h, n):
         rt.band_rows(H, 0, 0, n)
     with pytest.raises(rt.RtError):
         rt.band_rows(H, band_h, n, n)
+
+
+def test_loader_rejects_overflowing_literals_like_the_reference(rt, tmp_path, capfd):
+    """`iss >> double` (libstdc++ num_get) sets failbit when a literal overflows, so include/scene_loader.h:63-101
+    warns and skips the line; underflow is accepted."""
+    p = tmp_path / "ovf.txt"
+    p.write_text("sphere 0 0 -5 1e999 1 1 1 0 1 10\nsphere 0 0 -5 1 1 1 1 0 1 10\nlight 1 2 3 1 1 1 -1e400\nlight 1 2 3 1 1 1e-400 1\n")
+    sc = rt.load_scene(str(p))
+    assert sc.nspheres == 1 and sc.nlights == 1 and sc.lights[0][5] == 0.0
+    assert capfd.readouterr().err.count("Warning") == 2
+    ref = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+    if os.path.exists(ref):
+        out = subprocess.run([ref, "dump", str(p)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True).stdout
+        assert "spheres 1" in out and "lights 1" in out
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/scripts/compare_ppm.py"), reason="reference tree not present")
+def test_compare_rule_against_the_reference_script_itself(rt, oracle, scenes, tmp_path):
+    """rt.compare_rgb is what the GPU tests gate RGB with on the GPU box (no /root/reference there): here, where the
+    reference tree exists, scripts/compare_ppm.py itself judges the same image pairs and must agree -- on an oracle
+    render against perturbed copies on both sides of the 0.1 % / 1 LSB threshold."""
+    base = oracle.render(scenes["simple"], 160, 90, 5)["rgb"]
+    a = tmp_path / "a.ppm"
+    rt.write_ppm(str(a), base)
+    rng = np.random.default_rng(5)
+    n = base.size
+    for k, (nbad, delta) in enumerate([(0, 0), (n // 2, 1), (int(n * 0.0009), 2), (int(n * 0.0011) + 1, 2), (n // 50, 3)]):
+        x = base.astype(np.int64).ravel().copy()
+        idx = rng.choice(n, nbad, replace=False)
+        x[idx] = np.where(x[idx] + delta <= 255, x[idx] + delta, x[idx] - delta)
+        img = x.reshape(base.shape).astype(np.uint8)
+        b = tmp_path / ("b%d.ppm" % k)
+        rt.write_ppm(str(b), img)
+        for tol in (0.5, 1.0):
+            p = subprocess.run(["python3", "/root/reference/scripts/compare_ppm.py", str(a), str(b), str(tol)], stdout=subprocess.PIPE, text=True)
+            ok, pct, _ = rt.compare_rgb(base, img, tol)
+            assert (p.returncode == 0) == ok, (k, tol, p.stdout, pct)
+            assert ("Diff pixels: %.2f%%" % pct) in p.stdout
