@@ -52,16 +52,53 @@ struct WaveArgs {
   unsigned int *work_counter;      // per-launch chunk counter
   Best *cand;                      // LBVH scenes, level >= 1: per queued ray, the closest-hit candidate k_closest1_dyn found
   unsigned int *work_counter2;     // ... and that kernel's item counter
+  // whole-frame kernel (kernels_frame.cuh): the control words of this frame, those of the next one (zeroed by the kernel
+  // on its way out) and both ray queues; the level-dependent pointers above are derived from these (lvl_at)
+  unsigned int *ctl, *ctl_next;
+  RayRec *queue[2];
+  unsigned int *shade_done;        // per chunk of hits: (chunk, light) items finished so far (self-resetting)
 };
+
+// Control words (u32) of one frame: [0] tile counter, [4] grid-barrier arrivals, [5] error word; per level k <= 33: tail
+// chunk counter, shadow / shade / closest work counters, hits of level k (x64: blocks in use), rays entering level k,
+// shade-done counters of the (chunk, light) items
+enum { CTL_TILE = 0, CTL_BARRIER = 4, CTL_ERR = 5, CTL_TAIL = 8, CTL_SHADOW = 48, CTL_SHADE = 88, CTL_CLOSEST = 128, CTL_HITS = 168, CTL_RAYS = 208,
+       CTL_WORDS = 256 };
+
+// The level-dependent part of a launch.  The per-level kernels fill it from their arguments (lvl_of), the whole-frame
+// kernel derives it from the control words (lvl_at).
+struct Lvl {
+  int level;
+  unsigned int *hit_count;                     // 64 x hit blocks in use at this level
+  unsigned int *work_closest, *work_shadow, *work_shade;
+  RayRec *q_in; const unsigned int *q_in_count; // rays entering this level (level >= 1)
+  RayRec *q_out; unsigned int *q_out_count;     // rays leaving it
+};
+__device__ __forceinline__ Lvl lvl_of(const WaveArgs &w) {
+  Lvl v;
+  v.level = w.f.level; v.hit_count = w.hit_count;
+  v.work_closest = v.work_shadow = v.work_shade = w.work_counter;
+  v.q_in = w.f.q_in; v.q_in_count = w.f.q_in_count; v.q_out = w.f.q_out; v.q_out_count = w.f.q_out_count;
+  return v;
+}
+__device__ __forceinline__ Lvl lvl_at(const WaveArgs &w, int level) {
+  Lvl v;
+  v.level = level; v.hit_count = w.ctl + CTL_HITS + level;
+  v.work_closest = level == 0 ? w.ctl + CTL_TILE : w.ctl + CTL_CLOSEST + level;
+  v.work_shadow = w.ctl + CTL_SHADOW + level; v.work_shade = w.ctl + CTL_SHADE + level;
+  v.q_in = w.queue[(level + 1) & 1]; v.q_in_count = w.ctl + CTL_RAYS + level;
+  v.q_out = w.queue[level & 1]; v.q_out_count = w.ctl + CTL_RAYS + level + 1;
+  return v;
+}
 
 // Allocates the block of a work item with (m0, m1) = ballots of its candidate hits; slot[r] = where this
 // lane's hit r goes.  One atomic per work item.
-__device__ __forceinline__ void hit_block(const WaveArgs &w, unsigned m0, unsigned m1, unsigned (&slot)[2]) {
+__device__ __forceinline__ void hit_block(const WaveArgs &w, unsigned int *hit_count, unsigned m0, unsigned m1, unsigned (&slot)[2]) {
   const int lane = threadIdx.x & 31;
   const unsigned n = (unsigned)(__popc(m0) + __popc(m1));
   unsigned base = 0;
   if (n != 0u) {
-    if (lane == 0) { base = atomicAdd(w.hit_count, 64u); w.hit_n[base >> 6] = n; }
+    if (lane == 0) { base = atomicAdd(hit_count, 64u); w.hit_n[base >> 6] = n; }
     base = __shfl_sync(kFull, base, 0);
   }
   const unsigned lt = (1u << lane) - 1u;
@@ -159,17 +196,13 @@ __device__ __forceinline__ int cta_fetch(unsigned int *counter, unsigned char *s
 
 // ---------------------------------------------------------------------------------------------
 // LEVEL 0 closest hit: each warp pulls 16x4-pixel tiles, two vertically adjacent pixels per lane.
+// tabs: where table 0 (the camera table) is read from (shared memory when staged); wbase: the per-warp compacted tables
 template <int kMode>
-__global__ void __launch_bounds__(kThreads, RT_CLOSEST_CTAS) k_closest0(const WaveArgs w) {
-  extern __shared__ __align__(128) unsigned char smem[];
+__device__ __forceinline__ void closest0_body(const WaveArgs &w, const Lvl &lv, unsigned char *smem, const unsigned char *tabs, unsigned char *wbase) {
   const FastArgs &a = w.f;
-  const unsigned char *tabs = a.tabs;
-  if (kMode == kTabSmem) { stage_tables(smem, a.tabs, a.stage_bytes); tabs = smem + kSmemHeader; }
-  if (kMode == kTabStream) ring_init(smem);
-  RT_PDL_SYNC();
   const Tab camg = tab_at(a.tabs, a, 0);             // global view (gmin / perm of the streamed mode)
   const Tab cam = tab_at(tabs, a, 0);
-  const WarpBuf wb = warp_buf(smem + kSmemHeader + (kMode == kTabBvh ? 0u : ((a.stage_bytes + 127u) & ~127u)));   // kTabSmem / kTabBvh
+  const WarpBuf wb = warp_buf(wbase);                                                                                // kTabSmem / kTabBvh
   const BundleBuf bb = bundle_buf(smem + kSmemHeader + kWarps * kWarpBufBytes);                                      // kTabBvh only
   unsigned ring_phase = 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -181,11 +214,11 @@ __global__ void __launch_bounds__(kThreads, RT_CLOSEST_CTAS) k_closest0(const Wa
   for (;;) {
     int tile;
     if (kMode == kTabStream) {
-      const int ct = cta_fetch(a.tile_counter, smem);
+      const int ct = cta_fetch(lv.work_closest, smem);
       if (ct * kWarps >= a.nwtiles) break;
       tile = ct * kWarps + warp;
     } else {
-      tile = warp_fetch(a.tile_counter);
+      tile = warp_fetch(lv.work_closest);
       if (tile >= a.nwtiles) break;
     }
     const bool tile_ok = tile < a.nwtiles;
@@ -269,7 +302,7 @@ __global__ void __launch_bounds__(kThreads, RT_CLOSEST_CTAS) k_closest0(const Wa
       best[0] = q.best[0]; best[1] = q.best[1];
     }
     unsigned hslot[2];
-    hit_block(w, __ballot_sync(kFull, live[0] && best[0].idx >= 0), __ballot_sync(kFull, live[1] && best[1].idx >= 0), hslot);
+    hit_block(w, lv.hit_count, __ballot_sync(kFull, live[0] && best[0].idx >= 0), __ballot_sync(kFull, live[1] && best[1].idx >= 0), hslot);
 #pragma unroll
     for (int r = 0; r < 2; r++) {
       bool hit = false;
@@ -322,28 +355,35 @@ __global__ void __launch_bounds__(kThreads, RT_CLOSEST_CTAS) k_closest0(const Wa
   }
   if (a.r.counters) flush_counts(a.r.counters, 0, c_closest, c_hits, 0, 0, c_fp64, c_viol, (unsigned long long)a.N, c_cand, c_walks, c_fall);
 }
+template <int kMode>
+__global__ void __launch_bounds__(kThreads, RT_CLOSEST_CTAS) k_closest0(const WaveArgs w) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const FastArgs &a = w.f;
+  const unsigned char *tabs = a.tabs;
+  if (kMode == kTabSmem) { stage_tables(smem, a.tabs, a.stage_bytes); tabs = smem + kSmemHeader; }
+  if (kMode == kTabStream) ring_init(smem);
+  RT_PDL_SYNC();
+  Lvl lv = lvl_of(w);
+  lv.work_closest = a.tile_counter;
+  closest0_body<kMode>(w, lv, smem, tabs, smem + kSmemHeader + (kMode == kTabBvh ? 0u : ((a.stage_bytes + 127u) & ~127u)));
+}
 
 // ---------------------------------------------------------------------------------------------
 // LEVEL >= 1 closest hit: reflected rays from the RayRec queue, 64 per warp fetch, two per lane.
-template <bool kSmem, bool kBvh>
-__global__ void __launch_bounds__(kThreads, RT_CLOSEST_CTAS) k_closest1(const WaveArgs w) {
-  extern __shared__ __align__(128) unsigned char smem[];
+// gen: the general table (shared memory when staged)
+template <bool kBvh>
+__device__ __forceinline__ void closest1_body(const WaveArgs &w, const Lvl &lv, const float4 *gen) {
   const FastArgs &a = w.f;
-  // staged: the general table only (it follows the (1+L) shared-origin tables)
-  const unsigned char *tabs = a.tabs + (size_t)(a.L + 1) * a.tstride;
-  if (kSmem) { stage_tables(smem, tabs, a.stage_bytes); tabs = smem + kSmemHeader; }
-  RT_PDL_SYNC();
-  const unsigned nq = *a.q_in_count;
+  const unsigned nq = __ldcg(lv.q_in_count);
   if (nq == 0u) return;
-  const float4 *gen = reinterpret_cast<const float4 *>(tabs);
-  const int lane = threadIdx.x & 31, depth = a.r.max_depth, level = a.level;
+  const int lane = threadIdx.x & 31, depth = a.r.max_depth, level = lv.level;
   unsigned c_closest = 0, c_hits = 0, c_fp64 = 0, c_viol = 0;
-  const RayRec *qin = a.q_in;
+  const RayRec *qin = lv.q_in;
   // few rays (deep levels): one ray per lane, so that twice as many warps share the work
   const bool two = nq >= gridDim.x * (unsigned)kWarps * 64u;
   const unsigned per = two ? 64u : 32u;
   for (;;) {
-    const int chunk = warp_fetch(w.work_counter);
+    const int chunk = warp_fetch(lv.work_closest);
     if ((unsigned)chunk * per >= nq) break;
     bool live[2];
     unsigned qi[2], pix[2];
@@ -375,7 +415,7 @@ __global__ void __launch_bounds__(kThreads, RT_CLOSEST_CTAS) k_closest1(const Wa
       closest_general<2>(gen, a.npairs, a.N, ox, oy, oz, dx, dy, dz, live, a.d64, a.gS2, a.g_dtmax, a.r.sph64, src, best);
     }
     unsigned hslot[2];
-    hit_block(w, __ballot_sync(kFull, live[0] && best[0].idx >= 0), __ballot_sync(kFull, live[1] && best[1].idx >= 0), hslot);
+    hit_block(w, lv.hit_count, __ballot_sync(kFull, live[0] && best[0].idx >= 0), __ballot_sync(kFull, live[1] && best[1].idx >= 0), hslot);
 #pragma unroll
     for (int r = 0; r < 2; r++) {
       bool hit = false;
@@ -398,6 +438,75 @@ __global__ void __launch_bounds__(kThreads, RT_CLOSEST_CTAS) k_closest1(const Wa
   }
   if (a.r.counters) flush_counts(a.r.counters, level, c_closest, c_hits, 0, 0, c_fp64, c_viol, (unsigned long long)a.N);
 }
+template <bool kSmem, bool kBvh>
+__global__ void __launch_bounds__(kThreads, RT_CLOSEST_CTAS) k_closest1(const WaveArgs w) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const FastArgs &a = w.f;
+  // staged: the general table only (it follows the (1+L) shared-origin tables)
+  const unsigned char *tabs = a.tabs + (size_t)(a.L + 1) * a.tstride;
+  if (kSmem) { stage_tables(smem, tabs, a.stage_bytes); tabs = smem + kSmemHeader; }
+  RT_PDL_SYNC();
+  closest1_body<kBvh>(w, lvl_of(w), reinterpret_cast<const float4 *>(tabs));
+}
+
+// ---------------------------------------------------------------------------------------------
+// SHADE of ONE hit (lane local, no warp-level operations): include/scene.h:89-121 in FP32 with the occlusion bits of
+// the shadow queries (bit l of occm = light l occluded), then src/main.cpp:43-55 -- the pixel is final (written here),
+// or the path continues: returns true and *rec is the exact FP64 reflected ray for the next level's queue.
+__device__ __forceinline__ bool shade_one(const WaveArgs &w, const Lvl &lv, const HitRec &hr, unsigned long long occm, RayRec &rec) {
+  const FastArgs &a = w.f;
+  const int L = a.L, level = lv.level;
+  const float4 m = __ldg(&a.r.mat[hr.idx]);
+  const float2 mx = __ldg(&a.r.matx[hr.idx]);
+  float sr = g_frame.ambient[0] * m.x, sg = g_frame.ambient[1] * m.y, sb = g_frame.ambient[2] * m.z;
+  for (int l = 0; l < L; l++) {
+    if ((occm >> l) & 1ull) continue;
+    // light_dir = normalized(light - point): FP64 difference, FP32 normalisation (colour only)
+    const float wx = (float)(g_frame.light_pos[l][0] - hr.px), wy = (float)(g_frame.light_pos[l][1] - hr.py),
+                wz = (float)(g_frame.light_pos[l][2] - hr.pz);
+    const float inv = rsqrtf(fmaf(wz, wz, fmaf(wy, wy, wx * wx)));
+    const float lx = wx * inv, ly = wy * inv, lz = wz * inv;
+    const float nl = hr.nx * lx + hr.ny * ly + hr.nz * lz;
+    const float kd = (1.0f - m.w) * fmaxf(0.0f, nl);
+    // reflect(-light_dir, n) = -l + 2 (l.n) n   (include/vec3.h:31-33)
+    const float rx = 2.0f * nl * hr.nx - lx, ry = 2.0f * nl * hr.ny - ly, rz = 2.0f * nl * hr.nz - lz;
+    const float rdv = fmaxf(0.0f, rx * hr.vx + ry * hr.vy + rz * hr.vz);
+    const float spec = 0.5f * (mx.x == 0.0f ? 1.0f : __powf(rdv, mx.x));
+    sr += g_frame.light_col[l][0] * spec + m.x * kd;
+    sg += g_frame.light_col[l][1] * spec + m.y * kd;
+    sb += g_frame.light_col[l][2] * spec + m.z * kd;
+  }
+  if (a.r.shadow_mask) a.r.shadow_mask[(size_t)hr.pix * a.r.max_depth + level] = (unsigned)(occm & 0xffffffffull);
+  float cr = hr.ar, cg = hr.ag, cb = hr.ab, wt = hr.wt;
+  bool cont = false;
+  if (mx.y > 0.5f) {                          // reflectivity > 0, decided in double on the host
+    const float refl = m.w, k = wt * (1.0f - refl);
+    cr += k * sr; cg += k * sg; cb += k * sb;
+    wt *= refl;
+    if (level + 1 < a.r.max_depth) {
+      // exact reflected ray: the incoming direction is re-derived from its source, the normal from
+      // the exact hit point (src/main.cpp:35,45-48)
+      RaySrc src;
+      if (level == 0) {
+        const int W = a.r.W;
+        const int lr = (int)(hr.pix / (unsigned)W), x = (int)(hr.pix - (unsigned)lr * (unsigned)W);
+        src = RaySrc{a.r.su, a.r.sv, x, rt_local_to_global_row(a.r.bands, lr), nullptr};
+      } else {
+        src = RaySrc{nullptr, nullptr, 0, 0, lv.q_in + hr.src};
+      }
+      const ExactRay e = exact_ray(src);
+      const double4 s = ld_sph64(&a.r.sph64[hr.idx]);
+      const d3 p = rtx::mk(hr.px, hr.py, hr.pz);
+      reflected_ray_from_center(e.d, p, rtx::mk(s.x, s.y, s.z), &rec);
+      rec.pix = hr.pix; rec.wt = wt; rec.ar = cr; rec.ag = cg; rec.ab = cb; rec.pad = 0;
+      cont = true;
+    }
+  } else {
+    cr += wt * sr; cg += wt * sg; cb += wt * sb;
+  }
+  if (!cont) write_final(a.r, hr.pix, cr, cg, cb);
+  return cont;
+}
 
 // ---------------------------------------------------------------------------------------------
 // SHADOW: a warp fetch is 64 consecutive hits; a lane owns hits 2*lane and 2*lane+1 of the chunk and
@@ -408,19 +517,18 @@ __global__ void __launch_bounds__(kThreads, RT_CLOSEST_CTAS) k_closest1(const Wa
 // origin p + l*EPS lies strictly inside the sphere the point is on, so the reference's query returns
 // that sphere's exit distance, which is shorter than the distance to any light outside that sphere
 // (flag bit 30 of Tab::inv, set on the host): occluded, no table walk needed.
-template <int kMode>
-__global__ void __launch_bounds__(kThreads, RT_SHADOW_CTAS) k_shadow(const WaveArgs w) {
-  extern __shared__ __align__(128) unsigned char smem[];
+// tabs: where the L light tables are read from (shared memory when staged); wbase: the per-warp compacted tables.
+// kFuse (whole-frame kernel): the warp that knows the last occlusion bit of a chunk of hits also SHADES it -- directly
+// from its registers when it ran all lights of the chunk itself, or, when the (chunk, light) items of a chunk are spread
+// over several warps, as the last of them to arrive (one arrival counter per chunk; the occlusion bytes of the others
+// are read back through L2) -- so the 80-byte hit records are not streamed from HBM a second time by a shade kernel.
+template <int kMode, bool kFuse>
+__device__ __forceinline__ void shadow_body(const WaveArgs &w, const Lvl &lv, unsigned char *smem, const unsigned char *tabs, unsigned char *wbase) {
   const FastArgs &a = w.f;
-  // staged: the L light tables
   const unsigned char *gtabs = a.tabs + a.tstride;
-  const unsigned char *tabs = gtabs;
-  if (kMode == kTabSmem && a.L > 0) { stage_tables(smem, tabs, a.stage_bytes); tabs = smem + kSmemHeader; }
-  if (kMode == kTabStream) ring_init(smem);
-  RT_PDL_SYNC();
-  const unsigned nh = *w.hit_count;
-  if (nh == 0u || a.L == 0) return;
-  const WarpBuf wb = warp_buf(smem + kSmemHeader + (kMode == kTabBvh ? 0u : ((a.stage_bytes + 127u) & ~127u)));   // kTabSmem / kTabBvh
+  const unsigned nh = __ldcg(lv.hit_count);
+  if (nh == 0u || (a.L == 0 && !kFuse)) return;
+  const WarpBuf wb = warp_buf(wbase);                                                                                // kTabSmem / kTabBvh
   const BundleBuf bb = bundle_buf(smem + kSmemHeader + kWarps * kWarpBufBytes);                                      // kTabBvh only
   unsigned ring_phase = 0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -429,21 +537,22 @@ __global__ void __launch_bounds__(kThreads, RT_SHADOW_CTAS) k_shadow(const WaveA
   const unsigned nchunks = two ? nh / 64u : nh / 32u;            // nh = 64 x blocks
   // few chunks (reflection levels >= 1): one (chunk, light) item per fetch instead of (chunk, all lights) -- L times
   // as many, L times shorter items, so the warps of the machine share them evenly
-  const bool lightpar = kMode != kTabStream && nchunks < 4u * gridDim.x * (unsigned)kWarps;
+  const bool lightpar = kMode != kTabStream && a.L > 1 && nchunks < 4u * gridDim.x * (unsigned)kWarps;
   const unsigned nitems = lightpar ? nchunks * (unsigned)a.L : nchunks;
-  unsigned c_fp64 = 0, c_cand = 0, c_walks = 0, c_fall = 0;
+  unsigned c_fp64 = 0, c_cand = 0, c_walks = 0, c_fall = 0, c_shadow = 0, c_occ = 0;
   for (;;) {
     unsigned chunk;
     if (kMode == kTabStream) {
-      const unsigned cc = (unsigned)cta_fetch(w.work_counter, smem);
+      const unsigned cc = (unsigned)cta_fetch(lv.work_shadow, smem);
       if (cc * kWarps >= nchunks) break;
       chunk = cc * kWarps + warp;
     } else {
-      chunk = (unsigned)warp_fetch(w.work_counter);
+      chunk = (unsigned)warp_fetch(lv.work_shadow);
       if (chunk >= nitems) break;
     }
     int l_beg = 0, l_end = a.L;
     if (lightpar) { l_beg = (int)(chunk % (unsigned)a.L); l_end = l_beg + 1; chunk /= (unsigned)a.L; }
+    unsigned long long occm[2] = {0ull, 0ull};         // kFuse: occlusion bits of this lane's two hits
     const unsigned h0 = two ? chunk * 64u + 2u * lane : chunk * 32u + lane;
     const unsigned hend = (h0 & ~63u) + (h0 < nh ? w.hit_n[h0 >> 6] : 0u);   // end of the block's live slots
     bool have[2];
@@ -542,14 +651,59 @@ __global__ void __launch_bounds__(kThreads, RT_SHADOW_CTAS) k_shadow(const WaveA
         occ[0] = q.occ[0]; occ[1] = q.occ[1];
       }
       c_fp64 += (unsigned)n64;
+      if (kFuse && !lightpar) {                        // this warp runs every light of the chunk: the bits stay in registers
+        if (occ[0] || shortcut[0]) occm[0] |= 1ull << l;
+        if (occ[1] || shortcut[1]) occm[1] |= 1ull << l;
+        continue;
+      }
       // two adjacent bytes per lane -> one 16-bit store when both exist
       const unsigned o0 = (occ[0] || shortcut[0]) ? 1u : 0u, o1 = (occ[1] || shortcut[1]) ? 256u : 0u;
       unsigned char *o = w.occ + (size_t)l * w.hit_cap + h0;
       if (have[1]) *reinterpret_cast<unsigned short *>(o) = (unsigned short)(o0 | o1);
       else if (have[0]) o[0] = (unsigned char)o0;
     }
+    if (!kFuse) continue;
+    if (lightpar) {
+      // the last of the chunk's L items to arrive shades it; its own bytes are in L2 after the fence, the others' are
+      // read back with L1-bypassing loads
+      __threadfence();
+      __syncwarp();
+      unsigned last = 0u;
+      if (lane == 0) {
+        last = atomicAdd(&w.shade_done[chunk], 1u) == (unsigned)a.L - 1u ? 1u : 0u;
+        if (last) w.shade_done[chunk] = 0u;            // ready for the next level / frame
+      }
+      if (!__shfl_sync(kFull, last, 0)) continue;
+      __threadfence();
+#pragma unroll
+      for (int r = 0; r < 2; r++)
+        if (have[r])
+          for (int l = 0; l < a.L; l++)
+            if (__ldcg(w.occ + (size_t)l * w.hit_cap + h0 + r)) occm[r] |= 1ull << l;
+    }
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      bool cont = false;
+      RayRec rec;
+      if (have[r]) {
+        c_shadow += (unsigned)a.L; c_occ += (unsigned)__popcll(occm[r]);
+        cont = shade_one(w, lv, w.hits[h0 + r], occm[r], rec);
+      }
+      queue_push(cont, rec, lv.q_out, lv.q_out_count);
+    }
   }
-  if (a.r.counters) flush_counts(a.r.counters, 99, 0, 0, 0, 0, c_fp64, 0, 0, c_cand, c_walks, c_fall);
+  if (a.r.counters) flush_counts(a.r.counters, 99, 0, 0, c_shadow, c_occ, c_fp64, 0, (unsigned long long)a.N, c_cand, c_walks, c_fall);
+}
+template <int kMode>
+__global__ void __launch_bounds__(kThreads, RT_SHADOW_CTAS) k_shadow(const WaveArgs w) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const FastArgs &a = w.f;
+  // staged: the L light tables
+  const unsigned char *tabs = a.tabs + a.tstride;
+  if (kMode == kTabSmem && a.L > 0) { stage_tables(smem, tabs, a.stage_bytes); tabs = smem + kSmemHeader; }
+  if (kMode == kTabStream) ring_init(smem);
+  RT_PDL_SYNC();
+  shadow_body<kMode, false>(w, lvl_of(w), smem, tabs, smem + kSmemHeader + (kMode == kTabBvh ? 0u : ((a.stage_bytes + 127u) & ~127u)));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -702,76 +856,47 @@ __global__ void __launch_bounds__(kThreads, RT_DYN_CTAS) k_shadow_dyn(const Wave
 #ifndef RT_SHADE_CTAS
 #define RT_SHADE_CTAS 4
 #endif
-__global__ void __launch_bounds__(kThreads, RT_SHADE_CTAS) k_shade(const WaveArgs w) {
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// The items of this phase cost the same (one hit per lane), so the chunks are dealt out STATICALLY -- warp g of G takes
+// chunks g, g + G, ... -- instead of through an atomic counter: the counter's round trip was a third of this
+// memory-latency-bound kernel's stall samples.  The record of the lane's NEXT hit is prefetched into L1 meanwhile.
+__device__ __forceinline__ void shade_body(const WaveArgs &w, const Lvl &lv) {
   const FastArgs &a = w.f;
-  RT_PDL_SYNC();
-  const unsigned nh = *w.hit_count;
+  const unsigned nh = __ldcg(lv.hit_count);
   if (nh == 0u) return;
-  const int lane = threadIdx.x & 31, level = a.level, L = a.L, W = a.r.W;
+  const int lane = threadIdx.x & 31, L = a.L;
   unsigned c_shadow = 0, c_occ = 0;
-  for (;;) {
-    const unsigned chunk = (unsigned)warp_fetch(w.work_counter);
-    if (chunk * 32u >= nh) break;
+  const unsigned G = gridDim.x * (unsigned)kWarps;
+  for (unsigned chunk = blockIdx.x * (unsigned)kWarps + (threadIdx.x >> 5); chunk * 32u < nh; chunk += G) {
     const unsigned h = chunk * 32u + lane;
+    {
+      const unsigned hn = h + G * 32u;
+      if (hn < nh) {
+        const unsigned char *q = reinterpret_cast<const unsigned char *>(w.hits + hn);
+        prefetch_l1(q); prefetch_l1(q + 64);
+        if (lane == 0) prefetch_l1(w.hit_n + (hn >> 6));
+        if (lane < L) prefetch_l1(w.occ + (size_t)lane * w.hit_cap + hn);
+      }
+    }
     const bool live = (h & 63u) < w.hit_n[h >> 6] && w.hits[h].idx >= 0;
     bool cont = false;
     RayRec rec;
     if (live) {
       const HitRec hr = w.hits[h];
-      const float4 m = __ldg(&a.r.mat[hr.idx]);
-      const float2 mx = __ldg(&a.r.matx[hr.idx]);
-      float sr = g_frame.ambient[0] * m.x, sg = g_frame.ambient[1] * m.y, sb = g_frame.ambient[2] * m.z;
-      unsigned smask = 0;
-      for (int l = 0; l < L; l++) {
-        c_shadow++;
-        if (w.occ[(size_t)l * w.hit_cap + h]) { c_occ++; if (l < 32) smask |= 1u << l; continue; }
-        // light_dir = normalized(light - point): FP64 difference, FP32 normalisation (colour only)
-        const float wx = (float)(g_frame.light_pos[l][0] - hr.px), wy = (float)(g_frame.light_pos[l][1] - hr.py),
-                    wz = (float)(g_frame.light_pos[l][2] - hr.pz);
-        const float inv = rsqrtf(fmaf(wz, wz, fmaf(wy, wy, wx * wx)));
-        const float lx = wx * inv, ly = wy * inv, lz = wz * inv;
-        const float nl = hr.nx * lx + hr.ny * ly + hr.nz * lz;
-        const float kd = (1.0f - m.w) * fmaxf(0.0f, nl);
-        // reflect(-light_dir, n) = -l + 2 (l.n) n   (include/vec3.h:31-33)
-        const float rx = 2.0f * nl * hr.nx - lx, ry = 2.0f * nl * hr.ny - ly, rz = 2.0f * nl * hr.nz - lz;
-        const float rdv = fmaxf(0.0f, rx * hr.vx + ry * hr.vy + rz * hr.vz);
-        const float spec = 0.5f * (mx.x == 0.0f ? 1.0f : __powf(rdv, mx.x));
-        sr += g_frame.light_col[l][0] * spec + m.x * kd;
-        sg += g_frame.light_col[l][1] * spec + m.y * kd;
-        sb += g_frame.light_col[l][2] * spec + m.z * kd;
-      }
-      if (a.r.shadow_mask) a.r.shadow_mask[(size_t)hr.pix * a.r.max_depth + level] = smask;
-      float cr = hr.ar, cg = hr.ag, cb = hr.ab, wt = hr.wt;
-      bool final_ = true;
-      if (mx.y > 0.5f) {                          // reflectivity > 0, decided in double on the host
-        const float refl = m.w, k = wt * (1.0f - refl);
-        cr += k * sr; cg += k * sg; cb += k * sb;
-        wt *= refl;
-        if (level + 1 < a.r.max_depth) {
-          // exact reflected ray: the incoming direction is re-derived from its source, the normal from
-          // the exact hit point (src/main.cpp:35,45-48)
-          RaySrc src;
-          if (level == 0) {
-            const int lr = (int)(hr.pix / (unsigned)W), x = (int)(hr.pix - (unsigned)lr * (unsigned)W);
-            src = RaySrc{a.r.su, a.r.sv, x, rt_local_to_global_row(a.r.bands, lr), nullptr};
-          } else {
-            src = RaySrc{nullptr, nullptr, 0, 0, a.q_in + hr.src};
-          }
-          const ExactRay e = exact_ray(src);
-          const double4 s = ld_sph64(&a.r.sph64[hr.idx]);
-          const d3 p = rtx::mk(hr.px, hr.py, hr.pz);
-          reflected_ray_from_center(e.d, p, rtx::mk(s.x, s.y, s.z), &rec);
-          rec.pix = hr.pix; rec.wt = wt; rec.ar = cr; rec.ag = cg; rec.ab = cb; rec.pad = 0;
-          cont = true; final_ = false;
-        }
-      } else {
-        cr += wt * sr; cg += wt * sg; cb += wt * sb;
-      }
-      if (final_) write_final(a.r, hr.pix, cr, cg, cb);
+      unsigned long long occm = 0ull;
+      for (int l = 0; l < L; l++)
+        if (w.occ[(size_t)l * w.hit_cap + h]) occm |= 1ull << l;
+      c_shadow += (unsigned)L; c_occ += (unsigned)__popcll(occm);
+      cont = shade_one(w, lv, hr, occm, rec);
     }
-    queue_push(cont, rec, a.q_out, a.q_out_count);
+    queue_push(cont, rec, lv.q_out, lv.q_out_count);
   }
   if (a.r.counters) flush_counts(a.r.counters, 99, 0, 0, c_shadow, c_occ, 0, 0, (unsigned long long)a.N);
+}
+__global__ void __launch_bounds__(kThreads, RT_SHADE_CTAS) k_shade(const WaveArgs w) {
+  RT_PDL_SYNC();
+  shade_body(w, lvl_of(w));
 }
 
 }  // namespace rtf

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -17,6 +18,7 @@ __constant__ RtFrameConst g_frame;
 #include "kernels_exact.cuh"
 #include "kernels_fast.cuh"
 #include "kernels_wave.cuh"
+#include "kernels_frame.cuh"
 
 cudaError_t rtk_set_frame_const(const RtFrameConst *host_const, cudaStream_t stream) {
   return cudaMemcpyToSymbolAsync(g_frame, host_const, sizeof(RtFrameConst), 0, cudaMemcpyHostToDevice, stream);
@@ -35,7 +37,7 @@ int rtk_launch_exact(const RtRenderArgs &args, cudaStream_t stream) {
 namespace {
 
 constexpr size_t kMaxSmemTables = 96 * 1024;    // stage a kernel's tables in shared memory up to this size (2 CTAs/SM stay resident)
-constexpr int kCtlWords = 256;                  // device control words, layout: enum CTL_* below
+constexpr int kCtlWords = rtf::CTL_WORDS;        // device control words per frame, layout: enum CTL_* (kernels_wave.cuh); two sets (see rtk_launch_fast)
 
 inline float float_up(double x) {               // smallest float >= x
   float f = (float)x;
@@ -62,6 +64,8 @@ int rtk_fast_init(int) {
   RTK_TRY(cudaFuncSetAttribute(rtf::k_shadow<rtf::kTabStream>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   RTK_TRY(cudaFuncSetAttribute(rtf::k_shadow<rtf::kTabBvh>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   RTK_TRY(cudaFuncSetAttribute(rtf::k_closest0<rtf::kTabBvh>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  RTK_TRY(cudaFuncSetAttribute(rtf::k_frame<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  RTK_TRY(cudaFuncSetAttribute(rtf::k_frame<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   return 0;
 }
 
@@ -358,7 +362,8 @@ void rtk_fast_free_scene(RtFastScene *fs, int release_tables) {
 }
 
 void rtk_fast_free_work(RtFastWork *w) {
-  cudaFree(w->queue[0]); cudaFree(w->queue[1]); cudaFree(w->ctl); cudaFree(w->hits); cudaFree(w->occ); cudaFree(w->hit_n); cudaFree(w->cand);
+  cudaFree(w->queue[0]); cudaFree(w->queue[1]); cudaFree(w->ctl_base); cudaFree(w->hits); cudaFree(w->occ); cudaFree(w->hit_n); cudaFree(w->cand);
+  cudaFree(w->shade_done); w->shade_done = nullptr; w->ctl_base = nullptr;
   w->cand = nullptr; w->cand_cap = 0;
   if (w->h_fb) { cudaFreeHost(w->h_fb); cudaEventDestroy(w->fb_event); }
   w->h_fb = nullptr; w->fb_pending = 0; w->fb_levels = 0;
@@ -389,14 +394,19 @@ int resident_grid(K kernel, size_t smem, int num_sms, int threads = rtf::kThread
 // The first failing launch of a frame is remembered (g_launch_err, thread local) and reported by rtk_launch_fast.
 thread_local cudaError_t g_launch_err = cudaSuccess;
 template <typename K, typename A>
-void launch(K kernel, int grid, int block, size_t smem, cudaStream_t stream, bool pdl, const A &arg) {
+void launch(K kernel, int grid, int block, size_t smem, cudaStream_t stream, bool pdl, const A &arg, bool cooperative = false) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
   cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = pdl ? 1u : 0u;
+  if (cooperative) {            // every CTA of the grid co-resident (the whole-frame kernel has grid-wide barriers)
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+  } else {
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+  }
+  cfg.attrs = at; cfg.numAttrs = (pdl || cooperative) ? 1u : 0u;
   const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, arg);
   if (e != cudaSuccess && g_launch_err == cudaSuccess) g_launch_err = e;
 }
@@ -406,13 +416,20 @@ inline size_t bvh_smem() { return rtf::kSmemHeader + rtf::kWarps * (size_t)(rtf:
 inline size_t staged_smem(size_t bytes) { return rtf::kSmemHeader + ((bytes + 127) & ~(size_t)127) + rtf::kWarps * (size_t)rtf::kWarpBufBytes; }
 // control words (u32): [0] tile counter; per level k <= 33: tail chunk counter, shadow / shade / closest work
 // counters, hits of level k, rays entering level k
-enum { CTL_TILE = 0, CTL_TAIL = 8, CTL_SHADOW = 48, CTL_SHADE = 88, CTL_CLOSEST = 128, CTL_HITS = 168, CTL_RAYS = 208 };
+using rtf::CTL_TILE; using rtf::CTL_TAIL; using rtf::CTL_SHADOW; using rtf::CTL_SHADE; using rtf::CTL_CLOSEST; using rtf::CTL_HITS; using rtf::CTL_RAYS;
 }  // namespace
 
 int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork *w, cudaStream_t stream,
                     const cudaEvent_t *marks) {
   const size_t npix = (size_t)args.W * args.bands.local_rows;
-  if (!w->ctl) RTK_TRY(cudaMalloc(&w->ctl, kCtlWords * sizeof(unsigned int)));
+  if (!w->ctl_base) {
+    // two sets of control words: the whole-frame kernel zeroes the set of the NEXT frame on its way out, so no memset
+    // precedes it in steady state
+    RTK_TRY(cudaMalloc(&w->ctl_base, 2 * kCtlWords * sizeof(unsigned int)));
+    RTK_TRY(cudaMemsetAsync(w->ctl_base, 0, 2 * kCtlWords * sizeof(unsigned int), stream));
+    w->ctl_clean[0] = w->ctl_clean[1] = 1; w->ctl_cur = 0;
+  }
+  w->ctl = w->ctl_base + (size_t)w->ctl_cur * kCtlWords;
   // blocked hit queue: one 64-slot block per 16x4 tile (level 0: tiles x 64 >= pixels) or per 64 queued rays (level >= 1:
   // at most pixels / 64 + 1 blocks).  With few rays (fewer than one per lane of the resident grid) k_closest1 takes 32 rays
   // per block instead: fewer than grid x 8 warps x 2 blocks; the slack term covers the largest resident grid (4 CTAs/SM).
@@ -424,6 +441,9 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
     w->queue[0] = w->queue[1] = nullptr; w->hits = nullptr; w->occ = nullptr; w->hit_n = nullptr; w->queue_cap = w->hit_cap = w->occ_bytes = 0;
     RTK_TRY(cudaMalloc(&w->hits, hit_cap * sizeof(rtf::HitRec)));
     RTK_TRY(cudaMalloc(&w->hit_n, (hit_cap / 64) * sizeof(unsigned int)));
+    cudaFree(w->shade_done); w->shade_done = nullptr;
+    RTK_TRY(cudaMalloc(&w->shade_done, (hit_cap / 32 + 1) * sizeof(unsigned int)));
+    RTK_TRY(cudaMemsetAsync(w->shade_done, 0, (hit_cap / 32 + 1) * sizeof(unsigned int), stream));
     w->occ_bytes = hit_cap * (size_t)(fs->L > 0 ? fs->L : 1);
     RTK_TRY(cudaMalloc(&w->occ, w->occ_bytes));
     w->hit_cap = hit_cap;
@@ -440,7 +460,16 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
     RTK_TRY(cudaMalloc(&w->cand, npix * sizeof(rtf::Best)));
     w->cand_cap = npix;
   }
-  RTK_TRY(cudaMemsetAsync(w->ctl, 0, kCtlWords * sizeof(unsigned int), stream));
+  // whole-frame kernel: small scenes (every table in shared memory at 2 CTAs/SM), no per-level event marks wanted
+  const size_t all_tables = (size_t)(fs->L + 1) * fs->tstride + (size_t)fs->npairs * 32;
+  static const int frame_env = getenv("RT_FRAME") ? atoi(getenv("RT_FRAME")) : -1;      // A/B: 0 = wavefront kernels only
+  const int frame_opt = w->frame_kernel >= 0 ? w->frame_kernel : frame_env;
+  // (measured: the per-level kernels win -- each has its own register budget and occupancy -- so the whole-frame kernel
+  // runs only on request: rt_set_option frame_kernel 1 / RT_FRAME=1)
+  const bool use_frame = frame_opt > 0 && !fs->bvh_nodes && all_tables <= kMaxSmemTables && marks == nullptr && args.max_depth > 0 &&
+                         w->wave_levels <= 0;
+  if (!use_frame || !w->ctl_clean[w->ctl_cur]) RTK_TRY(cudaMemsetAsync(w->ctl, 0, kCtlWords * sizeof(unsigned int), stream));
+  w->ctl_clean[w->ctl_cur] = 0;
   if (args.max_depth <= 0 && !args.fb && !args.out_remap) RTK_TRY(cudaMemsetAsync(args.rgb, 0, npix * 3, stream));   // src/main.cpp:17-18: black (other output modes: the caller clears)
 
   g_launch_err = cudaSuccess;
@@ -502,6 +531,33 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
       w->fb_levels = lv; w->fb_key = w->fb_pending_key; w->fb_pending = 0;
     }
     if (w->fb_levels > 0 && w->fb_key == fb_key) wave_levels = w->fb_levels;
+  }
+  if (use_frame) {
+    wa.ctl = w->ctl; wa.ctl_next = w->ctl_base + (size_t)(w->ctl_cur ^ 1) * kCtlWords;
+    wa.queue[0] = (rtf::RayRec *)w->queue[0]; wa.queue[1] = (rtf::RayRec *)w->queue[1];
+    wa.shade_done = w->shade_done;
+    a.level = 0;
+    a.stage_bytes = (unsigned)all_tables;
+    const size_t smem = staged_smem(all_tables);
+    static const bool fuse = !(getenv("RT_FUSE") && getenv("RT_FUSE")[0] == '0');      // A/B: 0 = shading as its own phase
+    int g = fuse ? resident_grid(rtf::k_frame<true>, smem, w->num_sms) : resident_grid(rtf::k_frame<false>, smem, w->num_sms);
+    const int cta_tiles = (a.nwtiles + rtf::kWarps - 1) / rtf::kWarps;
+    if (g > cta_tiles) g = cta_tiles;                  // (a tiny frame: fewer CTAs than fit is still co-resident)
+    if (fuse) launch(rtf::k_frame<true>, g, rtf::kThreads, smem, stream, false, wa, true);
+    else launch(rtf::k_frame<false>, g, rtf::kThreads, smem, stream, false, wa, true);
+    if (getenv("RT_FRAME_TRACE")) {                    // diagnostics: phase boundaries seen by CTA 0 (ns timer)
+      unsigned int tr[14];
+      cudaStreamSynchronize(stream);
+      cudaMemcpy(tr, w->ctl + 242, sizeof(tr), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "k_frame phases (us):");
+      for (int k = 1; k < 14 && tr[k]; k++) fprintf(stderr, " %.1f", (tr[k] - tr[k - 1]) * 1e-3);
+      fprintf(stderr, "\n");
+    }
+    w->ctl_clean[w->ctl_cur ^ 1] = 1;                  // zeroed by the kernel
+    w->ctl_cur ^= 1;
+    cudaError_t e = cudaGetLastError();
+    if (g_launch_err != cudaSuccess) e = g_launch_err;
+    return e == cudaSuccess ? 1 : -(int)e;
   }
   for (int level = 0; level < args.max_depth && level < wave_levels; level++) {
     a.level = level;

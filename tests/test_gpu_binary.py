@@ -78,3 +78,27 @@ def test_ray_cuda_flags_and_multi_gpu_bands(rt, workdir):
     assert (workdir / "one.ppm").read_bytes() == (workdir / "four.ppm").read_bytes()
     rc, out = run([os.path.join(PKG, "ray_cuda"), "scenes/missing.txt"], workdir)
     assert rc != 0 and "Could not open scene file" in out
+
+
+@pytest.mark.parametrize("flags", [[], ["-p"], ["-t", "32", "scenes/medium.txt"]])
+def test_reference_hybrid_links_against_the_kernel_shim(rt, oracle, workdir, flags):
+    """The reference's OWN hybrid renderer (src/main_hybrid.cpp, unmodified, built by oracle/Makefile where it lies)
+    linked against libkernel_shim.so in place of its kernel.o: launch_gpu_kernel / upload_lights_and_ambience keep the
+    signatures of src/kernel.cu:185-207, so the tile scheduler, the three-stream launch loop and the bulk download of
+    src/main_hybrid.cpp:373-706 run unchanged.  Its image (CPU tiles: the reference's FP64 code; GPU tiles: this library
+    on the FP32 scene structs the caller uploads) must pass the compare_ppm.py gate against the serial renderer at
+    ray_hybrid's own size (1080x720, depth 3: src/main_hybrid.cpp:42-43,715)."""
+    exe = os.path.join(REF, "ray_hybrid_shim")
+    if not os.path.exists(exe) or not oracle.ref_available():
+        pytest.skip("oracle/_ref/ray_hybrid_shim was not built (needs /root/reference at build time)")
+    out = workdir / "output_hybrid.ppm"
+    if os.path.exists(out):
+        os.remove(out)
+    rc, log = run([exe] + flags, workdir)
+    assert rc == 0, log
+    assert "Hybrid rendering time:" in log and os.path.getsize(out) > 1000
+    scene = [f for f in flags if f.endswith(".txt")] or ["scenes/simple.txt"]
+    oracle.ref_harness("render", scene[0], 1080, 720, 3, "serial_1080.ppm", cwd=str(workdir))
+    compare(rt, workdir / "serial_1080.ppm", out, 0.5)
+    dist = [l for l in log.splitlines() if l.startswith("Distribution:")]
+    assert dist and " tiles to GPU" in dist[0] or "GPU" in dist[0], log       # (src/main_hybrid.cpp:426: some tiles did go to the GPU)
