@@ -58,6 +58,45 @@ def load_workload(name):
     return rtb200.load_scene(os.path.join(ROOT, "tests", "golden", "scenes", sc + ".txt"))
 
 
+class _PlainScene:
+    """Scene arrays for the reference arm / cpu baseline WITHOUT the product library: that arm must not load
+    librt_b200.so (the driver records which .so files each arm loads)."""
+
+    def __init__(self, spheres, lights, ambient, camera):
+        import numpy as np
+        self.spheres = np.asarray(spheres, dtype=np.float64).reshape(-1, 10)
+        self.lights = np.asarray(lights, dtype=np.float64).reshape(-1, 7)
+        self.ambient = np.asarray(ambient, dtype=np.float64).reshape(3)
+        self.camera = np.asarray(camera, dtype=np.float64).reshape(7)
+
+
+def load_workload_plain(name):
+    """The same scenes as load_workload, parsed in Python (the fixtures are plain directive lines in the grammar of
+    include/scene_loader.h:15-21; defaults as include/scene.h:22,31)."""
+    sc = WORKLOADS[name][0]
+    if sc.startswith("synth:"):
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import gen_scene
+        _, n, seed = sc.split(":")
+        return _PlainScene(*gen_scene.generate(int(n), int(seed)))
+    sph, lig, amb, cam = [], [], [0.0, 0.0, 0.0], [0.0, 0.0, 0.0, 0.0, 0.0, -1.0, 60.0]
+    with open(os.path.join(ROOT, "tests", "golden", "scenes", sc + ".txt")) as f:
+        for line in f:
+            t = line.split("#")[0].split()
+            if not t:
+                continue
+            v = [float(x) for x in t[1:]]
+            if t[0] == "sphere" and len(v) >= 10:
+                sph.append(v[:10])
+            elif t[0] == "light" and len(v) >= 7:
+                lig.append(v[:7])
+            elif t[0] == "ambient" and len(v) >= 3:
+                amb = v[:3]
+            elif t[0] == "camera" and len(v) >= 7:
+                cam = v[:7]
+    return _PlainScene(sph, lig, amb, cam)
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock and clock-event (throttle) reasons of one GPU through NVML while the
     timed regions run."""
@@ -118,27 +157,21 @@ def ncu_traffic():
         return None
 
 
-def ncu_executed():
-    """FP32-pipe and issue-slot utilisation of the dominant kernel from the committed ncu capture (profiles/): the
-    EXECUTED counterpart of the algorithmic roofline fraction."""
+def ncu_executed(workload="complex"):
+    """EXECUTED FP32 work of one frame from the committed ncu capture of this workload (profiles/r02_executed_<workload>.json,
+    written by scripts/ncu_opcodes.py from an `ncu --set full --import-source on` run of scripts/ncu_target.py): executed
+    flops, their fraction of the FFMA peak over the serialised kernel times, and per kernel the FMA-pipe / issue-slot /
+    occupancy / L1 / instruction-cache figures the north star names."""
     try:
-        out, take = {}, False
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_full_summary.txt")) as f:
-            for line in f:
-                if line.startswith("==="):
-                    if take:
-                        break
-                    take = "k_shadow" in line
-                elif take:
-                    p = line.split()
-                    for key, name in (("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "fma_pipe_active_pct"),
-                                      ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_slots_active_pct"),
-                                      ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved_occupancy_pct"),
-                                      ("launch__registers_per_thread", "registers_per_thread")):
-                        if p and p[0] == key:
-                            out[name] = round(float(p[1]), 2)
-        out["source"] = "profiles/r01_ncu_full_summary.txt (ncu --set full of this bench command; first k_shadow launch)"
-        return out
+        with open(os.path.join(ROOT, "profiles", "r02_executed_%s.json" % workload)) as f:
+            d = json.load(f)
+        return {"fp32_flops_executed_per_frame": d["fp32_flops_executed"], "fp64_flops_executed_per_frame": d["fp64_flops_executed"],
+                "executed_frac": round(d["executed_fp32_frac_of_peak"], 4), "sum_kernel_us_under_ncu": round(d["sum_us"], 1),
+                "kernels": [{"name": k["name"], "us": round(k["us"], 1), "executed_frac": round(k["executed_fp32_frac_of_peak"] or 0, 4),
+                             "fma_pipe_active_pct": k["fma_pipe_pct"], "issue_slots_active_pct": k["issue_pct"],
+                             "achieved_occupancy_pct": k["occupancy_pct"], "l1_hit_pct": k["l1_hit_pct"], "icache_hit_pct": k["icache_hit_pct"],
+                             "smem_wavefronts": k["smem_wavefronts"], "registers_per_thread": k["regs"]} for k in d["kernels"]],
+                "source": "profiles/r02_executed_%s.json (ncu --set full --import-source on, scripts/ncu_opcodes.py)" % workload}
     except Exception:  # noqa: BLE001
         return None
 
@@ -161,7 +194,7 @@ def run_reference_frames(steps, warmup, budget_s=150.0, workload="complex"):
     (every `pix_step`-th pixel) sized so the run fits the budget.  Falls back to the C port."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py
-    scene = load_workload(workload)
+    scene = load_workload_plain(workload)
     scene_file = SCENE
     if WORKLOADS[workload][0].startswith("synth:"):
         # the reference reads scene FILES: write the synthetic scene in its text grammar (%.6f = the same doubles)
@@ -405,22 +438,32 @@ def main_b200(args, rank, local_rank, world):
         ach = frame_flops / (ms_per_step * 1e-3) * 1e-12
         bundle = {"walks": int(st.bundle_walks), "candidates_per_walk": round(st.bundle_candidates / max(1, st.bundle_walks), 2),
                   "note": "a culled warp-level table walk tests only the spheres its ray bundle's cone can touch"}
-        roof = {"bound": "fp32", "unit": "TFLOP/s", "peak": round(peak * 1e-12, 2), "bundle_culling": bundle,
-                "note": "achieved = ALGORITHMIC flops (16 x spheres x rays: the reference's brute force) / time; bundle culling and "
-                        "early-out legitimately skip most of those tests, so the fraction can exceed 1; the executed FP32-pipe share "
-                        "is in profiles/ (ncu sm__pipe_fma_cycles_active)",
+        lbvh = scene.nspheres >= 1024 or args.accel == 2
+        # `frac` = WHOLE-FRAME algorithmic fraction: the reference's brute-force work (16 flop x spheres x rays) retired per
+        # second over the measured FFMA issue peak.  It is NOT pipe utilisation: culling / early-out skip most of those
+        # tests.  What the FP32 pipe really executed is `executed` (ncu capture of this command, profiles/).
+        roof = {"bound": "fp32", "unit": "TFLOP/s", "peak": round(peak * 1e-12, 2), "achieved": round(ach, 2),
+                "frac": None if lbvh else round(ach / (peak * 1e-12), 4),
+                "kernel": "whole frame: all %d launches of a step" % launches_per_step, "flops": frame_flops, "flop_per_test": FLOP_PER_TEST,
+                "note": "achieved = ALGORITHMIC flops (16 x spheres x rays: the reference's brute force, SURVEY 8d) / frame time; "
+                        "frac = achieved / measured FFMA peak for the whole frame; executed.* = what the kernels really issued "
+                        "(ncu per-opcode thread-instruction counts: FFMA 2, FFMA2 4, FMUL/FADD 1, FMUL2/FADD2 2 flop)",
                 "peak_source": "measured live: FFMA issue peak of this GPU (rt_measure_fp32_peak, SM clock %.0f MHz); "
-                               "MEASURED_PEAKS.json has no FP32 entry" % peak_mhz,
-                "flop_per_test": FLOP_PER_TEST, "traffic": ncu_traffic(), "executed": ncu_executed(),
-                "frame": {"achieved": round(ach, 2), "frac": round(ach / (peak * 1e-12), 4), "flops": frame_flops}}
+                               "MEASURED_PEAKS.json has no FP32 entry (nominal 148 x 128 x 2 x 1.965 GHz = 74.5)" % peak_mhz,
+                "bundle_culling": bundle, "traffic": ncu_traffic(), "executed": ncu_executed(args.workload)}
+        if lbvh:
+            roof["note_lbvh"] = ("LBVH workload: a brute-force-based fraction is meaningless here (SURVEY 8d), frac is null; "
+                                 "candidates_per_walk / fp64 counts are the executed-work figures")
+            roof["lbvh"] = {"bundle_walks": int(st.bundle_walks), "candidates_per_bundle_walk": bundle["candidates_per_walk"],
+                            "bundle_fallbacks": int(st.bundle_fallbacks), "fp64_sphere_evaluations_per_ray": round(st.fp64_intersections / max(1, rays), 4)}
         if k_ms:
             a0 = FLOP_PER_TEST * nsph * k_rays / (k_ms * 1e-3) * 1e-12
-            roof.update({"kernel": "k_shadow, reflection level 0 (one any-hit query per light per camera-ray hit)",
-                         "achieved": round(a0, 2), "frac": round(a0 / (peak * 1e-12), 4), "kernel_ms": round(k_ms, 5),
-                         "kernel_rays": k_rays, "kernel_flops": FLOP_PER_TEST * nsph * k_rays,
-                         "kernel_share_of_frame": round(k_ms / frame_ms, 4), "level0_ms": round(lvl0_ms, 5)})
-        else:
-            roof.update({"kernel": "whole frame (all levels)", "achieved": round(ach, 2), "frac": round(ach / (peak * 1e-12), 4)})
+            roof["dominant_kernel"] = {"kernel": "k_shadow, reflection level 0 (one any-hit query per light per camera-ray hit)",
+                                       "kernel_ms": round(k_ms, 5), "kernel_rays": k_rays, "kernel_flops_algorithmic": FLOP_PER_TEST * nsph * k_rays,
+                                       "kernel_share_of_frame": round(k_ms / frame_ms, 4), "level0_ms": round(lvl0_ms, 5),
+                                       "algorithmic_speedup": round(a0 / (peak * 1e-12), 4),
+                                       "algorithmic_speedup_note": "algorithmic flops of this kernel's rays / its time / FFMA peak; > 1 means "
+                                                                   "the kernel does not execute the brute-force work it is charged with (bundle culling)"}
         line["roofline"] = roof
         if n == 1 and not args.no_cpu_baseline:
             try:

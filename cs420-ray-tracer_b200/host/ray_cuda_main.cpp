@@ -78,7 +78,8 @@ int main(int argc, char **argv) {
     else if (rt_render(ctx, W, H, depth, rgb.data(), &st) != RT_OK) return die("rt_render");
     if (st.ms_device < best) best = st.ms_device;
   }
-  std::printf("GPU rendering time: %g seconds\n", best * 1e-3);
+  // fixed notation: the reference's scripts cut the number out with grep -oE "[0-9]+\.[0-9]+" (scripts/benchmark.sh:32-34)
+  std::printf("GPU rendering time: %.6f seconds\n", best * 1e-3);
   unsigned long long rays = st.closest_queries + st.shadow_queries;
   std::printf("rays: %llu closest + %llu shadow = %llu (%.1f Mrays/s), %d kernel launches\n",
               (unsigned long long)st.closest_queries, (unsigned long long)st.shadow_queries, rays,

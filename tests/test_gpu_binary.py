@@ -102,3 +102,26 @@ def test_reference_hybrid_links_against_the_kernel_shim(rt, oracle, workdir, fla
     compare(rt, workdir / "serial_1080.ppm", out, 0.5)
     dist = [l for l in log.splitlines() if l.startswith("Distribution:")]
     assert dist and " tiles to GPU" in dist[0] or "GPU" in dist[0], log       # (src/main_hybrid.cpp:426: some tiles did go to the GPU)
+
+
+def test_benchmark_csv_has_the_reference_format(workdir):
+    """scripts/benchmark_csv.py = the reference's scripts/benchmark.sh report for this binary: same CSV header
+    (scripts/benchmark.sh:29), one row per (implementation, scene, threads, iteration), the time cut from the program's
+    own `time:` line the way extract_time() does (scripts/benchmark.sh:32-34), and the summary table of :193-236."""
+    out = workdir / "bench_csv"
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "benchmark_csv.py"), "--iterations", "1", "--threads", "4",
+                        "--out", str(out)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout
+    assert "Average Execution Times (seconds):" in p.stdout
+    csvs = [f for f in os.listdir(out) if f.startswith("benchmark_") and f.endswith(".csv")]
+    assert len(csvs) == 1
+    lines = (out / csvs[0]).read_text().strip().split("\n")
+    assert lines[0] == "Implementation,Scene,Threads,Iteration,Time(s),Pixels/s,Speedup"
+    rows = [l.split(",") for l in lines[1:]]
+    cuda = [r for r in rows if r[0] == "CUDA"]
+    assert sorted(r[1] for r in cuda) == ["complex.txt", "medium.txt", "simple.txt"]
+    for r in rows:
+        assert len(r) == 7 and float(r[4]) > 0 and abs(float(r[5]) - 1280 * 720 / float(r[4])) <= 1.0 + 1e-6 * float(r[5])
+    if os.path.exists(os.path.join(REF, "ray_serial")):
+        assert {r[0] for r in rows} == {"Serial", "OpenMP", "CUDA"}
+        assert all(float(r[6]) > 10.0 for r in cuda)         # the reference's own bar for its CUDA build: >= 10x serial (scripts/benchmark.sh:298)
