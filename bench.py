@@ -363,20 +363,42 @@ def main_b200(args, rank, local_rank, world):
             r.render(W, H, DEPTH, out=host_frame, want_stats=False)
         d2h = W * H * 3
     else:
-        host_frame = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory() if rank == 0 else None
+        # N > 1: ONE host frame in shared memory (POSIX shm, page-locked by every rank's process); every rank renders its
+        # bands and copies them over ITS OWN host link straight to their image positions (rt_render_bands_host) -- the
+        # N downloads run concurrently and nothing crosses between the GPUs.  "Frame complete" = a sequence flag per rank
+        # in the same shared segment, back-pressure = rank 0's acknowledge word.
+        from multiprocessing import shared_memory
+        import numpy as np
+        nbytes = H * W * 3
+        box = [None]
+        if rank == 0:
+            shm = shared_memory.SharedMemory(create=True, size=nbytes + 4096)
+            box = [shm.name]
+        dist.broadcast_object_list(box, src=0)
+        if rank != 0:
+            shm = shared_memory.SharedMemory(name=box[0])
+        host_frame = np.ndarray((H, W, 3), dtype=np.uint8, buffer=shm.buf)
+        words = np.ndarray((256,), dtype=np.uint32, buffer=shm.buf, offset=nbytes + (-nbytes) % 1024)
+        if rank == 0:
+            host_frame[:] = 0
+            words[:] = 0
+        dist.barrier()
+        frame_ptr = host_frame.ctypes.data
+        rtb200.host_register(frame_ptr, nbytes)
+        seq = [0]
 
         def step_e2e():
+            seq[0] += 1
+            k = seq[0]
             r.upload(scene)
-            if peer:
-                pf.render(DEPTH, stream.cuda_stream)
-                if rank == 0:
-                    host_frame.copy_(full, non_blocking=True)
-                pf.release(stream.cuda_stream)      # after the copy: the next frame may overwrite rank 0's buffer
-            else:
-                step_device()
-                if rank == 0:
-                    host_frame.copy_(full, non_blocking=True)
-            torch.cuda.synchronize()
+            while int(words[128]) < k - 1:              # frame k-1 consumed by rank 0?
+                pass
+            r.render_bands_host(W, H, DEPTH, BAND_H, rank, n, frame_ptr)   # returns when this rank's rows are in host memory
+            words[rank] = k
+            if rank == 0:
+                while any(int(words[j]) < k for j in range(n)):           # the whole frame is in host memory
+                    pass
+                words[128] = k
         d2h = W * H * 3
     h2d = r.scene_bytes()
     Ke = max(1, min(K, 200))
@@ -395,6 +417,23 @@ def main_b200(args, rank, local_rank, world):
     if n > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item())
+    e2e_check = None
+    if n > 1:
+        # the host frame the ranks assembled must be rank 0's own full-frame render, byte for byte
+        if rank == 0:
+            host_frame[:] = 0
+        dist.barrier()
+        step_e2e()
+        dist.barrier()
+        if rank == 0:
+            own, _ = r.render(W, H, DEPTH)
+            e2e_check = "identical" if np.array_equal(own, host_frame) else "DIFFERENT"
+        dist.barrier()
+        rtb200.host_unregister(frame_ptr)
+        del host_frame, words
+        shm.close()
+        if rank == 0:
+            shm.unlink()
 
     # ---- dominant kernel (level-0 k_shadow) timed alone with the library's CUDA events
     k_ms, lvl0_ms, frame_ms, k_rays = None, None, None, None
@@ -430,8 +469,8 @@ def main_b200(args, rank, local_rank, world):
             "e2e": {"value": round(rays / e2e_s * 1e-6, 1), "unit": "Mrays/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_s * 1e3, 4), "steps": Ke,
                     "path": "rt_upload_scene + rt_render into pinned host memory" if n == 1 else
-                            ("rt_upload_scene + rt_render_bands_frame (peer stores) + copy to pinned host on rank 0" if peer else
-                             "rt_upload_scene + rt_render_bands + NCCL gather + copy to pinned host on rank 0")},
+                            "rt_upload_scene + rt_render_bands_host on every rank: bands copied over each GPU's own host link into one "
+                            "shared page-locked host frame (POSIX shm), completion flags in the same segment"},
             "gpu_launches": launches_per_step * K,
             "clocks": sampler.summary(),
         }
@@ -475,6 +514,9 @@ def main_b200(args, rank, local_rank, world):
                                         "sample": "failed: %r" % (e,)}
         if frame_check is not None:
             line["frame_check"] = frame_check
+            line["e2e"]["frame_check"] = e2e_check
+            if e2e_check == "DIFFERENT":
+                frame_check = "DIFFERENT"
         print(json.dumps(line), flush=True)
         if frame_check == "DIFFERENT":
             raise RuntimeError("the frame assembled from %d ranks differs from rank 0's own full-frame render" % n)

@@ -12,7 +12,7 @@ The directory name contains a hyphen, so import it through ``rtb200.py`` at the 
 """
 from .api import (  # noqa: F401
     RtError, RtStats, Scene, Renderer, MultiRenderer, load_library, library_path, load_scene, write_ppm,
-    band_rows, band_row_list, measure_fp32_peak, ABI_SYMBOLS,
+    band_rows, band_row_list, measure_fp32_peak, host_register, host_unregister, ABI_SYMBOLS,
 )
 from .ppmtools import read_ppm, compare_rgb, ppm_text  # noqa: F401
 from .build import build_all, build_library  # noqa: F401

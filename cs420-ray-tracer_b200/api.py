@@ -22,7 +22,7 @@ ABI_SYMBOLS = [
     "rt_render", "rt_render_debug", "rt_render_bands", "rt_band_rows", "rt_band_row_list",
     "rt_host_alloc", "rt_host_free", "rt_write_ppm", "rt_measure_fp32_peak",
     "rt_create_multi", "rt_multi_destroy", "rt_multi_ranks", "rt_multi_ctx", "rt_multi_set_option", "rt_multi_upload_scene",
-    "rt_multi_render",
+    "rt_multi_render", "rt_render_bands_host", "rt_host_register", "rt_host_unregister",
 ]
 
 
@@ -109,6 +109,9 @@ def load_library():
     lib.rt_multi_set_option.argtypes = [vp, C.c_char_p, C.c_longlong]
     lib.rt_multi_upload_scene.argtypes = [vp, vp, i, vp, i, vp, vp, vp, C.c_double]
     lib.rt_multi_render.argtypes = [vp, i, i, i, i, vp, C.POINTER(RtStats)]
+    lib.rt_render_bands_host.argtypes = [vp, i, i, i, i, i, i, vp, C.POINTER(RtStats)]
+    lib.rt_host_register.argtypes = [vp, C.c_size_t]
+    lib.rt_host_unregister.argtypes = [vp]
     for name in ABI_SYMBOLS:
         getattr(lib, name)
     _lib = lib
@@ -181,6 +184,14 @@ def measure_fp32_peak(device=0):
     f, m = C.c_double(), C.c_double()
     _check(load_library().rt_measure_fp32_peak(int(device), C.byref(f), C.byref(m)), "rt_measure_fp32_peak")
     return f.value, m.value
+
+
+def host_register(ptr, nbytes):
+    _check(load_library().rt_host_register(C.c_void_p(ptr), nbytes), "rt_host_register")
+
+
+def host_unregister(ptr):
+    _check(load_library().rt_host_unregister(C.c_void_p(ptr)), "rt_host_unregister")
 
 
 def band_rows(H, band_h, rank, nranks):
@@ -330,6 +341,14 @@ class Renderer:
         _check(self._lib.rt_render_debug(self._h, W, H, depth, out.ctypes.data, hit.ctypes.data, mask.ctypes.data,
                                          C.byref(st) if want_stats else None), "rt_render_debug")
         return out, hit, mask, st
+
+    def render_bands_host(self, W, H, depth, band_h, rank, nranks, host_ptr, want_stats=False):
+        """rt_render_bands_host: this rank's bands rendered and copied to their image positions of a (shared, pinned)
+        host frame over this GPU's own host link; returns when they have landed."""
+        st = RtStats()
+        _check(self._lib.rt_render_bands_host(self._h, W, H, depth, band_h, rank, nranks, C.c_void_p(host_ptr),
+                                              C.byref(st) if want_stats else None), "rt_render_bands_host")
+        return st
 
     def render_bands_device(self, W, H, depth, band_h, rank, nranks, dev_ptr, stream_ptr=None, want_stats=False):
         """Asynchronous banded render into device memory (e.g. a torch tensor's data_ptr())."""

@@ -78,6 +78,8 @@ struct FastArgs {
   int tables_in_smem;
   rtb::BvhView bvh;           // large scenes: candidates come from the LBVH instead of a table walk (bvh.cuh)
   int nbig, big[8];           // spheres too large for the LBVH (a ground sphere ...): tested for every ray instead
+  unsigned queue_cap;         // records per ray queue
+  unsigned int *err;          // the frame's error word (bounds guards; 0 = clean)
 };
 
 // One shared-origin table: sphere pairs in sorted order, per-group minimum distance, original indices
@@ -1053,13 +1055,17 @@ __device__ __forceinline__ bool bundle_traverse(const FastArgs &a, const BundleB
 
 // ---------------------------------------------------------------------------------------------
 // warp-ballot compaction: rays still alive are appended densely to the next level's queue
-__device__ __forceinline__ void queue_push(bool want, const RayRec &rec, RayRec *q, unsigned int *count) {
+// Guard (compute-sanitizer is not available on this pool, so the kernels check their own queue bounds): a push that
+// would run past the queue's capacity is dropped and flagged in the frame's error word instead of written.
+enum { RT_GUARD_HIT_BLOCKS = 1u, RT_GUARD_RAY_QUEUE = 2u };
+__device__ __forceinline__ void queue_push(bool want, const RayRec &rec, RayRec *q, unsigned int *count, unsigned cap, unsigned int *err) {
   const unsigned mk = __ballot_sync(kFull, want);
   if (mk == 0) return;
   const int lane = threadIdx.x & 31, leader = __ffs(mk) - 1;
   unsigned base = 0;
   if (lane == leader) base = atomicAdd(count, (unsigned)__popc(mk));
   base = __shfl_sync(kFull, base, leader);
+  if (base + (unsigned)__popc(mk) > cap) { if (lane == leader) atomicOr(err, (unsigned)RT_GUARD_RAY_QUEUE); return; }
   if (want) q[base + __popc(mk & ((1u << lane) - 1u))] = rec;
 }
 

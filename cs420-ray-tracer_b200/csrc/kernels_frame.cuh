@@ -41,7 +41,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int *ctl, unsigned &target
       while (*bar < target) {
         __nanosleep(32);
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 1000000000ULL) { atomicExch(ctl + CTL_ERR, 1u); break; }
+        if (t1 - t0 > 1000000000ULL) { atomicOr(ctl + CTL_ERR, 4u); break; }
       }
     }
     __threadfence();

@@ -98,7 +98,11 @@ __device__ __forceinline__ void hit_block(const WaveArgs &w, unsigned int *hit_c
   const unsigned n = (unsigned)(__popc(m0) + __popc(m1));
   unsigned base = 0;
   if (n != 0u) {
-    if (lane == 0) { base = atomicAdd(hit_count, 64u); w.hit_n[base >> 6] = n; }
+    if (lane == 0) {
+      base = atomicAdd(hit_count, 64u);
+      if (base + 64u > w.hit_cap) { atomicOr(w.f.err, (unsigned)RT_GUARD_HIT_BLOCKS); base = 0u; }   // guard: never past the buffer (flagged; block 0 is sacrificed)
+      w.hit_n[base >> 6] = n;
+    }
     base = __shfl_sync(kFull, base, 0);
   }
   const unsigned lt = (1u << lane) - 1u;
@@ -689,7 +693,7 @@ __device__ __forceinline__ void shadow_body(const WaveArgs &w, const Lvl &lv, un
         c_shadow += (unsigned)a.L; c_occ += (unsigned)__popcll(occm[r]);
         cont = shade_one(w, lv, w.hits[h0 + r], occm[r], rec);
       }
-      queue_push(cont, rec, lv.q_out, lv.q_out_count);
+      queue_push(cont, rec, lv.q_out, lv.q_out_count, a.queue_cap, a.err);
     }
   }
   if (a.r.counters) flush_counts(a.r.counters, 99, 0, 0, c_shadow, c_occ, c_fp64, 0, (unsigned long long)a.N, c_cand, c_walks, c_fall);
@@ -890,7 +894,7 @@ __device__ __forceinline__ void shade_body(const WaveArgs &w, const Lvl &lv) {
       c_shadow += (unsigned)L; c_occ += (unsigned)__popcll(occm);
       cont = shade_one(w, lv, hr, occm, rec);
     }
-    queue_push(cont, rec, lv.q_out, lv.q_out_count);
+    queue_push(cont, rec, lv.q_out, lv.q_out_count, a.queue_cap, a.err);
   }
   if (a.r.counters) flush_counts(a.r.counters, 99, 0, 0, c_shadow, c_occ, 0, 0, (unsigned long long)a.N);
 }

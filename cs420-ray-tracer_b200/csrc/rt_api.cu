@@ -77,6 +77,7 @@ struct rt_ctx {
   float *d_fb = nullptr; size_t fb_cap = 0;   // float sample frame of a supersampled render
   // buffers
   uint8_t *d_rgb = nullptr; size_t rgb_cap = 0;
+  uint8_t *d_part = nullptr; size_t part_cap = 0;   // compact band buffer of rt_render_bands_host / rt_multi_render
   int32_t *d_hit = nullptr; size_t hit_cap = 0;
   uint32_t *d_mask = nullptr; size_t mask_cap = 0;
   unsigned long long *d_counters = nullptr;
@@ -150,6 +151,7 @@ extern "C" void rt_destroy(rt_ctx *c) {
   free_scene(c);
   rtk_fast_free_work(&c->work);
   cudaFree(c->d_su); cudaFree(c->d_sv);
+  cudaFree(c->d_part);
   cudaFree(c->d_rgb); cudaFree(c->d_hit); cudaFree(c->d_mask); cudaFree(c->d_counters); cudaFree(c->d_fb);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -324,6 +326,15 @@ static int collect_stats(rt_ctx *c, rt_stats *stats) {
   }
   stats->kernel_launches = c->pend_launches;
   stats->rows_rendered = c->pend_rows;
+  if (c->mode == 0 && c->pend_rows > 0) {
+    // compute-sanitizer cannot run on this pool: the kernels guard their own queue bounds and report here
+    unsigned int word = 0;
+    const int er = rtk_fast_last_error(&c->work, &word);
+    if (er != 0) return rt_fail(RT_ERR_CUDA, std::string("render: reading the error word failed: ") + cudaGetErrorString((cudaError_t)-er));
+    if (word != 0)
+      return rt_fail(RT_ERR_STATE, "render: device-side guard tripped (bit 0: hit-block buffer, bit 1: ray queue, else: grid barrier timeout): word " +
+                                       std::to_string(word));
+  }
   if (c->pend_counters) {
     unsigned long long cnt[RT_CNT_TOTAL];
     RT_CUDA(cudaMemcpy(cnt, c->d_counters, sizeof(cnt), cudaMemcpyDeviceToHost));
@@ -563,11 +574,65 @@ extern "C" int rt_measure_fp32_peak(int device, double *flops_per_s, double *sm_
 // caller's host frame: a band is band_h consecutive rows = one contiguous run both in the rank's compact buffer and in
 // the frame, so the whole share of a rank is ONE strided copy (cudaMemcpy2DAsync; + one for a ragged last band).
 // Nothing crosses between the GPUs: for a frame that ends in host memory the gather of 8e is the host frame itself.
+// One rank's share of a frame that ends in HOST memory: renders the bands b with b % nranks == rank compactly into the
+// ctx's own device buffer and enqueues their copies to their image positions in host_rgb on the ctx stream.  A band is
+// band_h consecutive rows = one contiguous run both in the compact buffer and in the frame, so the full bands of a rank
+// are ONE strided copy (cudaMemcpy2DAsync), a ragged last band (H % band_h rows) one more.  Does not wait.
+static int enqueue_bands_to_host(rt_ctx *c, int W, int H, int depth, int band_h, int rank, int nranks, uint8_t *host_rgb, rt_stats *stats) {
+  const size_t row_bytes = (size_t)W * 3, band_bytes = row_bytes * (size_t)band_h;
+  const int rows = rt_band_rows(H, band_h, rank, nranks);
+  if (rows < 0) return rows;
+  RT_CUDA(cudaSetDevice(c->device));
+  int rc = ensure_cap(c->d_part, c->part_cap, (size_t)(rows > 0 ? rows : 1) * row_bytes + 16);
+  if (rc) return rc;
+  rc = render_common(c, W, H, depth, band_h, rank, nranks, c->d_part, nullptr, nullptr, c->stream, stats, nullptr, true);
+  if (rc) return rc;
+  if (rows == 0) return RT_OK;
+  const int nb_all = (H + band_h - 1) / band_h;
+  int nb = 0, nfull = 0;
+  for (int b = rank; b < nb_all; b += nranks) { nb++; if ((b + 1) * band_h <= H) nfull++; }
+  if (nfull > 0)
+    RT_CUDA(cudaMemcpy2DAsync(host_rgb + (size_t)rank * band_bytes, (size_t)nranks * band_bytes, c->d_part, band_bytes, band_bytes, (size_t)nfull,
+                              cudaMemcpyDeviceToHost, c->stream));
+  if (nb > nfull) {
+    const int b = rank + nfull * nranks, tail_rows = H - b * band_h;
+    RT_CUDA(cudaMemcpyAsync(host_rgb + (size_t)b * band_bytes, c->d_part + (size_t)nfull * band_bytes, (size_t)tail_rows * row_bytes,
+                            cudaMemcpyDeviceToHost, c->stream));
+  }
+  return RT_OK;
+}
+
+// One process per GPU (torchrun): every rank calls this with the SAME host frame -- shared memory that each process has
+// page-locked (rt_host_register) -- and its own (rank, nranks).  Every rank's bands travel over its own host link, all
+// ranks concurrently; nothing crosses between the GPUs.  Returns when this rank's rows have landed.
+extern "C" int rt_render_bands_host(rt_ctx *c, int W, int H, int depth, int band_h, int rank, int nranks, uint8_t *host_rgb, rt_stats *stats) {
+  if (!c || !host_rgb) return rt_fail(RT_ERR_ARG, "rt_render_bands_host: NULL argument");
+  if (W < 1 || H < 1 || depth < 0 || band_h < 1) return rt_fail(RT_ERR_ARG, "rt_render_bands_host: bad image size, depth or band height");
+  auto t0 = std::chrono::steady_clock::now();
+  int rc = enqueue_bands_to_host(c, W, H, depth, band_h, rank, nranks, host_rgb, stats);
+  if (rc) return rc;
+  if (stats && (rc = collect_stats(c, stats))) return rc;
+  RT_CUDA(cudaStreamSynchronize(c->stream));
+  if (stats) stats->ms_host = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return RT_OK;
+}
+
+// Page-locks memory the caller allocated (e.g. a POSIX shared-memory frame) so that device -> host copies into it are
+// asynchronous and run at full link rate; portable across the contexts of the process.
+extern "C" int rt_host_register(void *p, size_t bytes) {
+  if (!p || bytes == 0) return rt_fail(RT_ERR_ARG, "rt_host_register: bad argument");
+  RT_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+  return RT_OK;
+}
+extern "C" int rt_host_unregister(void *p) {
+  if (!p) return rt_fail(RT_ERR_ARG, "rt_host_unregister: NULL argument");
+  RT_CUDA(cudaHostUnregister(p));
+  return RT_OK;
+}
+
 struct rt_multi {
   int n = 0;
   std::vector<rt_ctx *> ctx;
-  std::vector<uint8_t *> part;       // per rank: compact band buffer on its device
-  std::vector<size_t> part_cap;
   void *registered = nullptr; size_t registered_bytes = 0;   // host frame pinned by us (cudaHostRegister) for async copies
 };
 
@@ -577,7 +642,6 @@ extern "C" void rt_multi_destroy(rt_multi *m) {
     if (!m->ctx[r]) continue;
     cudaSetDevice(m->ctx[r]->device);
     cudaStreamSynchronize(m->ctx[r]->stream);
-    if (r < (int)m->part.size()) cudaFree(m->part[r]);
     rt_destroy(m->ctx[r]);
   }
   if (m->registered) cudaHostUnregister(m->registered);
@@ -592,7 +656,7 @@ extern "C" int rt_create_multi(int ngpus, rt_multi **out) {
   rt_multi *m = new (std::nothrow) rt_multi();
   if (!m) return rt_fail(RT_ERR_NOMEM, "rt_create_multi: out of memory");
   m->n = ngpus;
-  m->ctx.assign((size_t)ngpus, nullptr); m->part.assign((size_t)ngpus, nullptr); m->part_cap.assign((size_t)ngpus, 0);
+  m->ctx.assign((size_t)ngpus, nullptr);
   for (int r = 0; r < ngpus; r++) {
     // more ranks than devices: ranks share devices round robin (same frame, no speed-up) -- lets a 1-GPU box run the
     // N-rank code path
@@ -637,7 +701,7 @@ extern "C" int rt_multi_render(rt_multi *m, int W, int H, int depth, int band_h,
   if (W < 1 || H < 1 || depth < 0 || band_h < 1) return rt_fail(RT_ERR_ARG, "rt_multi_render: bad image size, depth or band height");
   auto t0 = std::chrono::steady_clock::now();
   const int n = m->n;
-  const size_t row_bytes = (size_t)W * 3, band_bytes = row_bytes * (size_t)band_h;
+  const size_t row_bytes = (size_t)W * 3;
   // asynchronous device -> host copies need page-locked memory: pin the caller's frame once (kept while it stays the same
   // buffer); a frame that is already pinned (rt_host_alloc) reports cudaErrorHostMemoryAlreadyRegistered -- fine
   if (n > 1 && (m->registered != host_rgb || m->registered_bytes != row_bytes * H)) {
@@ -647,27 +711,8 @@ extern "C" int rt_multi_render(rt_multi *m, int W, int H, int depth, int band_h,
     else cudaGetLastError();                           // already pinned, or not pinnable: the copies still work (staged)
   }
   for (int r = 0; r < n; r++) {
-    rt_ctx *c = m->ctx[r];
-    const int rows = rt_band_rows(H, band_h, r, n);
-    if (rows < 0) return rows;
-    RT_CUDA(cudaSetDevice(c->device));
-    int rc = ensure_cap(m->part[r], m->part_cap[r], (size_t)(rows > 0 ? rows : 1) * row_bytes + 16);
+    const int rc = enqueue_bands_to_host(m->ctx[r], W, H, depth, band_h, r, n, host_rgb, stats);
     if (rc) return rc;
-    rc = render_common(c, W, H, depth, band_h, r, n, m->part[r], nullptr, nullptr, c->stream, stats, nullptr, true);
-    if (rc) return rc;
-    if (rows == 0) continue;
-    // bands r, r + n, r + 2n, ...: full bands as one strided copy, a ragged last band (H % band_h rows) separately
-    const int nb_all = (H + band_h - 1) / band_h;
-    int nb = 0, nfull = 0;
-    for (int b = r; b < nb_all; b += n) { nb++; if ((b + 1) * band_h <= H) nfull++; }
-    uint8_t *dst0 = host_rgb + (size_t)r * band_bytes;
-    if (nfull > 0)
-      RT_CUDA(cudaMemcpy2DAsync(dst0, (size_t)n * band_bytes, m->part[r], band_bytes, band_bytes, (size_t)nfull, cudaMemcpyDeviceToHost, c->stream));
-    if (nb > nfull) {
-      const int b = r + nfull * n, tail_rows = H - b * band_h;
-      RT_CUDA(cudaMemcpyAsync(host_rgb + (size_t)b * band_bytes, m->part[r] + (size_t)nfull * band_bytes, (size_t)tail_rows * row_bytes,
-                              cudaMemcpyDeviceToHost, c->stream));
-    }
   }
   rt_stats acc;
   memset(&acc, 0, sizeof(acc));

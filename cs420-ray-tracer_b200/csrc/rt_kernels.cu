@@ -240,6 +240,10 @@ int rtk_fast_build_scene(RtFastScene *fs, const double *sph, int N, const RtFram
   };
   std::vector<int> order((size_t)(N > 0 ? N : 1));
   std::vector<double> key((size_t)(N > 0 ? N : 1));
+  // LBVH scenes: the candidates of every query come from the hierarchy, the tables are only LOOKED UP by sphere (inv ->
+  // slot -> pair); nothing walks them in order, prunes by gmin or culls by cone.  So they keep index order -- no sort
+  // (five stable sorts of 100 k keys were most of a config-5 upload) -- and carry no cull data.
+  const bool lookup_only = N > 0 && (accel == 2 || (accel == 0 && N >= kBvhAutoSpheres));
   auto build_table = [&](int t, std::vector<int> &order, std::vector<double> &key) {
     unsigned char *base = h.data() + (size_t)t * fs->tstride;
     float4 *pairs = reinterpret_cast<float4 *>(base);
@@ -255,7 +259,7 @@ int rtk_fast_build_scene(RtFastScene *fs, const double *sph, int N, const RtFram
       key[i] = std::sqrt(x * x + y * y + z * z) - std::fabs(s[3]);
       order[i] = i;
     }
-    std::stable_sort(order.begin(), order.begin() + N, [&](int p, int q) { return key[p] < key[q]; });
+    if (!lookup_only) std::stable_sort(order.begin(), order.begin() + N, [&](int p, int q) { return key[p] < key[q]; });
     for (int slot = 0; slot < nslots; slot++) {
       if (slot >= N) {                                 // padding: never a candidate, always culled
         put(pairs, slot, 0.f, 0.f, 0.f, -1.0f); perm[slot] = -1;
@@ -270,7 +274,7 @@ int rtk_fast_build_scene(RtFastScene *fs, const double *sph, int N, const RtFram
       put(pairs, slot, (float)x, (float)y, (float)z, float_up(E - (oc2 - s[3] * s[3])));
       perm[slot] = i;
       // bundle culling (kernels_fast.cuh, cull_round): unit vector to the centre, cos / sin of the angular radius
-      {
+      if (!lookup_only) {
         const double n = std::sqrt(oc2), r = std::fabs(s[3]) * (1.0 + 1e-6) + 1e-12;
         if (n > r * (1.0 + 1e-6)) {
           const double sa = r / n, ca = std::sqrt((1.0 - sa) * (1.0 + sa));
@@ -286,6 +290,7 @@ int rtk_fast_build_scene(RtFastScene *fs, const double *sph, int N, const RtFram
     for (int g = 0; g < ngroups; g++) {
       const int slot = g * 2 * rtf::kGroupPairs;
       if (slot >= N) { gmin[g] = 3.0e38f; continue; }
+      if (lookup_only) { gmin[g] = -3.0e38f; continue; }   // (unsorted: never a reason to stop)
       const double k = key[order[slot]];
       gmin[g] = float_down(k - std::fabs(k) * 1e-6 - 1e-6 - delta64);
     }
@@ -361,9 +366,18 @@ void rtk_fast_free_scene(RtFastScene *fs, int release_tables) {
   fs->bvh_nodes = fs->bvh_leaves = nullptr; fs->bvh_nleaf = 0;
 }
 
+// The error word of the last frame launched (call after the stream has been synchronised): bounds guards of the hit /
+// ray queues, grid-barrier timeout of the whole-frame kernel.  0 = clean.
+int rtk_fast_last_error(const RtFastWork *w, unsigned int *word) {
+  *word = 0;
+  if (!w->last_err) return 0;
+  RTK_TRY(cudaMemcpy(word, w->last_err, sizeof(unsigned int), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 void rtk_fast_free_work(RtFastWork *w) {
   cudaFree(w->queue[0]); cudaFree(w->queue[1]); cudaFree(w->ctl_base); cudaFree(w->hits); cudaFree(w->occ); cudaFree(w->hit_n); cudaFree(w->cand);
-  cudaFree(w->shade_done); w->shade_done = nullptr; w->ctl_base = nullptr;
+  cudaFree(w->shade_done); w->shade_done = nullptr; w->ctl_base = nullptr; w->last_err = nullptr;
   w->cand = nullptr; w->cand_cap = 0;
   if (w->h_fb) { cudaFreeHost(w->h_fb); cudaEventDestroy(w->fb_event); }
   w->h_fb = nullptr; w->fb_pending = 0; w->fb_levels = 0;
@@ -486,6 +500,8 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
   a.wtiles_x = (args.W + rtf::kWTileW - 1) / rtf::kWTileW;
   a.nwtiles = a.wtiles_x * ((args.bands.local_rows + rtf::kWTileH - 1) / rtf::kWTileH);
   a.tile_counter = w->ctl + CTL_TILE;
+  a.queue_cap = (unsigned)w->queue_cap; a.err = w->ctl + rtf::CTL_ERR;
+  w->last_err = a.err;
   wa.hits = (rtf::HitRec *)w->hits; wa.hit_cap = (unsigned)hit_cap;   // THIS frame's slot count = the stride of the per-light occlusion rows (the allocation may be
                                                           // larger; with its size as stride a scene with more lights than the one the buffers were sized
                                                           // for would index past occ_bytes)

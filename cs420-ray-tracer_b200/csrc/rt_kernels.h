@@ -52,6 +52,7 @@ struct RtFastWork {
   unsigned int *ctl;     // device control words of the current frame: tile counter, per-level chunk counters, queue counts
   unsigned int *ctl_base; int ctl_cur, ctl_clean[2];   // two sets; clean = known to be all zero
   unsigned int *shade_done;   // whole-frame kernel: per chunk of hits, (chunk, light) shadow items finished (self-resetting)
+  unsigned int *last_err; // device: error word of the last frame launched (bounds guards, barrier timeout)
   int frame_kernel;      // -1 automatic (whole-frame kernel when every table fits in shared memory), 0 never, 1 = as automatic
   void *hits;            // HitRec queue of the current level (kernels_wave.cuh), 64-slot blocks
   unsigned int *hit_n;   // hits per block
@@ -65,6 +66,7 @@ int rtk_fast_init(int device);
 int rtk_fast_build_scene(RtFastScene *fs, const double *spheres, int N, const RtFrameConst *frame, int accel, cudaStream_t stream);
 void rtk_fast_free_scene(RtFastScene *fs, int release_tables);   // release_tables = 0: keep the table allocation
 void rtk_fast_free_work(RtFastWork *w);
+int rtk_fast_last_error(const RtFastWork *w, unsigned int *word);
 // marks (may be null): 3 events recorded after the level-0 closest-hit, shadow and shade kernels.
 int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork *w, cudaStream_t stream,
                     const cudaEvent_t *marks);

@@ -212,11 +212,22 @@ int rt_multi_upload_scene(rt_multi *m, const double *spheres, int nspheres, cons
 int rt_multi_render(rt_multi *m, int width, int height, int max_depth, int band_h, uint8_t *host_rgb,
                     rt_stats *stats);
 
+/* One process per GPU (torchrun): as rt_multi_render's per-rank half.  Every rank calls it with the SAME host frame
+ * (shared memory, W*H*3 bytes, row 0 = bottom) and its own (rank, nranks); the rank's bands are rendered and copied to
+ * their image positions over this GPU's host link.  Returns when this rank's rows have landed; the frame is complete
+ * when every rank has returned (the caller synchronises the ranks).  Page-lock the frame in every process first
+ * (rt_host_register) or the copies are staged through pageable memory.                          */
+int rt_render_bands_host(rt_ctx *ctx, int width, int height, int max_depth, int band_h, int rank,
+                         int nranks, uint8_t *host_rgb, rt_stats *stats);
+
 /* ---- pinned host memory -----------------------------------------------------------------
  * Page-locked buffers so that the frame copy of rt_render runs at full host-link rate.
  * (The reference does the same for its bulk copy: src/main_hybrid.cpp:524.)                 */
 int rt_host_alloc(size_t bytes, void **out);
 void rt_host_free(void *p);
+/* Page-locks / releases memory the caller allocated itself (e.g. a POSIX shared-memory frame).   */
+int rt_host_register(void *p, size_t bytes);
+int rt_host_unregister(void *p);
 
 /* ---- measurement -------------------------------------------------------------------------
  * FP32 FFMA issue peak of `device` in FLOP/s (8 independent chains/thread, all SMs busy) and

@@ -17,6 +17,13 @@ for label, scene, kw, sizes in [("tables/smem", cx, {}, [(97, 61, 4), (160, 90, 
             rgb, hit, mask, st = r.render_debug(W, H, D)
             print(label, W, H, D, "rays", st.closest_queries + st.shadow_queries, "viol", st.filter_violations)
         if kw.get("mode") != "exact":
+            # production launch sequence (no stats: programmatic dependent launch) and the whole-frame cooperative kernel
+            r.render(160, 90, 5, want_stats=False)
+            r.render(160, 90, 5, want_stats=False)
+            r.set_option("frame_kernel", 1)
+            r.render_debug(97, 61, 4)
+            r.render(160, 90, 5, want_stats=False)
+            r.set_option("frame_kernel", 0)
             r.set_option("antialias", 1)
             r.render(50, 30, 3)
             r.set_option("antialias", 0)
@@ -28,4 +35,7 @@ for label, scene, kw, sizes in [("tables/smem", cx, {}, [(97, 61, 4), (160, 90, 
             torch.cuda.synchronize()
             r.render_bands_frame(70, 40, 3, 16, 1, 2, fr.data_ptr())
             torch.cuda.synchronize()
+with rtb200.MultiRenderer(3) as m:                       # rt_create_multi: three ranks (sharing devices on a 1-GPU box)
+    m.upload(cx)
+    m.render(97, 61, 4, band_h=8)
 print("done")

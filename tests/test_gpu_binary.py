@@ -121,7 +121,7 @@ def test_benchmark_csv_has_the_reference_format(workdir):
     cuda = [r for r in rows if r[0] == "CUDA"]
     assert sorted(r[1] for r in cuda) == ["complex.txt", "medium.txt", "simple.txt"]
     for r in rows:
-        assert len(r) == 7 and float(r[4]) > 0 and abs(float(r[5]) - 1280 * 720 / float(r[4])) <= 1.0 + 1e-6 * float(r[5])
+        assert len(r) == 7 and float(r[4]) > 0 and abs(float(r[5]) - 1280 * 720 / float(r[4])) <= 1.0 + 1e-4 * float(r[5])   # (Time(s) is printed with 6 decimals)
     if os.path.exists(os.path.join(REF, "ray_serial")):
         assert {r[0] for r in rows} == {"Serial", "OpenMP", "CUDA"}
         assert all(float(r[6]) > 10.0 for r in cuda)         # the reference's own bar for its CUDA build: >= 10x serial (scripts/benchmark.sh:298)
