@@ -255,6 +255,69 @@ def main_reference(args, rank):
 
 
 # -------------------------------------------------------------------------------------------------
+def measure_extra(torch, dist, rtb200, local_rank, rank, n, workload, gather, steps=8, warmup=3):
+    """N > 1: a short device-timed run of ANOTHER BASELINE config in the same process group (the 8-GPU config the
+    north star names is config 4: synthetic 10 k spheres at 3840x2160), so that the driver's scaling record carries it.
+    Same method as the headline: CUDA events per step, L2 flushed between steps, max over ranks, assembled frame checked
+    against rank 0's own full-frame render."""
+    import numpy as np
+    _, w_, h_, d_, label = WORKLOADS[workload]
+    dev = torch.device("cuda", local_rank)
+    scene = load_workload(workload)
+    r = rtb200.Renderer(local_rank, mode="fast")
+    r.upload(scene)
+    stream = torch.cuda.current_stream(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    if gather == "peer":
+        pf = rtb200.PeerFrame(r, w_, h_, BAND_H, rank, n, dist)
+        full = pf.frame() if rank == 0 else None
+
+        def step():
+            pf.render(d_, stream.cuda_stream)
+            pf.release(stream.cuda_stream)
+    else:
+        bands = rtb200.BandGather(w_, h_, BAND_H, rank, n, dev, dist)
+        full = bands.full
+
+        def step():
+            r.render_bands_device(w_, h_, d_, BAND_H, rank, n, bands.part.data_ptr(), stream.cuda_stream)
+            bands.gather()
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for k in range(steps):
+        flush.fill_(k & 0xff)
+        ev[k][0].record(stream)
+        step()
+        ev[k][1].record(stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t = torch.tensor([sum(a.elapsed_time(b) for a, b in ev) / steps], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out = {"workload": label, "gather": gather, "n_gpus": n, "steps": steps, "ms_per_step": round(float(t.item()), 4)}
+    if rank == 0:
+        full.zero_()
+    torch.cuda.synchronize()
+    dist.barrier()
+    step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    if rank == 0:
+        own, st = r.render(w_, h_, d_)
+        rays = int(st.closest_queries + st.shadow_queries)
+        out.update({"rays_per_frame": rays, "value": round(rays / (out["ms_per_step"] * 1e-3) * 1e-6, 1), "unit": "Mrays/s",
+                    "frame_check": "identical" if np.array_equal(own, full.cpu().numpy()) else "DIFFERENT"})
+    torch.cuda.synchronize()
+    dist.barrier()
+    if gather == "peer":
+        pf.close()
+    r.close()
+    del flush
+    return out
+
+
 def main_b200(args, rank, local_rank, world):
     import torch
     import rtb200
@@ -452,6 +515,15 @@ def main_b200(args, rank, local_rank, world):
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
+    # ---- N > 1 on the headline workload: carry BASELINE config 4 (the one the north star names for 8 GPUs) in the same record
+    extra = []
+    if n > 1 and args.workload == "complex" and not args.no_extra:
+        for g in ("peer", "nccl"):
+            try:
+                extra.append(measure_extra(torch, dist, rtb200, local_rank, rank, n, "synth10k", g))
+            except Exception as e:  # noqa: BLE001
+                extra.append({"workload": "synth10k", "gather": g, "error": repr(e)})
+
     if rank == 0:
         peak, peak_mhz = rtb200.measure_fp32_peak(local_rank)
         nsph = scene.nspheres
@@ -512,6 +584,8 @@ def main_b200(args, rank, local_rank, world):
             except Exception as e:  # noqa: BLE001
                 line["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "reference",
                                         "sample": "failed: %r" % (e,)}
+        if extra:
+            line["extra_workloads"] = extra
         if frame_check is not None:
             line["frame_check"] = frame_check
             line["e2e"]["frame_check"] = e2e_check
@@ -542,6 +616,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="complex", choices=sorted(WORKLOADS))
     ap.add_argument("--accel", type=int, default=None, help="0 auto, 1 table walks, 2 LBVH (rt_set_option accel)")
+    ap.add_argument("--no-extra", action="store_true", help="N > 1: skip the extra_workloads block (config 4)")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="N > 1: how the bands reach rank 0")
     args = ap.parse_args()
     global SCENE, W, H, DEPTH, WORKLOAD
@@ -560,6 +635,10 @@ def main():
         if args.accel is not None:
             cmd += ["--accel", str(args.accel)]
         cmd += ["--gather", args.gather]
+        if args.no_extra:
+            cmd += ["--no-extra"]
+        if args.no_cpu_baseline:
+            cmd += ["--no-cpu-baseline"]
         return subprocess.call(cmd)
     return main_b200(args, rank, local_rank, world)
 
