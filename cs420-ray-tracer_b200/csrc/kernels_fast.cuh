@@ -78,6 +78,8 @@ struct FastArgs {
   int tables_in_smem;
   rtb::BvhView bvh;           // large scenes: candidates come from the LBVH instead of a table walk (bvh.cuh)
   int nbig, big[8];           // spheres too large for the LBVH (a ground sphere ...): tested for every ray instead
+  unsigned two_mult, lp_mult; // work-granularity thresholds in units of (warps of the grid): two rays / hits per lane from
+                              // two_mult x 64 per warp on; one (chunk, light) item per fetch below lp_mult chunks per warp
   unsigned queue_cap;         // records per ray queue
   unsigned int *err;          // the frame's error word (bounds guards; 0 = clean)
 };

@@ -315,7 +315,7 @@ __device__ __forceinline__ void closest0_body(const WaveArgs &w, const Lvl &lv, 
         if (best[r].idx >= 0) {
           HitRec *rec = w.hits + hslot[r];
           hit = finish_hit(a, best[r], src[r], pix[r], 0u, 1.0f, 0.f, 0.f, 0.f, rec, &c_viol, &c_fp64);
-          if (!hit) rec->idx = -1;                   // (filter violation resolved to a miss: dead slot)
+          if (!hit) { rec->idx = -1; rec->pix = pix[r]; }   // (filter violation resolved to a miss: dead slot)
           if (a.r.hit_idx) a.r.hit_idx[(size_t)pix[r] * depth] = hit ? rec->idx : -1;
         } else if (a.r.hit_idx) a.r.hit_idx[(size_t)pix[r] * depth] = -1;
       }
@@ -384,7 +384,7 @@ __device__ __forceinline__ void closest1_body(const WaveArgs &w, const Lvl &lv, 
   unsigned c_closest = 0, c_hits = 0, c_fp64 = 0, c_viol = 0;
   const RayRec *qin = lv.q_in;
   // few rays (deep levels): one ray per lane, so that twice as many warps share the work
-  const bool two = nq >= gridDim.x * (unsigned)kWarps * 64u;
+  const bool two = nq >= gridDim.x * (unsigned)kWarps * 64u * a.two_mult;
   const unsigned per = two ? 64u : 32u;
   for (;;) {
     const int chunk = warp_fetch(lv.work_closest);
@@ -457,7 +457,10 @@ __global__ void __launch_bounds__(kThreads, RT_CLOSEST_CTAS) k_closest1(const Wa
 // SHADE of ONE hit (lane local, no warp-level operations): include/scene.h:89-121 in FP32 with the occlusion bits of
 // the shadow queries (bit l of occm = light l occluded), then src/main.cpp:43-55 -- the pixel is final (written here),
 // or the path continues: returns true and *rec is the exact FP64 reflected ray for the next level's queue.
-__device__ __forceinline__ bool shade_one(const WaveArgs &w, const Lvl &lv, const HitRec &hr, unsigned long long occm, RayRec &rec) {
+// stage != nullptr: a final pixel is not written to the frame but quantised into stage[0..2] (the caller emits whole
+// 16-byte row segments of its tile), *is_final tells which it was.
+__device__ __forceinline__ bool shade_one(const WaveArgs &w, const Lvl &lv, const HitRec &hr, unsigned long long occm, RayRec &rec,
+                                          unsigned char *stage = nullptr) {
   const FastArgs &a = w.f;
   const int L = a.L, level = lv.level;
   const float4 m = __ldg(&a.r.mat[hr.idx]);
@@ -508,7 +511,10 @@ __device__ __forceinline__ bool shade_one(const WaveArgs &w, const Lvl &lv, cons
   } else {
     cr += wt * sr; cg += wt * sg; cb += wt * sb;
   }
-  if (!cont) write_final(a.r, hr.pix, cr, cg, cb);
+  if (!cont) {
+    if (stage) { stage[0] = (unsigned char)quant8(cr); stage[1] = (unsigned char)quant8(cg); stage[2] = (unsigned char)quant8(cb); }
+    else write_final(a.r, hr.pix, cr, cg, cb);
+  }
   return cont;
 }
 
@@ -537,11 +543,11 @@ __device__ __forceinline__ void shadow_body(const WaveArgs &w, const Lvl &lv, un
   unsigned ring_phase = 0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // few hits (deep levels): one hit per lane, so that twice as many warps share the work
-  const bool two = kMode == kTabStream || nh >= gridDim.x * (unsigned)kWarps * 64u;
+  const bool two = kMode == kTabStream || nh >= gridDim.x * (unsigned)kWarps * 64u * a.two_mult;
   const unsigned nchunks = two ? nh / 64u : nh / 32u;            // nh = 64 x blocks
   // few chunks (reflection levels >= 1): one (chunk, light) item per fetch instead of (chunk, all lights) -- L times
   // as many, L times shorter items, so the warps of the machine share them evenly
-  const bool lightpar = kMode != kTabStream && a.L > 1 && nchunks < 4u * gridDim.x * (unsigned)kWarps;
+  const bool lightpar = kMode != kTabStream && a.L > 1 && nchunks < a.lp_mult * gridDim.x * (unsigned)kWarps;
   const unsigned nitems = lightpar ? nchunks * (unsigned)a.L : nchunks;
   unsigned c_fp64 = 0, c_cand = 0, c_walks = 0, c_fall = 0, c_shadow = 0, c_occ = 0;
   for (;;) {
@@ -872,6 +878,57 @@ __device__ __forceinline__ void shade_body(const WaveArgs &w, const Lvl &lv) {
   const int lane = threadIdx.x & 31, L = a.L;
   unsigned c_shadow = 0, c_occ = 0;
   const unsigned G = gridDim.x * (unsigned)kWarps;
+  // Level 0, 8-bit frame in this rank's own compact buffer: the 64 slots of a hit block are the hits of ONE 16x4-pixel
+  // tile, which k_closest0 has already written (sky pixels final, hit pixels zero) as twelve 16-byte row segments.  The
+  // warp takes the whole block, reads those segments back, drops its finished pixels into them in shared memory and
+  // stores them again: 128-bit loads / stores instead of three byte stores per shaded pixel.  (Not for frames assembled
+  // in another GPU's memory: the read-back would cross NVLink.)
+  const bool tiled = lv.level == 0 && a.r.fb == nullptr && a.r.out_remap == 0 && (a.r.W & 15) == 0 &&
+                     (reinterpret_cast<unsigned long long>(a.r.rgb) & 15ull) == 0ull;
+  if (tiled) {
+    __shared__ __align__(16) unsigned char s_tiles[kWarps][kWTileH * kWTileW * 3];
+    unsigned char *s_tile = s_tiles[threadIdx.x >> 5];
+    const unsigned W = (unsigned)a.r.W, rows = (unsigned)a.r.bands.local_rows;
+    for (unsigned blk = blockIdx.x * (unsigned)kWarps + (threadIdx.x >> 5); blk * 64u < nh; blk += G) {
+      {
+        const unsigned bn = blk + G;
+        if (bn * 64u < nh) {
+          const unsigned char *q = reinterpret_cast<const unsigned char *>(w.hits + bn * 64u + lane);
+          prefetch_l1(q); prefetch_l1(q + 64);
+          if (lane == 0) prefetch_l1(w.hit_n + bn);
+        }
+      }
+      const unsigned nslots = w.hit_n[blk];
+      const unsigned pix0 = w.hits[blk * 64u].pix;                  // slot 0 of a block in use always carries its pixel
+      const unsigned ty0 = (pix0 / W) & ~(unsigned)(kWTileH - 1), tx0 = (pix0 % W) & ~(unsigned)(kWTileW - 1);
+      const bool whole = ty0 + kWTileH <= rows;                      // (W % 16 == 0: every tile is whole in x)
+      unsigned char *seg = a.r.rgb + ((size_t)(ty0 + lane / 3) * W + tx0) * 3 + (lane % 3) * 16;
+      if (whole && lane < kWTileH * 3) *reinterpret_cast<uint4 *>(s_tile + lane * 16) = *reinterpret_cast<const uint4 *>(seg);
+      __syncwarp();
+#pragma unroll 1
+      for (int half = 0; half < 2; half++) {
+        const unsigned h = blk * 64u + (unsigned)half * 32u + lane;
+        const bool live = (h & 63u) < nslots && w.hits[h].idx >= 0;
+        bool cont = false;
+        RayRec rec;
+        if (live) {
+          const HitRec hr = w.hits[h];
+          unsigned long long occm = 0ull;
+          for (int l = 0; l < L; l++)
+            if (w.occ[(size_t)l * w.hit_cap + h]) occm |= 1ull << l;
+          c_shadow += (unsigned)L; c_occ += (unsigned)__popcll(occm);
+          const unsigned y = hr.pix / W, x = hr.pix - y * W;
+          cont = shade_one(w, lv, hr, occm, rec, whole ? s_tile + ((y - ty0) * kWTileW + (x - tx0)) * 3 : nullptr);
+        }
+        queue_push(cont, rec, lv.q_out, lv.q_out_count, a.queue_cap, a.err);
+      }
+      __syncwarp();
+      if (whole && lane < kWTileH * 3) *reinterpret_cast<uint4 *>(seg) = *reinterpret_cast<const uint4 *>(s_tile + lane * 16);
+      __syncwarp();
+    }
+    if (a.r.counters) flush_counts(a.r.counters, 99, 0, 0, c_shadow, c_occ, 0, 0, (unsigned long long)a.N);
+    return;
+  }
   for (unsigned chunk = blockIdx.x * (unsigned)kWarps + (threadIdx.x >> 5); chunk * 32u < nh; chunk += G) {
     const unsigned h = chunk * 32u + lane;
     {

@@ -55,7 +55,7 @@ inline float float_down(double x) {             // largest float <= x
 }  // namespace
 
 int rtk_fast_init(int) {
-  const int big = 227 * 1024;
+  const int big = 224 * 1024;        // (some kernels carry a little static shared memory on top)
   RTK_TRY(cudaFuncSetAttribute(rtf::k_bounce<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   RTK_TRY(cudaFuncSetAttribute(rtf::k_closest0<rtf::kTabSmem>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   RTK_TRY(cudaFuncSetAttribute(rtf::k_closest0<rtf::kTabStream>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
@@ -436,6 +436,8 @@ using rtf::CTL_TILE; using rtf::CTL_TAIL; using rtf::CTL_SHADOW; using rtf::CTL_
 int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork *w, cudaStream_t stream,
                     const cudaEvent_t *marks) {
   const size_t npix = (size_t)args.W * args.bands.local_rows;
+  static const unsigned two_mult = getenv("RT_TWO_MULT") ? (unsigned)atoi(getenv("RT_TWO_MULT")) : 1u;   // tunables (A/B on the GPU)
+  static const unsigned lp_mult = getenv("RT_LP_MULT") ? (unsigned)atoi(getenv("RT_LP_MULT")) : 4u;
   if (!w->ctl_base) {
     // two sets of control words: the whole-frame kernel zeroes the set of the NEXT frame on its way out, so no memset
     // precedes it in steady state
@@ -448,7 +450,7 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
   // at most pixels / 64 + 1 blocks).  With few rays (fewer than one per lane of the resident grid) k_closest1 takes 32 rays
   // per block instead: fewer than grid x 8 warps x 2 blocks; the slack term covers the largest resident grid (4 CTAs/SM).
   const size_t hit_cap = ((size_t)((args.W + rtf::kWTileW - 1) / rtf::kWTileW) * ((args.bands.local_rows + rtf::kWTileH - 1) / rtf::kWTileH) + 2) * 64 +
-                         (size_t)w->num_sms * 4 * rtf::kWarps * 128;
+                         (size_t)w->num_sms * 4 * rtf::kWarps * 128 * (size_t)two_mult;
   if (w->hit_cap < hit_cap || w->occ_bytes < hit_cap * (size_t)(fs->L > 0 ? fs->L : 1) || (args.max_depth > 1 && w->queue_cap < npix)) {
     RTK_TRY(cudaStreamSynchronize(stream));
     cudaFree(w->queue[0]); cudaFree(w->queue[1]); cudaFree(w->hits); cudaFree(w->occ); cudaFree(w->hit_n);
@@ -500,6 +502,7 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
   a.wtiles_x = (args.W + rtf::kWTileW - 1) / rtf::kWTileW;
   a.nwtiles = a.wtiles_x * ((args.bands.local_rows + rtf::kWTileH - 1) / rtf::kWTileH);
   a.tile_counter = w->ctl + CTL_TILE;
+  a.two_mult = two_mult; a.lp_mult = lp_mult;
   a.queue_cap = (unsigned)w->queue_cap; a.err = w->ctl + rtf::CTL_ERR;
   w->last_err = a.err;
   wa.hits = (rtf::HitRec *)w->hits; wa.hit_cap = (unsigned)hit_cap;   // THIS frame's slot count = the stride of the per-light occlusion rows (the allocation may be
