@@ -889,17 +889,25 @@ __device__ __forceinline__ void shade_body(const WaveArgs &w, const Lvl &lv) {
     __shared__ __align__(16) unsigned char s_tiles[kWarps][kWTileH * kWTileW * 3];
     unsigned char *s_tile = s_tiles[threadIdx.x >> 5];
     const unsigned W = (unsigned)a.r.W, rows = (unsigned)a.r.bands.local_rows;
+    unsigned pix_next = 0u;
+    {
+      const unsigned b0 = blockIdx.x * (unsigned)kWarps + (threadIdx.x >> 5);
+      if (b0 * 64u < nh) pix_next = w.hits[b0 * 64u].pix;
+    }
     for (unsigned blk = blockIdx.x * (unsigned)kWarps + (threadIdx.x >> 5); blk * 64u < nh; blk += G) {
+      const unsigned pix0 = pix_next;                               // slot 0 of a block in use always carries its pixel
       {
+        // the warp's NEXT block: its records, and (one block later, when its first pixel is known) its tile's row
+        // segments, are pulled into L1 while this block is shaded
         const unsigned bn = blk + G;
         if (bn * 64u < nh) {
           const unsigned char *q = reinterpret_cast<const unsigned char *>(w.hits + bn * 64u + lane);
           prefetch_l1(q); prefetch_l1(q + 64);
           if (lane == 0) prefetch_l1(w.hit_n + bn);
+          pix_next = w.hits[bn * 64u].pix;
         }
       }
       const unsigned nslots = w.hit_n[blk];
-      const unsigned pix0 = w.hits[blk * 64u].pix;                  // slot 0 of a block in use always carries its pixel
       const unsigned ty0 = (pix0 / W) & ~(unsigned)(kWTileH - 1), tx0 = (pix0 % W) & ~(unsigned)(kWTileW - 1);
       const bool whole = ty0 + kWTileH <= rows;                      // (W % 16 == 0: every tile is whole in x)
       unsigned char *seg = a.r.rgb + ((size_t)(ty0 + lane / 3) * W + tx0) * 3 + (lane % 3) * 16;
@@ -924,6 +932,10 @@ __device__ __forceinline__ void shade_body(const WaveArgs &w, const Lvl &lv) {
       }
       __syncwarp();
       if (whole && lane < kWTileH * 3) *reinterpret_cast<uint4 *>(seg) = *reinterpret_cast<const uint4 *>(s_tile + lane * 16);
+      if (blk + G < nh / 64u + 1u && (blk + G) * 64u < nh && lane < kWTileH * 3) {   // next tile's segments -> L1 (pix_next has landed by now)
+        const unsigned ny0 = (pix_next / W) & ~(unsigned)(kWTileH - 1), nx0 = (pix_next % W) & ~(unsigned)(kWTileW - 1);
+        if (ny0 + kWTileH <= rows) prefetch_l1(a.r.rgb + ((size_t)(ny0 + lane / 3) * W + nx0) * 3 + (lane % 3) * 16);
+      }
       __syncwarp();
     }
     if (a.r.counters) flush_counts(a.r.counters, 99, 0, 0, c_shadow, c_occ, 0, 0, (unsigned long long)a.N);

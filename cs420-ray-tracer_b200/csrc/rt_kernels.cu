@@ -82,8 +82,25 @@ constexpr int RT_MAX_LEVELS_INTERNAL = 32;
 constexpr int kBvhAutoSpheres = 1024;   // automatic mode: scenes from this size on are traversed through the LBVH
 
 // Device build of the LBVH (bvh.cuh) over cen[i] = (c_i - C0, r_i) in FP32; eps inflates every box.
-static int bvh_build(RtFastScene *fs, const std::vector<float4> &cen, const std::vector<int> &orig, float eps, cudaStream_t stream) {
-  const int n = (int)cen.size(), nleaf = (n + rtb::kLeafSize - 1) / rtb::kLeafSize, nint = nleaf > 1 ? nleaf - 1 : 1;
+// Inputs of the device LBVH build, written ON THE DEVICE from the raw sphere rows (large scenes: no host loop, no
+// host -> device copy of a second sphere array): cen[k] = (c - C0 in FP32, radius rounded up), orig[k] = sphere index, for
+// the spheres that are not in `big` (at most 8, ascending k keeps index order).
+struct BuildBig { int n; int idx[8]; };
+__global__ void k_bvh_inputs(const double *__restrict__ raw, int N, double c0x, double c0y, double c0z, BuildBig big,
+                             float4 *__restrict__ cen, int *__restrict__ orig) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  int before = 0;
+  for (int k = 0; k < big.n; k++) { if (big.idx[k] == i) return; before += big.idx[k] < i; }
+  const double *s = raw + (size_t)i * 10;
+  cen[i - before] = make_float4((float)(s[0] - c0x), (float)(s[1] - c0y), (float)(s[2] - c0z), __double2float_ru(fabs(s[3])));
+  orig[i - before] = i;
+}
+
+// `cen` / `orig` host arrays, or nullptr + raw_dev: the inputs are produced on the device by k_bvh_inputs from the raw rows
+static int bvh_build(RtFastScene *fs, int n, const float4 *h_cen, const int *h_orig, const double *raw_dev, int N_all, const double *c0,
+                     const BuildBig &big, float eps, cudaStream_t stream) {
+  const int nleaf = (n + rtb::kLeafSize - 1) / rtb::kLeafSize, nint = nleaf > 1 ? nleaf - 1 : 1;
   // one scratch arena and the node array, both kept (grow-only) across uploads: cudaMalloc / cudaFree cost milliseconds
   // each once gigabytes of frame buffers are allocated, and a build needs seventeen arrays
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -115,8 +132,12 @@ static int bvh_build(RtFastScene *fs, const std::vector<float4> &cen, const std:
       *flags = (int *)(sc + o_flags);
   fs->bvh_nodes = fs->bvh_nodes_buf;
   BV(cudaEventCreate(&e0)); BV(cudaEventCreate(&e1));
-  BV(cudaMemcpyAsync(d_cen, cen.data(), (size_t)n * 16, cudaMemcpyHostToDevice, stream));
-  BV(cudaMemcpyAsync(d_orig, orig.data(), (size_t)n * 4, cudaMemcpyHostToDevice, stream));
+  if (h_cen) {
+    BV(cudaMemcpyAsync(d_cen, h_cen, (size_t)n * 16, cudaMemcpyHostToDevice, stream));
+    BV(cudaMemcpyAsync(d_orig, h_orig, (size_t)n * 4, cudaMemcpyHostToDevice, stream));
+  } else {
+    k_bvh_inputs<<<(N_all + 255) / 256, 256, 0, stream>>>(raw_dev, N_all, c0[0], c0[1], c0[2], big, d_cen, d_orig);
+  }
   {
     const int init[6] = {0x7f7fffff, 0x7f7fffff, 0x7f7fffff, (int)0x80800000, (int)0x80800000, (int)0x80800000};   // ord(+max) / ord(-max)
     BV(cudaMemcpyAsync(bounds, init, sizeof(init), cudaMemcpyHostToDevice, stream));
@@ -150,6 +171,52 @@ done:
   if (e1) cudaEventDestroy(e1);
   if (rc != 0) fs->bvh_nodes = nullptr;
   return rc;
+}
+
+// LOOKUP-ONLY tables (LBVH scenes) built on the device: one thread per (table, slot).  Slot order = sphere index, no
+// sort, no cull data (see lookup_only below); the same formulas and roundings as the host loop of build_table.
+struct BuildArgs {
+  const double *raw;          // N x 10 sphere rows (file column order), device
+  unsigned char *arena;       // tables | general table | ... (layout of RtFastScene)
+  double origin[RT_MAX_LIGHTS + 1][3];
+  int N, L, npairs, ngroups;
+  unsigned tstride, gmin_off, perm_off, inv_off;
+  size_t o_s64, o_mat, o_matx;
+  double delta64, c0[3], S, u;
+};
+__device__ __forceinline__ float dev_float_up(double x) { return __double2float_ru(x); }
+__device__ __forceinline__ void dev_put(float4 *pairs, int slot, float x, float y, float z, float w) {
+  float *A = reinterpret_cast<float *>(pairs + (size_t)(slot >> 1) * 2) + (slot & 1);
+  A[0] = x; A[2] = y; A[4] = z; A[6] = w;
+}
+__global__ void k_build_lookup(const BuildArgs b) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y, nslots = 2 * b.npairs;
+  if (slot >= nslots) return;
+  if (t <= b.L) {                                      // shared-origin table t (camera, lights)
+    unsigned char *base = b.arena + (size_t)t * b.tstride;
+    float4 *pairs = reinterpret_cast<float4 *>(base);
+    int *perm = reinterpret_cast<int *>(base + b.perm_off), *inv = reinterpret_cast<int *>(base + b.inv_off);
+    float *gmin = reinterpret_cast<float *>(base + b.gmin_off);
+    if ((slot & 7) == 0) gmin[slot >> 3] = slot < b.N ? -3.0e38f : 3.0e38f;
+    if (slot >= b.N) { dev_put(pairs, slot, 0.f, 0.f, 0.f, -1.0f); perm[slot] = -1; return; }
+    const double *s = b.raw + (size_t)slot * 10;
+    const double x = __dsub_rn(s[0], b.origin[t][0]), y = __dsub_rn(s[1], b.origin[t][1]), z = __dsub_rn(s[2], b.origin[t][2]);
+    const double oc2 = __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)), r2 = __dmul_rn(s[3], s[3]);
+    const double E = 2.01 * 9.5367431640625e-07 * oc2 * (1 + 1e-9) + b.delta64;
+    dev_put(pairs, slot, (float)x, (float)y, (float)z, dev_float_up(E - (oc2 - r2)));
+    perm[slot] = slot;
+    inv[slot] = slot | ((oc2 - r2 > 1e-6 * (oc2 + r2) + 4.0 * b.delta64) ? 0x40000000 : 0);
+  } else {                                             // general table + exact geometry + materials
+    float4 *pairs = reinterpret_cast<float4 *>(b.arena + (size_t)(b.L + 1) * b.tstride);
+    if (slot >= b.N) { dev_put(pairs, slot, 0.f, 0.f, 0.f, -1.0e30f); return; }
+    const double *s = b.raw + (size_t)slot * 10;
+    const double r = fabs(s[3]);
+    const double rho = r * r * (1 + 40 * b.u) + 12 * b.u * b.S * r + 64 * b.u * b.u * b.S * b.S + b.delta64;
+    dev_put(pairs, slot, (float)(s[0] - b.c0[0]), (float)(s[1] - b.c0[1]), (float)(s[2] - b.c0[2]), dev_float_up(rho));
+    reinterpret_cast<double4 *>(b.arena + b.o_s64)[slot] = make_double4(s[0], s[1], s[2], __dmul_rn(s[3], s[3]));
+    reinterpret_cast<float4 *>(b.arena + b.o_mat)[slot] = make_float4((float)s[4], (float)s[5], (float)s[6], (float)s[7]);
+    reinterpret_cast<float2 *>(b.arena + b.o_matx)[slot] = make_float2((float)s[9], s[7] > 0 ? 1.0f : 0.0f);
+  }
 }
 
 int rtk_fast_build_scene(RtFastScene *fs, const double *sph, int N, const RtFrameConst *f, int accel, cudaStream_t stream) {
@@ -198,12 +265,19 @@ int rtk_fast_build_scene(RtFastScene *fs, const double *sph, int N, const RtFram
   fs->gS2 = float_up(S * S * 1.0001);
   fs->g_dtmax = float_up(80.0 * u * S);
 
+  // LBVH scenes: the candidates of every query come from the hierarchy, the tables are only LOOKED UP by sphere (inv ->
+  // slot -> pair); nothing walks them in order, prunes by gmin or culls by cone.  So they keep index order -- no sort
+  // (five stable sorts of 100 k keys were most of a config-5 upload) -- and carry no cull data; from kDeviceBuildSpheres
+  // spheres on they are written by a kernel from the raw rows (k_build_lookup) instead of staged on the host.
+  const bool lookup_only = N > 0 && (accel == 2 || (accel == 0 && N >= kBvhAutoSpheres));
+  constexpr int kDeviceBuildSpheres = 2048;
+  const bool device_build = lookup_only && N >= kDeviceBuildSpheres && !(getenv("RT_HOST_BUILD") && getenv("RT_HOST_BUILD")[0] == '1');
   // byte layout of one shared-origin table
   const unsigned pairs_bytes = (unsigned)npairs * 32u;
   const unsigned gmin_bytes = ((unsigned)ngroups * 4u + 15u) & ~15u;
   const unsigned perm_bytes = (unsigned)nslots * 4u;
   const unsigned inv_bytes = (((unsigned)(N > 0 ? N : 1)) * 4u + 15u) & ~15u;
-  const unsigned cullA_bytes = (unsigned)nslots * 16u, cullB_bytes = (unsigned)nslots * 4u;
+  const unsigned cullA_bytes = lookup_only ? 0u : (unsigned)nslots * 16u, cullB_bytes = lookup_only ? 0u : (unsigned)nslots * 4u;
   fs->gmin_off = pairs_bytes; fs->perm_off = pairs_bytes + gmin_bytes; fs->inv_off = fs->perm_off + perm_bytes;
   fs->cullA_off = fs->inv_off + inv_bytes; fs->cullB_off = fs->cullA_off + cullA_bytes;
   fs->tstride = fs->cullB_off + cullB_bytes;
@@ -214,6 +288,31 @@ int rtk_fast_build_scene(RtFastScene *fs, const double *sph, int N, const RtFram
   const size_t n1 = (size_t)(N > 0 ? N : 1);
   const size_t o_s64 = (total + 255) & ~(size_t)255, o_mat = o_s64 + n1 * sizeof(double4), o_matx = o_mat + n1 * sizeof(float4);
   const size_t arena = ((o_matx + n1 * sizeof(float2)) + 255) & ~(size_t)255;
+  if (fs->tabs_cap < arena) {
+    cudaFree(fs->tabs); fs->tabs = nullptr; fs->tabs_cap = 0;
+    RTK_TRY(cudaMalloc(&fs->tabs, arena));
+    fs->tabs_cap = arena;
+  }
+  fs->sph64 = (unsigned char *)fs->tabs + o_s64; fs->mat = (unsigned char *)fs->tabs + o_mat; fs->matx = (unsigned char *)fs->tabs + o_matx;
+  if (device_build) {
+    const size_t raw_bytes = (size_t)N * 10 * sizeof(double);
+    if (fs->raw_cap < raw_bytes) {
+      cudaFree(fs->raw_dev); fs->raw_dev = nullptr; fs->raw_cap = 0;
+      RTK_TRY(cudaMalloc(&fs->raw_dev, raw_bytes));
+      fs->raw_cap = raw_bytes;
+    }
+    RTK_TRY(cudaMemcpyAsync(fs->raw_dev, sph, raw_bytes, cudaMemcpyHostToDevice, stream));
+    BuildArgs b;
+    memset(&b, 0, sizeof(b));
+    b.raw = (const double *)fs->raw_dev; b.arena = (unsigned char *)fs->tabs;
+    for (int k = 0; k < 3; k++) { b.origin[0][k] = f->cam_pos[k]; b.c0[k] = fs->c0[k]; }
+    for (int l = 0; l < L; l++) for (int k = 0; k < 3; k++) b.origin[l + 1][k] = f->light_pos[l][k];
+    b.N = N; b.L = L; b.npairs = npairs; b.ngroups = ngroups;
+    b.tstride = fs->tstride; b.gmin_off = fs->gmin_off; b.perm_off = fs->perm_off; b.inv_off = fs->inv_off;
+    b.o_s64 = o_s64; b.o_mat = o_mat; b.o_matx = o_matx; b.delta64 = delta64; b.S = S; b.u = u;
+    k_build_lookup<<<dim3((unsigned)(nslots + 255) / 256, (unsigned)(L + 2)), 256, 0, stream>>>(b);
+    RTK_TRY(cudaGetLastError());
+  } else {
   if (fs->h_stage_cap < arena) {
     if (fs->h_stage) cudaFreeHost(fs->h_stage);
     fs->h_stage = nullptr; fs->h_stage_cap = 0;
@@ -240,10 +339,6 @@ int rtk_fast_build_scene(RtFastScene *fs, const double *sph, int N, const RtFram
   };
   std::vector<int> order((size_t)(N > 0 ? N : 1));
   std::vector<double> key((size_t)(N > 0 ? N : 1));
-  // LBVH scenes: the candidates of every query come from the hierarchy, the tables are only LOOKED UP by sphere (inv ->
-  // slot -> pair); nothing walks them in order, prunes by gmin or culls by cone.  So they keep index order -- no sort
-  // (five stable sorts of 100 k keys were most of a config-5 upload) -- and carry no cull data.
-  const bool lookup_only = N > 0 && (accel == 2 || (accel == 0 && N >= kBvhAutoSpheres));
   auto build_table = [&](int t, std::vector<int> &order, std::vector<double> &key) {
     unsigned char *base = h.data() + (size_t)t * fs->tstride;
     float4 *pairs = reinterpret_cast<float4 *>(base);
@@ -314,14 +409,9 @@ int rtk_fast_build_scene(RtFastScene *fs, const double *sph, int N, const RtFram
       put(pairs, i, (float)(s[0] - fs->c0[0]), (float)(s[1] - fs->c0[1]), (float)(s[2] - fs->c0[2]), float_up(rho));
     }
   }
-  if (fs->tabs_cap < arena) {
-    cudaFree(fs->tabs); fs->tabs = nullptr; fs->tabs_cap = 0;
-    RTK_TRY(cudaMalloc(&fs->tabs, arena));
-    fs->tabs_cap = arena;
-  }
-  fs->sph64 = (unsigned char *)fs->tabs + o_s64; fs->mat = (unsigned char *)fs->tabs + o_mat; fs->matx = (unsigned char *)fs->tabs + o_matx;
   RTK_TRY(cudaMemcpyAsync(fs->tabs, h.data(), arena, cudaMemcpyHostToDevice, stream));
-  RTK_TRY(cudaStreamSynchronize(stream));   // h goes out of scope
+  }   // host build
+  RTK_TRY(cudaStreamSynchronize(stream));   // the staging buffer / the caller's sphere rows may be reused from here on
   fs->bvh_nodes = fs->bvh_leaves = nullptr; fs->bvh_nleaf = 0; fs->bvh_build_ms = 0; fs->nbig = 0;
   if (N > 0 && (accel == 2 || (accel == 0 && N >= kBvhAutoSpheres))) {
     // Spheres far larger than the typical one (a ground sphere ...) stay out of the hierarchy: their boxes would make
@@ -337,18 +427,28 @@ int rtk_fast_build_scene(RtFastScene *fs, const double *sph, int N, const RtFram
     if (bigs.size() > 8 || (int)bigs.size() == N) bigs.resize(bigs.size() > 8 ? 8 : 0);
     fs->nbig = (int)bigs.size();
     for (int k = 0; k < fs->nbig; k++) fs->big[k] = bigs[k];
-    std::vector<float4> cen;
-    std::vector<int> orig;
-    cen.reserve((size_t)N); orig.reserve((size_t)N);
-    for (int i = 0; i < N; i++) {
-      if (std::find(bigs.begin(), bigs.end(), i) != bigs.end()) continue;
-      const double *s = sph + (size_t)i * 10;
-      cen.push_back(make_float4((float)(s[0] - fs->c0[0]), (float)(s[1] - fs->c0[1]), (float)(s[2] - fs->c0[2]), float_up(rad[i])));
-      orig.push_back(i);
-    }
     // box inflation: FP32 rounding of recentred centres / ray origins (<= u S each) and the 12u direction error over
     // any distance <= 2S inside the scene ball, with a 2x reserve: 64u * 3S
-    const int r = bvh_build(fs, cen, orig, float_up(64.0 * u * 3.0 * S), stream);
+    const float eps = float_up(64.0 * u * 3.0 * S);
+    BuildBig big;
+    memset(&big, 0, sizeof(big));
+    big.n = fs->nbig;
+    for (int k = 0; k < fs->nbig; k++) big.idx[k] = fs->big[k];
+    int r;
+    if (device_build) {
+      r = bvh_build(fs, N - fs->nbig, nullptr, nullptr, (const double *)fs->raw_dev, N, fs->c0, big, eps, stream);
+    } else {
+      std::vector<float4> cen;
+      std::vector<int> orig;
+      cen.reserve((size_t)N); orig.reserve((size_t)N);
+      for (int i = 0; i < N; i++) {
+        if (std::find(bigs.begin(), bigs.end(), i) != bigs.end()) continue;
+        const double *s = sph + (size_t)i * 10;
+        cen.push_back(make_float4((float)(s[0] - fs->c0[0]), (float)(s[1] - fs->c0[1]), (float)(s[2] - fs->c0[2]), float_up(rad[i])));
+        orig.push_back(i);
+      }
+      r = bvh_build(fs, (int)cen.size(), cen.data(), orig.data(), nullptr, N, fs->c0, big, eps, stream);
+    }
     if (r != 0) return r;
   }
   return 0;
@@ -360,8 +460,9 @@ void rtk_fast_free_scene(RtFastScene *fs, int release_tables) {
     if (fs->h_stage) cudaFreeHost(fs->h_stage);
     fs->h_stage = nullptr; fs->h_stage_cap = 0;
     fs->sph64 = fs->mat = fs->matx = nullptr;
-    cudaFree(fs->bvh_nodes_buf); cudaFree(fs->bvh_scratch);
+    cudaFree(fs->bvh_nodes_buf); cudaFree(fs->bvh_scratch); cudaFree(fs->raw_dev);
     fs->bvh_nodes_buf = fs->bvh_scratch = nullptr; fs->bvh_nodes_cap = fs->bvh_scratch_cap = 0;
+    fs->raw_dev = nullptr; fs->raw_cap = 0;
   }
   fs->bvh_nodes = fs->bvh_leaves = nullptr; fs->bvh_nleaf = 0;
 }
@@ -400,7 +501,9 @@ int resident_grid(K kernel, size_t smem, int num_sms, int threads = rtf::kThread
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem) != cudaSuccess || nb < 1) nb = 1;
     it = cache.emplace(key, nb).first;
   }
-  return it->second * num_sms;
+  // RT_GRID_DIV (experiments): a fraction of the resident grid, so that the kernels of two contexts can share the SMs
+  static const int grid_div = getenv("RT_GRID_DIV") ? std::max(1, atoi(getenv("RT_GRID_DIV"))) : 1;
+  return std::max(1, it->second * num_sms / grid_div);
 }
 // Launch with programmatic dependent launch (PDL): the grid may start while the previous kernel of the stream is
 // still draining, run its prologue (table staging) and then block in griddepcontrol.wait (RT_PDL_SYNC in the kernels)

@@ -21,6 +21,7 @@ struct RtFastScene {
   // host->device copy per upload
   void *sph64, *mat, *matx;   // device: N x double4, N x float4, N x float2
   void *h_stage; size_t h_stage_cap;   // pinned host staging of the whole arena
+  void *raw_dev; size_t raw_cap;       // large LBVH scenes: the raw sphere rows on the device (tables are built there)
   unsigned tstride;       // bytes per shared-origin table
   unsigned gmin_off, perm_off, inv_off, cullA_off, cullB_off;
   size_t bytes_primary;   // staged by k_primary: (1+L) * tstride
