@@ -434,6 +434,57 @@ __device__ __forceinline__ unsigned flagged_bits(unsigned hist, int np, bool liv
 }
 
 // ---------------------------------------------------------------------------------------------
+// LANE-COOPERATIVE chunk tests (the tail kernel at its deep levels: a warp that holds only a few live rays).  The chunk
+// tests above give every lane ITS ray and walk the pairs serially; with a handful of live lanes that is one warp's
+// dependency chain over the whole table for a few rays' worth of work.  Here the roles are swapped: for each live ray
+// in turn (its direction broadcast by shuffle) all 32 lanes test 32 DIFFERENT pairs of the chunk at once, and the ballot
+// of the flags, reordered to the history-word convention of flagged_bits (bit i <-> pair p0 + np - 1 - i), goes to the
+// lane that owns the ray.  Per (ray, pair) the arithmetic is exactly that of chunk_test_shared / closest_general, so
+// the flags -- and everything that follows from them -- are identical.
+__device__ __forceinline__ unsigned coop_chunk_shared(const float4 *__restrict__ pairs, int p0, int np, float dx, float dy, float dz, bool live) {
+  const int lane = threadIdx.x & 31;
+  unsigned mine = 0u, lm = __ballot_sync(kFull, live);
+  float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A;
+  if (lane < np) { A = pairs[2 * (p0 + lane)]; B = pairs[2 * (p0 + lane) + 1]; }
+  const float2 X = make_float2(A.x, A.y), Y = make_float2(A.z, A.w), Z = make_float2(B.x, B.y), Wv = make_float2(B.z, B.w);
+  while (lm != 0u) {
+    const int k = __ffs(lm) - 1;
+    lm &= lm - 1u;
+    const float bx = __shfl_sync(kFull, dx, k), by = __shfl_sync(kFull, dy, k), bz = __shfl_sync(kFull, dz, k);
+    float2 t = __fmul2_rn(X, make_float2(bx, bx)); t = __ffma2_rn(Y, make_float2(by, by), t); t = __ffma2_rn(Z, make_float2(bz, bz), t);
+    const float2 D = __ffma2_rn(t, t, Wv);
+    const bool flagged = lane < np && ((fbits(D.x) & fbits(D.y)) & kSign) == 0u;      // not (both spheres certainly missed)
+    const unsigned m = __ballot_sync(kFull, flagged);
+    if (lane == k) mine = __brev(m) >> (32 - np);
+  }
+  return mine;
+}
+__device__ __forceinline__ unsigned coop_chunk_general(const float4 *__restrict__ pairs, int p0, int np, float nox, float noy, float noz,
+                                                       float idx, float idy, float idz, float dtmax, bool live) {
+  const int lane = threadIdx.x & 31;
+  unsigned mine = 0u, lm = __ballot_sync(kFull, live);
+  float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A;
+  if (lane < np) { A = pairs[2 * (p0 + lane)]; B = pairs[2 * (p0 + lane) + 1]; }
+  const float2 CX = make_float2(A.x, A.y), CY = make_float2(A.z, A.w), CZ = make_float2(B.x, B.y), NR_ = make_float2(-B.z, -B.w);
+  const float2 dtm = make_float2(dtmax, dtmax);
+  while (lm != 0u) {
+    const int k = __ffs(lm) - 1;
+    lm &= lm - 1u;
+    const float ox = __shfl_sync(kFull, nox, k), oy = __shfl_sync(kFull, noy, k), oz = __shfl_sync(kFull, noz, k);
+    const float ix = __shfl_sync(kFull, idx, k), iy = __shfl_sync(kFull, idy, k), iz = __shfl_sync(kFull, idz, k);
+    const float2 x = __fadd2_rn(CX, make_float2(ox, ox)), y = __fadd2_rn(CY, make_float2(oy, oy)), z = __fadd2_rn(CZ, make_float2(oz, oz));
+    float2 t = __ffma2_rn(x, make_float2(ix, ix), dtm); t = __ffma2_rn(y, make_float2(iy, iy), t); t = __ffma2_rn(z, make_float2(iz, iz), t);
+    float2 q = __ffma2_rn(x, x, NR_); q = __ffma2_rn(y, y, q); q = __ffma2_rn(z, z, q);
+    const float2 D = __ffma2_rn(t, t, make_float2(-q.x, -q.y));
+    const unsigned rej = (fbits(D.x) | (fbits(t.x) & ~fbits(q.x))) & (fbits(D.y) | (fbits(t.y) & ~fbits(q.y)));
+    const unsigned m = __ballot_sync(kFull, lane < np && (rej & kSign) == 0u);
+    if (lane == k) mine = __brev(m) >> (32 - np);
+  }
+  return mine;
+}
+constexpr int kCoopMaxLive = 12;     // a warp with at most this many live rays tests them lane-cooperatively
+
+// ---------------------------------------------------------------------------------------------
 // Bundle culling.
 //
 // Cone of a warp's rays: axis a = normalised sum of the (FP32, unit) directions, cos(theta) = the
@@ -635,7 +686,7 @@ __device__ __forceinline__ void closest_general(const float4 *__restrict__ pairs
                                                 const float (&oy)[NR], const float (&oz)[NR], const float (&dx)[NR],
                                                 const float (&dy)[NR], const float (&dz)[NR], const bool (&live)[NR], float d64,
                                                 float gS2, float dtmax, const double4 *sph64, const RaySrc (&src)[NR],
-                                                Best (&best)[NR]) {
+                                                Best (&best)[NR], const bool coop = false) {
   const float kInfl = 1.0f + 24.0f * 5.9604645e-8f;
   float2 nox[NR], noy[NR], noz[NR], idx2[NR], idy2[NR], idz2[NR];
   const float2 dtm = make_float2(dtmax, dtmax);
@@ -651,6 +702,10 @@ __device__ __forceinline__ void closest_general(const float4 *__restrict__ pairs
     unsigned h[NR];
 #pragma unroll
     for (int r = 0; r < NR; r++) h[r] = kFull;
+    if (NR == 1 && coop) {
+      // (flagged bits -> history word: flagged_bits() below inverts it again)
+      h[0] = ~coop_chunk_general(pairs, p0, np, nox[0].x, noy[0].x, noz[0].x, idx2[0].x, idy2[0].x, idz2[0].x, dtmax, live[0]);
+    } else
 #pragma unroll 1
     for (int p = p0; p < p0 + np; p += 2) {
 #pragma unroll
@@ -721,7 +776,8 @@ template <int NR>
 __device__ __forceinline__ bool shadow_range(ShadowQ<NR> &q, const float4 *__restrict__ pairs, const float *gmin, const int *perm, int pbeg,
                                              int pend, int light, const float (&dx)[NR], const float (&dy)[NR], const float (&dz)[NR],
                                              const float (&so)[NR], const int (&self)[NR], const float (&cosl)[NR],
-                                             const double *const (&p64)[NR], float d64, const double4 *sph64, int &n_fp64) {
+                                             const double *const (&p64)[NR], float d64, const double4 *sph64, int &n_fp64,
+                                             const bool coop = false) {
   float2 dx2[NR], dy2[NR], dz2[NR];
 #pragma unroll
   for (int r = 0; r < NR; r++) { dx2[r] = make_float2(dx[r], dx[r]); dy2[r] = make_float2(dy[r], dy[r]); dz2[r] = make_float2(dz[r], dz[r]); }
@@ -730,7 +786,8 @@ __device__ __forceinline__ bool shadow_range(ShadowQ<NR> &q, const float4 *__res
     if (gmin[p0 / kGroupPairs] > q.wcut) return false;
     const int np = min(kChunkPairs, pend - p0);
     unsigned h[NR], f[NR], any = 0u;
-    chunk_test_shared<NR>(pairs, p0, np, dx2, dy2, dz2, h);
+    if (NR == 1 && coop) h[0] = ~coop_chunk_shared(pairs, p0, np, dx[0], dy[0], dz[0], q.open[0]);
+    else chunk_test_shared<NR>(pairs, p0, np, dx2, dy2, dz2, h);
 #pragma unroll
     for (int r = 0; r < NR; r++) {
       f[r] = flagged_bits(h[r], np, q.open[r]);
@@ -777,10 +834,10 @@ template <int NR>
 __device__ __forceinline__ void shadow_light(const Tab T, int npairs, int light, const float (&dx)[NR], const float (&dy)[NR],
                                              const float (&dz)[NR], const float (&so)[NR], const bool (&want)[NR],
                                              const int (&self)[NR], const float (&cosl)[NR], const double *const (&p64)[NR], float d64,
-                                             const double4 *sph64, bool (&occ)[NR], int &n_fp64) {
+                                             const double4 *sph64, bool (&occ)[NR], int &n_fp64, const bool coop = false) {
   ShadowQ<NR> q;
   shadow_begin<NR>(q, T.inv, so, want, self, cosl);
-  shadow_range<NR>(q, T.pairs, T.gmin, T.perm, 0, npairs, light, dx, dy, dz, so, self, cosl, p64, d64, sph64, n_fp64);
+  shadow_range<NR>(q, T.pairs, T.gmin, T.perm, 0, npairs, light, dx, dy, dz, so, self, cosl, p64, d64, sph64, n_fp64, coop);
 #pragma unroll
   for (int r = 0; r < NR; r++) occ[r] = q.occ[r];
 }
@@ -1124,11 +1181,15 @@ __global__ void __launch_bounds__(kTailThreads, RT_TAIL_CTAS) k_bounce(const Fas
   int n_fp64 = 0;
   unsigned c_cand = 0, c_walks = 0;
   RayRec *qin = a.q_in;
+  // rays per warp fetch: the queue is spread over ALL resident warps (a warp's chain gets shorter with fewer rays: its
+  // drain loops run for the slowest lane, and from kCoopMaxLive live rays down the tests turn lane-cooperative), 32 at most
+  const unsigned nwarps = gridDim.x * (unsigned)(kTailThreads / 32);
+  const unsigned per = min(32u, max(4u, (nq + nwarps - 1u) / nwarps));
   for (;;) {
     const int chunk = warp_fetch(a.chunk_counter);
-    if ((unsigned)chunk * 32u >= nq) break;
-    const unsigned qi = (unsigned)chunk * 32u + lane;
-    bool live[1] = {qi < nq};
+    if ((unsigned)chunk * per >= nq) break;
+    const unsigned qi = (unsigned)chunk * per + lane;
+    bool live[1] = {(unsigned)lane < per && qi < nq};
     unsigned pix = 0;
     float ox[1] = {0.f}, oy[1] = {0.f}, oz[1] = {0.f}, dx[1] = {0.f}, dy[1] = {0.f}, dz[1] = {0.f};
     float wt = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
@@ -1143,8 +1204,10 @@ __global__ void __launch_bounds__(kTailThreads, RT_TAIL_CTAS) k_bounce(const Fas
     for (int level = a.level;; level++) {
       Best best[1];
       best_init(best[0]);
+      // few live rays in this warp (the deep levels): the sphere tests run lane-cooperatively (coop_chunk_*)
+      const bool coop = kSmem && !kBvh && __popc(__ballot_sync(kFull, live[0])) <= kCoopMaxLive;
       if (kBvh) { if (live[0]) best[0] = bvh_closest_general(a, gen, ox[0], oy[0], oz[0], dx[0], dy[0], dz[0], src[0]); }
-      else closest_general<1>(gen, a.npairs, a.N, ox, oy, oz, dx, dy, dz, live, a.d64, a.gS2, a.g_dtmax, a.r.sph64, src, best);
+      else closest_general<1>(gen, a.npairs, a.N, ox, oy, oz, dx, dy, dz, live, a.d64, a.gS2, a.g_dtmax, a.r.sph64, src, best, coop);
       bool hit = false, final_ = false, cont = false;
       int idx[1] = {-1};
       double t64 = 0;
@@ -1201,6 +1264,7 @@ __global__ void __launch_bounds__(kTailThreads, RT_TAIL_CTAS) k_bounce(const Fas
           }
           const double *const pp[1] = {&p.x};
           if (kBvh) { if (hit) occ[0] = bvh_shadow(a, tab_at(tabs, a, l), recentred(a, g_frame.light_pos[l]), l, sdx[0], sdy[0], sdz[0], so[0], idx[0], cosl[0], &p.x, n_fp64); }
+          else if (kSmem && coop) shadow_light<1>(tab_at(tabs, a, l), a.npairs, l, sdx, sdy, sdz, so, want, idx, cosl, pp, a.d64, a.r.sph64, occ, n_fp64, true);
           else if (kSmem) shadow_light_culled<1>(tab_at(tabs, a, l), a.npairs, wb, l, sdx, sdy, sdz, so, want, idx, cosl, pp, a.d64, a.r.sph64, occ, n_fp64, c_cand, c_walks);
           else shadow_light<1>(tab_at(tabs, a, l), a.npairs, l, sdx, sdy, sdz, so, want, idx, cosl, pp, a.d64, a.r.sph64, occ, n_fp64);
           if (!hit) continue;
