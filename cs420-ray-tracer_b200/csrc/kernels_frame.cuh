@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(kThreads, RT_FRAME_CTAS) k_frame(const WaveArg
   const int depth = a.r.max_depth;
   for (int level = 0; level < depth; level++) {
     const Lvl lv = lvl_at(w, level);
-    if (level == 0) closest0_body<kTabSmem>(w, lv, smem, tabs, wbase);
+    if (level == 0) closest0_body<kTabSmem>(w, lv, smem, tabs, wbase, !kFuse && tile_path(a));   // (fused shading writes pixel by pixel)
     else closest1_body<false>(w, lv, gen);
     grid_barrier(w.ctl, target);
     trace_stamp(w.ctl, tk);

@@ -200,9 +200,33 @@ __device__ __forceinline__ int cta_fetch(unsigned int *counter, unsigned char *s
 
 // ---------------------------------------------------------------------------------------------
 // LEVEL 0 closest hit: each warp pulls 16x4-pixel tiles, two vertically adjacent pixels per lane.
-// tabs: where table 0 (the camera table) is read from (shared memory when staged); wbase: the per-warp compacted tables
+// Level-0 tiles that contain hits are written ONCE, as whole 16-byte row segments, by the shading pass (shade_body): it
+// knows the finished hit pixels and recomputes the sky colour of the others exactly as k_closest0 would have (same FP64
+// camera direction, same FP32 normalisation).  tile_path() = the output modes where that applies; k_closest0 then stores
+// only tiles WITHOUT hits itself.
+__device__ __forceinline__ bool tile_path(const FastArgs &a) {
+  return a.r.fb == nullptr && (a.r.out_remap == 0 || a.r.out_remap == 2) && (a.r.W & 15) == 0 &&
+         (reinterpret_cast<unsigned long long>(a.r.rgb) & 15ull) == 0ull && a.r.hit_idx == nullptr;
+}
+__device__ __forceinline__ float camera_dir_y(const FastArgs &a, int x, int j, float &fx_, float &fz_) {
+  // include/camera.h:21-22 in FP64 (un-normalised), then an FP32 unit vector
+  const d3 v = rtx::add(rtx::add(ldc3(g_frame.fwd), rtx::scale(ldc3(g_frame.right), a.r.su[x])), rtx::scale(ldc3(g_frame.up), a.r.sv[j]));
+  const float fx = (float)v.x, fy = (float)v.y, fz = (float)v.z;
+  const float inv = rsqrtf(fmaf(fz, fz, fmaf(fy, fy, fx * fx)));
+  fx_ = fx * inv; fz_ = fz * inv;
+  return fy * inv;
+}
+// sky (src/main.cpp:26-30) quantised: r | g << 8 | b << 16
+__device__ __forceinline__ unsigned sky_rgb8(float dy) {
+  const float ts = 0.5f * (dy + 1.0f);
+  return quant8((1.0f - ts) + 0.5f * ts) | (quant8((1.0f - ts) + 0.7f * ts) << 8) | (quant8((1.0f - ts) + ts) << 16);
+}
+
+// tabs: where table 0 (the camera table) is read from (shared memory when staged); wbase: the per-warp compacted tables;
+// defer_mixed: tiles with hits are stored by the shading pass (tile_path)
 template <int kMode>
-__device__ __forceinline__ void closest0_body(const WaveArgs &w, const Lvl &lv, unsigned char *smem, const unsigned char *tabs, unsigned char *wbase) {
+__device__ __forceinline__ void closest0_body(const WaveArgs &w, const Lvl &lv, unsigned char *smem, const unsigned char *tabs, unsigned char *wbase,
+                                              const bool defer_mixed) {
   const FastArgs &a = w.f;
   const Tab camg = tab_at(a.tabs, a, 0);             // global view (gmin / perm of the streamed mode)
   const Tab cam = tab_at(tabs, a, 0);
@@ -306,7 +330,10 @@ __device__ __forceinline__ void closest0_body(const WaveArgs &w, const Lvl &lv, 
       best[0] = q.best[0]; best[1] = q.best[1];
     }
     unsigned hslot[2];
-    hit_block(w, lv.hit_count, __ballot_sync(kFull, live[0] && best[0].idx >= 0), __ballot_sync(kFull, live[1] && best[1].idx >= 0), hslot);
+    const unsigned hm0 = __ballot_sync(kFull, live[0] && best[0].idx >= 0), hm1 = __ballot_sync(kFull, live[1] && best[1].idx >= 0);
+    hit_block(w, lv.hit_count, hm0, hm1, hslot);
+    // a whole tile with a hit block: the shading pass stores it (tile_path)
+    const bool deferred = defer_mixed && (hm0 | hm1) != 0u && tx0 + kWTileW <= W && ty0 + kWTileH <= rows;
 #pragma unroll
     for (int r = 0; r < 2; r++) {
       bool hit = false;
@@ -334,7 +361,7 @@ __device__ __forceinline__ void closest0_body(const WaveArgs &w, const Lvl &lv, 
     }
     if (!kBytes) continue;                           // float / remapped output: only finished pixels are written
     __syncwarp();
-    if (!tile_ok) { __syncwarp(); continue; }
+    if (!tile_ok || deferred) { __syncwarp(); continue; }
     if (tx0 + kWTileW <= W && (W & 15) == 0) {
       // 3 x 16-byte stores per 48-byte row segment (src/main.cpp:84-86 quantiser applied above)
       if (lane < kWTileH * 3) {
@@ -369,7 +396,7 @@ __global__ void __launch_bounds__(kThreads, RT_CLOSEST_CTAS) k_closest0(const Wa
   RT_PDL_SYNC();
   Lvl lv = lvl_of(w);
   lv.work_closest = a.tile_counter;
-  closest0_body<kMode>(w, lv, smem, tabs, smem + kSmemHeader + (kMode == kTabBvh ? 0u : ((a.stage_bytes + 127u) & ~127u)));
+  closest0_body<kMode>(w, lv, smem, tabs, smem + kSmemHeader + (kMode == kTabBvh ? 0u : ((a.stage_bytes + 127u) & ~127u)), tile_path(a));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -878,40 +905,38 @@ __device__ __forceinline__ void shade_body(const WaveArgs &w, const Lvl &lv) {
   const int lane = threadIdx.x & 31, L = a.L;
   unsigned c_shadow = 0, c_occ = 0;
   const unsigned G = gridDim.x * (unsigned)kWarps;
-  // Level 0, 8-bit frame in this rank's own compact buffer: the 64 slots of a hit block are the hits of ONE 16x4-pixel
-  // tile, which k_closest0 has already written (sky pixels final, hit pixels zero) as twelve 16-byte row segments.  The
-  // warp takes the whole block, reads those segments back, drops its finished pixels into them in shared memory and
-  // stores them again: 128-bit loads / stores instead of three byte stores per shaded pixel.  (Not for frames assembled
-  // in another GPU's memory: the read-back would cross NVLink.)
-  const bool tiled = lv.level == 0 && a.r.fb == nullptr && a.r.out_remap == 0 && (a.r.W & 15) == 0 &&
-                     (reinterpret_cast<unsigned long long>(a.r.rgb) & 15ull) == 0ull;
-  if (tiled) {
+  // Level 0, 8-bit frame: the 64 slots of a hit block are the hits of ONE 16x4-pixel tile.  The warp takes the whole
+  // block and stores the whole tile as twelve 16-byte row segments: every pixel starts as the sky colour of its camera
+  // ray (what k_closest0 would have written), the finished hits overwrite theirs in shared memory, the hits whose path
+  // continues are overwritten later by the level that finishes them.  k_closest0 leaves such tiles alone (tile_path).
+  if (lv.level == 0 && tile_path(a)) {
     __shared__ __align__(16) unsigned char s_tiles[kWarps][kWTileH * kWTileW * 3];
     unsigned char *s_tile = s_tiles[threadIdx.x >> 5];
     const unsigned W = (unsigned)a.r.W, rows = (unsigned)a.r.bands.local_rows;
-    unsigned pix_next = 0u;
-    {
-      const unsigned b0 = blockIdx.x * (unsigned)kWarps + (threadIdx.x >> 5);
-      if (b0 * 64u < nh) pix_next = w.hits[b0 * 64u].pix;
-    }
+    const bool frame = a.r.out_remap == 2;
     for (unsigned blk = blockIdx.x * (unsigned)kWarps + (threadIdx.x >> 5); blk * 64u < nh; blk += G) {
-      const unsigned pix0 = pix_next;                               // slot 0 of a block in use always carries its pixel
       {
-        // the warp's NEXT block: its records, and (one block later, when its first pixel is known) its tile's row
-        // segments, are pulled into L1 while this block is shaded
         const unsigned bn = blk + G;
         if (bn * 64u < nh) {
           const unsigned char *q = reinterpret_cast<const unsigned char *>(w.hits + bn * 64u + lane);
           prefetch_l1(q); prefetch_l1(q + 64);
           if (lane == 0) prefetch_l1(w.hit_n + bn);
-          pix_next = w.hits[bn * 64u].pix;
         }
       }
       const unsigned nslots = w.hit_n[blk];
+      const unsigned pix0 = w.hits[blk * 64u].pix;                  // slot 0 of a block in use always carries its pixel
       const unsigned ty0 = (pix0 / W) & ~(unsigned)(kWTileH - 1), tx0 = (pix0 % W) & ~(unsigned)(kWTileW - 1);
       const bool whole = ty0 + kWTileH <= rows;                      // (W % 16 == 0: every tile is whole in x)
-      unsigned char *seg = a.r.rgb + ((size_t)(ty0 + lane / 3) * W + tx0) * 3 + (lane % 3) * 16;
-      if (whole && lane < kWTileH * 3) *reinterpret_cast<uint4 *>(s_tile + lane * 16) = *reinterpret_cast<const uint4 *>(seg);
+      if (whole) {
+#pragma unroll
+        for (int r = 0; r < 2; r++) {                                // the lane's two pixels of the tile, as in k_closest0
+          const unsigned ly = (unsigned)(lane >> 4) * 2u + (unsigned)r, lx = (unsigned)lane & 15u;
+          float fx, fz;
+          const unsigned c = sky_rgb8(camera_dir_y(a, (int)(tx0 + lx), rt_local_to_global_row(a.r.bands, (int)(ty0 + ly)), fx, fz));
+          unsigned char *q = s_tile + (ly * kWTileW + lx) * 3;
+          q[0] = (unsigned char)c; q[1] = (unsigned char)(c >> 8); q[2] = (unsigned char)(c >> 16);
+        }
+      }
       __syncwarp();
 #pragma unroll 1
       for (int half = 0; half < 2; half++) {
@@ -931,10 +956,10 @@ __device__ __forceinline__ void shade_body(const WaveArgs &w, const Lvl &lv) {
         queue_push(cont, rec, lv.q_out, lv.q_out_count, a.queue_cap, a.err);
       }
       __syncwarp();
-      if (whole && lane < kWTileH * 3) *reinterpret_cast<uint4 *>(seg) = *reinterpret_cast<const uint4 *>(s_tile + lane * 16);
-      if (blk + G < nh / 64u + 1u && (blk + G) * 64u < nh && lane < kWTileH * 3) {   // next tile's segments -> L1 (pix_next has landed by now)
-        const unsigned ny0 = (pix_next / W) & ~(unsigned)(kWTileH - 1), nx0 = (pix_next % W) & ~(unsigned)(kWTileW - 1);
-        if (ny0 + kWTileH <= rows) prefetch_l1(a.r.rgb + ((size_t)(ny0 + lane / 3) * W + nx0) * 3 + (lane % 3) * 16);
+      if (whole && lane < kWTileH * 3) {
+        const unsigned ty = (unsigned)lane / 3u, sg = (unsigned)lane % 3u;
+        const size_t orow = frame ? (size_t)rt_local_to_global_row(a.r.bands, (int)(ty0 + ty)) : (size_t)(ty0 + ty);
+        *reinterpret_cast<uint4 *>(a.r.rgb + (orow * W + tx0) * 3 + sg * 16) = *reinterpret_cast<const uint4 *>(s_tile + lane * 16);
       }
       __syncwarp();
     }

@@ -466,3 +466,36 @@ def test_whole_frame_kernel_option(rt, oracle, scenes, name, W, H, D):
         r.set_option("frame_kernel", 0)
         b, _ = r.render(W, H, D)
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("mode", ["fast", "bvh"])
+@pytest.mark.parametrize("name,W,H,D", [("complex", 320, 180, 5), ("complex", 1920, 1080, 5), ("medium", 336, 61, 3), ("simple", 1280, 720, 10),
+                                        ("complex", 200, 120, 4), ("medium", 97, 61, 3), ("complex", 64, 6, 2)])
+def test_tile_store_path_equals_the_pixel_store_path(rt, oracle, scenes, name, W, H, D, mode):
+    """Frames without debug buffers take the production store path: level-0 tiles that contain hits are written once,
+    as whole 16-byte row segments, by the shading pass (W % 16 == 0; k_closest0 stores only hit-free tiles), everything
+    else pixel by pixel.  rt_render_debug keeps the pixel-by-pixel path, so the two must agree byte for byte -- at
+    widths that are and are not multiples of 16, heights that are not multiples of 4, for whole frames and row bands."""
+    import torch
+    with rt.Renderer(0, mode=mode) as r:
+        r.upload(scenes[name])
+        dbg = r.render_debug(W, H, D)[0]
+        for _ in range(2):
+            fast, _ = r.render(W, H, D, want_stats=False)
+            assert np.array_equal(dbg, fast)
+        with_stats, _ = r.render(W, H, D)
+        assert np.array_equal(dbg, with_stats)
+        out = np.zeros_like(dbg)
+        for rank in range(3):
+            rows = rt.band_row_list(H, 8, rank, 3)
+            buf = torch.zeros(len(rows) * W * 3 + 16, dtype=torch.uint8, device="cuda:0")
+            r.render_bands_device(W, H, D, 8, rank, 3, buf.data_ptr(), None, want_stats=True)
+            out[rows] = buf[:len(rows) * W * 3].cpu().numpy().reshape(len(rows), W, 3)
+        assert np.array_equal(dbg, out)
+        frame = torch.zeros((H, W, 3), dtype=torch.uint8, device="cuda:0")
+        torch.cuda.synchronize()
+        for rank in range(2):
+            r.render_bands_frame(W, H, D, 16, rank, 2, frame.data_ptr(), None, want_stats=True)
+        assert np.array_equal(dbg, frame.cpu().numpy())
+    ok, pct, mx = rt.compare_rgb(oracle.render(scenes[name], W, H, D)["rgb"], dbg, 0.5)
+    assert ok and mx <= 2
