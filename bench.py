@@ -148,11 +148,13 @@ class ClockSampler(threading.Thread):
         return out
 
 
-def ncu_traffic():
-    """dram bytes (read + write) of one launch of the dominant kernel from the committed `ncu --set full` capture."""
+def ncu_traffic(workload="complex"):
+    """DRAM bytes (read + write) of ONE FRAME -- all launches of a step, summed -- from the committed `ncu --set full` capture
+    of this workload (profiles/r02_executed_<workload>.json, dram__bytes_read.sum + dram__bytes_write.sum per launch)."""
     try:
-        with open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")) as f:
-            return json.load(f)["dram_bytes_per_launch"]
+        with open(os.path.join(ROOT, "profiles", "r02_executed_%s.json" % workload)) as f:
+            d = json.load(f)
+        return int(sum((k.get("dram_read_mb") or 0) + (k.get("dram_write_mb") or 0) for k in d["kernels"]) * 1e6)
     except Exception:  # noqa: BLE001
         return None
 
@@ -561,7 +563,7 @@ def main_b200(args, rank, local_rank, world):
                         "(ncu per-opcode thread-instruction counts: FFMA 2, FFMA2 4, FMUL/FADD 1, FMUL2/FADD2 2 flop)",
                 "peak_source": "measured live: FFMA issue peak of this GPU (rt_measure_fp32_peak, SM clock %.0f MHz); "
                                "MEASURED_PEAKS.json has no FP32 entry (nominal 148 x 128 x 2 x 1.965 GHz = 74.5)" % peak_mhz,
-                "bundle_culling": bundle, "traffic": ncu_traffic(), "executed": ncu_executed(args.workload)}
+                "bundle_culling": bundle, "traffic": ncu_traffic(args.workload), "executed": ncu_executed(args.workload)}
         if lbvh:
             roof["note_lbvh"] = ("LBVH workload: a brute-force-based fraction is meaningless here (SURVEY 8d), frac is null; "
                                  "candidates_per_walk / fp64 counts are the executed-work figures")
