@@ -526,8 +526,9 @@ __device__ __forceinline__ Cone warp_cone(const float (&dx)[NR], const float (&d
 
 // Per-warp compacted table in shared memory: same layout as a shared-origin table, so the chunk test
 // and the slow paths run on it unchanged.  kCandMax candidates = one 32-pair chunk per fill.
-constexpr int kCandMax = 64;
-constexpr unsigned kWarpBufBytes = kCandMax * 16 + kCandMax * 4 + 32 + 96;   // pairs | perm | gmin | pad -> 1408 (multiple of 128)
+constexpr int kCandMax = 96;             // room for one more DOUBLE culling round (64 slots) on top of 32 collected candidates
+constexpr unsigned kWarpBufBytes = kCandMax * 16 + kCandMax * 4 + 48 + 80;   // pairs | perm | gmin | pad -> 2048 (multiple of 128)
+static_assert(kWarpBufBytes % 128 == 0 && kCandMax % 8 == 0, "warp table layout");
 struct WarpBuf { float4 *pairs; int *perm; float *gmin; };
 __device__ __forceinline__ WarpBuf warp_buf(unsigned char *base) {
   unsigned char *p = base + (threadIdx.x >> 5) * kWarpBufBytes;
@@ -561,6 +562,40 @@ __device__ __forceinline__ unsigned cull_round(const Tab &T, int base, int nslot
     if ((rank & 7) == 0) wb.gmin[rank >> 3] = T.gmin[slot >> 3];    // lower bound of this and every later key
   }
   return mk;
+}
+// Two culling rounds at once: lane l looks at slots base + l AND base + 32 + l.  The two cone tests are independent
+// dependency chains in one basic block (the single round is bound by its own chain: shared-memory load -> 5 dependent FMAs
+// -> compare -> ballot -> compaction), and half the loop iterations, ballots and cut-off checks remain.  Same test, same
+// survivor order (table order), so the compacted table is the one two single rounds would have produced.
+__device__ __forceinline__ void cull_round2(const Tab &T, int base, int nslots, const Cone &c, float wcut, const WarpBuf &wb, int ncand,
+                                            unsigned &mk0, unsigned &mk1) {
+  const int lane = threadIdx.x & 31, s0 = base + lane, s1 = s0 + 32;
+  const int i0 = min(s0, nslots - 1), i1 = min(s1, nslots - 1);
+  const float4 u0 = T.cullA[i0], u1 = T.cullA[i1];
+  const float a0 = T.cullB[i0], a1 = T.cullB[i1];
+  const float g0 = T.gmin[i0 >> 3], g1 = T.gmin[i1 >> 3];
+  const float d0 = fabsf(fmaf(u0.z, c.az, fmaf(u0.y, c.ay, u0.x * c.ax))), d1 = fabsf(fmaf(u1.z, c.az, fmaf(u1.y, c.ay, u1.x * c.ax)));
+  const bool keep0 = s0 < nslots && !(d0 < fmaf(c.cth, u0.w, -fmaf(c.sth, a0, 2e-5f))) && !(g0 > wcut);
+  const bool keep1 = s1 < nslots && !(d1 < fmaf(c.cth, u1.w, -fmaf(c.sth, a1, 2e-5f))) && !(g1 > wcut);
+  mk0 = __ballot_sync(kFull, keep0);
+  mk1 = __ballot_sync(kFull, keep1);
+  const unsigned lt = (1u << lane) - 1u;
+  if (keep0) {
+    const int rank = ncand + __popc(mk0 & lt);
+    const float *src = reinterpret_cast<const float *>(T.pairs) + (s0 >> 1) * 8 + (s0 & 1);
+    float *dst = reinterpret_cast<float *>(wb.pairs) + (rank >> 1) * 8 + (rank & 1);
+    dst[0] = src[0]; dst[2] = src[2]; dst[4] = src[4]; dst[6] = src[6];
+    wb.perm[rank] = T.perm[s0];
+    if ((rank & 7) == 0) wb.gmin[rank >> 3] = g0;
+  }
+  if (keep1) {
+    const int rank = ncand + __popc(mk0) + __popc(mk1 & lt);
+    const float *src = reinterpret_cast<const float *>(T.pairs) + (s1 >> 1) * 8 + (s1 & 1);
+    float *dst = reinterpret_cast<float *>(wb.pairs) + (rank >> 1) * 8 + (rank & 1);
+    dst[0] = src[0]; dst[2] = src[2]; dst[4] = src[4]; dst[6] = src[6];
+    wb.perm[rank] = T.perm[s1];
+    if ((rank & 7) == 0) wb.gmin[rank >> 3] = g1;
+  }
 }
 // Pads the warp's table to a whole group of 8 spheres with never-hit entries; returns its pair count.
 __device__ __forceinline__ int cull_finish(const WarpBuf &wb, int ncand) {
@@ -658,10 +693,12 @@ __device__ __forceinline__ void closest_shared_culled(const Tab T, int npairs, c
   int ncand = 0;
   bool more = true;
 #pragma unroll 1
-  for (int base = 0; base < nslots && more; base += 32) {
+  for (int base = 0; base < nslots && more; base += 64) {
     if (T.gmin[base >> 3] > q.wcut) break;           // the rest of the table is beyond every ray's best hit
-    ncand += __popc(cull_round(T, base, nslots, cone, q.wcut, wb, ncand));
-    if (ncand > kCandMax - 32 || base + 32 >= nslots) {
+    unsigned mk0, mk1;
+    cull_round2(T, base, nslots, cone, q.wcut, wb, ncand, mk0, mk1);
+    ncand += __popc(mk0) + __popc(mk1);
+    if (ncand > kCandMax - 64 || base + 64 >= nslots) {
       if (ncand > 0) {
         c_cand += (unsigned)ncand;
         const int np = cull_finish(wb, ncand);
@@ -860,18 +897,21 @@ __device__ __forceinline__ void shadow_light_culled(const Tab T, int npairs, con
   int ncand = 0;
   bool more = true;
 #pragma unroll 1
-  for (int base = 0; base < nslots && more; base += 32) {
-    const bool beyond = T.gmin[base >> 3] > q.wcut;  // the rest of the table is farther from the light than every open point
+  for (int base = 0; base < nslots && more; base += 64) {
+    bool beyond = T.gmin[base >> 3] > q.wcut;        // the rest of the table is farther from the light than every open point
     if (!beyond) {
-      const unsigned mk = cull_round(T, base, nslots, cone, q.wcut, wb, ncand);
+      unsigned mk0, mk1;
+      cull_round2(T, base, nslots, cone, q.wcut, wb, ncand, mk0, mk1);
 #pragma unroll
       for (int r = 0; r < NR; r++) {                 // where did this ray's lit self sphere go?
         const unsigned b = (unsigned)(q.tslot[r] - base);
-        if (b < 32u && ((mk >> b) & 1u)) q.sslot[r] = ncand + __popc(mk & ((1u << b) - 1u));
+        if (b < 32u) { if ((mk0 >> b) & 1u) q.sslot[r] = ncand + __popc(mk0 & ((1u << b) - 1u)); }
+        else if (b < 64u) { if ((mk1 >> (b - 32u)) & 1u) q.sslot[r] = ncand + __popc(mk0) + __popc(mk1 & ((1u << (b - 32u)) - 1u)); }
       }
-      ncand += __popc(mk);
+      ncand += __popc(mk0) + __popc(mk1);
+      beyond = base + 32 < nslots && T.gmin[(base + 32) >> 3] > q.wcut;   // (the second half already ran into the cut-off)
     }
-    if (beyond || ncand > kCandMax - 32 || base + 32 >= nslots) {
+    if (beyond || ncand > kCandMax - 64 || base + 64 >= nslots) {
       if (ncand > 0) {
         c_cand += (unsigned)ncand;
         const int np = cull_finish(wb, ncand);

@@ -918,9 +918,12 @@ __device__ __forceinline__ void shade_body(const WaveArgs &w, const Lvl &lv) {
       {
         const unsigned bn = blk + G;
         if (bn * 64u < nh) {
-          const unsigned char *q = reinterpret_cast<const unsigned char *>(w.hits + bn * 64u + lane);
-          prefetch_l1(q); prefetch_l1(q + 64);
+          // the whole next block: 64 records of 80 bytes = 40 lines of 128 bytes, one or two per lane; its occlusion bytes
+          const unsigned char *q = reinterpret_cast<const unsigned char *>(w.hits + bn * 64u) + lane * 128;
+          prefetch_l1(q);
+          if (lane < 8) prefetch_l1(q + 32 * 128);
           if (lane == 0) prefetch_l1(w.hit_n + bn);
+          if (lane < L) prefetch_l1(w.occ + (size_t)lane * w.hit_cap + bn * 64u);
         }
       }
       const unsigned nslots = w.hit_n[blk];

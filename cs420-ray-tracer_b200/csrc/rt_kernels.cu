@@ -36,7 +36,7 @@ int rtk_launch_exact(const RtRenderArgs &args, cudaStream_t stream) {
 // fast path, host side
 namespace {
 
-constexpr size_t kMaxSmemTables = 96 * 1024;    // stage a kernel's tables in shared memory up to this size (2 CTAs/SM stay resident)
+constexpr size_t kMaxSmemTables = 90 * 1024;    // stage a kernel's tables in shared memory up to this size (2 CTAs/SM stay resident)
 constexpr int kCtlWords = rtf::CTL_WORDS;        // device control words per frame, layout: enum CTL_* (kernels_wave.cuh); two sets (see rtk_launch_fast)
 
 inline float float_up(double x) {               // smallest float >= x
