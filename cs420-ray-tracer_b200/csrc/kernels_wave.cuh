@@ -20,6 +20,8 @@
 #ifndef RT_KERNELS_WAVE_CUH
 #define RT_KERNELS_WAVE_CUH
 
+#include <type_traits>
+
 #include "kernels_fast.cuh"
 
 #ifndef RT_SHADOW_CTAS
@@ -38,7 +40,7 @@ struct __align__(16) HitRec {      // 80 bytes
   unsigned pix;                    // local pixel index lr*W + x
   unsigned src;                    // level >= 1: index of the ray in the level's RayRec queue
   float wt, ar, ag, ab;            // carried weight / colour (front to back)
-  unsigned pad;
+  unsigned pad;                    // occlusion bits of the hit's shadow queries (bit l = light l occluded; scenes with <= 32 lights)
 };
 
 struct WaveArgs {
@@ -48,7 +50,9 @@ struct WaveArgs {
   HitRec *hits; unsigned int *hit_count;   // *hit_count = 64 x blocks in use
   unsigned int *hit_n;             // hits per block
   unsigned hit_cap;                // slots
-  unsigned char *occ;              // [L][hit_cap] occlusion bytes
+  unsigned char *occ;              // [L][hit_cap] occlusion bytes (scenes with more than 32 lights)
+  int occ_bits;                    // <= 32 lights: the occlusion bits travel in the hit record itself (HitRec::pad): one word
+                                   // written by the shadow pass, read with the record by the shading pass
   unsigned int *work_counter;      // per-launch chunk counter
   Best *cand;                      // LBVH scenes, level >= 1: per queued ray, the closest-hit candidate k_closest1_dyn found
   unsigned int *work_counter2;     // ... and that kernel's item counter
@@ -589,7 +593,9 @@ __device__ __forceinline__ void shadow_body(const WaveArgs &w, const Lvl &lv, un
     }
     int l_beg = 0, l_end = a.L;
     if (lightpar) { l_beg = (int)(chunk % (unsigned)a.L); l_end = l_beg + 1; chunk /= (unsigned)a.L; }
-    unsigned long long occm[2] = {0ull, 0ull};         // kFuse: occlusion bits of this lane's two hits
+    // occlusion bits of this lane's two hits (fused shading: up to 64 lights; record bits: <= 32, half the registers)
+    typedef unsigned long long OccT;
+    OccT occm[2] = {0, 0};                             // (fused shading only)
     const unsigned h0 = two ? chunk * 64u + 2u * lane : chunk * 32u + lane;
     const unsigned hend = (h0 & ~63u) + (h0 < nh ? w.hit_n[h0 >> 6] : 0u);   // end of the block's live slots
     bool have[2];
@@ -689,8 +695,13 @@ __device__ __forceinline__ void shadow_body(const WaveArgs &w, const Lvl &lv, un
       }
       c_fp64 += (unsigned)n64;
       if (kFuse && !lightpar) {                        // this warp runs every light of the chunk: the bits stay in registers
-        if (occ[0] || shortcut[0]) occm[0] |= 1ull << l;
-        if (occ[1] || shortcut[1]) occm[1] |= 1ull << l;
+        if (occ[0] || shortcut[0]) occm[0] |= (OccT)1 << l;
+        if (occ[1] || shortcut[1]) occm[1] |= (OccT)1 << l;
+        continue;
+      }
+      if (w.occ_bits) {                                // one fire-and-forget RED.OR per OCCLUDED (hit, light) into the hit record
+        if (have[0] && (occ[0] || shortcut[0])) atomicOr(&w.hits[h0].pad, 1u << l);
+        if (have[1] && (occ[1] || shortcut[1])) atomicOr(&w.hits[h0 + 1].pad, 1u << l);
         continue;
       }
       // two adjacent bytes per lane -> one 16-bit store when both exist
@@ -714,17 +725,20 @@ __device__ __forceinline__ void shadow_body(const WaveArgs &w, const Lvl &lv, un
       __threadfence();
 #pragma unroll
       for (int r = 0; r < 2; r++)
-        if (have[r])
-          for (int l = 0; l < a.L; l++)
-            if (__ldcg(w.occ + (size_t)l * w.hit_cap + h0 + r)) occm[r] |= 1ull << l;
+        if (have[r]) {
+          if (w.occ_bits) occm[r] = __ldcg(&w.hits[h0 + r].pad);
+          else
+            for (int l = 0; l < a.L; l++)
+              if (__ldcg(w.occ + (size_t)l * w.hit_cap + h0 + r)) occm[r] |= (OccT)1 << l;
+        }
     }
 #pragma unroll
     for (int r = 0; r < 2; r++) {
       bool cont = false;
       RayRec rec;
       if (have[r]) {
-        c_shadow += (unsigned)a.L; c_occ += (unsigned)__popcll(occm[r]);
-        cont = shade_one(w, lv, w.hits[h0 + r], occm[r], rec);
+        c_shadow += (unsigned)a.L; c_occ += (unsigned)__popcll((unsigned long long)occm[r]);
+        cont = shade_one(w, lv, w.hits[h0 + r], (unsigned long long)occm[r], rec);
       }
       queue_push(cont, rec, lv.q_out, lv.q_out_count, a.queue_cap, a.err);
     }
@@ -851,7 +865,7 @@ __global__ void __launch_bounds__(kThreads, RT_DYN_CTAS) k_shadow_dyn(const Wave
             const Tab T = tab_at(gtabs, a, light);
             const float backthr = -fmaxf(4.0f * kEps * rsqrtf((float)a.r.sph64[self].w), 1e-4f);   // -4 EPS / r
             if (cosl < backthr && (T.inv[self] & 0x40000000) != 0) {
-              w.occ[(size_t)light * w.hit_cap + slot] = 1;                        // self-shadow shortcut (see k_shadow)
+              if (w.occ_bits) atomicOr(&w.hits[slot].pad, 1u << light); else w.occ[(size_t)light * w.hit_cap + slot] = 1;   // self-shadow shortcut (see k_shadow)
             } else {
               m = __fmaf_ru(1.9073486e-6f, so + kEps, 1e-7f);                     // as in shadow_begin
               const float3 o = recentred(a, g_frame.light_pos[light]);
@@ -876,9 +890,9 @@ __global__ void __launch_bounds__(kThreads, RT_DYN_CTAS) k_shadow_dyn(const Wave
           const int sl = __ldg(&T.inv[cand]) & 0x3fffffff;
           const int rc = slow_shadow(T.pairs, T.perm, sl >> 1, dx, dy, dz, so, m, self, cosl, &w.hits[slot].px, light, a.d64, a.r.sph64);
           c_fp64 += (unsigned)(rc >> 1);
-          if (rc & 1) { w.occ[(size_t)light * w.hit_cap + slot] = 1; active = false; }
+          if (rc & 1) { if (w.occ_bits) atomicOr(&w.hits[slot].pad, 1u << light); else w.occ[(size_t)light * w.hit_cap + slot] = 1; active = false; }
         } else if (cand == -1) {
-          w.occ[(size_t)light * w.hit_cap + slot] = 0;
+          if (!w.occ_bits) w.occ[(size_t)light * w.hit_cap + slot] = 0;
           active = false;
         }
       }
@@ -893,6 +907,10 @@ __global__ void __launch_bounds__(kThreads, RT_DYN_CTAS) k_shadow_dyn(const Wave
 #ifndef RT_SHADE_CTAS
 #define RT_SHADE_CTAS 4
 #endif
+#ifndef RT_SHADE_UNROLL
+#define RT_SHADE_UNROLL 1
+#endif
+constexpr int kShadeUnroll = RT_SHADE_UNROLL;   // 2: both halves of a hit block in one basic block (more loads in flight, more registers)
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // The items of this phase cost the same (one hit per lane), so the chunks are dealt out STATICALLY -- warp g of G takes
@@ -923,7 +941,7 @@ __device__ __forceinline__ void shade_body(const WaveArgs &w, const Lvl &lv) {
           prefetch_l1(q);
           if (lane < 8) prefetch_l1(q + 32 * 128);
           if (lane == 0) prefetch_l1(w.hit_n + bn);
-          if (lane < L) prefetch_l1(w.occ + (size_t)lane * w.hit_cap + bn * 64u);
+          if (!w.occ_bits && lane < L) prefetch_l1(w.occ + (size_t)lane * w.hit_cap + bn * 64u);
         }
       }
       const unsigned nslots = w.hit_n[blk];
@@ -941,7 +959,7 @@ __device__ __forceinline__ void shade_body(const WaveArgs &w, const Lvl &lv) {
         }
       }
       __syncwarp();
-#pragma unroll 1
+#pragma unroll kShadeUnroll
       for (int half = 0; half < 2; half++) {
         const unsigned h = blk * 64u + (unsigned)half * 32u + lane;
         const bool live = (h & 63u) < nslots && w.hits[h].idx >= 0;
@@ -949,9 +967,12 @@ __device__ __forceinline__ void shade_body(const WaveArgs &w, const Lvl &lv) {
         RayRec rec;
         if (live) {
           const HitRec hr = w.hits[h];
-          unsigned long long occm = 0ull;
-          for (int l = 0; l < L; l++)
-            if (w.occ[(size_t)l * w.hit_cap + h]) occm |= 1ull << l;
+          unsigned long long occm = hr.pad;
+          if (!w.occ_bits) {
+            occm = 0ull;
+            for (int l = 0; l < L; l++)
+              if (w.occ[(size_t)l * w.hit_cap + h]) occm |= 1ull << l;
+          }
           c_shadow += (unsigned)L; c_occ += (unsigned)__popcll(occm);
           const unsigned y = hr.pix / W, x = hr.pix - y * W;
           cont = shade_one(w, lv, hr, occm, rec, whole ? s_tile + ((y - ty0) * kWTileW + (x - tx0)) * 3 : nullptr);
@@ -977,7 +998,7 @@ __device__ __forceinline__ void shade_body(const WaveArgs &w, const Lvl &lv) {
         const unsigned char *q = reinterpret_cast<const unsigned char *>(w.hits + hn);
         prefetch_l1(q); prefetch_l1(q + 64);
         if (lane == 0) prefetch_l1(w.hit_n + (hn >> 6));
-        if (lane < L) prefetch_l1(w.occ + (size_t)lane * w.hit_cap + hn);
+        if (!w.occ_bits && lane < L) prefetch_l1(w.occ + (size_t)lane * w.hit_cap + hn);
       }
     }
     const bool live = (h & 63u) < w.hit_n[h >> 6] && w.hits[h].idx >= 0;
@@ -985,9 +1006,12 @@ __device__ __forceinline__ void shade_body(const WaveArgs &w, const Lvl &lv) {
     RayRec rec;
     if (live) {
       const HitRec hr = w.hits[h];
-      unsigned long long occm = 0ull;
-      for (int l = 0; l < L; l++)
-        if (w.occ[(size_t)l * w.hit_cap + h]) occm |= 1ull << l;
+      unsigned long long occm = hr.pad;
+      if (!w.occ_bits) {
+        occm = 0ull;
+        for (int l = 0; l < L; l++)
+          if (w.occ[(size_t)l * w.hit_cap + h]) occm |= 1ull << l;
+      }
       c_shadow += (unsigned)L; c_occ += (unsigned)__popcll(occm);
       cont = shade_one(w, lv, hr, occm, rec);
     }

@@ -612,6 +612,7 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
                                                           // larger; with its size as stride a scene with more lights than the one the buffers were sized
                                                           // for would index past occ_bytes)
   wa.occ = w->occ; wa.hit_n = w->hit_n;
+  wa.occ_bits = fs->L <= 32 && !(getenv("RT_OCC_BYTES") && getenv("RT_OCC_BYTES")[0] == '1');   // (A/B: 1 = occlusion bytes for every scene)
   const size_t pairs_bytes = (size_t)fs->npairs * 32;
   const size_t light_bytes = (size_t)fs->L * fs->tstride;
   // per kernel: its tables are staged whole when they fit, else streamed (shared-origin tables) or read through L1/L2 (general table)

@@ -499,3 +499,14 @@ def test_tile_store_path_equals_the_pixel_store_path(rt, oracle, scenes, name, W
         assert np.array_equal(dbg, frame.cpu().numpy())
     ok, pct, mx = rt.compare_rgb(oracle.render(scenes[name], W, H, D)["rgb"], dbg, 0.5)
     assert ok and mx <= 2
+
+
+@pytest.mark.parametrize("mode", ["fast", "bvh"])
+@pytest.mark.parametrize("nl", [32, 33, 40])
+def test_many_lights(rt, oracle, renderers, scenes, nl, mode):
+    """Up to 32 lights the occlusion bits of a hit travel in its record; above that in per-light byte arrays: both sides
+    of the switch, hit indices / shadow masks (first 32 lights) / counters against the oracle."""
+    g = np.random.default_rng(nl)
+    sc = scenes["medium"]
+    lights = np.column_stack([g.uniform(-15, 15, nl), g.uniform(2, 14, nl), g.uniform(-25, 8, nl), g.uniform(0.05, 0.2, (nl, 3)), np.ones(nl)])
+    check(rt, oracle, renderers[mode], rt.Scene(sc.spheres, lights, sc.ambient, sc.camera), 96, 54, 3)
