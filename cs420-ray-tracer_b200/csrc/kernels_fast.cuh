@@ -482,6 +482,28 @@ __device__ __forceinline__ unsigned coop_chunk_general(const float4 *__restrict_
   }
   return mine;
 }
+// ... and for queries that each walk their OWN shared-origin table (shadow_mixed below: lane k's query goes to light
+// light[k], whose table starts at tabs + light[k] * tstride): the table of the query in turn is read by all lanes
+__device__ __forceinline__ unsigned coop_chunk_mixed(const unsigned char *tabs, unsigned tstride, int light, int p0, int np, float dx, float dy,
+                                                     float dz, bool live) {
+  const int lane = threadIdx.x & 31;
+  unsigned mine = 0u, lm = __ballot_sync(kFull, live);
+  while (lm != 0u) {
+    const int k = __ffs(lm) - 1;
+    lm &= lm - 1u;
+    const float4 *pk = reinterpret_cast<const float4 *>(tabs + (size_t)__shfl_sync(kFull, light, k) * tstride);
+    float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A;
+    if (lane < np) { A = pk[2 * (p0 + lane)]; B = pk[2 * (p0 + lane) + 1]; }
+    const float2 X = make_float2(A.x, A.y), Y = make_float2(A.z, A.w), Z = make_float2(B.x, B.y), Wv = make_float2(B.z, B.w);
+    const float bx = __shfl_sync(kFull, dx, k), by = __shfl_sync(kFull, dy, k), bz = __shfl_sync(kFull, dz, k);
+    float2 t = __fmul2_rn(X, make_float2(bx, bx)); t = __ffma2_rn(Y, make_float2(by, by), t); t = __ffma2_rn(Z, make_float2(bz, bz), t);
+    const float2 D = __ffma2_rn(t, t, Wv);
+    const bool flagged = lane < np && ((fbits(D.x) & fbits(D.y)) & kSign) == 0u;
+    const unsigned m = __ballot_sync(kFull, flagged);
+    if (lane == k) mine = __brev(m) >> (32 - np);
+  }
+  return mine;
+}
 constexpr int kCoopMaxLive = 12;     // a warp with at most this many live rays tests them lane-cooperatively
 
 // ---------------------------------------------------------------------------------------------
@@ -809,21 +831,29 @@ __device__ __forceinline__ void shadow_begin(ShadowQ<NR> &q, const int *inv, con
 }
 
 // returns false once the warp needs nothing further from this (sorted) table
-template <int NR>
+// kMixed: every lane walks the table of ITS OWN light (pairs / gmin / perm / light differ per lane; all tables have the same
+// shape), so "nothing further" is a vote over the lanes' own cut-offs instead of one comparison with the warp's;
+// mixed_tabs / tstride: where table t starts (for the lane-cooperative chunk test of that mode)
+template <int NR, bool kMixed = false>
 __device__ __forceinline__ bool shadow_range(ShadowQ<NR> &q, const float4 *__restrict__ pairs, const float *gmin, const int *perm, int pbeg,
                                              int pend, int light, const float (&dx)[NR], const float (&dy)[NR], const float (&dz)[NR],
                                              const float (&so)[NR], const int (&self)[NR], const float (&cosl)[NR],
                                              const double *const (&p64)[NR], float d64, const double4 *sph64, int &n_fp64,
-                                             const bool coop = false) {
+                                             const bool coop = false, const unsigned char *mixed_tabs = nullptr, unsigned tstride = 0u,
+                                             unsigned long long *prof = nullptr) {
   float2 dx2[NR], dy2[NR], dz2[NR];
 #pragma unroll
   for (int r = 0; r < NR; r++) { dx2[r] = make_float2(dx[r], dx[r]); dy2[r] = make_float2(dy[r], dy[r]); dz2[r] = make_float2(dz[r], dz[r]); }
 #pragma unroll 1
   for (int p0 = pbeg; p0 < pend; p0 += kChunkPairs) {
-    if (gmin[p0 / kGroupPairs] > q.wcut) return false;
+    if (kMixed) { if (!__any_sync(kFull, q.open[0] && !(gmin[p0 / kGroupPairs] > q.cut[0]))) return false; }
+    else if (gmin[p0 / kGroupPairs] > q.wcut) return false;
     const int np = min(kChunkPairs, pend - p0);
     unsigned h[NR], f[NR], any = 0u;
-    if (NR == 1 && coop) h[0] = ~coop_chunk_shared(pairs, p0, np, dx[0], dy[0], dz[0], q.open[0]);
+    long long pt0 = 0;
+    if (prof) pt0 = clock64();
+    if (NR == 1 && kMixed && coop) h[0] = ~coop_chunk_mixed(mixed_tabs, tstride, light, p0, np, dx[0], dy[0], dz[0], q.open[0]);
+    else if (NR == 1 && coop) h[0] = ~coop_chunk_shared(pairs, p0, np, dx[0], dy[0], dz[0], q.open[0]);
     else chunk_test_shared<NR>(pairs, p0, np, dx2, dy2, dz2, h);
 #pragma unroll
     for (int r = 0; r < NR; r++) {
@@ -838,11 +868,13 @@ __device__ __forceinline__ bool shadow_range(ShadowQ<NR> &q, const float4 *__res
       }
       any |= f[r];
     }
+    if (prof) { const long long t = clock64(); prof[0] += (unsigned long long)(t - pt0); prof[3]++; pt0 = t; }
     if (__any_sync(kFull, any != 0u)) {
 #pragma unroll
       for (int r = 0; r < NR; r++) {
         unsigned fr = f[r];
         while (__any_sync(kFull, fr != 0u)) {
+          if (prof) prof[2]++;
           if (fr != 0u) {
             const int bit = 31 - __clz(fr);
             const int pi = p0 + np - 1 - bit;
@@ -861,6 +893,7 @@ __device__ __forceinline__ bool shadow_range(ShadowQ<NR> &q, const float4 *__res
 #pragma unroll
       for (int r = 0; r < NR; r++) c = fmaxf(c, q.open[r] ? q.cut[r] : -3.0e38f);   // decided rays stop holding the warp
       q.wcut = wmaxf(c);
+      if (prof) prof[1] += (unsigned long long)(clock64() - pt0);
       if (q.wcut < -1.0e38f) return false;
     }
   }
@@ -877,6 +910,24 @@ __device__ __forceinline__ void shadow_light(const Tab T, int npairs, int light,
   shadow_range<NR>(q, T.pairs, T.gmin, T.perm, 0, npairs, light, dx, dy, dz, so, self, cosl, p64, d64, sph64, n_fp64, coop);
 #pragma unroll
   for (int r = 0; r < NR; r++) occ[r] = q.occ[r];
+}
+
+// One any-hit query PER LANE, each towards its own light (the tail kernel packs the (hit, light) queries of a warp onto
+// its lanes: ceil(hits x L / 32) walks instead of L walks with the lanes of the missed rays idle).  Same chunk tests, same
+// slow paths and deciders per (ray, sphere) as shadow_light, so the same booleans.
+__device__ __forceinline__ bool shadow_mixed(const unsigned char *tabs, const FastArgs &a, int light, float dx, float dy, float dz, float so,
+                                             bool want, int self, float cosl, const double *p64, int &n_fp64, const bool coop,
+                                             unsigned long long *prof = nullptr) {
+  const Tab T = tab_at(tabs, a, light);
+  const float dxa[1] = {dx}, dya[1] = {dy}, dza[1] = {dz}, soa[1] = {so}, cosla[1] = {cosl};
+  const bool wanta[1] = {want};
+  const int selfa[1] = {self};
+  const double *const pa[1] = {p64};
+  ShadowQ<1> q;
+  shadow_begin<1>(q, T.inv, soa, wanta, selfa, cosla);
+  shadow_range<1, true>(q, T.pairs, T.gmin, T.perm, 0, a.npairs, light, dxa, dya, dza, soa, selfa, cosla, pa, a.d64, a.r.sph64, n_fp64, coop, tabs,
+                        a.tstride, prof);
+  return q.occ[0];
 }
 
 // The same query with bundle culling (T staged in shared memory, wb = this warp's compacted table).
@@ -1204,6 +1255,17 @@ __device__ __forceinline__ void flush_counters(const FastArgs &a, Counters &c, i
 #define RT_TAIL_CTAS 2
 #endif
 constexpr int kTailThreads = RT_TAIL_THREADS;
+#ifdef RT_TAIL_TRACE
+// diagnostics build only (scripts/probe_tail_trace.py): per warp (first chunk), per level, SM-clock stamps of the phases
+constexpr int kTraceWarps = 4096, kTraceLevels = 6, kTraceStamps = 12;
+__device__ unsigned long long g_tail_trace[kTraceWarps * kTraceLevels * kTraceStamps];
+#define RT_TT(k, extra) do { const unsigned long long x_ = (unsigned long long)(extra);   /* (warp-wide: ballots inside) */ \
+    if (tt_on && lane == 0 && level - a.level < kTraceLevels) g_tail_trace[(tt_warp * kTraceLevels + (level - a.level)) * kTraceStamps + (k)] = (unsigned long long)clock64() | (x_ << 48); } while (0)
+#define RT_TG(k) do { if (tt_on && lane == 0 && level - a.level < kTraceLevels) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); g_tail_trace[(tt_warp * kTraceLevels + (level - a.level)) * kTraceStamps + (k)] = t_; } } while (0)
+#else
+#define RT_TT(k, extra) do { } while (0)
+#define RT_TG(k) do { } while (0)
+#endif
 template <bool kSmem, bool kBvh>
 __global__ void __launch_bounds__(kTailThreads, RT_TAIL_CTAS) k_bounce(const FastArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -1225,6 +1287,10 @@ __global__ void __launch_bounds__(kTailThreads, RT_TAIL_CTAS) k_bounce(const Fas
   // drain loops run for the slowest lane, and from kCoopMaxLive live rays down the tests turn lane-cooperative), 32 at most
   const unsigned nwarps = gridDim.x * (unsigned)(kTailThreads / 32);
   const unsigned per = min(32u, max(4u, (nq + nwarps - 1u) / nwarps));
+#ifdef RT_TAIL_TRACE
+  const unsigned tt_warp = blockIdx.x * (unsigned)(kTailThreads / 32) + (threadIdx.x >> 5);
+  bool tt_on = tt_warp < (unsigned)kTraceWarps;
+#endif
   for (;;) {
     const int chunk = warp_fetch(a.chunk_counter);
     if ((unsigned)chunk * per >= nq) break;
@@ -1246,8 +1312,10 @@ __global__ void __launch_bounds__(kTailThreads, RT_TAIL_CTAS) k_bounce(const Fas
       best_init(best[0]);
       // few live rays in this warp (the deep levels): the sphere tests run lane-cooperatively (coop_chunk_*)
       const bool coop = kSmem && !kBvh && __popc(__ballot_sync(kFull, live[0])) <= kCoopMaxLive;
+      RT_TT(0, __popc(__ballot_sync(kFull, live[0]))); RT_TG(6);
       if (kBvh) { if (live[0]) best[0] = bvh_closest_general(a, gen, ox[0], oy[0], oz[0], dx[0], dy[0], dz[0], src[0]); }
       else closest_general<1>(gen, a.npairs, a.N, ox, oy, oz, dx, dy, dz, live, a.d64, a.gS2, a.g_dtmax, a.r.sph64, src, best, coop);
+      RT_TT(1, 0);
       bool hit = false, final_ = false, cont = false;
       int idx[1] = {-1};
       double t64 = 0;
@@ -1273,9 +1341,10 @@ __global__ void __launch_bounds__(kTailThreads, RT_TAIL_CTAS) k_bounce(const Fas
           final_ = true;
         }
       }
+      RT_TT(2, __popc(__ballot_sync(kFull, hit)));
       // ---- shading of the hit (include/scene.h:89-121 in FP32, shadow booleans exact)
       d3 p = rtx::mk(0, 0, 0), n = p;
-      float nx = 0.f, ny = 0.f, nz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f, sr = 0.f, sg = 0.f, sb = 0.f;
+      float nx = 0.f, ny = 0.f, nz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f, sr = 0.f, sg = 0.f, sb = 0.f, backthr = 0.f;
       float4 m = make_float4(0, 0, 0, 0); float2 mx = make_float2(0, 0);
       unsigned smask = 0u;
       if (hit) {
@@ -1286,12 +1355,63 @@ __global__ void __launch_bounds__(kTailThreads, RT_TAIL_CTAS) k_bounce(const Fas
         // view_dir = normalized(origin - hit) = -d up to rounding (src/main.cpp:38); colour only
         vx = -(float)d64v.x; vy = -(float)d64v.y; vz = -(float)d64v.z;
         sr = g_frame.ambient[0] * m.x; sg = g_frame.ambient[1] * m.y; sb = g_frame.ambient[2] * m.z;
+        backthr = -fmaxf(4.0f * kEps * rsqrtf((float)a.r.sph64[idx[0]].w), 1e-4f);          // -4 EPS / r (self-shadow shortcut, see k_shadow)
       }
-      if (kBvh || __any_sync(kFull, hit)) {
+      RT_TT(3, 0);
+#ifdef RT_TAIL_TRACE
+      unsigned long long tt_prof[4] = {0ull, 0ull, 0ull, 0ull};
+#endif
+      // ---- the shadow queries of the warp's hits: occm = occlusion bits of this lane's hit (bit l = light l)
+      unsigned long long occm = 0ull;
+      const unsigned hm = __ballot_sync(kFull, hit);
+      const int H = __popc(hm);
+      if (kSmem && !kBvh && L > 1 && (H * L + 31) / 32 < L) {
+        // few hits: the H x L (hit, light) queries are PACKED onto the lanes -- query q = (hit q / L, light q % L), each
+        // walking its own light's table (shadow_mixed) -- ceil(H L / 32) walks instead of L walks at H / 32 lane use;
+        // the hit's data comes from its owner lane by shuffle, the answers go back as a ballot
+        const int ord = __popc(hm & ((1u << lane) - 1u));                       // this lane's hit is hit number `ord` of the warp
+        const int Q = H * L;
+        for (int q0 = 0; q0 < Q; q0 += 32) {
+          const int qq = q0 + lane;
+          const bool act = qq < Q;
+          const int ho = act ? qq / L : 0, l = act ? qq - ho * L : 0;
+          const int owner = (int)__fns(hm, 0u, ho + 1) & 31;
+          d3 pq;
+          pq.x = __shfl_sync(kFull, p.x, owner); pq.y = __shfl_sync(kFull, p.y, owner); pq.z = __shfl_sync(kFull, p.z, owner);
+          const float qnx = __shfl_sync(kFull, nx, owner), qny = __shfl_sync(kFull, ny, owner), qnz = __shfl_sync(kFull, nz, owner);
+          const int qself = __shfl_sync(kFull, idx[0], owner);
+          const float qback = __shfl_sync(kFull, backthr, owner);
+          float sdx = 0.f, sdy = 0.f, sdz = 0.f, so = 0.f, cosl = 0.f;
+          bool shortcut = false;
+          if (act) {
+            // direction light -> point: FP64 difference, FP32 normalisation (error <= 12u, see filter_math.cuh)
+            const d3 w = rtx::sub(pq, ldc3(g_frame.light_pos[l]));
+            const float wx = (float)w.x, wy = (float)w.y, wz = (float)w.z;
+            const float l2 = fmaf(wz, wz, fmaf(wy, wy, wx * wx));
+            const float inv = rsqrtf(l2);
+            sdx = wx * inv; sdy = wy * inv; sdz = wz * inv;
+            so = l2 * inv - kEps;
+            cosl = -(qnx * sdx + qny * sdy + qnz * sdz);                        // n . light_dir
+            // the point faces away from the light and the light is outside its sphere: occluded by that sphere, no walk
+            shortcut = cosl < qback && (tab_at(tabs, a, l).inv[qself] & 0x40000000) != 0;
+          }
+          const bool wantq = act && !shortcut;
+          const bool coopq = __popc(__ballot_sync(kFull, wantq)) <= kCoopMaxLive;
+#ifdef RT_TAIL_TRACE
+          const bool o = shadow_mixed(tabs, a, l, sdx, sdy, sdz, so, wantq, qself, cosl, &pq.x, n_fp64, coopq, tt_prof);
+#else
+          const bool o = shadow_mixed(tabs, a, l, sdx, sdy, sdz, so, wantq, qself, cosl, &pq.x, n_fp64, coopq);
+#endif
+          const unsigned wm = __ballot_sync(kFull, act && (o || shortcut));
+          const int lo = max(ord * L, q0), hi = min(ord * L + L, q0 + 32);       // this hit's queries that ran in this round
+          if (hit && lo < hi)
+            occm |= (unsigned long long)((wm >> (lo - q0)) & (hi - lo >= 32 ? kFull : (1u << (hi - lo)) - 1u)) << (lo - ord * L);
+        }
+      } else if (kBvh || hm != 0u) {
         for (int l = 0; l < L; l++) {
           float sdx[1] = {0.f}, sdy[1] = {0.f}, sdz[1] = {0.f}, so[1] = {0.f}, cosl[1] = {0.f};
           bool occ[1] = {false};
-          const bool want[1] = {hit};
+          bool shortcut = false;
           if (hit) {
             // direction light -> point: FP64 difference, FP32 normalisation (error <= 12u, see filter_math.cuh)
             const d3 w = rtx::sub(p, ldc3(g_frame.light_pos[l]));
@@ -1301,20 +1421,33 @@ __global__ void __launch_bounds__(kTailThreads, RT_TAIL_CTAS) k_bounce(const Fas
             sdx[0] = wx * inv; sdy[0] = wy * inv; sdz[0] = wz * inv;
             so[0] = l2 * inv - kEps;
             cosl[0] = -(nx * sdx[0] + ny * sdy[0] + nz * sdz[0]);             // n . light_dir
+            shortcut = cosl[0] < backthr && (tab_at(tabs, a, l).inv[idx[0]] & 0x40000000) != 0;   // (see k_shadow)
           }
+          const bool want[1] = {hit && !shortcut};
           const double *const pp[1] = {&p.x};
-          if (kBvh) { if (hit) occ[0] = bvh_shadow(a, tab_at(tabs, a, l), recentred(a, g_frame.light_pos[l]), l, sdx[0], sdy[0], sdz[0], so[0], idx[0], cosl[0], &p.x, n_fp64); }
+          if (!kBvh && !__any_sync(kFull, want[0])) { if (shortcut) occm |= 1ull << l; continue; }
+          if (kBvh) { if (want[0]) occ[0] = bvh_shadow(a, tab_at(tabs, a, l), recentred(a, g_frame.light_pos[l]), l, sdx[0], sdy[0], sdz[0], so[0], idx[0], cosl[0], &p.x, n_fp64); }
           else if (kSmem && coop) shadow_light<1>(tab_at(tabs, a, l), a.npairs, l, sdx, sdy, sdz, so, want, idx, cosl, pp, a.d64, a.r.sph64, occ, n_fp64, true);
           else if (kSmem) shadow_light_culled<1>(tab_at(tabs, a, l), a.npairs, wb, l, sdx, sdy, sdz, so, want, idx, cosl, pp, a.d64, a.r.sph64, occ, n_fp64, c_cand, c_walks);
           else shadow_light<1>(tab_at(tabs, a, l), a.npairs, l, sdx, sdy, sdz, so, want, idx, cosl, pp, a.d64, a.r.sph64, occ, n_fp64);
-          if (!hit) continue;
-          cnt.shadow++;
-          if (occ[0]) { cnt.occluded++; if (l < 32) smask |= 1u << l; continue; }
-          // include/scene.h:104-117 in FP32; light_dir = -(dx,dy,dz)
-          const float ndl = fmaxf(0.0f, cosl[0]);
+          if (occ[0] || shortcut) occm |= 1ull << l;
+        }
+      }
+      // ---- Phong of the un-occluded lights (include/scene.h:104-117 in FP32)
+      if (hit) {
+        cnt.shadow += L; cnt.occluded += __popcll(occm);
+        smask = (unsigned)(occm & 0xffffffffull);
+        for (int l = 0; l < L; l++) {
+          if ((occm >> l) & 1ull) continue;
+          const d3 w = rtx::sub(p, ldc3(g_frame.light_pos[l]));
+          const float wx = (float)w.x, wy = (float)w.y, wz = (float)w.z;
+          const float inv = rsqrtf(fmaf(wz, wz, fmaf(wy, wy, wx * wx)));
+          const float sdx = wx * inv, sdy = wy * inv, sdz = wz * inv;           // light_dir = -(sdx, sdy, sdz)
+          const float cosl = -(nx * sdx + ny * sdy + nz * sdz);
+          const float ndl = fmaxf(0.0f, cosl);
           const float kd = (1.0f - m.w) * ndl;
-          const float dn = -cosl[0];                                              // dot(-light_dir, n)
-          const float rx = sdx[0] - 2.0f * nx * dn, ry = sdy[0] - 2.0f * ny * dn, rz = sdz[0] - 2.0f * nz * dn;
+          const float dn = -cosl;                                              // dot(-light_dir, n)
+          const float rx = sdx - 2.0f * nx * dn, ry = sdy - 2.0f * ny * dn, rz = sdz - 2.0f * nz * dn;
           const float rdv = fmaxf(0.0f, rx * vx + ry * vy + rz * vz);
           const float spec = 0.5f * (mx.x == 0.0f ? 1.0f : __powf(rdv, mx.x));
           sr += g_frame.light_col[l][0] * spec + m.x * kd;
@@ -1322,6 +1455,11 @@ __global__ void __launch_bounds__(kTailThreads, RT_TAIL_CTAS) k_bounce(const Fas
           sb += g_frame.light_col[l][2] * spec + m.z * kd;
         }
       }
+      RT_TT(4, 0);
+#ifdef RT_TAIL_TRACE
+      if (tt_on && lane == 0 && level - a.level < kTraceLevels)
+        for (int k = 0; k < 4; k++) g_tail_trace[(tt_warp * kTraceLevels + (level - a.level)) * kTraceStamps + 8 + k] = tt_prof[k];
+#endif
       // continuation: src/main.cpp:43-55 unrolled front to back
       if (hit) {
         if (a.r.shadow_mask) a.r.shadow_mask[(size_t)pix * a.r.max_depth + level] = smask;
@@ -1349,9 +1487,13 @@ __global__ void __launch_bounds__(kTailThreads, RT_TAIL_CTAS) k_bounce(const Fas
         if (lane == 0 && c_walks) { atomicAdd(&a.r.counters[RT_CNT_CAND], (unsigned long long)c_cand); atomicAdd(&a.r.counters[RT_CNT_WALKS], (unsigned long long)c_walks); }
         c_cand = c_walks = 0;
       }
+      RT_TT(5, __popc(__ballot_sync(kFull, cont))); RT_TG(7);
       live[0] = cont;
       if (!__any_sync(kFull, cont)) break;
     }
+#ifdef RT_TAIL_TRACE
+    tt_on = false;                                   // (first chunk of the warp only)
+#endif
   }
 }
 

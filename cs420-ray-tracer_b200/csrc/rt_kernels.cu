@@ -868,3 +868,14 @@ double rtk_measure_fp32_peak(int device, double *sm_clock_mhz) {
   if (cudaGetLastError() != cudaSuccess) return -3;
   return 2.0 * grid * block * (double)iters * 16 * 8 / (best * 1e-3);
 }
+
+#ifdef RT_TAIL_TRACE
+// diagnostics build only: copies the tail kernel's phase stamps out (scripts/probe_tail_trace.py)
+extern "C" int rt_debug_tail_trace(unsigned long long *out, int n) {
+  const size_t total = sizeof(rtf::g_tail_trace);
+  const size_t want = (size_t)n * sizeof(unsigned long long);
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(out, rtf::g_tail_trace, want < total ? want : total) != cudaSuccess) return -1;
+  return (int)((want < total ? want : total) / sizeof(unsigned long long));
+}
+#endif
