@@ -1364,25 +1364,49 @@ __global__ void __launch_bounds__(kTailThreads, RT_TAIL_CTAS) k_bounce(const Fas
       // ---- the shadow queries of the warp's hits: occm = occlusion bits of this lane's hit (bit l = light l)
       unsigned long long occm = 0ull;
       const unsigned hm = __ballot_sync(kFull, hit);
-      const int H = __popc(hm);
-      if (kSmem && !kBvh && L > 1 && (H * L + 31) / 32 < L) {
-        // few hits: the H x L (hit, light) queries are PACKED onto the lanes -- query q = (hit q / L, light q % L), each
-        // walking its own light's table (shadow_mixed) -- ceil(H L / 32) walks instead of L walks at H / 32 lane use;
-        // the hit's data comes from its owner lane by shuffle, the answers go back as a ballot
-        const int ord = __popc(hm & ((1u << lane) - 1u));                       // this lane's hit is hit number `ord` of the warp
-        const int Q = H * L;
-        for (int q0 = 0; q0 < Q; q0 += 32) {
-          const int qq = q0 + lane;
-          const bool act = qq < Q;
-          const int ho = act ? qq / L : 0, l = act ? qq - ho * L : 0;
-          const int owner = (int)__fns(hm, 0u, ho + 1) & 31;
+      // per hit and light: the self-shadow shortcut (the point faces away from the light and the light is outside its sphere:
+      // occluded by that sphere, no walk; see k_shadow) settles about half of the queries; `need` = the lights left to walk
+      unsigned long long need = 0ull;
+      if (kSmem && !kBvh && hit) {
+        for (int l = 0; l < L; l++) {
+          const d3 w = rtx::sub(p, ldc3(g_frame.light_pos[l]));
+          const float wx = (float)w.x, wy = (float)w.y, wz = (float)w.z;
+          const float inv = rsqrtf(fmaf(wz, wz, fmaf(wy, wy, wx * wx)));
+          const float cosl = -(nx * (wx * inv) + ny * (wy * inv) + nz * (wz * inv));
+          if (cosl < backthr && (tab_at(tabs, a, l).inv[idx[0]] & 0x40000000) != 0) occm |= 1ull << l; else need |= 1ull << l;
+        }
+      }
+      const int Qn = kSmem && !kBvh ? (int)__reduce_add_sync(kFull, (unsigned)__popcll(need)) : 0;
+      if (kSmem && !kBvh && L > 1 && (Qn + 31) / 32 < L) {
+        // few queries: they are PACKED onto the lanes, 32 per round -- each lane walks the table of its own query's light
+        // (shadow_mixed) -- ceil(Qn / 32) walks instead of L walks with the lanes of missed rays and settled queries idle.
+        // A round's queries are listed in the warp's scratch table (owner lane << 8 | light); the hit's data comes from
+        // its owner lane by shuffle, the answers go back as a ballot.
+        int *list = wb.perm;
+        unsigned long long rem = need;
+        while (__any_sync(kFull, rem != 0ull)) {
+          const int c = __popcll(rem);
+          int incl = c;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(kFull, incl, d); if (lane >= d) incl += v; }
+          const int excl = incl - c, take = max(0, min(c, 32 - excl));
+          unsigned long long taken = 0ull;
+          for (int k = 0; k < take; k++) {
+            const int l = __ffsll((long long)rem) - 1;
+            rem &= rem - 1ull; taken |= 1ull << l;
+            list[excl + k] = (lane << 8) | l;
+          }
+          __syncwarp();
+          const int total = min(32, __shfl_sync(kFull, incl, 31));
+          const bool act = lane < total;
+          const int e = act ? list[lane] : 0;
+          __syncwarp();
+          const int owner = e >> 8, l = e & 255;
           d3 pq;
           pq.x = __shfl_sync(kFull, p.x, owner); pq.y = __shfl_sync(kFull, p.y, owner); pq.z = __shfl_sync(kFull, p.z, owner);
           const float qnx = __shfl_sync(kFull, nx, owner), qny = __shfl_sync(kFull, ny, owner), qnz = __shfl_sync(kFull, nz, owner);
           const int qself = __shfl_sync(kFull, idx[0], owner);
-          const float qback = __shfl_sync(kFull, backthr, owner);
           float sdx = 0.f, sdy = 0.f, sdz = 0.f, so = 0.f, cosl = 0.f;
-          bool shortcut = false;
           if (act) {
             // direction light -> point: FP64 difference, FP32 normalisation (error <= 12u, see filter_math.cuh)
             const d3 w = rtx::sub(pq, ldc3(g_frame.light_pos[l]));
@@ -1392,20 +1416,18 @@ __global__ void __launch_bounds__(kTailThreads, RT_TAIL_CTAS) k_bounce(const Fas
             sdx = wx * inv; sdy = wy * inv; sdz = wz * inv;
             so = l2 * inv - kEps;
             cosl = -(qnx * sdx + qny * sdy + qnz * sdz);                        // n . light_dir
-            // the point faces away from the light and the light is outside its sphere: occluded by that sphere, no walk
-            shortcut = cosl < qback && (tab_at(tabs, a, l).inv[qself] & 0x40000000) != 0;
           }
-          const bool wantq = act && !shortcut;
-          const bool coopq = __popc(__ballot_sync(kFull, wantq)) <= kCoopMaxLive;
 #ifdef RT_TAIL_TRACE
-          const bool o = shadow_mixed(tabs, a, l, sdx, sdy, sdz, so, wantq, qself, cosl, &pq.x, n_fp64, coopq, tt_prof);
+          const bool o = shadow_mixed(tabs, a, l, sdx, sdy, sdz, so, act, qself, cosl, &pq.x, n_fp64, total <= kCoopMaxLive, tt_prof);
 #else
-          const bool o = shadow_mixed(tabs, a, l, sdx, sdy, sdz, so, wantq, qself, cosl, &pq.x, n_fp64, coopq);
+          const bool o = shadow_mixed(tabs, a, l, sdx, sdy, sdz, so, act, qself, cosl, &pq.x, n_fp64, total <= kCoopMaxLive);
 #endif
-          const unsigned wm = __ballot_sync(kFull, act && (o || shortcut));
-          const int lo = max(ord * L, q0), hi = min(ord * L + L, q0 + 32);       // this hit's queries that ran in this round
-          if (hit && lo < hi)
-            occm |= (unsigned long long)((wm >> (lo - q0)) & (hi - lo >= 32 ? kFull : (1u << (hi - lo)) - 1u)) << (lo - ord * L);
+          const unsigned wm = __ballot_sync(kFull, act && o);
+          for (int k = 0; taken != 0ull; k++) {          // this lane's queries of the round: list positions excl, excl + 1, ...
+            const int l2 = __ffsll((long long)taken) - 1;
+            taken &= taken - 1ull;
+            if ((wm >> (excl + k)) & 1u) occm |= 1ull << l2;
+          }
         }
       } else if (kBvh || hm != 0u) {
         for (int l = 0; l < L; l++) {
@@ -1421,7 +1443,7 @@ __global__ void __launch_bounds__(kTailThreads, RT_TAIL_CTAS) k_bounce(const Fas
             sdx[0] = wx * inv; sdy[0] = wy * inv; sdz[0] = wz * inv;
             so[0] = l2 * inv - kEps;
             cosl[0] = -(nx * sdx[0] + ny * sdy[0] + nz * sdz[0]);             // n . light_dir
-            shortcut = cosl[0] < backthr && (tab_at(tabs, a, l).inv[idx[0]] & 0x40000000) != 0;   // (see k_shadow)
+            shortcut = cosl[0] < backthr && (tab_at(tabs, a, l).inv[idx[0]] & 0x40000000) != 0;   // (self-shadow shortcut, see k_shadow)
           }
           const bool want[1] = {hit && !shortcut};
           const double *const pp[1] = {&p.x};

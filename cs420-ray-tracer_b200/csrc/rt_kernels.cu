@@ -281,6 +281,9 @@ int rtk_fast_build_scene(RtFastScene *fs, const double *sph, int N, const RtFram
   fs->gmin_off = pairs_bytes; fs->perm_off = pairs_bytes + gmin_bytes; fs->inv_off = fs->perm_off + perm_bytes;
   fs->cullA_off = fs->inv_off + inv_bytes; fs->cullB_off = fs->cullA_off + cullA_bytes;
   fs->tstride = fs->cullB_off + cullB_bytes;
+  // stride = 32 (mod 128) bytes: when the lanes of a warp walk DIFFERENT lights' tables in step (shadow_mixed), the same
+  // pair of four consecutive tables lies in four different bank groups of shared memory
+  fs->tstride += (32u + 128u - fs->tstride % 128u) % 128u;
   fs->bytes_primary = (size_t)(L + 1) * fs->tstride;
   fs->bytes_bounce = (size_t)L * fs->tstride + pairs_bytes;
   const size_t total = (size_t)(L + 1) * fs->tstride + pairs_bytes;
