@@ -232,17 +232,25 @@ __device__ __noinline__ int exact_bruteforce(const double4 *sph64, int n, d3 o, 
   tbest = t;
   return idx;
 }
-// src/main.cpp:32,35 : hit point and unit normal
-struct HitGeom { d3 p, n; };
+// src/main.cpp:32,35 : the exact hit point, and the unit normal as an FP32 vector.  The normal of the hit record feeds the
+// colour and two sign tests with wide margins (lit side: n.l > 1e-3, self-shadow shortcut: n.l < -1e-4) -- FP32 accuracy
+// is all they need, so it is the exact FP64 difference p - c normalised in FP32 (2-3 ulp) instead of the reference's FP64
+// normalisation (one FP64 square root and three divisions per hit: a quarter of the exact finish).  The EXACT normal the
+// reflected ray is built from is formed where a ray continues (reflected_ray_from_center).  One copy of this code serves
+// every kernel, so a hit gets the same FP32 normal whichever kernel finishes it.
+struct HitGeom { d3 p; float nx, ny, nz; };
 __device__ __noinline__ HitGeom hit_geometry(const double4 *sph64, int idx, d3 o, d3 d, double t) {
   const double4 s = ld_sph64(&sph64[idx]);
   HitGeom h;
   h.p = rtx::hit_point(o, d, t);
-  h.n = rtx::normal_at(h.p, rtx::mk(s.x, s.y, s.z));
+  const float fx = (float)rtx::dsub(h.p.x, s.x), fy = (float)rtx::dsub(h.p.y, s.y), fz = (float)rtx::dsub(h.p.z, s.z);
+  const float inv = rsqrtf(__fmaf_rn(fz, fz, __fmaf_rn(fy, fy, __fmul_rn(fx, fx))));
+  h.nx = __fmul_rn(fx, inv); h.ny = __fmul_rn(fy, inv); h.nz = __fmul_rn(fz, inv);
   return h;
 }
-// src/main.cpp:45-48 : the reflected ray as the Ray ctor stores it
-__device__ __noinline__ void reflected_ray(d3 d, d3 p, d3 n, RayRec *rec) {
+// src/main.cpp:35,45-48 from the exact hit point and the sphere centre: exact normal, reflected ray as the Ray ctor stores it
+__device__ __noinline__ void reflected_ray_from_center(d3 d, d3 p, d3 c, RayRec *rec) {
+  const d3 n = rtx::normal_at(p, c);
   d3 o2, d2;
   rtx::reflect_ray(d, p, n, 0.001, o2, d2);
   rec->ox = o2.x; rec->oy = o2.y; rec->oz = o2.z; rec->dx = d2.x; rec->dy = d2.y; rec->dz = d2.z;
@@ -1252,7 +1260,7 @@ __device__ __forceinline__ void flush_counters(const FastArgs &a, Counters &c, i
 #define RT_TAIL_THREADS 128
 #endif
 #ifndef RT_TAIL_CTAS
-#define RT_TAIL_CTAS 2
+#define RT_TAIL_CTAS 3
 #endif
 constexpr int kTailThreads = RT_TAIL_THREADS;
 #ifdef RT_TAIL_TRACE
@@ -1343,15 +1351,15 @@ __global__ void __launch_bounds__(kTailThreads, RT_TAIL_CTAS) k_bounce(const Fas
       }
       RT_TT(2, __popc(__ballot_sync(kFull, hit)));
       // ---- shading of the hit (include/scene.h:89-121 in FP32, shadow booleans exact)
-      d3 p = rtx::mk(0, 0, 0), n = p;
+      d3 p = rtx::mk(0, 0, 0);
       float nx = 0.f, ny = 0.f, nz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f, sr = 0.f, sg = 0.f, sb = 0.f, backthr = 0.f;
       float4 m = make_float4(0, 0, 0, 0); float2 mx = make_float2(0, 0);
       unsigned smask = 0u;
       if (hit) {
         const HitGeom hg = hit_geometry(a.r.sph64, idx[0], o64, d64v, t64);   // src/main.cpp:32,35
-        p = hg.p; n = hg.n;
+        p = hg.p;
         m = __ldg(&a.r.mat[idx[0]]); mx = __ldg(&a.r.matx[idx[0]]);
-        nx = (float)n.x; ny = (float)n.y; nz = (float)n.z;
+        nx = hg.nx; ny = hg.ny; nz = hg.nz;
         // view_dir = normalized(origin - hit) = -d up to rounding (src/main.cpp:38); colour only
         vx = -(float)d64v.x; vy = -(float)d64v.y; vz = -(float)d64v.z;
         sr = g_frame.ambient[0] * m.x; sg = g_frame.ambient[1] * m.y; sb = g_frame.ambient[2] * m.z;
@@ -1491,7 +1499,8 @@ __global__ void __launch_bounds__(kTailThreads, RT_TAIL_CTAS) k_bounce(const Fas
           wt *= refl;
           if (level + 1 < a.r.max_depth) {
             RayRec *rec = qin + qi;                 // in place: the exact ray of the next level is re-read from here
-            reflected_ray(d64v, p, n, rec);
+            const double4 sc = ld_sph64(&a.r.sph64[idx[0]]);
+            reflected_ray_from_center(d64v, p, rtx::mk(sc.x, sc.y, sc.z), rec);
             ox[0] = (float)(rec->ox - a.c0[0]); oy[0] = (float)(rec->oy - a.c0[1]); oz[0] = (float)(rec->oz - a.c0[2]);
             dx[0] = (float)rec->dx; dy[0] = (float)rec->dy; dz[0] = (float)rec->dz;
             cont = true;

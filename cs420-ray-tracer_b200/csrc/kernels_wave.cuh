@@ -30,6 +30,9 @@
 #ifndef RT_CLOSEST_CTAS
 #define RT_CLOSEST_CTAS 2
 #endif
+#ifndef RT_CLOSEST0_CTAS
+#define RT_CLOSEST0_CTAS RT_CLOSEST_CTAS
+#endif
 namespace rtf {
 
 struct __align__(16) HitRec {      // 80 bytes
@@ -134,14 +137,6 @@ __device__ __noinline__ void flush_counts(unsigned long long *counters, int leve
   }
 }
 
-// src/main.cpp:35,45-48 from the exact hit point and the sphere centre
-__device__ __noinline__ void reflected_ray_from_center(d3 d, d3 p, d3 c, RayRec *rec) {
-  const d3 n = rtx::normal_at(p, c);
-  d3 o2, d2;
-  rtx::reflect_ray(d, p, n, 0.001, o2, d2);
-  rec->ox = o2.x; rec->oy = o2.y; rec->oz = o2.z; rec->dx = d2.x; rec->dy = d2.y; rec->dz = d2.z;
-}
-
 // Exact t of the winner + hit record (out of line: FP64 heavy, once per hit ray)
 __device__ __noinline__ bool finish_hit(const FastArgs &a, Best b, RaySrc src, unsigned pix, unsigned srcidx, float wt, float ar, float ag,
                                         float ab, HitRec *out, unsigned *viol, unsigned *nfp64) {
@@ -154,7 +149,7 @@ __device__ __noinline__ bool finish_hit(const FastArgs &a, Best b, RaySrc src, u
   if (bi < 0) return false;
   const HitGeom g = hit_geometry(a.r.sph64, bi, e.o, e.d, t);
   out->px = g.p.x; out->py = g.p.y; out->pz = g.p.z;
-  out->nx = (float)g.n.x; out->ny = (float)g.n.y; out->nz = (float)g.n.z;
+  out->nx = g.nx; out->ny = g.ny; out->nz = g.nz;
   out->vx = -(float)e.d.x; out->vy = -(float)e.d.y; out->vz = -(float)e.d.z;   // view_dir = -d up to rounding (src/main.cpp:38)
   out->idx = bi; out->pix = pix; out->src = srcidx; out->wt = wt; out->ar = ar; out->ag = ag; out->ab = ab; out->pad = 0;
   return true;
@@ -391,7 +386,7 @@ __device__ __forceinline__ void closest0_body(const WaveArgs &w, const Lvl &lv, 
   if (a.r.counters) flush_counts(a.r.counters, 0, c_closest, c_hits, 0, 0, c_fp64, c_viol, (unsigned long long)a.N, c_cand, c_walks, c_fall);
 }
 template <int kMode>
-__global__ void __launch_bounds__(kThreads, RT_CLOSEST_CTAS) k_closest0(const WaveArgs w) {
+__global__ void __launch_bounds__(kThreads, RT_CLOSEST0_CTAS) k_closest0(const WaveArgs w) {
   extern __shared__ __align__(128) unsigned char smem[];
   const FastArgs &a = w.f;
   const unsigned char *tabs = a.tabs;

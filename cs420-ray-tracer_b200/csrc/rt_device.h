@@ -32,6 +32,7 @@ struct RtBands {
 };
 
 __host__ __device__ inline int rt_local_to_global_row(const RtBands &b, int lr) {
+  if (b.nranks == 1) return lr;                     // (one rank owns every band: no integer division per pixel)
   int lb = lr / b.band_h;
   return (lb * b.nranks + b.rank) * b.band_h + (lr - lb * b.band_h);
 }

@@ -12,7 +12,7 @@ stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
 buf = torch.empty(H * W * 3 + 16, dtype=torch.uint8, device="cuda:0")
 for n in (1, 8):
     prev = 0
-    for D in (1, 2, 3, 4, 5, 6, 8):
+    for D in ([int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else (1, 2, 3, 4, 5, 6, 8)):
         for _ in range(5): r.render_bands_device(W, H, D, 16, 0, n, buf.data_ptr(), stream.cuda_stream)
         torch.cuda.synchronize()
         ms = []
