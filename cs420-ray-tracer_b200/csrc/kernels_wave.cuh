@@ -35,16 +35,24 @@
 #endif
 namespace rtf {
 
+// A camera-ray hit (level 0) has no queue record, carries weight 1 and no colour yet: there the words of (vy, vz), (src, wt)
+// and (ar, ag) hold the EXACT unit direction of the camera ray as three doubles (finish_hit / hit_d0x..z: k_closest0 has it;
+// the shading pass would otherwise redo its two FP64 normalisations for every hit that reflects); view direction = -(float)d0.
+// (Plain fields and register-level bit casts, not a union: the record keeps moving as five 128-bit words.)
 struct __align__(16) HitRec {      // 80 bytes
   double px, py, pz;               // exact FP64 hit point (src/main.cpp:32)
-  float nx, ny, nz;                // unit normal, FP32 copy (colour + lit-side test only)
-  float vx, vy, vz;                // view direction = -ray direction, FP32 (colour only)
+  float nx, ny, nz;                // unit normal, FP32 (colour + lit-side test only)
+  float vx, vy, vz;                // view direction = -ray direction, FP32 (colour only; level >= 1)
   int idx;                         // sphere index
   unsigned pix;                    // local pixel index lr*W + x
   unsigned src;                    // level >= 1: index of the ray in the level's RayRec queue
   float wt, ar, ag, ab;            // carried weight / colour (front to back)
   unsigned pad;                    // occlusion bits of the hit's shadow queries (bit l = light l occluded; scenes with <= 32 lights)
 };
+__device__ __forceinline__ double hit_d0x(const HitRec &h) { return __hiloint2double(__float_as_int(h.vz), __float_as_int(h.vy)); }
+__device__ __forceinline__ double hit_d0y(const HitRec &h) { return __hiloint2double(__float_as_int(h.wt), (int)h.src); }
+__device__ __forceinline__ double hit_d0z(const HitRec &h) { return __hiloint2double(__float_as_int(h.ag), __float_as_int(h.ar)); }
+static_assert(sizeof(HitRec) == 80, "hit record layout");
 
 struct WaveArgs {
   FastArgs f;
@@ -148,9 +156,17 @@ __device__ __noinline__ bool finish_hit(const FastArgs &a, Best b, RaySrc src, u
   if (!ok) { (*viol)++; bi = exact_bruteforce(a.r.sph64, a.N, e.o, e.d, e.a, t); }
   if (bi < 0) return false;
   const HitGeom g = hit_geometry(a.r.sph64, bi, e.o, e.d, t);
+  // (the words of the record are formed first and stored unconditionally, in order: five 128-bit stores)
+  float vx = -(float)e.d.x, vy = -(float)e.d.y, vz = -(float)e.d.z;   // view_dir = -d up to rounding (src/main.cpp:38)
+  if (src.rec == nullptr) {                      // camera ray: the exact direction travels with the hit (see HitRec)
+    vx = 0.f; ab = 0.f;
+    vy = __int_as_float(__double2loint(e.d.x)); vz = __int_as_float(__double2hiint(e.d.x));
+    srcidx = (unsigned)__double2loint(e.d.y); wt = __int_as_float(__double2hiint(e.d.y));
+    ar = __int_as_float(__double2loint(e.d.z)); ag = __int_as_float(__double2hiint(e.d.z));
+  }
   out->px = g.p.x; out->py = g.p.y; out->pz = g.p.z;
   out->nx = g.nx; out->ny = g.ny; out->nz = g.nz;
-  out->vx = -(float)e.d.x; out->vy = -(float)e.d.y; out->vz = -(float)e.d.z;   // view_dir = -d up to rounding (src/main.cpp:38)
+  out->vx = vx; out->vy = vy; out->vz = vz;
   out->idx = bi; out->pix = pix; out->src = srcidx; out->wt = wt; out->ar = ar; out->ag = ag; out->ab = ab; out->pad = 0;
   return true;
 }
@@ -492,6 +508,8 @@ __device__ __forceinline__ bool shade_one(const WaveArgs &w, const Lvl &lv, cons
   const float4 m = __ldg(&a.r.mat[hr.idx]);
   const float2 mx = __ldg(&a.r.matx[hr.idx]);
   float sr = g_frame.ambient[0] * m.x, sg = g_frame.ambient[1] * m.y, sb = g_frame.ambient[2] * m.z;
+  const bool cam = level == 0;                  // camera-ray hit: exact direction in the record, weight 1, no colour yet
+  const float vx = cam ? -(float)hit_d0x(hr) : hr.vx, vy = cam ? -(float)hit_d0y(hr) : hr.vy, vz = cam ? -(float)hit_d0z(hr) : hr.vz;
   for (int l = 0; l < L; l++) {
     if ((occm >> l) & 1ull) continue;
     // light_dir = normalized(light - point): FP64 difference, FP32 normalisation (colour only)
@@ -503,34 +521,28 @@ __device__ __forceinline__ bool shade_one(const WaveArgs &w, const Lvl &lv, cons
     const float kd = (1.0f - m.w) * fmaxf(0.0f, nl);
     // reflect(-light_dir, n) = -l + 2 (l.n) n   (include/vec3.h:31-33)
     const float rx = 2.0f * nl * hr.nx - lx, ry = 2.0f * nl * hr.ny - ly, rz = 2.0f * nl * hr.nz - lz;
-    const float rdv = fmaxf(0.0f, rx * hr.vx + ry * hr.vy + rz * hr.vz);
+    const float rdv = fmaxf(0.0f, rx * vx + ry * vy + rz * vz);
     const float spec = 0.5f * (mx.x == 0.0f ? 1.0f : __powf(rdv, mx.x));
     sr += g_frame.light_col[l][0] * spec + m.x * kd;
     sg += g_frame.light_col[l][1] * spec + m.y * kd;
     sb += g_frame.light_col[l][2] * spec + m.z * kd;
   }
   if (a.r.shadow_mask) a.r.shadow_mask[(size_t)hr.pix * a.r.max_depth + level] = (unsigned)(occm & 0xffffffffull);
-  float cr = hr.ar, cg = hr.ag, cb = hr.ab, wt = hr.wt;
+  float cr = cam ? 0.f : hr.ar, cg = cam ? 0.f : hr.ag, cb = cam ? 0.f : hr.ab, wt = cam ? 1.0f : hr.wt;
   bool cont = false;
   if (mx.y > 0.5f) {                          // reflectivity > 0, decided in double on the host
     const float refl = m.w, k = wt * (1.0f - refl);
     cr += k * sr; cg += k * sg; cb += k * sb;
     wt *= refl;
     if (level + 1 < a.r.max_depth) {
-      // exact reflected ray: the incoming direction is re-derived from its source, the normal from
-      // the exact hit point (src/main.cpp:35,45-48)
-      RaySrc src;
-      if (level == 0) {
-        const int W = a.r.W;
-        const int lr = (int)(hr.pix / (unsigned)W), x = (int)(hr.pix - (unsigned)lr * (unsigned)W);
-        src = RaySrc{a.r.su, a.r.sv, x, rt_local_to_global_row(a.r.bands, lr), nullptr};
-      } else {
-        src = RaySrc{nullptr, nullptr, 0, 0, lv.q_in + hr.src};
-      }
-      const ExactRay e = exact_ray(src);
+      // exact reflected ray: the incoming direction comes with the record (camera ray) or from the ray's queue record,
+      // the normal from the exact hit point (src/main.cpp:35,45-48)
+      d3 din;
+      if (cam) din = rtx::mk(hit_d0x(hr), hit_d0y(hr), hit_d0z(hr));
+      else { const RayRec &q = lv.q_in[hr.src]; din = rtx::mk(q.dx, q.dy, q.dz); }
       const double4 s = ld_sph64(&a.r.sph64[hr.idx]);
       const d3 p = rtx::mk(hr.px, hr.py, hr.pz);
-      reflected_ray_from_center(e.d, p, rtx::mk(s.x, s.y, s.z), &rec);
+      reflected_ray_from_center(din, p, rtx::mk(s.x, s.y, s.z), &rec);
       rec.pix = hr.pix; rec.wt = wt; rec.ar = cr; rec.ag = cg; rec.ab = cb; rec.pad = 0;
       cont = true;
     }
