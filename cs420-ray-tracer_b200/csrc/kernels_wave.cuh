@@ -758,7 +758,9 @@ __global__ void __launch_bounds__(kThreads, RT_SHADOW_CTAS) k_shadow(const WaveA
   const FastArgs &a = w.f;
   // staged: the L light tables
   const unsigned char *tabs = a.tabs + a.tstride;
-  if (kMode == kTabSmem && a.L > 0) { stage_tables(smem, tabs, a.stage_bytes); tabs = smem + kSmemHeader; }
+  // (the pointer is switched UNCONDITIONALLY in this mode -- a scene without lights never dereferences it -- so that the
+  // compiler knows the tables are in shared memory: LDS instead of generic loads in every walk)
+  if (kMode == kTabSmem) { if (a.L > 0) stage_tables(smem, tabs, a.stage_bytes); tabs = smem + kSmemHeader; }
   if (kMode == kTabStream) ring_init(smem);
   RT_PDL_SYNC();
   shadow_body<kMode, false>(w, lvl_of(w), smem, tabs, smem + kSmemHeader + (kMode == kTabBvh ? 0u : ((a.stage_bytes + 127u) & ~127u)));
