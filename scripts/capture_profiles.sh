@@ -26,7 +26,14 @@ python scripts/ncu_summary.py $O/bvh10k_full.ncu-rep > $O/ncu_bvh10k_summary.txt
 python scripts/ncu_opcodes.py $O/bvh10k_full.ncu-rep 72.4 --json $O/executed_synth10k.json > $O/executed_synth10k.txt 2>&1
 for k in k_closest0 "k_shadow" k_shade k_closest1 k_bounce; do python scripts/ncu_lines.py $O/complex_full.ncu-rep "$k" 25 smp > $O/lines_$k.txt 2>&1; done
 rm -f $O/bvh10k_full.ncu-rep $O/complex_full.ncu-rep
+if [ -n "$RT_CAPTURE_CSV" ]; then
 python scripts/benchmark_csv.py --iterations 2 --threads 1,4,16 --out $O/benchmark_results > $O/benchmark_csv.log 2>&1
 rm -f $O/benchmark_results/*.ppm
+fi
+# phase stamps of the tail kernel (diagnostics build of the same sources, scripts/build_variant.sh trace -DRT_TAIL_TRACE)
+if [ -f cs420-ray-tracer_b200/build/trace/librt_b200.so ]; then
+RTB200_LIB=cs420-ray-tracer_b200/build/trace/librt_b200.so timeout 120 python scripts/probe_tail_trace.py 1 8 > $O/tail_phase_trace.txt 2>&1
+fi
+timeout 200 python scripts/probe_depth2.py > $O/depth_increments.txt 2>&1
 python scripts/probe_e2e.py > $O/e2e_breakdown.log 2>&1
 ls -la $O
