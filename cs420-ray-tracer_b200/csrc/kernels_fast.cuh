@@ -116,6 +116,41 @@ __device__ __forceinline__ float wmaxf(float v) {
   return v;
 }
 __device__ __forceinline__ unsigned quant8(float c) { return (unsigned)(int)(255.99f * fminf(1.0f, c)); }
+
+// ---- colour arithmetic with a FIXED operation order.  Several kernels (and several inlined copies inside one kernel: the tile
+// and the pixel path of k_shade, the wavefront and the tail) compute the colour of the same pixel, and their results must
+// agree bit for bit (assembled N-GPU frames are compared with single-GPU ones).  Written as ordinary expressions the compiler
+// contracts a*b + c*d into an FMA one way in one copy and the other way in the next; explicit intrinsics are never contracted.
+struct Rgb { float r, g, b; };
+__device__ __forceinline__ Rgb sky_colour(float dy) {              // src/main.cpp:26-30: (1-t) white + t (0.5, 0.7, 1)
+  const float ts = __fmul_rn(0.5f, __fadd_rn(dy, 1.0f)), w = __fsub_rn(1.0f, ts);
+  Rgb c;
+  c.r = __fmaf_rn(0.5f, ts, w); c.g = __fmaf_rn(0.7f, ts, w); c.b = __fadd_rn(w, ts);
+  return c;
+}
+__device__ __forceinline__ void add_scaled(float &cr, float &cg, float &cb, float k, float sr, float sg, float sb) {
+  cr = __fmaf_rn(k, sr, cr); cg = __fmaf_rn(k, sg, cg); cb = __fmaf_rn(k, sb, cb);
+}
+// Phong terms of ONE un-occluded light at a hit (include/scene.h:104-117): point p (exact), unit normal n, view direction v,
+// material m = (R, G, B, reflectivity), shininess; adds to (sr, sg, sb)
+__device__ __forceinline__ void phong_light(int l, double px, double py, double pz, float nx, float ny, float nz, float vx, float vy, float vz,
+                                            float4 m, float shin, float &sr, float &sg, float &sb) {
+  // light_dir = normalized(light - point): FP64 difference, FP32 normalisation (colour only)
+  const float wx = (float)__dsub_rn(g_frame.light_pos[l][0], px), wy = (float)__dsub_rn(g_frame.light_pos[l][1], py),
+              wz = (float)__dsub_rn(g_frame.light_pos[l][2], pz);
+  const float inv = rsqrtf(__fmaf_rn(wz, wz, __fmaf_rn(wy, wy, __fmul_rn(wx, wx))));
+  const float lx = __fmul_rn(wx, inv), ly = __fmul_rn(wy, inv), lz = __fmul_rn(wz, inv);
+  const float nl = __fmaf_rn(nz, lz, __fmaf_rn(ny, ly, __fmul_rn(nx, lx)));
+  const float kd = __fmul_rn(__fsub_rn(1.0f, m.w), fmaxf(0.0f, nl));
+  // reflect(-light_dir, n) = -l + 2 (l.n) n   (include/vec3.h:31-33)
+  const float t2 = __fmul_rn(2.0f, nl);
+  const float rx = __fmaf_rn(t2, nx, -lx), ry = __fmaf_rn(t2, ny, -ly), rz = __fmaf_rn(t2, nz, -lz);
+  const float rdv = fmaxf(0.0f, __fmaf_rn(rz, vz, __fmaf_rn(ry, vy, __fmul_rn(rx, vx))));
+  const float spec = __fmul_rn(0.5f, shin == 0.0f ? 1.0f : __powf(rdv, shin));
+  sr = __fadd_rn(sr, __fmaf_rn(g_frame.light_col[l][0], spec, __fmul_rn(m.x, kd)));
+  sg = __fadd_rn(sg, __fmaf_rn(g_frame.light_col[l][1], spec, __fmul_rn(m.y, kd)));
+  sb = __fadd_rn(sb, __fmaf_rn(g_frame.light_col[l][2], spec, __fmul_rn(m.z, kd)));
+}
 // A finished pixel: 8-bit quantised (src/main.cpp:84-86) or, for tile renders / supersampling, FP32 colour.
 __device__ __forceinline__ void write_final(const RtRenderArgs &r, unsigned pix, float cr, float cg, float cb) {
   size_t o = pix;
@@ -550,6 +585,9 @@ __device__ __forceinline__ Cone warp_cone(const float (&dx)[NR], const float (&d
   mn = fmaxf(mn, 0.0f);                              // non-negative floats order like their bit patterns
   c.cth = __uint_as_float(__reduce_min_sync(kFull, __float_as_uint(mn))) - 2e-6f;
   c.ok = l2 >= 1.0f && c.cth >= 0.5f;
+#ifdef RT_NO_CULL
+  c.ok = false;                                      // diagnostics build: every walk covers the whole table
+#endif
   c.sth = fmaf(sqrtf(fmaxf(0.0f, fmaf(-c.cth, c.cth, 1.0f))), 1.0001f, 1e-4f);
   return c;
 }
@@ -722,21 +760,28 @@ __device__ __forceinline__ void closest_shared_culled(const Tab T, int npairs, c
   const int nslots = 2 * npairs;
   int ncand = 0;
   bool more = true;
+  // (the candidates collected so far are walked BEFORE the loop is left at the cut-off: the rounds since the last fill may
+  // hold a sphere nearer than the best hit the cut-off was computed from -- found by scripts/fuzz_parity.py on a
+  // 1705-sphere scene: a fill, then a round with <= 32 survivors, then the cut-off; tests/test_gpu_parity.py keeps the scene)
+  int base = 0;
 #pragma unroll 1
-  for (int base = 0; base < nslots && more; base += 64) {
-    if (T.gmin[base >> 3] > q.wcut) break;           // the rest of the table is beyond every ray's best hit
-    unsigned mk0, mk1;
-    cull_round2(T, base, nslots, cone, q.wcut, wb, ncand, mk0, mk1);
-    ncand += __popc(mk0) + __popc(mk1);
-    if (ncand > kCandMax - 64 || base + 64 >= nslots) {
-      if (ncand > 0) {
-        c_cand += (unsigned)ncand;
-        const int np = cull_finish(wb, ncand);
-        more = closest_shared_range<NR>(q, wb.pairs, wb.gmin, wb.perm, 0, np, dx, dy, dz, live, d64, sph64, src);
-        __syncwarp();
-        ncand = 0;
-      }
+  for (;;) {
+    const bool last = base >= nslots || T.gmin[base >> 3] > q.wcut;   // nothing further to collect: the table ends, or its
+    if (!last) {                                                      // rest is beyond every ray's best hit
+      unsigned mk0, mk1;
+      cull_round2(T, base, nslots, cone, q.wcut, wb, ncand, mk0, mk1);
+      ncand += __popc(mk0) + __popc(mk1);
+      base += 64;
+      if (ncand <= kCandMax - 64 && base < nslots) continue;
     }
+    if (ncand > 0) {
+      c_cand += (unsigned)ncand;
+      const int np = cull_finish(wb, ncand);
+      more = closest_shared_range<NR>(q, wb.pairs, wb.gmin, wb.perm, 0, np, dx, dy, dz, live, d64, sph64, src);
+      __syncwarp();
+      ncand = 0;
+    }
+    if (last || !more || base >= nslots) break;
   }
 #pragma unroll
   for (int r = 0; r < NR; r++) best[r] = q.best[r];
@@ -1344,8 +1389,8 @@ __global__ void __launch_bounds__(kTailThreads, RT_TAIL_CTAS) k_bounce(const Fas
         }
         if (a.r.hit_idx) a.r.hit_idx[(size_t)pix * depth + level] = idx[0];
         if (!hit) {                                  // sky, src/main.cpp:26-30
-          const float ts = 0.5f * (dy[0] + 1.0f);
-          cr += wt * ((1.0f - ts) + 0.5f * ts); cg += wt * ((1.0f - ts) + 0.7f * ts); cb += wt * ((1.0f - ts) + ts);
+          const Rgb sky = sky_colour(dy[0]);
+          add_scaled(cr, cg, cb, wt, sky.r, sky.g, sky.b);
           final_ = true;
         }
       }
@@ -1467,23 +1512,8 @@ __global__ void __launch_bounds__(kTailThreads, RT_TAIL_CTAS) k_bounce(const Fas
       if (hit) {
         cnt.shadow += L; cnt.occluded += __popcll(occm);
         smask = (unsigned)(occm & 0xffffffffull);
-        for (int l = 0; l < L; l++) {
-          if ((occm >> l) & 1ull) continue;
-          const d3 w = rtx::sub(p, ldc3(g_frame.light_pos[l]));
-          const float wx = (float)w.x, wy = (float)w.y, wz = (float)w.z;
-          const float inv = rsqrtf(fmaf(wz, wz, fmaf(wy, wy, wx * wx)));
-          const float sdx = wx * inv, sdy = wy * inv, sdz = wz * inv;           // light_dir = -(sdx, sdy, sdz)
-          const float cosl = -(nx * sdx + ny * sdy + nz * sdz);
-          const float ndl = fmaxf(0.0f, cosl);
-          const float kd = (1.0f - m.w) * ndl;
-          const float dn = -cosl;                                              // dot(-light_dir, n)
-          const float rx = sdx - 2.0f * nx * dn, ry = sdy - 2.0f * ny * dn, rz = sdz - 2.0f * nz * dn;
-          const float rdv = fmaxf(0.0f, rx * vx + ry * vy + rz * vz);
-          const float spec = 0.5f * (mx.x == 0.0f ? 1.0f : __powf(rdv, mx.x));
-          sr += g_frame.light_col[l][0] * spec + m.x * kd;
-          sg += g_frame.light_col[l][1] * spec + m.y * kd;
-          sb += g_frame.light_col[l][2] * spec + m.z * kd;
-        }
+        for (int l = 0; l < L; l++)
+          if (!((occm >> l) & 1ull)) phong_light(l, p.x, p.y, p.z, nx, ny, nz, vx, vy, vz, m, mx.x, sr, sg, sb);
       }
       RT_TT(4, 0);
 #ifdef RT_TAIL_TRACE
@@ -1494,9 +1524,9 @@ __global__ void __launch_bounds__(kTailThreads, RT_TAIL_CTAS) k_bounce(const Fas
       if (hit) {
         if (a.r.shadow_mask) a.r.shadow_mask[(size_t)pix * a.r.max_depth + level] = smask;
         if (mx.y > 0.5f) {                          // reflectivity > 0, decided in double on the host
-          const float refl = m.w, k = wt * (1.0f - refl);
-          cr += k * sr; cg += k * sg; cb += k * sb;
-          wt *= refl;
+          const float refl = m.w, k = __fmul_rn(wt, __fsub_rn(1.0f, refl));
+          add_scaled(cr, cg, cb, k, sr, sg, sb);
+          wt = __fmul_rn(wt, refl);
           if (level + 1 < a.r.max_depth) {
             RayRec *rec = qin + qi;                 // in place: the exact ray of the next level is re-read from here
             const double4 sc = ld_sph64(&a.r.sph64[idx[0]]);
@@ -1508,7 +1538,7 @@ __global__ void __launch_bounds__(kTailThreads, RT_TAIL_CTAS) k_bounce(const Fas
             final_ = true;                          // depth exhausted: the child contributes black
           }
         } else {
-          cr += wt * sr; cg += wt * sg; cb += wt * sb;
+          add_scaled(cr, cg, cb, wt, sr, sg, sb);
           final_ = true;
         }
       }

@@ -233,8 +233,8 @@ __device__ __forceinline__ float camera_dir_y(const FastArgs &a, int x, int j, f
 }
 // sky (src/main.cpp:26-30) quantised: r | g << 8 | b << 16
 __device__ __forceinline__ unsigned sky_rgb8(float dy) {
-  const float ts = 0.5f * (dy + 1.0f);
-  return quant8((1.0f - ts) + 0.5f * ts) | (quant8((1.0f - ts) + 0.7f * ts) << 8) | (quant8((1.0f - ts) + ts) << 16);
+  const Rgb c = sky_colour(dy);
+  return quant8(c.r) | (quant8(c.g) << 8) | (quant8(c.b) << 16);
 }
 
 // tabs: where table 0 (the camera table) is read from (shared memory when staged); wbase: the per-warp compacted tables;
@@ -363,15 +363,15 @@ __device__ __forceinline__ void closest0_body(const WaveArgs &w, const Lvl &lv, 
       }
       c_hits += hit;
       // sky (src/main.cpp:26-30) is final now; hit pixels are written by k_shade / later levels
-      const float ts = 0.5f * (dy[r] + 1.0f);
+      const Rgb skyc = sky_colour(dy[r]);
       const bool sky = live[r] && !hit;
       if (kBytes) {
         unsigned char *q = s_rgb + (((lane >> 4) * 2 + r) * kWTileW + (lane & 15)) * 3;
-        q[0] = (unsigned char)quant8(sky ? (1.0f - ts) + 0.5f * ts : 0.f);
-        q[1] = (unsigned char)quant8(sky ? (1.0f - ts) + 0.7f * ts : 0.f);
-        q[2] = (unsigned char)quant8(sky ? (1.0f - ts) + ts : 0.f);
+        q[0] = (unsigned char)quant8(sky ? skyc.r : 0.f);
+        q[1] = (unsigned char)quant8(sky ? skyc.g : 0.f);
+        q[2] = (unsigned char)quant8(sky ? skyc.b : 0.f);
       } else if (sky) {
-        write_final(a.r, pix[r], (1.0f - ts) + 0.5f * ts, (1.0f - ts) + 0.7f * ts, (1.0f - ts) + ts);
+        write_final(a.r, pix[r], skyc.r, skyc.g, skyc.b);
       }
     }
     if (!kBytes) continue;                           // float / remapped output: only finished pixels are written
@@ -474,9 +474,10 @@ __device__ __forceinline__ void closest1_body(const WaveArgs &w, const Lvl &lv, 
         }
         if (a.r.hit_idx) a.r.hit_idx[(size_t)pix[r] * depth + level] = hit ? w.hits[hslot[r]].idx : -1;
         if (!hit) {                                // sky through the mirror(s): the pixel is final
-          const float ts = 0.5f * (dy[r] + 1.0f);
-          write_final(a.r, pix[r], cr[r] + wt[r] * ((1.0f - ts) + 0.5f * ts), cg[r] + wt[r] * ((1.0f - ts) + 0.7f * ts),
-                      cb[r] + wt[r] * ((1.0f - ts) + ts));
+          const Rgb skyc = sky_colour(dy[r]);
+          float fr = cr[r], fg = cg[r], fb = cb[r];
+          add_scaled(fr, fg, fb, wt[r], skyc.r, skyc.g, skyc.b);
+          write_final(a.r, pix[r], fr, fg, fb);
         }
       }
       c_hits += hit;
@@ -510,30 +511,15 @@ __device__ __forceinline__ bool shade_one(const WaveArgs &w, const Lvl &lv, cons
   float sr = g_frame.ambient[0] * m.x, sg = g_frame.ambient[1] * m.y, sb = g_frame.ambient[2] * m.z;
   const bool cam = level == 0;                  // camera-ray hit: exact direction in the record, weight 1, no colour yet
   const float vx = cam ? -(float)hit_d0x(hr) : hr.vx, vy = cam ? -(float)hit_d0y(hr) : hr.vy, vz = cam ? -(float)hit_d0z(hr) : hr.vz;
-  for (int l = 0; l < L; l++) {
-    if ((occm >> l) & 1ull) continue;
-    // light_dir = normalized(light - point): FP64 difference, FP32 normalisation (colour only)
-    const float wx = (float)(g_frame.light_pos[l][0] - hr.px), wy = (float)(g_frame.light_pos[l][1] - hr.py),
-                wz = (float)(g_frame.light_pos[l][2] - hr.pz);
-    const float inv = rsqrtf(fmaf(wz, wz, fmaf(wy, wy, wx * wx)));
-    const float lx = wx * inv, ly = wy * inv, lz = wz * inv;
-    const float nl = hr.nx * lx + hr.ny * ly + hr.nz * lz;
-    const float kd = (1.0f - m.w) * fmaxf(0.0f, nl);
-    // reflect(-light_dir, n) = -l + 2 (l.n) n   (include/vec3.h:31-33)
-    const float rx = 2.0f * nl * hr.nx - lx, ry = 2.0f * nl * hr.ny - ly, rz = 2.0f * nl * hr.nz - lz;
-    const float rdv = fmaxf(0.0f, rx * vx + ry * vy + rz * vz);
-    const float spec = 0.5f * (mx.x == 0.0f ? 1.0f : __powf(rdv, mx.x));
-    sr += g_frame.light_col[l][0] * spec + m.x * kd;
-    sg += g_frame.light_col[l][1] * spec + m.y * kd;
-    sb += g_frame.light_col[l][2] * spec + m.z * kd;
-  }
+  for (int l = 0; l < L; l++)
+    if (!((occm >> l) & 1ull)) phong_light(l, hr.px, hr.py, hr.pz, hr.nx, hr.ny, hr.nz, vx, vy, vz, m, mx.x, sr, sg, sb);
   if (a.r.shadow_mask) a.r.shadow_mask[(size_t)hr.pix * a.r.max_depth + level] = (unsigned)(occm & 0xffffffffull);
   float cr = cam ? 0.f : hr.ar, cg = cam ? 0.f : hr.ag, cb = cam ? 0.f : hr.ab, wt = cam ? 1.0f : hr.wt;
   bool cont = false;
   if (mx.y > 0.5f) {                          // reflectivity > 0, decided in double on the host
-    const float refl = m.w, k = wt * (1.0f - refl);
-    cr += k * sr; cg += k * sg; cb += k * sb;
-    wt *= refl;
+    const float refl = m.w, k = __fmul_rn(wt, __fsub_rn(1.0f, refl));
+    add_scaled(cr, cg, cb, k, sr, sg, sb);
+    wt = __fmul_rn(wt, refl);
     if (level + 1 < a.r.max_depth) {
       // exact reflected ray: the incoming direction comes with the record (camera ray) or from the ray's queue record,
       // the normal from the exact hit point (src/main.cpp:35,45-48)
@@ -547,7 +533,7 @@ __device__ __forceinline__ bool shade_one(const WaveArgs &w, const Lvl &lv, cons
       cont = true;
     }
   } else {
-    cr += wt * sr; cg += wt * sg; cb += wt * sb;
+    add_scaled(cr, cg, cb, wt, sr, sg, sb);
   }
   if (!cont) {
     if (stage) { stage[0] = (unsigned char)quant8(cr); stage[1] = (unsigned char)quant8(cg); stage[2] = (unsigned char)quant8(cb); }

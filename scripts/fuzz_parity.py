@@ -11,6 +11,7 @@ first, count = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (1
 BIG = len(sys.argv) > 3 and sys.argv[3] == "big"          # 300..4000 spheres: streamed tables (accel=1) and the LBVH
 if BIG:
     import gen_scene
+first0 = first
 rs = {"fast": rtb200.Renderer(0, accel=1 if BIG else None), "bvh": rtb200.Renderer(0, mode="bvh")}
 bad = 0
 for seed in range(first, first + count):
@@ -31,6 +32,10 @@ for seed in range(first, first + count):
         li = sc.lights.copy(); li[:, :3] = li[:, :3] * k + off
         cm = sc.camera.copy(); cm[:3] = cm[:3] * k + off; cm[3:6] = cm[3:6] * k + off
         sc = rtb200.Scene(sp, li, sc.ambient, cm)
+    if not BIG and seed % 7 == 3:                          # many lights: both sides of the 32-light switch of the occlusion bits, several
+        nl = int(g.integers(6, 41))                        # rounds of packed shadow queries in the tail kernel
+        li = np.column_stack([g.uniform(-8, 8, (nl, 3)) - np.array([0, -4, 6]), g.uniform(0.05, 0.3, (nl, 3)), np.ones(nl)])
+        sc = rtb200.Scene(sc.spheres, li, sc.ambient, sc.camera)
     if seed % 37 == 0:
         sc = rtb200.Scene(sc.spheres, sc.lights[:0], sc.ambient, sc.camera)      # no lights
     if seed % 41 == 0:
@@ -95,5 +100,7 @@ for seed in range(first, first + count):
         ok_rgb, pct, mx = rtb200.compare_rgb(osamp["rgb"], rgb, 0.5)
         if not (okk and ok_rgb and mx <= 2):
             bad += 1; print("MISMATCH seed %d: supersampling hit %s rgb %s max %d" % (seed, okk, ok_rgb, mx))
+    if (seed - first0 + 1) % 100 == 0:
+        print("... %d scenes so far, %d mismatches" % (seed - first0 + 1, bad), flush=True)
 print("fuzz: %d scenes x %d modes, %d mismatches" % (count, len(rs), bad))
 sys.exit(1 if bad else 0)

@@ -510,3 +510,29 @@ def test_many_lights(rt, oracle, renderers, scenes, nl, mode):
     sc = scenes["medium"]
     lights = np.column_stack([g.uniform(-15, 15, nl), g.uniform(2, 14, nl), g.uniform(-25, 8, nl), g.uniform(0.05, 0.2, (nl, 3)), np.ones(nl)])
     check(rt, oracle, renderers[mode], rt.Scene(sc.spheres, lights, sc.ambient, sc.camera), 96, 54, 3)
+
+
+def test_candidates_pending_at_the_cutoff_are_walked(rt, oracle):
+    """Regression (scripts/fuzz_parity.py, large scenes): the bundle-culled camera walk fills its per-warp table, walks it,
+    collects a further round with <= 32 survivors and THEN reaches the distance cut-off -- the survivors of that last
+    round must still be walked (one of them was the closest sphere of a pixel; the walk used to leave the loop first).
+    1705 spheres with wide pixel cones (45 x 57 pixels) through the table path."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    import gen_scene
+    sc = rt.Scene(*gen_scene.generate(1705, 92992, 0.05, 1.4764311835476813))
+    with rt.Renderer(0, accel=1) as r:
+        check(rt, oracle, r, sc, 45, 57, 6)
+
+
+@pytest.mark.parametrize("mode", ["fast", "bvh"])
+@pytest.mark.parametrize("seed,W,H,D", [(83424, 224, 176, 1), (5, 96, 54, 4), (11, 130, 40, 3)])
+def test_every_store_path_gives_the_same_pixels(rt, renderers, seed, W, H, D, mode):
+    """rt_render (whole tiles stored by the shading pass) and rt_render_debug (pixel by pixel) run different inlined copies
+    of the same colour code; the arithmetic is written with explicit intrinsics (phong_light, add_scaled, sky_colour) so that
+    no copy is contracted into FMAs differently from another (seed 83424 once differed by one LSB in one pixel)."""
+    r = renderers[mode]
+    r.upload(_random_scene(rt, seed))
+    plain = r.render(W, H, D)[0]
+    dbg = r.render_debug(W, H, D)[0]
+    assert np.array_equal(plain, dbg)
