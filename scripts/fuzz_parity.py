@@ -1,5 +1,5 @@
 """Long-running parity fuzz (not part of the test suite): random adversarial scenes vs the oracle, all kernel families.
-usage: fuzz_parity.py [first_seed] [count]"""
+usage: fuzz_parity.py [first_seed] [count] [big|mid]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests"), os.path.join(ROOT, "scripts")):
@@ -8,7 +8,8 @@ import numpy as np
 import rtb200, oracle_py
 from test_gpu_parity import _random_scene
 first, count = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (100, 200)
-BIG = len(sys.argv) > 3 and sys.argv[3] == "big"          # 300..4000 spheres: streamed tables (accel=1) and the LBVH
+MID = len(sys.argv) > 3 and sys.argv[3] == "mid"          # 60..300 spheres: tables in shared memory, several fills of a culled walk
+BIG = len(sys.argv) > 3 and sys.argv[3] in ("big", "mid") # 300..4000 spheres: streamed tables (accel=1) and the LBVH
 if BIG:
     import gen_scene
 first0 = first
@@ -17,7 +18,7 @@ bad = 0
 for seed in range(first, first + count):
     g = np.random.default_rng(seed)
     if BIG:
-        sc = rtb200.Scene(*gen_scene.generate(int(g.integers(300, 4000)), seed, 0.05, float(g.uniform(0.3, 1.5))))
+        sc = rtb200.Scene(*gen_scene.generate(int(g.integers(60, 300) if MID else g.integers(300, 4000)), seed, 0.05, float(g.uniform(0.3, 1.5))))
     else:
         sc = _random_scene(rtb200, seed)
     if BIG:

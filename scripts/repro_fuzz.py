@@ -1,4 +1,4 @@
-"""Re-runs ONE scene of scripts/fuzz_parity.py and prints what differs (pixels, levels, values).  usage: repro_fuzz.py seed [big]"""
+"""Re-runs ONE scene of scripts/fuzz_parity.py and prints what differs (pixels, levels, values).  usage: repro_fuzz.py seed [big|mid]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests"), os.path.join(ROOT, "scripts")):
@@ -6,11 +6,11 @@ for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests"), os.pa
 import numpy as np
 import rtb200, oracle_py
 from test_gpu_parity import _random_scene
-seed = int(sys.argv[1]); BIG = len(sys.argv) > 2 and sys.argv[2] == "big"
+seed = int(sys.argv[1]); MID = len(sys.argv) > 2 and sys.argv[2] == "mid"; BIG = len(sys.argv) > 2 and sys.argv[2] in ("big", "mid")
 g = np.random.default_rng(seed)
 if BIG:
     import gen_scene
-    sc = rtb200.Scene(*gen_scene.generate(int(g.integers(300, 4000)), seed, 0.05, float(g.uniform(0.3, 1.5))))
+    sc = rtb200.Scene(*gen_scene.generate(int(g.integers(60, 300) if MID else g.integers(300, 4000)), seed, 0.05, float(g.uniform(0.3, 1.5))))
     W, H, D = int(g.integers(16, 120)), int(g.integers(16, 70)), int(g.integers(1, 7))
 else:
     sc = _random_scene(rtb200, seed)
