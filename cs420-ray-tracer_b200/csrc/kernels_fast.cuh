@@ -3,9 +3,10 @@
 // Work decomposition (wavefront with compacted queues, warps schedule themselves):
 //   levels 0 and 1 run as phase-separated wavefront kernels (kernels_wave.cuh); this file holds the
 //   query primitives they share and
-//   k_bounce    the tail (levels >= 2, one launch): consumes the ray queue, 32 rays per warp fetch,
-//               general-origin closest hit, Phong + one any-hit shadow query per light; each lane
-//               follows its ray to termination, the queue record is updated in place.
+//   k_bounce    the tail (levels >= 2, one launch): consumes the ray queue, <= 32 rays per warp fetch,
+//               general-origin closest hit per lane, the (hit, light) shadow queries of the warp packed
+//               onto its lanes (shadow_mixed), Phong; each lane follows its ray to termination, the
+//               queue record is updated in place.
 // Sphere tables are staged once per CTA into shared memory with ONE TMA bulk copy
 // (cp.async.bulk + mbarrier) when they fit; larger ones are streamed tile by tile (kernels_wave.cuh) or, from
 // 1024 spheres on, replaced as the source of candidates by the device-built LBVH (bvh.cuh).
@@ -1297,10 +1298,13 @@ __device__ __forceinline__ void flush_counters(const FastArgs &a, Counters &c, i
 }
 
 // ---------------------------------------------------------------------------------------------
-// THE TAIL (levels >= wave_levels): reflected rays from the queue, one per lane, 32 per warp fetch;
+// THE TAIL (levels >= wave_levels): reflected rays from the queue, one per lane, <= 32 per warp fetch;
 // every lane follows its ray to termination, the queue record is updated in place.  Few rays are
 // left at these levels (a few percent of the frame), so the kernel is bound by the latency of one
-// warp's chain: closest hit -> exact t / geometry -> one shadow query per light -> Phong -> reflect.
+// warp's chain: closest hit -> exact t / geometry -> shadow queries -> Phong -> reflect.  The shadow
+// queries were two thirds of that chain when every light was walked in turn with the lanes of the missed
+// rays idle; now the self-shadow shortcut settles the back-facing half and the rest is packed 32 per walk
+// (profiles/r02_tail_phase_trace.txt; -DRT_TAIL_TRACE builds the phase stamps in).
 #ifndef RT_TAIL_THREADS
 #define RT_TAIL_THREADS 128
 #endif

@@ -8,7 +8,8 @@
 //   k_closest0   pixels      -> camera-table walk -> exact t -> hit point / normal -> HitRec block
 //                               (sky pixels are final: staged per warp, 128-bit stores)
 //   k_closest1   RayRec queue-> general-origin loop -> same, for reflected rays (misses are final)
-//   k_shadow     HitRec blocks (two hits per lane) x lights -> light-table walk -> one occlusion byte per (light, hit)
+//   k_shadow     HitRec blocks (two hits per lane) x lights -> light-table walk -> one occlusion bit per (light, hit)
+//                               in the hit's record (a byte array when the scene has more than 32 lights)
 //   k_shade      HitRec      -> Phong (include/scene.h:89-121) -> final pixel, or the reflected
 //                               ray appended to the RayRec queue (warp-ballot compaction)
 // Where the candidate spheres of a query come from is the template mode of k_closest0 / k_shadow (kTab*): a bundle-culled
