@@ -640,7 +640,7 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
   // small shares of a frame (one rank's bands of many): level 1 has too few rays to pay for three more launches
   int wave_levels = w->wave_levels > 0 ? w->wave_levels : (fs->bvh_nodes ? RT_MAX_LEVELS_INTERNAL : (npix >= 750000 ? 2 : 1));
   // ... better: the ray counts of the previous frame of this very (scene, size, depth).  A level runs as a wavefront when
-  // at least kWaveMinRays rays enter it (measured break-even: 83 k rays still win as a wavefront, 44 k do not), the rest goes to the tail.
+  // at least kWaveMinRays rays enter it (measured break-even: 67 k rays still win as a wavefront, 55 k do not), the rest goes to the tail.
   const unsigned long long fb_key = fs->generation * 1000003ull + (unsigned long long)npix * 131ull + (unsigned long long)args.max_depth;
   const bool fb_auto = w->wave_levels <= 0 && !fs->bvh_nodes && args.max_depth > 1;
   if (fb_auto) {
@@ -651,7 +651,7 @@ int rtk_launch_fast(const RtRenderArgs &args, const RtFastScene *fs, RtFastWork 
     const cudaError_t fbq = w->fb_pending ? cudaEventQuery(w->fb_event) : cudaErrorNotReady;
     if (fbq != cudaSuccess) cudaGetLastError();      // (cudaErrorNotReady must not surface as this call's launch error)
     if (w->fb_pending && fbq == cudaSuccess) {
-      constexpr unsigned kWaveMinRays = 75000u;
+      constexpr unsigned kWaveMinRays = 60000u;
       int lv = 1;
       while (lv < 33 && w->h_fb[lv] >= kWaveMinRays) lv++;
       w->fb_levels = lv; w->fb_key = w->fb_pending_key; w->fb_pending = 0;
