@@ -186,3 +186,34 @@ def test_compare_rule_against_the_reference_script_itself(rt, oracle, scenes, tm
             ok, pct, _ = rt.compare_rgb(base, img, tol)
             assert (p.returncode == 0) == ok, (k, tol, p.stdout, pct)
             assert ("Diff pixels: %.2f%%" % pct) in p.stdout
+
+
+def test_committed_bench_lines_follow_the_contract():
+    """The bench lines kept under profiles/ (what bench.py printed on a B200) carry every key of the measurement contract:
+    metric / value / e2e with its copy sizes / launch count / clocks / roofline with peak, achieved, fraction and measured
+    traffic / cpu_baseline; the reference arm's line names itself and repeats its value as e2e."""
+    import json
+    prof = os.path.join(ROOT, "profiles")
+
+    def last_json_line(name):
+        with open(os.path.join(prof, name)) as f:
+            return json.loads([ln for ln in f.read().splitlines() if ln.startswith("{")][-1])
+
+    d = last_json_line("r02_bench_n1.json")
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["higher_is_better"] is True and d["vs_baseline"] is None and d["warmup"] >= 3
+    assert "complex.txt" in d["config"]["workload"] and "l2" in d["config"]
+    assert d["gpu_launches"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] == 1920 * 1080 * 3
+    assert 0 < d["e2e"]["value"] < d["value"]                   # copies inside the timed region: end to end is slower
+    r = d["roofline"]
+    assert r["bound"] == "fp32" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3 and r["traffic"] > 0
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] > 0
+    ref = last_json_line("r02_bench_reference_n1.json")
+    assert ref["impl"] == "reference" and ref["e2e"]["value"] == ref["value"] and ref["e2e"]["h2d_bytes_per_step"] == 0
+    assert ref["config"]["workload"] == d["config"]["workload"] and ref["metric"] == d["metric"]
+    for n in (2, 4, 8):
+        m = last_json_line("r02_bench_n%d.json" % n)
+        assert m["n_gpus"] == n and m["scaling"] == "strong" and m.get("frame_check") == "identical" and m["value"] > d["value"]
