@@ -8,6 +8,7 @@ W, H = 1920, 1080
 D = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 r = rtb200.Renderer(0)
 r.upload(sc)
+r.set_option("level_timing", 1)               # event marks between the level-0 kernels (turns PDL off)
 buf = torch.empty(H * W * 3 + 16, dtype=torch.uint8, device="cuda:0")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:0")
 v = []
